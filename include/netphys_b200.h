@@ -1,0 +1,195 @@
+/* include/netphys_b200.h -- the drop-in boundary: C ABI of the B200 rigid-body hot path.
+ *
+ * Plain C, plain pointers and sizes, no CUDA or torch types.  Each entry point names the reference
+ * interface (dougfrazer/netphys, engine/) it replaces.  The C++ shim include/netphys/physics.h re-declares
+ * the reference's Physics / PhysicsShape / Physics_Update / DetectCollision on top of these calls, so
+ * code written against engine/physics.h + engine/physics_shape.h recompiles unchanged.
+ *
+ * Conventions
+ *   - every call returns NP_OK (0) or a negative np_status; np_last_error() gives the text.  Nothing aborts
+ *     (the reference asserts, engine/collision_detection.cpp:255,321).
+ *   - a np_world owns one CUDA device, one stream and all device memory of its bodies and shapes.  One host
+ *     thread per world.  np_world_step is asynchronous; every getter synchronises the world's stream.
+ *   - vectors are float[3]; matrices are row-major (matrix3: x1 x2 x3 / y1.. ; matrix4: x1..x4 / y1..,
+ *     engine/matrix.h:36-42,109-116), i.e. exactly the reference's member order.
+ *   - all arithmetic on the path is IEEE binary32 in the reference's operation order (no FMA contraction);
+ *     results are bit-identical to the reference built as described in oracle/Makefile.
+ *   - there is NO CPU fallback: without a CUDA device np_world_create fails with NP_ERR_NO_DEVICE.
+ */
+#ifndef NETPHYS_B200_H
+#define NETPHYS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NETPHYS_B200_ABI_VERSION 1
+
+typedef enum np_status {
+    NP_OK = 0,
+    NP_ERR_INVALID = -1,     /* bad handle / index / argument */
+    NP_ERR_NO_DEVICE = -2,   /* no CUDA device, or device is not sm_100 */
+    NP_ERR_CUDA = -3,        /* a CUDA call failed; see np_last_error() */
+    NP_ERR_CAPACITY = -4,    /* output buffer too small, or an internal hard cap was hit */
+    NP_ERR_UNSUPPORTED = -5  /* e.g. is3D == 0 (2-D mode), custom virtual PhysicsShape */
+} np_status;
+
+/* COLLISION_RESPONSE, engine/physics.h:13-17 */
+typedef enum np_collision_response { NP_COLLISION_RESPONSE_NONE = 0, NP_COLLISION_RESPONSE_IMPULSE = 1 } np_collision_response;
+
+/* StaticPhysicsData, engine/physics.h:36-51 (same fields, same order) */
+typedef struct np_static_physics_data {
+    float gravity[3];
+    float initial_position[3];
+    float initial_rotation[3];          /* Euler XYZ radians, engine/matrix.h:283-288 */
+    float mass;
+    float elasticity;
+    float static_friction_coeff;        /* unused by the reference path (friction block is commented out, physics.cpp:49-72) */
+    float dynamic_friction_coeff;
+    int32_t collision_response;         /* np_collision_response */
+    float moment_of_inertia;
+    float inertia_tensor[9];
+    float inverse_inertia_tensor[9];
+} np_static_physics_data;
+
+/* CollisionData, engine/physics.h:18-25.  depth is 0 (not garbage) when success == 0. */
+typedef struct np_collision_data {
+    float a_normal[3];
+    float b_normal[3];
+    float penetration_direction[3];
+    float depth;
+    int32_t success;
+} np_collision_data;
+
+/* Collision, engine/physics.h:26-31, with body indices (creation order) instead of Physics* */
+typedef struct np_collision {
+    int32_t a, b;
+    np_collision_data data;
+} np_collision;
+
+/* dynamic state of one body: Physics::m_position, m_rotation, m_linearMomentum, m_angularMomentum (physics.h:87-94) */
+typedef struct np_body_state {
+    float position[3], rotation[3], linear_momentum[3], angular_momentum[3];
+} np_body_state;
+
+/* the replication record of netphys_common/common.h:120-127 (CommandFrameObject, 36 bytes) */
+typedef struct np_snapshot_object {
+    uint32_t guid;
+    float pos[3];
+    float rot[4];        /* quaternion (w,x,y,z) of the body's Euler rotation */
+    uint32_t is_enabled;
+} np_snapshot_object;
+
+typedef struct np_world np_world;
+
+/* pair-search policy of np_world_step */
+typedef enum np_broadphase {
+    NP_BROADPHASE_EXACT = 0,  /* reference semantics: for each body i ascending, j = i+1.. until the first hit, then stop
+                                 (GetCollisions, engine/physics.cpp:116-145).  Collision list identical to the reference. */
+    NP_BROADPHASE_GRID = 1    /* uniform-grid AABB culling first (the TODO at collision_detection.cpp:698 / todo.txt:7);
+                                 candidates are then searched in the same ascending-j, first-hit order */
+} np_broadphase;
+
+typedef enum np_option {
+    NP_OPT_BROADPHASE = 1,        /* np_broadphase */
+    NP_OPT_GRID_CELL = 2,         /* float bits: grid cell edge; 0 = auto (largest AABB extent) */
+    NP_OPT_COUNTERS = 3           /* 1 = accumulate pair-test / hit / iteration counters (np_world_get_counters) */
+} np_option;
+
+typedef struct np_counters {
+    uint64_t steps;
+    uint64_t pair_tests;     /* DetectCollision evaluations */
+    uint64_t hits;
+    uint64_t gjk_steps;      /* DetectCollisionStep evaluations */
+    uint64_t support_pairs;  /* support(A,d) / support(B,-d) pairs, GJK + EPA, incl. the seed */
+    uint64_t epa_iters;      /* FindIntersectionPointsStep evaluations */
+    uint64_t epa_tri_tests;  /* closest-point-on-triangle evaluations of the EPA face scans */
+    uint64_t epa_overflow;   /* pairs re-run on the large-polytope path */
+    uint64_t candidates;     /* NP_BROADPHASE_GRID: AABB-overlapping pairs emitted */
+} np_counters;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int np_abi_version(void);
+const char* np_last_error(void);
+int np_device_count(void);                         /* CUDA devices visible; 0 when there is no driver/GPU */
+
+/* ---- world (the process-global body list of engine/physics.cpp:9 made explicit) ------------------ */
+np_world* np_world_create(int device);             /* device < 0: current device.  NULL on failure */
+void np_world_destroy(np_world* w);
+int np_world_set_option(np_world* w, int option, int64_t value);
+/* Bodies created after this call form a new ISLAND: an independent world that shares the store.  Pairs are
+ * only searched inside an island (RL-style batches of worlds, BASELINE configs[3]).  Returns the island id. */
+int np_world_begin_island(np_world* w);
+int np_world_body_count(const np_world* w);
+int np_world_synchronize(np_world* w);
+
+/* ---- shapes: MeshPhysicsShape, engine/physics_shape.h:62-74 --------------------------------------- */
+int np_shape_create_mesh(np_world* w, const float* xyz, int nverts);       /* m_mesh.m_vertexPos, physics_shape.h:28; returns shape id */
+int np_shape_create_sphere(np_world* w, float radius);                     /* CreateSphere, physics_shape.cpp:313-316 (162-vertex icosphere) */
+int np_shape_create_box(np_world* w, float width, float depth, float height); /* CreateBox, physics_shape.cpp:317-320 (depth ignored, :166) */
+int np_shape_vertex_count(const np_world* w, int shape);
+int np_shape_get_vertices(const np_world* w, int shape, float* xyz, int cap_verts);
+/* PhysicsShape::GetPointFurthestInDirection, physics_shape.h:59 (world = row-major 4x4) */
+int np_shape_support(np_world* w, int shape, const float dir[3], const float world[16], float out[3]);
+
+/* ---- bodies: class Physics, engine/physics.h:58-95 ------------------------------------------------ */
+int np_body_create(np_world* w, int shape, const np_static_physics_data* sd);            /* Physics::Physics, physics.cpp:11-18; returns body id */
+int np_body_create_batch(np_world* w, int n, const int32_t* shapes, const np_static_physics_data* sd); /* n ctor calls; returns first id */
+int np_body_reset(np_world* w, int body);                                                /* Physics::Reset, physics.cpp:166-172 */
+int np_body_get_state(np_world* w, int body, np_body_state* out);                         /* GetPosition/GetRotation (+ momenta) */
+int np_body_set_state(np_world* w, int body, const np_body_state* in);                    /* SetPosition/SetRotation, physics.h:82-85 */
+int np_body_get_transform(np_world* w, int body, float out16[16]);                        /* GetTransform, physics.h:70-76 */
+int np_body_apply_impulse_response(np_world* w, int body, const np_collision_data* data, const float normal[3]); /* physics.cpp:27-46 */
+int np_world_get_states(np_world* w, np_body_state* out, int cap);                        /* all bodies, creation order */
+int np_world_set_states(np_world* w, const np_body_state* in, int n);
+
+/* ---- the step: Physics_Update, engine/physics.h:99-100 / physics.cpp:148-163 ----------------------- */
+int np_world_step(np_world* w, float dt);
+int np_world_step_n(np_world* w, float dt, int steps);    /* `steps` consecutive Physics_Update(dt) calls, one submission */
+/* Physics::Update for every body only (physics.cpp:151-155), no collision phase */
+int np_world_integrate(np_world* w, float dt);
+/* collisions of the most recent step, in the reference's list order (ascending a) */
+int np_world_get_collisions(np_world* w, np_collision* out, int cap, int* count);
+/* host-buffer round trip of one step (the e2e path): upload `in` (may be NULL = keep device state),
+ * step, download all states into `out`.  Copies are inside the call. */
+int np_world_step_host(np_world* w, float dt, const np_body_state* in, np_body_state* out, int n);
+int np_world_get_counters(np_world* w, np_counters* out);
+/* device time (ms, CUDA events on the world's stream) of the kernels of the most recent np_world_step[_n]:
+ * [0] integrate+transform, [1] broad-phase, [2] narrow-phase (GJK+EPA), [3] resolve, [4] snapshot, [5] total */
+int np_world_last_step_ms(np_world* w, float out[6]);
+
+/* ---- narrow phase: DetectCollision, engine/physics.h:103-110 --------------------------------------- */
+int np_detect_collision(np_world* w, int shape_a, const float a_transform[16], int shape_b, const float b_transform[16],
+                        int is3D, np_collision_data* out /* may be NULL */, int* hit);
+/* n independent queries, host buffers; pose = position[3] rotation[3] -> GetTransform.  hit / out may be NULL. */
+int np_detect_collision_batch(np_world* w, int n, const int32_t* shape_a, const float* pose_a, const int32_t* shape_b,
+                              const float* pose_b, int32_t* hit, np_collision_data* out);
+/* same over device-resident buffers (SoA on the world's device); kernel_ms = device time of the GJK/EPA kernel */
+int np_detect_collision_batch_device(np_world* w, int n, const void* d_shape_a, const void* d_pose_a, const void* d_shape_b,
+                                     const void* d_pose_b, void* d_hit, void* d_out, float* kernel_ms);
+
+/* ---- replication snapshot (netphys_server/world_s.cpp:23-51 -> CommandFrameObject) ----------------- */
+int np_world_snapshot(np_world* w, np_snapshot_object* dst, int cap);      /* device -> host */
+/* device buffer holding the packed snapshot of the last step (for an NCCL all-gather by the host layer) */
+int np_world_snapshot_device(np_world* w, void** d_ptr, size_t* bytes);
+
+/* ---- device memory helpers for callers that keep buffers resident (bench, multi-GPU plumbing) ------- */
+void* np_device_alloc(np_world* w, size_t bytes);
+int np_device_free(np_world* w, void* p);
+int np_device_upload(np_world* w, void* d_dst, const void* h_src, size_t bytes);
+int np_device_download(np_world* w, void* h_dst, const void* d_src, size_t bytes);
+void* np_world_stream(np_world* w);                                        /* cudaStream_t */
+
+/* ---- self tests of device primitives (used by tests/; cheap) ---------------------------------------- */
+/* order-independent checksum of sinf/cosf over float bit patterns [start, start+count) computed on the device */
+int np_selftest_sincos_hash(np_world* w, uint32_t start, uint64_t count, uint64_t* hash_sin, uint64_t* hash_cos);
+/* util.h closest-point solvers on the device: kind 2/3/4 = line/triangle/tetrahedron; pts = kind points, origin query */
+int np_selftest_closest(np_world* w, int kind, const float* pts, int32_t* region, float uvw[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NETPHYS_B200_H */

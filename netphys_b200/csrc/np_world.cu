@@ -1,0 +1,722 @@
+// netphys_b200/csrc/np_world.cu -- host side of the C ABI declared in include/netphys_b200.h.
+//
+// A np_world keeps host mirrors of what the caller handed over (shapes, StaticPhysicsData, island ids)
+// and a structure-of-arrays body store in HBM (np_kernels.cuh).  Dynamic state lives on the device from
+// the first step on; getters copy it back.  Every device operation goes to the world's own stream.
+// There is no CPU execution path: without a device np_world_create fails.
+#include "../../include/netphys_b200.h"
+#include "np_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace np;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                                      \
+    do {                                                                                                              \
+        cudaError_t e_ = (call);                                                                                      \
+        if (e_ != cudaSuccess) return fail(NP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+struct HostShape { std::vector<float> xyz; };
+struct HostBody { np_static_physics_data sd; int shape; int island; };
+
+struct np_world {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    // host mirrors
+    std::vector<HostShape> shapes;
+    std::vector<HostBody> bodies;
+    std::vector<np_body_state> host_state;   // authoritative until the first upload, refreshed on demand
+    int island = 0;
+    // options
+    int broadphase = NP_BROADPHASE_EXACT;
+    float grid_cell = 0.0f;
+    int counters_on = 0;
+    // device store
+    bool dirty_bodies = true, dirty_shapes = true, dev_state_valid = false;
+    int cap = 0, dev_n = 0;
+    float *d_state = nullptr, *d_cst = nullptr, *d_xf = nullptr;
+    int* d_ints = nullptr;
+    float4* d_verts = nullptr; int *d_soff = nullptr, *d_scnt = nullptr; int total_verts = 0;
+    // per-step scratch
+    int *d_hit_j = nullptr, *d_cflags = nullptr; float4* d_contact = nullptr;
+    int* d_zero = nullptr;            // [ticket, big_count, pad(30), inc_cnt[cap], cursor[cap]]  -- one memset per step
+    int *d_inc_off = nullptr, *d_inc = nullptr, *d_sums = nullptr, *d_big_list = nullptr;
+    DevCounters* d_ctr = nullptr;
+    SnapObj* d_snap = nullptr;
+    BigArena arena = {};
+    // pinned staging for host round trips
+    float* h_stage = nullptr; size_t h_stage_bytes = 0;
+    // timing
+    cudaEvent_t ev[6] = {};
+    float last_ms[6] = {};
+    bool timed = false;
+    unsigned long long steps = 0;
+    // CUDA graph of one step (np_world_step_n)
+    cudaGraphExec_t graph = nullptr; float graph_dt = 0.0f;
+    int first_hit_blocks = 0, pairs_blocks = 0;
+};
+
+// ------------------------------------------------------------------------------------------------ helpers
+static StoreView view(np_world* w) { StoreView s; s.n = (int)w->bodies.size(); s.cap = w->cap; s.state = w->d_state; s.cst = w->d_cst; s.xf = w->d_xf; s.ints = w->d_ints; return s; }
+static ShapeView sview(np_world* w) { ShapeView s; s.verts = w->d_verts; s.off = w->d_soff; s.cnt = w->d_scnt; s.total_verts = w->total_verts; return s; }
+static int* d_ticket(np_world* w) { return w->d_zero; }
+static int* d_big_count(np_world* w) { return w->d_zero + 1; }
+static int* d_inc_cnt(np_world* w) { return w->d_zero + 32; }
+static int* d_cursor(np_world* w) { return w->d_zero + 32 + w->cap; }
+
+static void free_store(np_world* w)
+{
+    cudaFree(w->d_state); cudaFree(w->d_cst); cudaFree(w->d_xf); cudaFree(w->d_ints);
+    cudaFree(w->d_hit_j); cudaFree(w->d_cflags); cudaFree(w->d_contact); cudaFree(w->d_zero);
+    cudaFree(w->d_inc_off); cudaFree(w->d_inc); cudaFree(w->d_sums); cudaFree(w->d_big_list); cudaFree(w->d_snap);
+    w->d_state = w->d_cst = w->d_xf = nullptr; w->d_ints = nullptr; w->d_hit_j = w->d_cflags = nullptr; w->d_contact = nullptr;
+    w->d_zero = w->d_inc_off = w->d_inc = w->d_sums = w->d_big_list = nullptr; w->d_snap = nullptr;
+    w->cap = 0;
+}
+static int ensure_stage(np_world* w, size_t bytes)
+{
+    if (bytes <= w->h_stage_bytes) return NP_OK;
+    if (w->h_stage) cudaFreeHost(w->h_stage);
+    w->h_stage = nullptr; w->h_stage_bytes = 0;
+    CU(cudaMallocHost((void**)&w->h_stage, bytes));
+    w->h_stage_bytes = bytes;
+    return NP_OK;
+}
+static void drop_graph(np_world* w) { if (w->graph) { cudaGraphExecDestroy(w->graph); w->graph = nullptr; } }
+
+// state [12][cap] on the device  <->  np_body_state[n] on the host
+static int download_states(np_world* w, np_body_state* out, int n)
+{
+    if (n == 0) return NP_OK;
+    int r = ensure_stage(w, sizeof(float) * S_COUNT * (size_t)n); if (r) return r;
+    CU(cudaMemcpy2DAsync(w->h_stage, sizeof(float) * n, w->d_state, sizeof(float) * w->cap, sizeof(float) * n, S_COUNT, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    float* o = (float*)out;
+    for (int c = 0; c < S_COUNT; c++) { const float* src = w->h_stage + (size_t)c * n; for (int i = 0; i < n; i++) o[(size_t)i * 12 + c] = src[i]; }
+    return NP_OK;
+}
+static int upload_states(np_world* w, const np_body_state* in, int n)
+{
+    if (n == 0) return NP_OK;
+    int r = ensure_stage(w, sizeof(float) * S_COUNT * (size_t)n); if (r) return r;
+    const float* s = (const float*)in;
+    for (int c = 0; c < S_COUNT; c++) { float* dst = w->h_stage + (size_t)c * n; for (int i = 0; i < n; i++) dst[i] = s[(size_t)i * 12 + c]; }
+    CU(cudaMemcpy2DAsync(w->d_state, sizeof(float) * w->cap, w->h_stage, sizeof(float) * n, sizeof(float) * n, S_COUNT, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaStreamSynchronize(w->stream));   // the staging buffer is reused
+    return NP_OK;
+}
+
+static int ensure_device(np_world* w)
+{
+    CU(cudaSetDevice(w->device));
+    const int n = (int)w->bodies.size();
+    if (w->dirty_shapes) {
+        drop_graph(w);
+        cudaFree(w->d_verts); cudaFree(w->d_soff); cudaFree(w->d_scnt); w->d_verts = nullptr; w->d_soff = w->d_scnt = nullptr;
+        std::vector<float4> v; std::vector<int> off, cnt;
+        for (auto& s : w->shapes) {
+            off.push_back((int)v.size()); cnt.push_back((int)s.xyz.size() / 3);
+            for (size_t k = 0; k + 2 < s.xyz.size(); k += 3) v.push_back(make_float4(s.xyz[k], s.xyz[k + 1], s.xyz[k + 2], 0.0f));
+        }
+        w->total_verts = (int)v.size();
+        size_t nv = std::max<size_t>(v.size(), 1), ns = std::max<size_t>(off.size(), 1);
+        CU(cudaMalloc((void**)&w->d_verts, sizeof(float4) * nv)); CU(cudaMalloc((void**)&w->d_soff, sizeof(int) * ns)); CU(cudaMalloc((void**)&w->d_scnt, sizeof(int) * ns));
+        if (!v.empty()) CU(cudaMemcpyAsync(w->d_verts, v.data(), sizeof(float4) * v.size(), cudaMemcpyHostToDevice, w->stream));
+        if (!off.empty()) {
+            CU(cudaMemcpyAsync(w->d_soff, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, w->stream));
+            CU(cudaMemcpyAsync(w->d_scnt, cnt.data(), sizeof(int) * cnt.size(), cudaMemcpyHostToDevice, w->stream));
+        }
+        CU(cudaStreamSynchronize(w->stream));
+        w->dirty_shapes = false;
+    }
+    if (!w->dirty_bodies) return NP_OK;
+    drop_graph(w);
+    if (w->dev_state_valid && w->dev_n > 0) {   // bodies were added after stepping: keep what the device has
+        int r = download_states(w, w->host_state.data(), w->dev_n); if (r) return r;
+    }
+    if (n > w->cap) {
+        free_store(w);
+        int cap = std::max(1024, (n + 1023) / 1024 * 1024);
+        if (n > 4096) cap = std::max(cap, (int)std::min<long long>((long long)n * 5 / 4, 1LL << 30) / 1024 * 1024 + 1024);
+        w->cap = cap;
+        size_t c = (size_t)cap;
+        CU(cudaMalloc((void**)&w->d_state, sizeof(float) * S_COUNT * c)); CU(cudaMalloc((void**)&w->d_cst, sizeof(float) * C_COUNT * c));
+        CU(cudaMalloc((void**)&w->d_xf, sizeof(float) * X_COUNT * c)); CU(cudaMalloc((void**)&w->d_ints, sizeof(int) * I_COUNT * c));
+        CU(cudaMalloc((void**)&w->d_hit_j, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_cflags, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_contact, sizeof(float4) * c));
+        CU(cudaMalloc((void**)&w->d_zero, sizeof(int) * (32 + 2 * c))); CU(cudaMalloc((void**)&w->d_inc_off, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_inc, sizeof(int) * c));
+        CU(cudaMalloc((void**)&w->d_sums, sizeof(int) * (c / NP_SCAN_BLOCK + 2))); CU(cudaMalloc((void**)&w->d_big_list, sizeof(int) * c));
+        CU(cudaMalloc((void**)&w->d_snap, sizeof(SnapObj) * c));
+        CU(cudaMemsetAsync(w->d_state, 0, sizeof(float) * S_COUNT * c, w->stream));
+        CU(cudaMemsetAsync(w->d_hit_j, 0xff, sizeof(int) * c, w->stream)); CU(cudaMemsetAsync(w->d_cflags, 0, sizeof(int) * c, w->stream));
+        CU(cudaMemsetAsync(w->d_contact, 0, sizeof(float4) * c, w->stream));
+    }
+    const size_t cap = (size_t)w->cap;
+    // constants + ints, SoA
+    std::vector<float> cst(C_COUNT * cap, 0.0f); std::vector<int> ints(I_COUNT * cap, 0);
+    std::vector<int> island_end(n, n);
+    for (int i = n - 1, end = n; i >= 0; i--) { if (i + 1 < n && w->bodies[i + 1].island != w->bodies[i].island) end = i + 1; island_end[i] = end; }
+    for (int i = 0; i < n; i++) {
+        const np_static_physics_data& sd = w->bodies[i].sd;
+        cst[C_GX * cap + i] = sd.gravity[0]; cst[C_GY * cap + i] = sd.gravity[1]; cst[C_GZ * cap + i] = sd.gravity[2];
+        cst[C_MASS * cap + i] = sd.mass; cst[C_ELAST * cap + i] = sd.elasticity;
+        for (int k = 0; k < 9; k++) cst[(C_IINV0 + k) * cap + i] = sd.inverse_inertia_tensor[k];
+        ints[I_RESPONSE * cap + i] = sd.collision_response; ints[I_SHAPE * cap + i] = w->bodies[i].shape; ints[I_ISLAND_END * cap + i] = island_end[i];
+    }
+    CU(cudaMemcpyAsync(w->d_cst, cst.data(), sizeof(float) * C_COUNT * cap, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(w->d_ints, ints.data(), sizeof(int) * I_COUNT * cap, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    int r = upload_states(w, w->host_state.data(), n); if (r) return r;
+    if (n > 0) { k_transforms<<<(n + 255) / 256, 256, 0, w->stream>>>(view(w)); CU(cudaGetLastError()); }
+    w->dev_n = n; w->dev_state_valid = true; w->dirty_bodies = false;
+    // launch geometry of the persistent narrow-phase kernels
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_first_hit<true>, NP_NARROW_THREADS, sizeof(float4) * NP_SMEM_VERTS));
+    w->first_hit_blocks = std::max(1, per_sm) * w->sm_count;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs<true>, NP_NARROW_THREADS, sizeof(float4) * NP_SMEM_VERTS));
+    w->pairs_blocks = std::max(1, per_sm) * w->sm_count;
+    return NP_OK;
+}
+static int ensure_arena(np_world* w)
+{
+    if (w->arena.p) return NP_OK;
+    BigArena& a = w->arena; a.slots = 256; a.fbig = 4096;
+    size_t s = (size_t)a.slots;
+    CU(cudaMalloc((void**)&a.p, sizeof(float) * 3 * NP_EPA_MAX_VERTS * s)); CU(cudaMalloc((void**)&a.A, sizeof(float) * 3 * NP_EPA_MAX_VERTS * s));
+    CU(cudaMalloc((void**)&a.B, sizeof(float) * 3 * NP_EPA_MAX_VERTS * s)); CU(cudaMalloc((void**)&a.fn, sizeof(float) * 3 * a.fbig * s));
+    CU(cudaMalloc((void**)&a.fi, sizeof(uint32_t) * a.fbig * s)); CU(cudaMalloc((void**)&a.edge, sizeof(uint16_t) * 3 * a.fbig * s));
+    return NP_OK;
+}
+static bool shapes_in_smem(np_world* w) { return w->total_verts <= NP_SMEM_VERTS; }
+
+// the kernels of one Physics_Update, enqueued on the world's stream (capturable)
+static int enqueue_step(np_world* w, float dt, bool timed)
+{
+    const int n = (int)w->bodies.size();
+    if (n == 0) return NP_OK;
+    StoreView s = view(w); ShapeView sh = sview(w);
+    DevCounters* ctr = w->counters_on ? w->d_ctr : nullptr;
+    const int b256 = (n + 255) / 256;
+    if (timed) CU(cudaEventRecord(w->ev[0], w->stream));
+    k_integrate<<<b256, 256, 0, w->stream>>>(s, dt, 1);
+    if (timed) CU(cudaEventRecord(w->ev[1], w->stream));
+    // (grid broad-phase goes here)
+    if (timed) CU(cudaEventRecord(w->ev[2], w->stream));
+    CU(cudaMemsetAsync(w->d_zero, 0, sizeof(int) * (32 + 2 * (size_t)w->cap), w->stream));
+    int blocks = std::min(w->first_hit_blocks, (n + NP_NARROW_THREADS - 1) / NP_NARROW_THREADS);
+    if (shapes_in_smem(w))
+        k_first_hit<true><<<blocks, NP_NARROW_THREADS, sizeof(float4) * w->total_verts, w->stream>>>(s, sh, d_ticket(w), w->d_hit_j, w->d_contact, w->d_cflags, w->d_big_list, d_big_count(w), ctr);
+    else
+        k_first_hit<false><<<blocks, NP_NARROW_THREADS, 0, w->stream>>>(s, sh, d_ticket(w), w->d_hit_j, w->d_contact, w->d_cflags, w->d_big_list, d_big_count(w), ctr);
+    k_epa_big<<<(w->arena.slots + 63) / 64, 64, 0, w->stream>>>(s, sh, w->d_big_list, d_big_count(w), w->d_hit_j, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w->d_cflags, w->d_contact, w->arena);
+    if (timed) CU(cudaEventRecord(w->ev[3], w->stream));
+    k_count_incoming<<<b256, 256, 0, w->stream>>>(n, w->cap, w->d_hit_j, w->d_ints, d_inc_cnt(w));
+    const int sb = (n + NP_SCAN_BLOCK - 1) / NP_SCAN_BLOCK;
+    k_scan_block_sums<<<sb, NP_SCAN_BLOCK, 0, w->stream>>>(n, d_inc_cnt(w), w->d_sums);
+    k_scan_sums<<<1, 1024, 0, w->stream>>>(sb, w->d_sums);
+    k_scan_apply<<<sb, NP_SCAN_BLOCK, 0, w->stream>>>(n, d_inc_cnt(w), w->d_sums, w->d_inc_off);
+    k_fill_incoming<<<b256, 256, 0, w->stream>>>(n, w->cap, w->d_hit_j, w->d_ints, w->d_inc_off, d_cursor(w), w->d_inc);
+    k_resolve<<<b256, 256, 0, w->stream>>>(s, w->d_hit_j, w->d_contact, w->d_inc_off, d_inc_cnt(w), w->d_inc);
+    if (timed) CU(cudaEventRecord(w->ev[4], w->stream));
+    CU(cudaGetLastError());
+    return NP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ library
+extern "C" {
+
+int np_abi_version(void) { return NETPHYS_B200_ABI_VERSION; }
+const char* np_last_error(void) { return g_err.c_str(); }
+int np_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+np_world* np_world_create(int device)
+{
+    int ndev = np_device_count();
+    if (ndev <= 0) { fail(NP_ERR_NO_DEVICE, "no CUDA device: netphys_b200 has no CPU path"); return nullptr; }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= ndev) { fail(NP_ERR_INVALID, "device index out of range"); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        fail(NP_ERR_NO_DEVICE, "device is not sm_100 (the library is built for sm_100a only)"); return nullptr;
+    }
+    np_world* w = new np_world();
+    w->device = device; w->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fail(NP_ERR_CUDA, "cannot create stream"); delete w; return nullptr;
+    }
+    for (auto& e : w->ev) cudaEventCreate(&e);
+    if (cudaMalloc((void**)&w->d_ctr, sizeof(DevCounters)) != cudaSuccess || ensure_arena(w) != NP_OK) { fail(NP_ERR_CUDA, "cannot allocate device scratch"); np_world_destroy(w); return nullptr; }
+    cudaMemsetAsync(w->d_ctr, 0, sizeof(DevCounters), w->stream);
+    return w;
+}
+void np_world_destroy(np_world* w)
+{
+    if (!w) return;
+    cudaSetDevice(w->device);
+    if (w->stream) cudaStreamSynchronize(w->stream);
+    drop_graph(w); free_store(w);
+    cudaFree(w->d_verts); cudaFree(w->d_soff); cudaFree(w->d_scnt); cudaFree(w->d_ctr);
+    cudaFree(w->arena.p); cudaFree(w->arena.A); cudaFree(w->arena.B); cudaFree(w->arena.fn); cudaFree(w->arena.fi); cudaFree(w->arena.edge);
+    if (w->h_stage) cudaFreeHost(w->h_stage);
+    for (auto& e : w->ev) if (e) cudaEventDestroy(e);
+    if (w->stream) cudaStreamDestroy(w->stream);
+    delete w;
+}
+int np_world_set_option(np_world* w, int option, int64_t value)
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    switch (option) {
+    case NP_OPT_BROADPHASE:
+        if (value == NP_BROADPHASE_GRID) return fail(NP_ERR_UNSUPPORTED, "NP_BROADPHASE_GRID is not available in this build");
+        if (value != NP_BROADPHASE_EXACT) return fail(NP_ERR_INVALID, "unknown broad-phase");
+        w->broadphase = (int)value; drop_graph(w); return NP_OK;
+    case NP_OPT_GRID_CELL: { uint32_t u = (uint32_t)value; memcpy(&w->grid_cell, &u, 4); return NP_OK; }
+    case NP_OPT_COUNTERS: w->counters_on = value ? 1 : 0; drop_graph(w); return NP_OK;
+    default: return fail(NP_ERR_INVALID, "unknown option");
+    }
+}
+int np_world_begin_island(np_world* w) { if (!w) return fail(NP_ERR_INVALID, "null world"); if (!w->bodies.empty()) w->island++; return w->island; }
+int np_world_body_count(const np_world* w) { return w ? (int)w->bodies.size() : 0; }
+int np_world_synchronize(np_world* w) { if (!w) return fail(NP_ERR_INVALID, "null world"); CU(cudaSetDevice(w->device)); CU(cudaStreamSynchronize(w->stream)); return NP_OK; }
+
+// ------------------------------------------------------------------------------------------------ shapes
+int np_shape_create_mesh(np_world* w, const float* xyz, int nverts)
+{
+    if (!w || nverts < 0 || (nverts > 0 && !xyz)) return fail(NP_ERR_INVALID, "bad mesh");
+    if (nverts > 255 * 255) return fail(NP_ERR_CAPACITY, "mesh too large");
+    HostShape s; s.xyz.assign(xyz, xyz + 3 * (size_t)nverts);
+    w->shapes.push_back(std::move(s)); w->dirty_shapes = true;
+    return (int)w->shapes.size() - 1;
+}
+// Mesh::AddVertex, physics_shape.cpp:23-37: tolerant de-duplication, first match wins
+static void mesh_add(std::vector<V3>& mesh, V3 p)
+{
+    for (const V3& q : mesh) if (veq(q, p)) return;
+    mesh.push_back(p);
+}
+static int push_mesh(np_world* w, const std::vector<V3>& mesh)
+{
+    std::vector<float> xyz; for (const V3& p : mesh) { xyz.push_back(p.x); xyz.push_back(p.y); xyz.push_back(p.z); }
+    return np_shape_create_mesh(w, xyz.data(), (int)mesh.size());
+}
+int np_shape_create_box(np_world* w, float width, float depth, float height)            // CreateBoxMesh, physics_shape.cpp:163-217
+{
+    (void)depth;                                                                         // :166 half_depth = width / 2.0f
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    const float hw = width / 2.0f, hd = width / 2.0f, hh = height / 2.0f;
+    const V3 c[8] = { mk(hw, -hh, -hd), mk(hw, -hh, hd), mk(hw, hh, -hd), mk(hw, hh, hd), mk(-hw, -hh, -hd), mk(-hw, -hh, hd), mk(-hw, hh, -hd), mk(-hw, hh, hd) };
+    static const int tri[12][3] = { { 0, 1, 3 }, { 0, 3, 2 }, { 1, 5, 7 }, { 1, 7, 3 }, { 5, 4, 6 }, { 5, 6, 7 }, { 4, 0, 2 }, { 4, 2, 6 }, { 2, 3, 7 }, { 2, 7, 6 }, { 4, 5, 1 }, { 4, 1, 0 } };
+    std::vector<V3> mesh;
+    for (auto& t : tri) for (int k = 0; k < 3; k++) mesh_add(mesh, c[t[k]]);
+    return push_mesh(w, mesh);
+}
+int np_shape_create_sphere(np_world* w, float r)                                         // CreateIcosahadron(r, 3), physics_shape.cpp:42-162
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    const float PIf = 3.1415926535897932384626433832795028841971693993751f;             // lib.h:10
+    const float theta = 26.56505117707799f * PIf / 180.0f;
+    float st, ct; np_sincosf(theta, &st, &ct);
+    std::vector<V3> vl(12, mk(0.f, 0.f, 0.f));
+    for (int half = 0; half < 2; half++) {
+        float phi = 0;
+        for (int i = 1 + 5 * half; i < 6 + 5 * half; i++) {
+            float sp, cp; np_sincosf(phi, &sp, &cp);
+            vl[i].x = r * ct * cp; vl[i].y = r * ct * sp; vl[i].z = half ? r * st : r * -st;
+            phi = (float)((double)phi + (double)(2 * PIf) / 5.0);                        // :56 float += double
+        }
+    }
+    vl[0] = mk(0.0f, 0.0f, -r); vl[11] = mk(0.0f, 0.0f, r);
+    std::vector<int> idx = { 0, 2, 1, 0, 3, 2, 0, 4, 3, 0, 5, 4, 0, 1, 5, 1, 2, 7, 2, 3, 8, 3, 4, 9, 4, 5, 10, 5, 1, 6,
+                             1, 7, 6, 2, 8, 7, 3, 9, 8, 4, 10, 9, 5, 6, 10, 6, 7, 11, 7, 8, 11, 8, 9, 11, 9, 10, 11, 10, 6, 11 };
+    for (int round = 1; round < 3; round++) {                                            // numSubdivisions = 3: the loop body runs twice
+        std::vector<V3> nv; std::vector<int> nidx;
+        for (size_t j = 0; j + 2 < idx.size(); j += 3) {
+            V3 a = vl[idx[j]], b = vl[idx[j + 1]], c = vl[idx[j + 2]];
+            V3 x = mul(normalize(add(a, b)), r), y = mul(normalize(add(a, c)), r), z = mul(normalize(add(b, c)), r);
+            const V3 seq[12] = { a, x, y, x, b, z, z, y, x, z, c, y };                  // abc -> axy, xbz, zyx, zcy
+            for (const V3& p : seq) { nidx.push_back((int)nv.size()); nv.push_back(p); }
+        }
+        vl.swap(nv); idx.swap(nidx);
+    }
+    std::vector<V3> mesh;
+    for (const V3& p : vl) mesh_add(mesh, p);
+    return push_mesh(w, mesh);
+}
+int np_shape_vertex_count(const np_world* w, int shape) { if (!w || shape < 0 || shape >= (int)w->shapes.size()) return fail(NP_ERR_INVALID, "bad shape"); return (int)w->shapes[shape].xyz.size() / 3; }
+int np_shape_get_vertices(const np_world* w, int shape, float* xyz, int cap_verts)
+{
+    int n = np_shape_vertex_count(w, shape); if (n < 0) return n;
+    if (cap_verts < n || !xyz) return fail(NP_ERR_CAPACITY, "vertex buffer too small");
+    memcpy(xyz, w->shapes[shape].xyz.data(), sizeof(float) * 3 * (size_t)n);
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------ bodies
+int np_body_create_batch(np_world* w, int n, const int32_t* shapes, const np_static_physics_data* sd)
+{
+    if (!w || n < 0 || (n > 0 && (!shapes || !sd))) return fail(NP_ERR_INVALID, "bad arguments");
+    for (int i = 0; i < n; i++) if (shapes[i] < 0 || shapes[i] >= (int)w->shapes.size()) return fail(NP_ERR_INVALID, "bad shape id");
+    int first = (int)w->bodies.size();
+    if ((long long)first + n > (1LL << 30)) return fail(NP_ERR_CAPACITY, "too many bodies");
+    for (int i = 0; i < n; i++) {
+        HostBody b; b.sd = sd[i]; b.shape = shapes[i]; b.island = w->island;
+        w->bodies.push_back(b);
+        np_body_state st; memset(&st, 0, sizeof st);                                     // physics.cpp:11-18: pos/rot from the static data, momenta vector3() == 0
+        memcpy(st.position, sd[i].initial_position, 12); memcpy(st.rotation, sd[i].initial_rotation, 12);
+        w->host_state.push_back(st);
+    }
+    if (n > 0) w->dirty_bodies = true;
+    return first;
+}
+int np_body_create(np_world* w, int shape, const np_static_physics_data* sd) { int32_t s = shape; return np_body_create_batch(w, 1, &s, sd); }
+
+static int check_body(np_world* w, int body) { if (!w || body < 0 || body >= (int)w->bodies.size()) return fail(NP_ERR_INVALID, "bad body"); return NP_OK; }
+int np_body_get_state(np_world* w, int body, np_body_state* out)
+{
+    int r = check_body(w, body); if (r) return r;
+    if (!out) return fail(NP_ERR_INVALID, "null out");
+    if (!w->dev_state_valid || body >= w->dev_n) { *out = w->host_state[body]; return NP_OK; }
+    CU(cudaSetDevice(w->device));
+    CU(cudaMemcpy2DAsync(out, sizeof(float), w->d_state + body, sizeof(float) * w->cap, sizeof(float), S_COUNT, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return NP_OK;
+}
+int np_body_set_state(np_world* w, int body, const np_body_state* in)
+{
+    int r = check_body(w, body); if (r) return r;
+    if (!in) return fail(NP_ERR_INVALID, "null in");
+    w->host_state[body] = *in;
+    if (w->dev_state_valid && body < w->dev_n) {
+        CU(cudaSetDevice(w->device));
+        CU(cudaMemcpy2DAsync(w->d_state + body, sizeof(float) * w->cap, in, sizeof(float), sizeof(float), S_COUNT, cudaMemcpyHostToDevice, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+    }
+    return NP_OK;
+}
+int np_body_reset(np_world* w, int body)                                                 // Physics::Reset, physics.cpp:166-172
+{
+    int r = check_body(w, body); if (r) return r;
+    np_body_state st; memset(&st, 0, sizeof st);
+    memcpy(st.position, w->bodies[body].sd.initial_position, 12); memcpy(st.rotation, w->bodies[body].sd.initial_rotation, 12);
+    return np_body_set_state(w, body, &st);
+}
+int np_world_get_states(np_world* w, np_body_state* out, int cap)
+{
+    if (!w || !out) return fail(NP_ERR_INVALID, "bad arguments");
+    int n = (int)w->bodies.size();
+    if (cap < n) return fail(NP_ERR_CAPACITY, "state buffer too small");
+    if (!w->dev_state_valid) { memcpy(out, w->host_state.data(), sizeof(np_body_state) * (size_t)n); return n; }
+    CU(cudaSetDevice(w->device));
+    int r = download_states(w, out, w->dev_n); if (r) return r;
+    for (int i = w->dev_n; i < n; i++) out[i] = w->host_state[i];
+    return n;
+}
+int np_world_set_states(np_world* w, const np_body_state* in, int n)
+{
+    if (!w || !in || n != (int)w->bodies.size()) return fail(NP_ERR_INVALID, "bad arguments");
+    memcpy(w->host_state.data(), in, sizeof(np_body_state) * (size_t)n);
+    if (w->dev_state_valid && !w->dirty_bodies) { CU(cudaSetDevice(w->device)); return upload_states(w, in, n); }
+    w->dev_state_valid = false; w->dirty_bodies = true;      // next ensure_device uploads host_state
+    return NP_OK;
+}
+int np_body_get_transform(np_world* w, int body, float out16[16])                         // Physics::GetTransform, physics.h:70-76
+{
+    int r = check_body(w, body); if (r) return r;
+    if (!out16) return fail(NP_ERR_INVALID, "null out");
+    r = ensure_device(w); if (r) return r;
+    float* d = nullptr;
+    CU(cudaMallocAsync((void**)&d, 64, w->stream));
+    k_transform_one<<<1, 1, 0, w->stream>>>(view(w), body, d);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out16, d, 64, cudaMemcpyDeviceToHost, w->stream)); CU(cudaFreeAsync(d, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return NP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ step
+int np_world_step(np_world* w, float dt)
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    int r = ensure_device(w); if (r) return r;
+    r = enqueue_step(w, dt, true); if (r) return r;
+    w->timed = true; w->steps++;
+    return NP_OK;
+}
+int np_world_step_n(np_world* w, float dt, int steps)
+{
+    if (!w || steps < 0) return fail(NP_ERR_INVALID, "bad arguments");
+    int r = ensure_device(w); if (r) return r;
+    if (w->bodies.empty() || steps == 0) return NP_OK;
+    if (!w->graph || w->graph_dt != dt) {      // capture one step once, replay it `steps` times
+        drop_graph(w);
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
+        r = enqueue_step(w, dt, false);
+        cudaError_t e = cudaStreamEndCapture(w->stream, &g);
+        if (r) { if (g) cudaGraphDestroy(g); return r; }
+        if (e != cudaSuccess) return fail(NP_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&w->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { w->graph = nullptr; return fail(NP_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+        w->graph_dt = dt;
+    }
+    CU(cudaEventRecord(w->ev[0], w->stream));
+    for (int i = 0; i < steps; i++) CU(cudaGraphLaunch(w->graph, w->stream));
+    CU(cudaEventRecord(w->ev[5], w->stream));
+    w->timed = false; w->steps += (unsigned long long)steps;
+    return NP_OK;
+}
+int np_world_integrate(np_world* w, float dt)
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    int r = ensure_device(w); if (r) return r;
+    int n = (int)w->bodies.size(); if (n == 0) return NP_OK;
+    k_integrate<<<(n + 255) / 256, 256, 0, w->stream>>>(view(w), dt, 1);
+    CU(cudaGetLastError());
+    return NP_OK;
+}
+int np_world_get_collisions(np_world* w, np_collision* out, int cap, int* count)
+{
+    if (!w || !count) return fail(NP_ERR_INVALID, "bad arguments");
+    *count = 0;
+    int n = w->dev_n; if (!w->dev_state_valid || n == 0 || w->steps == 0) return NP_OK;
+    CU(cudaSetDevice(w->device));
+    std::vector<int> hj(n), fl(n); std::vector<float4> cd(n);
+    CU(cudaMemcpyAsync(hj.data(), w->d_hit_j, sizeof(int) * n, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaMemcpyAsync(fl.data(), w->d_cflags, sizeof(int) * n, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaMemcpyAsync(cd.data(), w->d_contact, sizeof(float4) * n, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    int k = 0;
+    for (int i = 0; i < n; i++) {
+        if (hj[i] < 0) continue;
+        if (out && k < cap) {
+            np_collision& c = out[k]; memset(&c, 0, sizeof c);
+            c.a = i; c.b = hj[i];
+            c.data.penetration_direction[0] = cd[i].x; c.data.penetration_direction[1] = cd[i].y; c.data.penetration_direction[2] = cd[i].z;
+            c.data.depth = cd[i].w; c.data.success = (fl[i] & NP_PAIR_SUCCESS) ? 1 : 0;
+        }
+        k++;
+    }
+    *count = k;
+    if (out && k > cap) return fail(NP_ERR_CAPACITY, "collision buffer too small");
+    return NP_OK;
+}
+int np_world_step_host(np_world* w, float dt, const np_body_state* in, np_body_state* out, int n)
+{
+    if (!w || !out || n != (int)w->bodies.size()) return fail(NP_ERR_INVALID, "bad arguments");
+    int r = ensure_device(w); if (r) return r;
+    if (in) { r = upload_states(w, in, n); if (r) return r; }
+    r = enqueue_step(w, dt, false); if (r) return r;
+    w->timed = false; w->steps++;
+    return download_states(w, out, n);
+}
+int np_world_get_counters(np_world* w, np_counters* out)
+{
+    if (!w || !out) return fail(NP_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(w->device));
+    DevCounters c;
+    CU(cudaMemcpyAsync(&c, w->d_ctr, sizeof c, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    out->steps = w->steps; out->pair_tests = c.pair_tests; out->hits = c.hits; out->gjk_steps = c.gjk_steps; out->support_pairs = c.support_pairs;
+    out->epa_iters = c.epa_iters; out->epa_tri_tests = c.epa_tri_tests; out->epa_overflow = c.epa_overflow; out->candidates = c.candidates;
+    return NP_OK;
+}
+int np_world_last_step_ms(np_world* w, float out[6])
+{
+    if (!w || !out) return fail(NP_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(w->device));
+    CU(cudaStreamSynchronize(w->stream));
+    for (int k = 0; k < 6; k++) out[k] = 0.0f;
+    if (w->steps == 0) return NP_OK;
+    if (w->timed) {
+        for (int k = 0; k < 4; k++) CU(cudaEventElapsedTime(&out[k], w->ev[k], w->ev[k + 1]));
+        CU(cudaEventElapsedTime(&out[5], w->ev[0], w->ev[4]));
+    } else CU(cudaEventElapsedTime(&out[5], w->ev[0], w->ev[5]));
+    return NP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ narrow phase
+static int run_pairs(np_world* w, int n, const int* d_sa, const float* d_pa, const int* d_sb, const float* d_pb, const float* d_xa, const float* d_xb,
+                     int* d_hit, float4* d_out, float* kernel_ms)
+{
+    // scratch: ticket + big_count + big_list
+    int* d_scr = nullptr;
+    CU(cudaMallocAsync((void**)&d_scr, sizeof(int) * (32 + (size_t)n), w->stream));
+    CU(cudaMemsetAsync(d_scr, 0, sizeof(int) * 32, w->stream));
+    ShapeView sh = sview(w);
+    DevCounters* ctr = w->counters_on ? w->d_ctr : nullptr;
+    int blocks = std::max(1, std::min(w->pairs_blocks ? w->pairs_blocks : w->sm_count * 4, (n + NP_NARROW_THREADS - 1) / NP_NARROW_THREADS));
+    if (kernel_ms) CU(cudaEventRecord(w->ev[0], w->stream));
+    if (shapes_in_smem(w))
+        k_pairs<true><<<blocks, NP_NARROW_THREADS, sizeof(float4) * w->total_verts, w->stream>>>(n, sh, d_sa, d_pa, d_sb, d_pb, d_xa, d_xb, d_scr, d_hit, d_out, d_scr + 32, d_scr + 1, ctr);
+    else
+        k_pairs<false><<<blocks, NP_NARROW_THREADS, 0, w->stream>>>(n, sh, d_sa, d_pa, d_sb, d_pb, d_xa, d_xb, d_scr, d_hit, d_out, d_scr + 32, d_scr + 1, ctr);
+    StoreView s = view(w);
+    k_epa_big<<<(w->arena.slots + 63) / 64, 64, 0, w->stream>>>(s, sh, d_scr + 32, d_scr + 1, nullptr, n, d_sa, d_pa, d_sb, d_pb, d_xa, d_xb, d_hit, d_out, w->arena);
+    if (kernel_ms) CU(cudaEventRecord(w->ev[5], w->stream));
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(d_scr, w->stream));
+    if (kernel_ms) { CU(cudaStreamSynchronize(w->stream)); CU(cudaEventElapsedTime(kernel_ms, w->ev[0], w->ev[5])); }
+    return NP_OK;
+}
+static int check_shapes(np_world* w, int n, const int32_t* a, const int32_t* b)
+{
+    int ns = (int)w->shapes.size();
+    for (int i = 0; i < n; i++) if (a[i] < 0 || a[i] >= ns || b[i] < 0 || b[i] >= ns) return fail(NP_ERR_INVALID, "bad shape id in pair list");
+    return NP_OK;
+}
+static void expand_out(int n, const int* flags, const float4* cd, int32_t* hit, np_collision_data* out)
+{
+    for (int i = 0; i < n; i++) {
+        if (hit) hit[i] = (flags[i] & NP_PAIR_HIT) ? 1 : 0;
+        if (out) {
+            memset(&out[i], 0, sizeof out[i]);
+            out[i].penetration_direction[0] = cd[i].x; out[i].penetration_direction[1] = cd[i].y; out[i].penetration_direction[2] = cd[i].z;
+            out[i].depth = cd[i].w; out[i].success = (flags[i] & NP_PAIR_SUCCESS) ? 1 : 0;
+        }
+    }
+}
+int np_detect_collision_batch(np_world* w, int n, const int32_t* shape_a, const float* pose_a, const int32_t* shape_b, const float* pose_b,
+                              int32_t* hit, np_collision_data* out)
+{
+    if (!w || n < 0 || (n > 0 && (!shape_a || !pose_a || !shape_b || !pose_b))) return fail(NP_ERR_INVALID, "bad arguments");
+    if (n == 0) return NP_OK;
+    int r = check_shapes(w, n, shape_a, shape_b); if (r) return r;
+    r = ensure_device(w); if (r) return r;
+    size_t N = (size_t)n;
+    char* d = nullptr;
+    size_t o_sa = 0, o_sb = o_sa + 4 * N, o_pa = o_sb + 4 * N, o_pb = o_pa + 24 * N, o_hit = o_pb + 24 * N, o_out = (o_hit + 4 * N + 15) / 16 * 16, total = o_out + 16 * N;
+    CU(cudaMallocAsync((void**)&d, total, w->stream));
+    CU(cudaMemcpyAsync(d + o_sa, shape_a, 4 * N, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + o_sb, shape_b, 4 * N, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(d + o_pa, pose_a, 24 * N, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + o_pb, pose_b, 24 * N, cudaMemcpyHostToDevice, w->stream));
+    r = run_pairs(w, n, (int*)(d + o_sa), (float*)(d + o_pa), (int*)(d + o_sb), (float*)(d + o_pb), nullptr, nullptr, (int*)(d + o_hit), (float4*)(d + o_out), nullptr);
+    if (r) { cudaFreeAsync(d, w->stream); return r; }
+    std::vector<int> fl(N); std::vector<float4> cd(N);
+    CU(cudaMemcpyAsync(fl.data(), d + o_hit, 4 * N, cudaMemcpyDeviceToHost, w->stream)); CU(cudaMemcpyAsync(cd.data(), d + o_out, 16 * N, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaFreeAsync(d, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    expand_out(n, fl.data(), cd.data(), hit, out);
+    return NP_OK;
+}
+int np_detect_collision(np_world* w, int shape_a, const float a_transform[16], int shape_b, const float b_transform[16], int is3D, np_collision_data* out, int* hit)
+{
+    if (!w || !a_transform || !b_transform) return fail(NP_ERR_INVALID, "bad arguments");
+    if (!is3D) return fail(NP_ERR_UNSUPPORTED, "2-D mode (is3D == false) is not implemented on the device");
+    int32_t sa = shape_a, sb = shape_b;
+    int r = check_shapes(w, 1, &sa, &sb); if (r) return r;
+    r = ensure_device(w); if (r) return r;
+    char* d = nullptr;
+    CU(cudaMallocAsync((void**)&d, 256, w->stream));
+    CU(cudaMemcpyAsync(d, a_transform, 64, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + 64, b_transform, 64, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(d + 128, &sa, 4, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + 132, &sb, 4, cudaMemcpyHostToDevice, w->stream));
+    r = run_pairs(w, 1, (int*)(d + 128), nullptr, (int*)(d + 132), nullptr, (float*)d, (float*)(d + 64), (int*)(d + 136), (float4*)(d + 144), nullptr);
+    if (r) { cudaFreeAsync(d, w->stream); return r; }
+    int fl; float4 cd;
+    CU(cudaMemcpyAsync(&fl, d + 136, 4, cudaMemcpyDeviceToHost, w->stream)); CU(cudaMemcpyAsync(&cd, d + 144, 16, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaFreeAsync(d, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    int32_t h; expand_out(1, &fl, &cd, &h, out);
+    if (hit) *hit = h;
+    return NP_OK;
+}
+int np_detect_collision_batch_device(np_world* w, int n, const void* d_shape_a, const void* d_pose_a, const void* d_shape_b, const void* d_pose_b,
+                                     void* d_hit, void* d_out, float* kernel_ms)
+{
+    if (!w || n < 0 || !d_shape_a || !d_pose_a || !d_shape_b || !d_pose_b || !d_hit || !d_out) return fail(NP_ERR_INVALID, "bad arguments");
+    int r = ensure_device(w); if (r) return r;
+    if (n == 0) return NP_OK;
+    return run_pairs(w, n, (const int*)d_shape_a, (const float*)d_pose_a, (const int*)d_shape_b, (const float*)d_pose_b, nullptr, nullptr, (int*)d_hit, (float4*)d_out, kernel_ms);
+}
+int np_shape_support(np_world* w, int shape, const float dir[3], const float world[16], float out[3])
+{
+    if (!w || !dir || !world || !out || shape < 0 || shape >= (int)w->shapes.size()) return fail(NP_ERR_INVALID, "bad arguments");
+    int r = ensure_device(w); if (r) return r;
+    float* d = nullptr;
+    CU(cudaMallocAsync((void**)&d, sizeof(float) * 32, w->stream));
+    CU(cudaMemcpyAsync(d, dir, 12, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + 4, world, 64, cudaMemcpyHostToDevice, w->stream));
+    k_selftest_support<<<1, 1, 0, w->stream>>>(sview(w), shape, d, d + 4, d + 24);
+    CU(cudaMemcpyAsync(out, d + 24, 12, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaFreeAsync(d, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return NP_OK;
+}
+int np_body_apply_impulse_response(np_world* w, int body, const np_collision_data* data, const float normal[3])
+{
+    // Physics::ApplyImpulseResponse (physics.cpp:27-46) as a stand-alone call on one body
+    int r = check_body(w, body); if (r) return r;
+    if (!data || !normal) return fail(NP_ERR_INVALID, "bad arguments");
+    r = ensure_device(w); if (r) return r;
+    k_impulse_one<<<1, 1, 0, w->stream>>>(view(w), body, mk(data->penetration_direction[0], data->penetration_direction[1], data->penetration_direction[2]),
+                                          data->depth, mk(normal[0], normal[1], normal[2]));
+    CU(cudaGetLastError());
+    return NP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ snapshot
+int np_world_snapshot_device(np_world* w, void** d_ptr, size_t* bytes)
+{
+    if (!w || !d_ptr || !bytes) return fail(NP_ERR_INVALID, "bad arguments");
+    int r = ensure_device(w); if (r) return r;
+    int n = (int)w->bodies.size();
+    if (n > 0) { k_snapshot<<<(n + 255) / 256, 256, 0, w->stream>>>(view(w), 0u, w->d_snap); CU(cudaGetLastError()); }
+    *d_ptr = w->d_snap; *bytes = sizeof(SnapObj) * (size_t)n;
+    return NP_OK;
+}
+int np_world_snapshot(np_world* w, np_snapshot_object* dst, int cap)
+{
+    if (!w || !dst) return fail(NP_ERR_INVALID, "bad arguments");
+    int n = (int)w->bodies.size();
+    if (cap < n) return fail(NP_ERR_CAPACITY, "snapshot buffer too small");
+    void* d; size_t bytes;
+    int r = np_world_snapshot_device(w, &d, &bytes); if (r) return r;
+    if (bytes) CU(cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------ device memory helpers
+void* np_device_alloc(np_world* w, size_t bytes) { if (!w) return nullptr; void* p = nullptr; if (cudaSetDevice(w->device) != cudaSuccess || cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { fail(NP_ERR_CUDA, "cudaMalloc failed"); return nullptr; } return p; }
+int np_device_free(np_world* w, void* p) { if (!w) return fail(NP_ERR_INVALID, "null world"); CU(cudaSetDevice(w->device)); CU(cudaStreamSynchronize(w->stream)); CU(cudaFree(p)); return NP_OK; }
+int np_device_upload(np_world* w, void* d_dst, const void* h_src, size_t bytes) { if (!w) return fail(NP_ERR_INVALID, "null world"); CU(cudaSetDevice(w->device)); CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, w->stream)); CU(cudaStreamSynchronize(w->stream)); return NP_OK; }
+int np_device_download(np_world* w, void* h_dst, const void* d_src, size_t bytes) { if (!w) return fail(NP_ERR_INVALID, "null world"); CU(cudaSetDevice(w->device)); CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, w->stream)); CU(cudaStreamSynchronize(w->stream)); return NP_OK; }
+void* np_world_stream(np_world* w) { return w ? (void*)w->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------------ self tests
+int np_selftest_sincos_hash(np_world* w, uint32_t start, uint64_t count, uint64_t* hash_sin, uint64_t* hash_cos)
+{
+    if (!w || !hash_sin || !hash_cos) return fail(NP_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(w->device));
+    unsigned long long* d = nullptr;
+    CU(cudaMallocAsync((void**)&d, 16, w->stream)); CU(cudaMemsetAsync(d, 0, 16, w->stream));
+    k_sincos_hash<<<w->sm_count * 8, 256, 0, w->stream>>>(start, (unsigned long long)count, d, d + 1);
+    CU(cudaGetLastError());
+    unsigned long long h[2];
+    CU(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, w->stream)); CU(cudaFreeAsync(d, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    *hash_sin = h[0]; *hash_cos = h[1];
+    return NP_OK;
+}
+int np_selftest_closest(np_world* w, int kind, const float* pts, int32_t* region, float uvw[3])
+{
+    if (!w || kind < 2 || kind > 4 || !pts || !region || !uvw) return fail(NP_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(w->device));
+    float* d = nullptr;
+    CU(cudaMallocAsync((void**)&d, sizeof(float) * 20, w->stream));
+    CU(cudaMemcpyAsync(d, pts, sizeof(float) * 3 * kind, cudaMemcpyHostToDevice, w->stream));
+    k_selftest_closest<<<1, 1, 0, w->stream>>>(kind, d, (int*)(d + 12), d + 13);
+    CU(cudaGetLastError());
+    float h[4];
+    CU(cudaMemcpyAsync(h, d + 12, 16, cudaMemcpyDeviceToHost, w->stream)); CU(cudaFreeAsync(d, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    memcpy(region, &h[0], 4); uvw[0] = h[1]; uvw[1] = h[2]; uvw[2] = h[3];
+    return NP_OK;
+}
+
+}  // extern "C"

@@ -806,3 +806,34 @@ void npo_detect_batch(int n, const float* shape_xyz, const int* shape_off, const
         if (ctr_sum) acc(ctr_sum, &jobs[t].ctr);
     }
 }
+
+/* ============================================================================================
+ * exhaustive sin/cos checks.  Inputs are enumerated by their 32-bit pattern.
+ *   npo_sincos_vs_libm  : mismatches of npo_sinf/npo_cosf against THIS box's libm sinf/cosf
+ *   npo_sincos_hash     : order-independent weighted checksum of a block, compared with the same
+ *                         checksum computed on the GPU (tests/test_gpu_sincos.py)
+ * ============================================================================================ */
+static inline uint32_t canon(float f) { uint32_t u = f2u(f); return ((u & 0x7fffffffu) > 0x7f800000u) ? 0x7fc00000u : u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+long long npo_sincos_vs_libm(unsigned start, unsigned long long count, unsigned* first_bad)
+{
+    long long bad = 0;
+    for (unsigned long long k = 0; k < count; k++) {
+        uint32_t u = (uint32_t)(start + k);
+        float x = u2f(u);
+        if (canon(npo_sinf(x)) != canon(sinf(x)) || canon(npo_cosf(x)) != canon(cosf(x))) { if (!bad && first_bad) *first_bad = u; bad++; }
+    }
+    return bad;
+}
+void npo_sincos_hash(unsigned start, unsigned long long count, unsigned long long* hs, unsigned long long* hc)
+{
+    uint64_t s = 0, c = 0;
+    for (unsigned long long k = 0; k < count; k++) {
+        uint32_t u = (uint32_t)(start + k);
+        float x = u2f(u);
+        uint64_t wgt = 2ull * u + 1ull;
+        s += wgt * (uint64_t)canon(npo_sinf(x));
+        c += wgt * (uint64_t)canon(npo_cosf(x));
+    }
+    *hs = s; *hc = c;
+}
