@@ -96,7 +96,8 @@ typedef enum np_broadphase {
 typedef enum np_option {
     NP_OPT_BROADPHASE = 1,        /* np_broadphase */
     NP_OPT_GRID_CELL = 2,         /* float bits: grid cell edge; 0 = auto (largest AABB extent) */
-    NP_OPT_COUNTERS = 3           /* 1 = accumulate pair-test / hit / iteration counters (np_world_get_counters) */
+    NP_OPT_COUNTERS = 3,          /* 1 = accumulate pair-test / hit / iteration counters (np_world_get_counters) */
+    NP_OPT_SNAPSHOT_EACH_STEP = 4 /* 1 = np_world_step also packs the replication snapshot (world_s.cpp:23-51) */
 } np_option;
 
 typedef struct np_counters {
@@ -109,6 +110,8 @@ typedef struct np_counters {
     uint64_t epa_tri_tests;  /* closest-point-on-triangle evaluations of the EPA face scans */
     uint64_t epa_overflow;   /* pairs re-run on the large-polytope path */
     uint64_t candidates;     /* NP_BROADPHASE_GRID: AABB-overlapping pairs emitted */
+    uint64_t support_verts;  /* vertices visited by all support evaluations (27 reference flops each) */
+    uint64_t kernel_launches;/* CUDA kernels this world has launched (host-side count) */
 } np_counters;
 
 /* ---- library ---------------------------------------------------------------------------------- */
@@ -175,6 +178,9 @@ int np_detect_collision_batch_device(np_world* w, int n, const void* d_shape_a, 
 int np_world_snapshot(np_world* w, np_snapshot_object* dst, int cap);      /* device -> host */
 /* device buffer holding the packed snapshot of the last step (for an NCCL all-gather by the host layer) */
 int np_world_snapshot_device(np_world* w, void** d_ptr, size_t* bytes);
+/* pack into a caller-owned DEVICE buffer instead (e.g. a torch tensor handed to ncclAllGather); NULL = internal buffer.
+ * guid_base is added to the body index (rank offset when worlds are sharded over GPUs). */
+int np_world_set_snapshot_target(np_world* w, void* d_dst, uint32_t guid_base);
 
 /* ---- device memory helpers for callers that keep buffers resident (bench, multi-GPU plumbing) ------- */
 void* np_device_alloc(np_world* w, size_t bytes);
@@ -182,10 +188,15 @@ int np_device_free(np_world* w, void* p);
 int np_device_upload(np_world* w, void* d_dst, const void* h_src, size_t bytes);
 int np_device_download(np_world* w, void* h_dst, const void* d_src, size_t bytes);
 void* np_world_stream(np_world* w);                                        /* cudaStream_t */
+/* benchmarking hygiene: overwrite a 256 MiB scratch on the world's stream so the next step starts with a cold L2 */
+int np_device_flush_l2(np_world* w);
 
 /* ---- self tests of device primitives (used by tests/; cheap) ---------------------------------------- */
 /* order-independent checksum of sinf/cosf over float bit patterns [start, start+count) computed on the device */
 int np_selftest_sincos_hash(np_world* w, uint32_t start, uint64_t count, uint64_t* hash_sin, uint64_t* hash_cos);
+/* measured non-FMA FP32 issue rate of this device (independent FADD/FMUL chains), in Tflop/s: the roofline
+ * denominator of the narrow phase, whose arithmetic may not be contracted into FMAs */
+int np_selftest_fp32_peak(np_world* w, float* tflops);
 /* util.h closest-point solvers on the device: kind 2/3/4 = line/triangle/tetrahedron; pts = kind points, origin query */
 int np_selftest_closest(np_world* w, int kind, const float* pts, int32_t* region, float uvw[3]);
 

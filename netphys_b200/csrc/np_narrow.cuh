@@ -1,23 +1,26 @@
-// netphys_b200/csrc/np_narrow.cuh -- GJK + EPA narrow phase as a per-thread state machine.
+// netphys_b200/csrc/np_narrow.cuh -- GJK and EPA as group-cooperative per-pair state machines.
 //
 // Replaces DetectCollision / DetectCollisionStep / FindIntersectionPoints[Step] and the simplex store
-// (reference engine/collision_detection.cpp:18-732, engine/simplex.h:5-76).  One thread owns one pair.
+// (reference engine/collision_detection.cpp:18-732, engine/simplex.h:5-76).
 //
-// B200 shape of the algorithm: the reference alternates "decide a direction" (simplex solve or EPA face
-// scan) and "evaluate the support pair".  The support pair is the hot loop (27 flop/vertex in the
-// reference) and is identical for GJK and EPA, so the machine is written as
-//
-//        loop:  [support pair for direction d]  ->  [consume: GJK tests / EPA expansion]  ->  [produce next d]
-//
-// with exactly ONE support evaluation per trip.  Lanes of a warp that are in different GJK iterations, or
-// already in EPA, still execute the support loop together (SIMT-convergent); only the cheaper consume /
-// produce phases diverge.  A finished lane is re-armed with new work by the caller (kernels in
-// np_kernels.cuh), so lanes do not idle behind the slowest pair of the warp.
-//
-// Storage: the GJK simplex (<= 4 points x {p,A,B}) lives in registers (every index is static after
-// unrolling).  The EPA polytope (<= 24 vertices, <= FMAX faces) lives in per-thread local memory; a pair
-// whose polytope outgrows FMAX is flagged NP_PAIR_OVERFLOW and re-run by the large-polytope kernel
-// (same code, global-memory arena) -- faces are never truncated.
+// B200 shape of the algorithm
+//   * A pair is owned by a GROUP of G lanes (G = 1, 4, 8 or 32; 32/G pairs per warp).  The hot loop of the
+//     reference -- the support mapping, 27 flop per vertex (physics_util.cpp:5-35) -- is strided over the
+//     group's lanes and finished with a shuffle arg-max whose tie-break (lower vertex index wins) reproduces
+//     the reference's strict '>' / first-maximum-wins scan bit for bit.  Small G maximises throughput when
+//     there are millions of pairs; G = 32 minimises latency when a step has only thousands (BASELINE
+//     configs[1]) and for 162-vertex shapes.
+//   * Everything that is not the support loop (simplex solve, search direction, termination tests) is
+//     evaluated redundantly by every lane of the group from identical inputs, so the lanes of a group never
+//     diverge and no communication is needed: the GJK simplex (<= 4 points x {p,A,B}) lives in registers.
+//   * GJK and EPA are separate kernels.  GJK decides hit/miss (and, in a world step, drives the ordered
+//     first-hit search); only hits reach EPA, carrying their final simplex (24 floats).  Each kernel is
+//     small enough for the instruction cache and GJK needs no local or shared memory at all.
+//   * The EPA polytope (<= 24 vertices, <= FMAX faces) is ONE copy per group: shared memory for G >= 4,
+//     per-thread local memory for G = 1.  The face scan (closest-point-on-triangle per face) and AddFace are
+//     strided over the lanes; the order-dependent horizon extraction is done by the group's lane 0.
+//     A polytope that outgrows FMAX is never truncated: the pair is queued for the large-polytope launch
+//     (same code, G = 32, global-memory arena).
 #pragma once
 #include "np_math.cuh"
 
@@ -28,7 +31,7 @@ namespace np {
 #define NP_EPA_MAX_STEPS 20        // collision_detection.cpp:728 (max_steps = maxIterations)
 #define NP_EPA_TOL 0.01f           // collision_detection.cpp:423
 
-enum PairFlags { NP_PAIR_HIT = 1, NP_PAIR_SUCCESS = 2, NP_PAIR_OVERFLOW = 4 };
+enum PairFlags { NP_PAIR_HIT = 1, NP_PAIR_SUCCESS = 2, NP_PAIR_OVERFLOW = 4, NP_PAIR_SEED_ALIVE = 8 };
 
 struct PairGeom {
     float Ra[9], Rb[9];
@@ -37,120 +40,73 @@ struct PairGeom {
     int na, nb;
 };
 
-struct PairStats { unsigned gjk_steps, support_pairs, epa_iters, epa_tri_tests; };
+struct PairStats { unsigned gjk_steps, support_pairs, support_verts, epa_iters, epa_tri_tests; };
 
-// PhysUtil_GetPointFurthestInDirection, physics_util.cpp:5-35: world*p per vertex, strict '>' from -inf,
-// first maximum wins, result starts at (0,0,0).
+// ---------------------------------------------------------------------------------------------------
+// group primitives
+// ---------------------------------------------------------------------------------------------------
+template <int G> NP_D int glane() { return (int)(threadIdx.x & (G - 1)); }
+template <int G> NP_D unsigned gmask()
+{
+    if (G == 32) return 0xffffffffu;
+    return ((1u << (G & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(G - 1));
+}
+template <int G> NP_D void gsync() { if (G > 1) __syncwarp(gmask<G>()); }
+
+// PhysUtil_GetPointFurthestInDirection, physics_util.cpp:5-35: world*p per vertex, strict '>' from -inf, first
+// maximum wins, result starts at (0,0,0).  Lane l scans vertices l, l+G, ...; the cross-lane reduction prefers the
+// larger dot product and, on equal dot products, the lower vertex index.
+template <int G>
 NP_D V3 support(const float4* __restrict__ v, int n, const float* R, V3 t, V3 d)
 {
     V3 best = mk(0.0f, 0.0f, 0.0f);
     float bd = -INFINITY;
-#pragma unroll 2
-    for (int k = 0; k < n; k++) {
+    int bi = 0x7fffffff;
+    for (int k = glane<G>(); k < n; k += G) {
         float4 q = v[k];
         V3 wp = xf_point(R, t, mk(q.x, q.y, q.z));
         float dp = dot(d, wp);
-        if (dp > bd) { bd = dp; best = wp; }
+        if (dp > bd) { bd = dp; best = wp; bi = k; }
+    }
+    if (G > 1) {
+        const unsigned m = gmask<G>();
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            float od = __shfl_xor_sync(m, bd, o, G);
+            int oi = __shfl_xor_sync(m, bi, o, G);
+            if ((od > bd) || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        int owner = (bi == 0x7fffffff) ? 0 : (bi & (G - 1));
+        best.x = __shfl_sync(m, best.x, owner, G); best.y = __shfl_sync(m, best.y, owner, G); best.z = __shfl_sync(m, best.z, owner, G);
     }
     return best;
 }
 
 NP_D V3 pick4(const V3* P, int k) { return k == 0 ? P[0] : (k == 1 ? P[1] : (k == 2 ? P[2] : P[3])); }
 
-// Per-thread polytope arena.  Storage pointers may be local (fast path) or global (large-polytope path).
-template <int FMAX>
-struct PolyLocal {
-    float p[NP_EPA_MAX_VERTS * 3], A[NP_EPA_MAX_VERTS * 3], B[NP_EPA_MAX_VERTS * 3];
-    float fn[FMAX * 3];
-    uint32_t fi[FMAX];                 // i0 | i1 << 8 | i2 << 16
-    uint16_t edge[3 * FMAX];           // va | vb << 8
-    static constexpr int fmax = FMAX;
-    static constexpr int emax = 3 * FMAX;
-    NP_D V3 P(int i) const { return mk(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
-    NP_D V3 gA(int i) const { return mk(A[3 * i], A[3 * i + 1], A[3 * i + 2]); }
-    NP_D V3 gB(int i) const { return mk(B[3 * i], B[3 * i + 1], B[3 * i + 2]); }
-    NP_D void setv(int i, V3 pp, V3 a, V3 b)
-    {
-        p[3 * i] = pp.x; p[3 * i + 1] = pp.y; p[3 * i + 2] = pp.z;
-        A[3 * i] = a.x; A[3 * i + 1] = a.y; A[3 * i + 2] = a.z;
-        B[3 * i] = b.x; B[3 * i + 1] = b.y; B[3 * i + 2] = b.z;
-    }
-    NP_D V3 N(int f) const { return mk(fn[3 * f], fn[3 * f + 1], fn[3 * f + 2]); }
-    NP_D void setf(int f, uint32_t idx, V3 n) { fi[f] = idx; fn[3 * f] = n.x; fn[3 * f + 1] = n.y; fn[3 * f + 2] = n.z; }
-    NP_D uint32_t F(int f) const { return fi[f]; }
-    NP_D void movef(int dst, int src) { fi[dst] = fi[src]; fn[3 * dst] = fn[3 * src]; fn[3 * dst + 1] = fn[3 * src + 1]; fn[3 * dst + 2] = fn[3 * src + 2]; }
-    NP_D uint16_t E(int e) const { return edge[e]; }
-    NP_D void setE(int e, uint16_t v) { edge[e] = v; }
-};
-
-// Same interface over a caller-provided global-memory arena (large-polytope path).
-struct PolyGlobal {
-    float* p; float* A; float* B; float* fn; uint32_t* fi; uint16_t* edge;
-    int fmax, emax;
-    NP_D V3 P(int i) const { return mk(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
-    NP_D V3 gA(int i) const { return mk(A[3 * i], A[3 * i + 1], A[3 * i + 2]); }
-    NP_D V3 gB(int i) const { return mk(B[3 * i], B[3 * i + 1], B[3 * i + 2]); }
-    NP_D void setv(int i, V3 pp, V3 a, V3 b)
-    {
-        p[3 * i] = pp.x; p[3 * i + 1] = pp.y; p[3 * i + 2] = pp.z;
-        A[3 * i] = a.x; A[3 * i + 1] = a.y; A[3 * i + 2] = a.z;
-        B[3 * i] = b.x; B[3 * i + 1] = b.y; B[3 * i + 2] = b.z;
-    }
-    NP_D V3 N(int f) const { return mk(fn[3 * f], fn[3 * f + 1], fn[3 * f + 2]); }
-    NP_D void setf(int f, uint32_t idx, V3 n) { fi[f] = idx; fn[3 * f] = n.x; fn[3 * f + 1] = n.y; fn[3 * f + 2] = n.z; }
-    NP_D uint32_t F(int f) const { return fi[f]; }
-    NP_D void movef(int dst, int src) { fi[dst] = fi[src]; fn[3 * dst] = fn[3 * src]; fn[3 * dst + 1] = fn[3 * src + 1]; fn[3 * dst + 2] = fn[3 * src + 2]; }
-    NP_D uint16_t E(int e) const { return edge[e]; }
-    NP_D void setE(int e, uint16_t v) { edge[e] = v; }
-};
-
-template <class Poly>
-struct PairMachine {
-    enum Mode { SEED = 0, GJK = 1, EPA = 2, DONE = 3 };
-
-    // GJK simplex in registers
+// ---------------------------------------------------------------------------------------------------
+// GJK: DetectCollisionStep loop of DetectCollision (collision_detection.cpp:620-713), registers only.
+// One trip = one support pair, then the second half of step k (termination tests, push) and the first half
+// of step k+1 (solve, containment test, next direction).
+// ---------------------------------------------------------------------------------------------------
+template <int G>
+struct GjkMachine {
+    enum { RUN = 0, MISS = 1, HIT = 2 };
     V3 P[4], A[4], B[4];
-    int nv;
-    int kn, k0, k1, k2;        // vertices the last solve keeps (applied lazily, after the duplicate test)
-    V3 d;                      // current search direction (EPA: the stored normal of the closest face)
-    float dist;                // EPA: distance of the closest face
-    int mode;
-    int gjk_steps, epa_steps;
-    int pnv, pnf;              // polytope sizes
-    // result
-    int flags; V3 pen; float depth;
+    V3 d;
+    int nv, kn, k0, k1, k2;    // kn,k0..k2: vertices the last solve keeps (applied lazily, after the duplicate test)
+    int steps, status, seed_alive;
 
     NP_D void begin()
     {
-        mode = SEED; nv = 0; gjk_steps = 0; epa_steps = 0; pnv = 0; pnf = 0;
-        flags = 0; pen = mk(0.0f, 0.0f, 0.0f); depth = 0.0f; dist = 0.0f;
-        d = mk(1.0f, 1.0f, 1.0f);                                                                 // collision_detection.cpp:702-703
-    }
-    NP_D bool done() const { return mode == DONE; }
-
-    // Simplex::AddFace, simplex.h:37-53
-    NP_D void add_face(Poly& poly, int va, int vb, int vc)
-    {
-        V3 a = poly.P(va), b = poly.P(vb), c = poly.P(vc);
-        V3 n = normalize(cross(sub(b, a), sub(c, a)));
-        V3 nn = (dot(n, a) != 0.0f) ? n : neg(n);                                                 // :52 float used as bool
-        poly.setf(pnf, (uint32_t)va | ((uint32_t)vb << 8) | ((uint32_t)vc << 16), nn);
-        pnf++;
+        nv = 0; steps = 0; status = RUN; seed_alive = 1;
+        d = mk(1.0f, 1.0f, 1.0f);                                                                 // :702-703 seed directions (1,1,1) / (-1,-1,-1)
     }
 
-    NP_D void finish_epa_converged()
+    NP_D void produce(PairStats& st)
     {
-        pen = neg(normalize(d));                                                                  // collision_detection.cpp:530
-        depth = dist;
-        flags |= NP_PAIR_SUCCESS;
-        mode = DONE;
-    }
-
-    // first half of DetectCollisionStep (collision_detection.cpp:620-658): solve, containment, direction
-    NP_D void produce_gjk(Poly& poly, PairStats& st)
-    {
-        if (gjk_steps >= NP_GJK_MAX_STEPS) { mode = DONE; return; }                               // :710 still CONTINUE => miss
-        gjk_steps++; st.gjk_steps++;
+        if (steps >= NP_GJK_MAX_STEPS) { status = MISS; return; }                                 // :710 still CONTINUE => returns false
+        steps++; st.gjk_steps++;
         kn = nv; k0 = 0; k1 = 1; k2 = 2;
         if (nv == 2) {                                                                            // SolveLine :18-54
             float u;
@@ -190,15 +146,7 @@ struct PairMachine {
             default: break;                    // ABCD, or None under NDEBUG (:255): four points stay => overlap
             }
         }
-        if (kn == 4) {                                                                            // :648-652 OVERLAP
-            flags |= NP_PAIR_HIT;
-#pragma unroll
-            for (int k = 0; k < 4; k++) poly.setv(k, P[k], A[k], B[k]);
-            pnv = 4; pnf = 0;
-            add_face(poly, 0, 1, 2); add_face(poly, 0, 2, 3); add_face(poly, 3, 1, 0); add_face(poly, 1, 3, 2);   // simplex.h:29-36
-            mode = EPA;
-            return;
-        }
+        if (kn == 4) { status = HIT; return; }                                                    // :648-652 OVERLAP
         V3 q0 = pick4(P, k0);
         if (kn == 1) d = dir1(q0);
         else {
@@ -206,20 +154,19 @@ struct PairMachine {
             if (kn == 2) d = dir2(q0, q1);
             else d = dir3(q0, q1, pick4(P, k2));
         }
-        if (feq(magsq(d), 0.0f)) mode = DONE;                                                     // :655-658 NO_OVERLAP
+        if (feq(magsq(d), 0.0f)) status = MISS;                                                   // :655-658 NO_OVERLAP
     }
 
-    // second half of DetectCollisionStep (:664-691)
-    NP_D void consume_gjk(V3 sa, V3 sb)
+    NP_D void consume(V3 sa, V3 sb)
     {
         V3 sp = sub(sa, sb);
-        if (dot(d, sp) < 0) { mode = DONE; return; }                                              // :667
+        if (dot(d, sp) < 0) { status = MISS; return; }                                            // :667
         bool dup = false;
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (k < nv && veq(sa, A[k]) && veq(sb, B[k])) dup = true;                             // :674-680 against the PRE-solve points
-        if (dup) { mode = DONE; return; }
-        // apply the solve's order-preserving compaction, then push
+        if (dup) { status = MISS; return; }
+        // the solve's order-preserving compaction, then push (:683-691)
         V3 nP[3], nA[3], nB[3];
         nP[0] = pick4(P, k0); nA[0] = pick4(A, k0); nB[0] = pick4(B, k0);
         nP[1] = pick4(P, k1); nA[1] = pick4(A, k1); nB[1] = pick4(B, k1);
@@ -229,76 +176,309 @@ struct PairMachine {
 #pragma unroll
         for (int k = 1; k < 4; k++)
             if (k == kn) { P[k] = sp; A[k] = sa; B[k] = sb; }
+        if (k0 != 0) seed_alive = 0;             // the seed (p = B - A) can only ever sit at index 0
         nv = kn + 1;
     }
 
-    // first half of FindIntersectionPointsStep (:412-425): closest face, distance test
-    NP_D void produce_epa(Poly& poly, PairStats& st)
+    // call while status == RUN
+    NP_D void trip(const PairGeom& g, PairStats& st)
     {
-        if (epa_steps >= NP_EPA_MAX_STEPS || pnf == 0) { mode = DONE; return; }                   // not converged: success stays false
-        epa_steps++; st.epa_iters++;
-        float best = 3.402823466e+38f; int bi = 0;                                                // GetClosestTriangleToOrigin :292-325
-        for (int f = 0; f < pnf; f++) {
-            uint32_t idx = poly.F(f);
-            V3 a = poly.P(idx & 0xff), b = poly.P((idx >> 8) & 0xff), c = poly.P((idx >> 16) & 0xff);
-            float u, v;
-            closest_triangle(a, b, c, &u, &v);
-            float dsq = magsq(add(add(a, mul(sub(b, a), u)), mul(sub(c, a), v)));
-            if (dsq < best) { best = dsq; bi = f; }
+        V3 sa = support<G>(g.va, g.na, g.Ra, g.ta, d);
+        V3 sb = support<G>(g.vb, g.nb, g.Rb, g.tb, neg(d));
+        st.support_pairs++; st.support_verts += (unsigned)(g.na + g.nb);
+        if (nv == 0) { A[0] = sa; B[0] = sb; P[0] = sub(sb, sa); nv = 1; }                        // :704  p = B - A
+        else consume(sa, sb);
+        if (status == RUN) produce(st);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// polytope storage policies (one polytope per group)
+// ---------------------------------------------------------------------------------------------------
+#define NP_POLY_ACCESSORS                                                                                              \
+    NP_D V3 P(int i) const { return mk(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }                                        \
+    NP_D V3 gA(int i) const { return mk(A[3 * i], A[3 * i + 1], A[3 * i + 2]); }                                       \
+    NP_D V3 gB(int i) const { return mk(B[3 * i], B[3 * i + 1], B[3 * i + 2]); }                                       \
+    NP_D void setv(int i, V3 pp, V3 a, V3 b)                                                                           \
+    {                                                                                                                  \
+        p[3 * i] = pp.x; p[3 * i + 1] = pp.y; p[3 * i + 2] = pp.z;                                                     \
+        A[3 * i] = a.x; A[3 * i + 1] = a.y; A[3 * i + 2] = a.z;                                                        \
+        B[3 * i] = b.x; B[3 * i + 1] = b.y; B[3 * i + 2] = b.z;                                                        \
+    }                                                                                                                  \
+    NP_D V3 N(int f) const { return mk(fn[3 * f], fn[3 * f + 1], fn[3 * f + 2]); }                                     \
+    NP_D void setf(int f, uint32_t idx, V3 n) { fi[f] = idx; fn[3 * f] = n.x; fn[3 * f + 1] = n.y; fn[3 * f + 2] = n.z; } \
+    NP_D uint32_t F(int f) const { return fi[f]; }                                                                     \
+    NP_D float D(int f) const { return fd[f]; }                                                                        \
+    NP_D void setD(int f, float v) { fd[f] = v; }                                                                      \
+    NP_D uint16_t E(int e) const { return edge[e]; }                                                                   \
+    NP_D void setE(int e, uint16_t v) { edge[e] = v; }
+
+template <int FMAX>
+struct PolyLocal {                      // G = 1: per-thread local memory
+    float p[NP_EPA_MAX_VERTS * 3], A[NP_EPA_MAX_VERTS * 3], B[NP_EPA_MAX_VERTS * 3];
+    float fn[FMAX * 3];
+    float fd[FMAX];                     // squared distance of the face's closest point to the origin (fixed once the face exists)
+    uint32_t fi[FMAX];                  // i0 | i1 << 8 | i2 << 16
+    uint16_t edge[3 * FMAX];            // va | vb << 8
+    int scratch[4];
+    static constexpr int fmax = FMAX;
+    static constexpr int emax = 3 * FMAX;
+    NP_POLY_ACCESSORS
+};
+struct PolyPtr {                        // shared memory (G >= 4) or the global large-polytope arena
+    float* p; float* A; float* B; float* fn; float* fd; uint32_t* fi; uint16_t* edge; int* scratch;
+    uint16_t* seq;      // overflow tiers: per horizon token, its sequence number among inserted edges of the same direction
+    uint16_t* tab;      // overflow tiers: [2][24*24] inserted / cancelled counters per directed edge
+    int fmax, emax;
+    NP_POLY_ACCESSORS
+};
+// words of shared memory one group's polytope needs
+__host__ __device__ constexpr int poly_words(int fmax) { return 3 * NP_EPA_MAX_VERTS * 3 + 3 * fmax + fmax + fmax + (3 * fmax + 1) / 2 + 4; }
+// the overflow tiers add the token sequence numbers and the directed-edge counter table
+__host__ __device__ constexpr int poly_words_fast(int fmax) { return poly_words(fmax) + (3 * fmax + 1) / 2 + NP_EPA_MAX_VERTS * NP_EPA_MAX_VERTS; }
+NP_D PolyPtr poly_from(float* base, int fmax, bool fast = false)
+{
+    PolyPtr q;
+    q.p = base; q.A = q.p + 3 * NP_EPA_MAX_VERTS; q.B = q.A + 3 * NP_EPA_MAX_VERTS; q.fn = q.B + 3 * NP_EPA_MAX_VERTS;
+    q.fd = q.fn + 3 * fmax; q.fi = (uint32_t*)(q.fd + fmax); q.scratch = (int*)(q.fi + fmax); q.edge = (uint16_t*)(q.scratch + 4);
+    q.seq = fast ? (uint16_t*)(base + poly_words(fmax)) : nullptr;
+    q.tab = fast ? q.seq + 2 * ((3 * fmax + 1) / 2) : nullptr;
+    q.fmax = fmax; q.emax = 3 * fmax;
+    return q;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// EPA: FindIntersectionPoints on an origin-enclosing simplex (collision_detection.cpp:412-566)
+// ---------------------------------------------------------------------------------------------------
+template <int G, class Poly, bool FAST = false>
+struct EpaMachine {
+    int pnv, pnf, steps;
+    V3 d;            // the stored normal of the closest face (the direction the polytope is pushed out along)
+    float dist;
+    int flags; V3 pen; float depth;
+    bool done;
+
+    // Simplex::AddFace, simplex.h:37-53 (called by one lane per face).  Also evaluates, once, what every later
+    // GetClosestTriangleToOrigin scan (:300-318) would recompute for this face: the squared distance of its closest
+    // point to the origin.  The face's vertices never change, so the value is the same bits on every scan.
+    NP_D void add_face_at(Poly& poly, int slot, int va, int vb, int vc)
+    {
+        V3 a = poly.P(va), b = poly.P(vb), c = poly.P(vc);
+        V3 n = normalize(cross(sub(b, a), sub(c, a)));
+        V3 nn = (dot(n, a) != 0.0f) ? n : neg(n);                                                 // :52 float used as bool
+        poly.setf(slot, (uint32_t)va | ((uint32_t)vb << 8) | ((uint32_t)vc << 16), nn);
+        float u, v;
+        closest_triangle(a, b, c, &u, &v);
+        poly.setD(slot, magsq(add(add(a, mul(sub(b, a), u)), mul(sub(c, a), v))));
+    }
+
+    // SetupForEPA (simplex.h:29-36) from the GJK result: 4 points {A,B}; p = A - B, except the surviving seed (B - A)
+    NP_D void begin(Poly& poly, const V3* A4, const V3* B4, int seed_alive)
+    {
+        pnv = 4; pnf = 4; steps = 0; flags = NP_PAIR_HIT; pen = mk(0.0f, 0.0f, 0.0f); depth = 0.0f; dist = 0.0f; done = false;
+        d = mk(0.0f, 0.0f, 0.0f);
+        if (glane<G>() == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) poly.setv(k, (k == 0 && seed_alive) ? sub(B4[0], A4[0]) : sub(A4[k], B4[k]), A4[k], B4[k]);
         }
+        gsync<G>();
+        const int f0[4][3] = { { 0, 1, 2 }, { 0, 2, 3 }, { 3, 1, 0 }, { 1, 3, 2 } };
+        if (G >= 4) { int l = glane<G>(); if (l < 4) add_face_at(poly, l, f0[l][0], f0[l][1], f0[l][2]); }
+        else if (glane<G>() == 0) {
+#pragma unroll
+            for (int l = 0; l < 4; l++) add_face_at(poly, l, f0[l][0], f0[l][1], f0[l][2]);
+        }
+        gsync<G>();
+    }
+
+    NP_D void converge()
+    {
+        pen = neg(normalize(d));                                                                  // :530
+        depth = dist;
+        flags |= NP_PAIR_SUCCESS;
+        done = true;
+    }
+
+    // first half of FindIntersectionPointsStep (:412-425): closest face, distance test
+    NP_D void produce(Poly& poly, PairStats& st)
+    {
+        if (steps >= NP_EPA_MAX_STEPS || pnf == 0) { done = true; return; }                       // not converged: success stays false
+        steps++; st.epa_iters++;
+        float best = 3.402823466e+38f; int bi = 0x7fffffff;                                       // GetClosestTriangleToOrigin :292-325
+        for (int f = glane<G>(); f < pnf; f += G) {
+            float dsq = poly.D(f);
+            if (dsq < best) { best = dsq; bi = f; }                                               // strict '<': first minimum wins
+        }
+        if (G > 1) {
+            const unsigned m = gmask<G>();
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                float od = __shfl_xor_sync(m, best, o, G);
+                int oi = __shfl_xor_sync(m, bi, o, G);
+                if ((od < best) || (od == best && oi < bi)) { best = od; bi = oi; }
+            }
+        }
+        if (bi == 0x7fffffff) bi = 0;            // every distance NaN: the reference's (zero-pinned) face_index stays 0
         st.epa_tri_tests += pnf;
         dist = sqrtf(best);
         d = poly.N(bi);                                                                           // :408 the STORED normal
-        if (!(dist > NP_EPA_TOL)) finish_epa_converged();                                         // :424, :523-531
+        if (!(dist > NP_EPA_TOL)) converge();                                                     // :424, :523-531
     }
 
     // second half of FindIntersectionPointsStep (:427-520)
-    NP_D void consume_epa(Poly& poly, V3 sa, V3 sb)
+    NP_D void consume(Poly& poly, V3 sa, V3 sb)
     {
+        const int gl = glane<G>();
+        const unsigned m = gmask<G>();
+        const int gbase = (int)((threadIdx.x & 31u) & ~(unsigned)(G - 1));     // first lane of this group inside the warp
         V3 sp = sub(sa, sb);
-        for (int i = 0; i < pnv; i++)
-            if (veq(sa, poly.gA(i), NP_EPA_TOL) && veq(sb, poly.gB(i), NP_EPA_TOL)) { finish_epa_converged(); return; }   // :435-446
-        // :469-510 remove faces whose stored normal faces the support POINT; horizon edges in insertion
-        // order with reverse-edge cancellation
-        int ne = 0, keep = 0;
-        bool overflow = false;
-        for (int f = 0; f < pnf; f++) {
-            uint32_t idx = poly.F(f);
-            if (dot(poly.N(f), sp) > 0) {
-                int v0 = idx & 0xff, v1 = (idx >> 8) & 0xff, v2 = (idx >> 16) & 0xff;
+        bool found = false;
+        for (int i = gl; i < pnv; i += G)
+            if (veq(sa, poly.gA(i), NP_EPA_TOL) && veq(sb, poly.gB(i), NP_EPA_TOL)) found = true; // :435-446
+        if (G > 1) found = (__ballot_sync(m, found) & m) != 0u;
+        if (found) { converge(); return; }
+        // :469-510 drop every face whose stored normal faces the support POINT, keep the rest in order, and collect the
+        // horizon: edges in insertion order, an edge cancelling the first earlier copy of its reverse.
+        // Faces are handled in rounds of G: visibility per lane, horizon edges by lane 0 (order dependent), then an
+        // order-preserving parallel compaction (read, sync, write; destinations never run ahead of the round).
+        int ne = 0, keep = 0, overflow = 0;
+        for (int base = 0; base < pnf; base += G) {
+            const int f = base + gl;
+            const bool valid = f < pnf;
+            uint32_t idx = 0; V3 fnrm = mk(0.f, 0.f, 0.f); float fdist = 0.f;
+            if (valid) { idx = poly.F(f); fnrm = poly.N(f); fdist = poly.D(f); }
+            const bool vis = valid && (dot(fnrm, sp) > 0);
+            unsigned vmask, kmask;
+            if (G > 1) { vmask = (__ballot_sync(m, vis) & m) >> gbase; kmask = (__ballot_sync(m, valid && !vis) & m) >> gbase; }
+            else { vmask = vis ? 1u : 0u; kmask = (valid && !vis) ? 1u : 0u; }
+            if (gl == 0) {
+                unsigned vm = vmask;
+                while (vm) {
+                    int bit = __ffs(vm) - 1; vm &= vm - 1;
+                    uint32_t fidx = poly.F(base + bit);
+                    int v0 = fidx & 0xff, v1 = (fidx >> 8) & 0xff, v2 = (fidx >> 16) & 0xff;
 #pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    int ea = k == 0 ? v0 : (k == 1 ? v1 : v2);
-                    int eb = k == 0 ? v1 : (k == 1 ? v2 : v0);
-                    uint16_t rev = (uint16_t)(eb | (ea << 8));
-                    int found = -1;
-                    for (int q = 0; q < ne; q++) if (poly.E(q) == rev) { found = q; break; }
-                    if (found >= 0) { for (int q = found; q + 1 < ne; q++) poly.setE(q, poly.E(q + 1)); ne--; }
-                    else if (ne < poly.emax) { poly.setE(ne, (uint16_t)(ea | (eb << 8))); ne++; }
-                    else overflow = true;
+                    for (int k = 0; k < 3; k++) {
+                        int ea = k == 0 ? v0 : (k == 1 ? v1 : v2);
+                        int eb = k == 0 ? v1 : (k == 1 ? v2 : v0);
+                        uint16_t rev = (uint16_t)(eb | (ea << 8));
+                        int hit = -1;
+                        for (int q = 0; q < ne; q++) if (poly.E(q) == rev) { hit = q; break; }
+                        if (hit >= 0) { for (int q = hit; q + 1 < ne; q++) poly.setE(q, poly.E(q + 1)); ne--; }
+                        else if (ne < poly.emax) { poly.setE(ne, (uint16_t)(ea | (eb << 8))); ne++; }
+                        else overflow = 1;
+                    }
                 }
-            } else { if (keep != f) poly.movef(keep, f); keep++; }
+            }
+            gsync<G>();                                                          // lane 0 has read its faces; everyone holds theirs in registers
+            if (valid && !vis) {
+                int dst = keep + __popc(kmask & ((1u << gl) - 1u));
+                if (dst != f) { poly.setf(dst, idx, fnrm); poly.setD(dst, fdist); }
+            }
+            keep += __popc(kmask);
+            gsync<G>();
         }
-        if (overflow || keep + ne > poly.fmax) { flags |= NP_PAIR_OVERFLOW; mode = DONE; return; }
-        pnf = keep;
-        int ni = pnv;
-        poly.setv(ni, sp, sa, sb); pnv++;                                                         // :512
-        for (int e = 0; e < ne; e++) { uint16_t ed = poly.E(e); add_face(poly, ed & 0xff, ed >> 8, ni); }   // :514-517
+        if (gl == 0) {
+            if (keep + ne > poly.fmax) overflow = 1;
+            if (!overflow) poly.setv(pnv, sp, sa, sb);                                            // :512
+            poly.scratch[0] = ne; poly.scratch[2] = overflow;
+        }
+        gsync<G>();
+        ne = poly.scratch[0]; overflow = poly.scratch[2];
+        if (overflow) { flags |= NP_PAIR_OVERFLOW; done = true; return; }
+        for (int e = gl; e < ne; e += G) { uint16_t ed = poly.E(e); add_face_at(poly, keep + e, ed & 0xff, ed >> 8, pnv); }   // :514-517
+        pnf = keep + ne; pnv++;
+        gsync<G>();
     }
 
-    // one trip: support pair, consume, produce.  Call only while !done().
-    NP_D void step(const PairGeom& g, Poly& poly, PairStats& st)
+    // Same expansion for polytopes with hundreds of faces (overflow tiers, one warp per pair).  The reference's
+    // UniqueEdges (:469-491) makes a new edge (a,b) erase the FIRST remaining copy of (b,a), else appends it.  Per
+    // directed edge that is a FIFO: the surviving copies of (a,b) are its inserted copies number [cancelled, added).
+    // Edges of different vertex pairs never interact, so every lane owns the pairs that hash to it and replays only
+    // their tokens, in order, with O(1) counter updates; survivors keep their insertion order.
+    NP_D void consume_fast(Poly& poly, V3 sa, V3 sb)
     {
-        V3 sa = support(g.va, g.na, g.Ra, g.ta, d);
-        V3 sb = support(g.vb, g.nb, g.Rb, g.tb, neg(d));
-        st.support_pairs++;
-        if (mode == SEED) {
-            A[0] = sa; B[0] = sb; P[0] = sub(sb, sa); nv = 1;                                     // :704  B - A
-            mode = GJK;
-        } else if (mode == GJK) consume_gjk(sa, sb);
-        else consume_epa(poly, sa, sb);
-        if (mode == GJK) produce_gjk(poly, st);
-        if (mode == EPA) produce_epa(poly, st);
+        static_assert(!FAST || G == 32, "fast horizon needs a full warp per pair");
+        const int gl = glane<G>();
+        const unsigned m = 0xffffffffu;
+        V3 sp = sub(sa, sb);
+        bool found = false;
+        for (int i = gl; i < pnv; i += G)
+            if (veq(sa, poly.gA(i), NP_EPA_TOL) && veq(sb, poly.gB(i), NP_EPA_TOL)) found = true;
+        found = __ballot_sync(m, found) != 0u;
+        if (found) { converge(); return; }
+        constexpr int NV2 = NP_EPA_MAX_VERTS * NP_EPA_MAX_VERTS;
+        for (int q = gl; q < NV2; q += G) poly.tab[q] = 0;                  // low byte pair: added | cancelled << 8 ... kept as one u16 each below
+        // pass 1: visibility, horizon tokens (3 per visible face, in face order), order-preserving compaction of the rest
+        int keep = 0, ntok = 0;
+        for (int base = 0; base < pnf; base += G) {
+            const int f = base + gl;
+            const bool valid = f < pnf;
+            uint32_t idx = 0; V3 fnrm = mk(0.f, 0.f, 0.f); float fdist = 0.f;
+            if (valid) { idx = poly.F(f); fnrm = poly.N(f); fdist = poly.D(f); }
+            const bool vis = valid && (dot(fnrm, sp) > 0);
+            const unsigned vmask = __ballot_sync(m, vis), kmask = __ballot_sync(m, valid && !vis);
+            if (vis) {
+                int t = ntok + 3 * __popc(vmask & ((1u << gl) - 1u));
+                int v0 = idx & 0xff, v1 = (idx >> 8) & 0xff, v2 = (idx >> 16) & 0xff;
+                if (t + 2 < poly.emax) { poly.setE(t, (uint16_t)(v0 | (v1 << 8))); poly.setE(t + 1, (uint16_t)(v1 | (v2 << 8))); poly.setE(t + 2, (uint16_t)(v2 | (v0 << 8))); }
+            }
+            ntok += 3 * __popc(vmask);
+            __syncwarp(m);
+            if (valid && !vis) {
+                int dst = keep + __popc(kmask & ((1u << gl) - 1u));
+                if (dst != f) { poly.setf(dst, idx, fnrm); poly.setD(dst, fdist); }
+            }
+            keep += __popc(kmask);
+            __syncwarp(m);
+        }
+        // pass 2: replay the tokens; tab[a*24+b] = inserted (low byte) | cancelled (high byte) of directed edge (a,b)
+        // (a face contributes each directed edge at most once and nf <= fmax, but counts are bounded by 255 per direction
+        //  only for polytopes of up to 255 faces sharing an edge -- beyond that the pair is handed to the next tier)
+        int bad = 0;
+        for (int t = 0; t < ntok; t++) {
+            uint16_t ed = poly.E(t);
+            int a = ed & 0xff, b = ed >> 8;
+            if ((((a ^ b) + 5 * (a & b)) & 31) != gl) continue;
+            uint16_t fw = poly.tab[a * NP_EPA_MAX_VERTS + b], rv = poly.tab[b * NP_EPA_MAX_VERTS + a];
+            if ((rv & 0xff) > (rv >> 8)) { poly.tab[b * NP_EPA_MAX_VERTS + a] = (uint16_t)(rv + 0x100); poly.seq[t] = 0xffff; }
+            else { poly.seq[t] = (uint16_t)(fw & 0xff); if ((fw & 0xff) == 0xff) bad = 1; poly.tab[a * NP_EPA_MAX_VERTS + b] = (uint16_t)(fw + 1); }
+        }
+        bad = __ballot_sync(m, bad != 0) != 0u;
+        __syncwarp(m);
+        // pass 3: survivors in insertion order -> new faces
+        int ne = 0;
+        for (int base = 0; base < ntok; base += G) {
+            const int t = base + gl;
+            bool alive = false; uint16_t ed = 0;
+            if (t < ntok) { ed = poly.E(t); uint16_t s = poly.seq[t]; alive = (s != 0xffff) && (s >= (poly.tab[(ed & 0xff) * NP_EPA_MAX_VERTS + (ed >> 8)] >> 8)); }
+            ne += __popc(__ballot_sync(m, alive));
+        }
+        if (bad || keep + ne > poly.fmax) { flags |= NP_PAIR_OVERFLOW; done = true; return; }
+        if (gl == 0) poly.setv(pnv, sp, sa, sb);
+        __syncwarp(m);
+        int slot = keep;
+        for (int base = 0; base < ntok; base += G) {
+            const int t = base + gl;
+            bool alive = false; uint16_t ed = 0;
+            if (t < ntok) { ed = poly.E(t); uint16_t s = poly.seq[t]; alive = (s != 0xffff) && (s >= (poly.tab[(ed & 0xff) * NP_EPA_MAX_VERTS + (ed >> 8)] >> 8)); }
+            const unsigned am = __ballot_sync(m, alive);
+            if (alive) add_face_at(poly, slot + __popc(am & ((1u << gl) - 1u)), ed & 0xff, ed >> 8, pnv);
+            slot += __popc(am);
+        }
+        pnf = keep + ne; pnv++;
+        __syncwarp(m);
+    }
+
+    // call while !done: [closest face] -> [support pair] -> [convergence test / expansion]
+    NP_D void trip(const PairGeom& g, Poly& poly, PairStats& st)
+    {
+        produce(poly, st);
+        if (done) return;
+        V3 sa = support<G>(g.va, g.na, g.Ra, g.ta, d);
+        V3 sb = support<G>(g.vb, g.nb, g.Rb, g.tb, neg(d));
+        st.support_pairs++; st.support_verts += (unsigned)(g.na + g.nb);
+        if constexpr (FAST) consume_fast(poly, sa, sb); else consume(poly, sa, sb);
     }
 };
 

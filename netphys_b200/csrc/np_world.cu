@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -39,6 +40,8 @@ struct np_world {
     int broadphase = NP_BROADPHASE_EXACT;
     float grid_cell = 0.0f;
     int counters_on = 0;
+    int snapshot_each_step = 0; void* snap_target = nullptr; uint32_t guid_base = 0;
+    void* d_flush = nullptr; unsigned long long launches = 0;
     // device store
     bool dirty_bodies = true, dirty_shapes = true, dev_state_valid = false;
     int cap = 0, dev_n = 0;
@@ -47,8 +50,11 @@ struct np_world {
     float4* d_verts = nullptr; int *d_soff = nullptr, *d_scnt = nullptr; int total_verts = 0;
     // per-step scratch
     int *d_hit_j = nullptr, *d_cflags = nullptr; float4* d_contact = nullptr;
-    int* d_zero = nullptr;            // [ticket, big_count, pad(30), inc_cnt[cap], cursor[cap]]  -- one memset per step
-    int *d_inc_off = nullptr, *d_inc = nullptr, *d_sums = nullptr, *d_big_list = nullptr;
+    int* d_zero = nullptr;            // [tickets and counts (32 ints), inc_cnt[cap], cursor[cap]]  -- one memset per step
+    int *d_inc_off = nullptr, *d_inc = nullptr, *d_sums = nullptr, *d_big_list = nullptr, *d_hit_list = nullptr;
+    float4* d_simplex = nullptr;      // GJK result of every hit: A[4], B[4]
+    int max_verts = 0;                // largest shape
+    int g_gjk_env = 0, g_epa_env = 0; // NP_G_GJK / NP_G_EPA overrides (tuning)
     DevCounters* d_ctr = nullptr;
     SnapObj* d_snap = nullptr;
     BigArena arena = {};
@@ -61,14 +67,12 @@ struct np_world {
     unsigned long long steps = 0;
     // CUDA graph of one step (np_world_step_n)
     cudaGraphExec_t graph = nullptr; float graph_dt = 0.0f;
-    int first_hit_blocks = 0, pairs_blocks = 0;
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
 static StoreView view(np_world* w) { StoreView s; s.n = (int)w->bodies.size(); s.cap = w->cap; s.state = w->d_state; s.cst = w->d_cst; s.xf = w->d_xf; s.ints = w->d_ints; return s; }
 static ShapeView sview(np_world* w) { ShapeView s; s.verts = w->d_verts; s.off = w->d_soff; s.cnt = w->d_scnt; s.total_verts = w->total_verts; return s; }
-static int* d_ticket(np_world* w) { return w->d_zero; }
-static int* d_big_count(np_world* w) { return w->d_zero + 1; }
+enum { Z_GJK_TICKET = 0, Z_HIT_COUNT, Z_EPA_TICKET, Z_MID_COUNT, Z_MID_TICKET, Z_BIG_COUNT, Z_BIG_TICKET };
 static int* d_inc_cnt(np_world* w) { return w->d_zero + 32; }
 static int* d_cursor(np_world* w) { return w->d_zero + 32 + w->cap; }
 
@@ -76,9 +80,9 @@ static void free_store(np_world* w)
 {
     cudaFree(w->d_state); cudaFree(w->d_cst); cudaFree(w->d_xf); cudaFree(w->d_ints);
     cudaFree(w->d_hit_j); cudaFree(w->d_cflags); cudaFree(w->d_contact); cudaFree(w->d_zero);
-    cudaFree(w->d_inc_off); cudaFree(w->d_inc); cudaFree(w->d_sums); cudaFree(w->d_big_list); cudaFree(w->d_snap);
+    cudaFree(w->d_inc_off); cudaFree(w->d_inc); cudaFree(w->d_sums); cudaFree(w->d_big_list); cudaFree(w->d_snap); cudaFree(w->d_hit_list); cudaFree(w->d_simplex);
     w->d_state = w->d_cst = w->d_xf = nullptr; w->d_ints = nullptr; w->d_hit_j = w->d_cflags = nullptr; w->d_contact = nullptr;
-    w->d_zero = w->d_inc_off = w->d_inc = w->d_sums = w->d_big_list = nullptr; w->d_snap = nullptr;
+    w->d_zero = w->d_inc_off = w->d_inc = w->d_sums = w->d_big_list = w->d_hit_list = nullptr; w->d_snap = nullptr; w->d_simplex = nullptr;
     w->cap = 0;
 }
 static int ensure_stage(np_world* w, size_t bytes)
@@ -127,6 +131,7 @@ static int ensure_device(np_world* w)
             for (size_t k = 0; k + 2 < s.xyz.size(); k += 3) v.push_back(make_float4(s.xyz[k], s.xyz[k + 1], s.xyz[k + 2], 0.0f));
         }
         w->total_verts = (int)v.size();
+        w->max_verts = 0; for (int c_ : cnt) w->max_verts = std::max(w->max_verts, c_);
         size_t nv = std::max<size_t>(v.size(), 1), ns = std::max<size_t>(off.size(), 1);
         CU(cudaMalloc((void**)&w->d_verts, sizeof(float4) * nv)); CU(cudaMalloc((void**)&w->d_soff, sizeof(int) * ns)); CU(cudaMalloc((void**)&w->d_scnt, sizeof(int) * ns));
         if (!v.empty()) CU(cudaMemcpyAsync(w->d_verts, v.data(), sizeof(float4) * v.size(), cudaMemcpyHostToDevice, w->stream));
@@ -154,6 +159,7 @@ static int ensure_device(np_world* w)
         CU(cudaMalloc((void**)&w->d_zero, sizeof(int) * (32 + 2 * c))); CU(cudaMalloc((void**)&w->d_inc_off, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_inc, sizeof(int) * c));
         CU(cudaMalloc((void**)&w->d_sums, sizeof(int) * (c / NP_SCAN_BLOCK + 2))); CU(cudaMalloc((void**)&w->d_big_list, sizeof(int) * c));
         CU(cudaMalloc((void**)&w->d_snap, sizeof(SnapObj) * c));
+        CU(cudaMalloc((void**)&w->d_hit_list, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_simplex, sizeof(float4) * 6 * c));
         CU(cudaMemsetAsync(w->d_state, 0, sizeof(float) * S_COUNT * c, w->stream));
         CU(cudaMemsetAsync(w->d_hit_j, 0xff, sizeof(int) * c, w->stream)); CU(cudaMemsetAsync(w->d_cflags, 0, sizeof(int) * c, w->stream));
         CU(cudaMemsetAsync(w->d_contact, 0, sizeof(float4) * c, w->stream));
@@ -176,25 +182,100 @@ static int ensure_device(np_world* w)
     int r = upload_states(w, w->host_state.data(), n); if (r) return r;
     if (n > 0) { k_transforms<<<(n + 255) / 256, 256, 0, w->stream>>>(view(w)); CU(cudaGetLastError()); }
     w->dev_n = n; w->dev_state_valid = true; w->dirty_bodies = false;
-    // launch geometry of the persistent narrow-phase kernels
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_first_hit<true>, NP_NARROW_THREADS, sizeof(float4) * NP_SMEM_VERTS));
-    w->first_hit_blocks = std::max(1, per_sm) * w->sm_count;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs<true>, NP_NARROW_THREADS, sizeof(float4) * NP_SMEM_VERTS));
-    w->pairs_blocks = std::max(1, per_sm) * w->sm_count;
     return NP_OK;
 }
 static int ensure_arena(np_world* w)
 {
-    if (w->arena.p) return NP_OK;
-    BigArena& a = w->arena; a.slots = 256; a.fbig = 4096;
-    size_t s = (size_t)a.slots;
-    CU(cudaMalloc((void**)&a.p, sizeof(float) * 3 * NP_EPA_MAX_VERTS * s)); CU(cudaMalloc((void**)&a.A, sizeof(float) * 3 * NP_EPA_MAX_VERTS * s));
-    CU(cudaMalloc((void**)&a.B, sizeof(float) * 3 * NP_EPA_MAX_VERTS * s)); CU(cudaMalloc((void**)&a.fn, sizeof(float) * 3 * a.fbig * s));
-    CU(cudaMalloc((void**)&a.fi, sizeof(uint32_t) * a.fbig * s)); CU(cudaMalloc((void**)&a.edge, sizeof(uint16_t) * 3 * a.fbig * s));
+    if (w->arena.base) return NP_OK;
+    w->arena.slots = w->sm_count * 2 * (NP_MID_THREADS / 32);             // one slot per warp of the TIER 2 launch
+    CU(cudaMalloc((void**)&w->arena.base, sizeof(float) * (size_t)poly_words_fast(NP_FBIG) * w->arena.slots));
     return NP_OK;
 }
 static bool shapes_in_smem(np_world* w) { return w->total_verts <= NP_SMEM_VERTS; }
+
+// ---- narrow-phase launch plumbing -------------------------------------------------------------------------------
+static size_t shapes_smem(np_world* w) { return shapes_in_smem(w) ? sizeof(float4) * (size_t)w->total_verts : 0; }
+template <int G> constexpr int epa_fmax() { return G == 4 ? 32 : 64; }
+template <int G> static size_t epa_smem(np_world* w) { return shapes_smem(w) + (G > 1 ? sizeof(float) * (size_t)poly_words(epa_fmax<G>()) * (NP_NARROW_THREADS / G) : 0); }
+
+template <typename K>
+static int persistent_blocks(np_world* w, K kernel, size_t smem, long long items, int G)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NP_NARROW_THREADS, smem) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
+    long long want = (items * G + NP_NARROW_THREADS - 1) / NP_NARROW_THREADS;
+    return (int)std::max<long long>(1, std::min<long long>((long long)std::max(1, per_sm) * w->sm_count, want));
+}
+// group size: few items -> wide groups (latency, whole-GPU occupancy); many items -> narrow groups (throughput)
+static int pick_group(np_world* w, long long items, int env, bool epa)
+{
+    if (env == 1 || env == 4 || env == 8 || env == 32) return env;
+    const long long resident = (long long)w->sm_count * 2048;
+    if (items * 32 <= resident * 2) return 32;            // latency regime: a warp per pair still fills the GPU
+    if (items * 8 <= resident * 2) return 8;
+    return epa ? 4 : 1;                                   // throughput regime (measured: tools/sweep_g.sh)
+}
+struct NarrowBufs { int* zero; int* hit_j; int* flags; float4* contact; float4* simplex; int* hit_list; int* big_list; };
+
+template <int G>
+static int launch_gjk(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevCounters* ctr)
+{
+    size_t smem = shapes_smem(w);
+    int blocks = persistent_blocks(w, k_gjk<G>, smem, in.n, G);
+    k_gjk<G><<<blocks, NP_NARROW_THREADS, smem, w->stream>>>(in, sview(w), shapes_in_smem(w) ? 1 : 0, b.zero + Z_GJK_TICKET, b.hit_j, b.flags, b.contact, b.simplex,
+                                                             b.hit_list, b.zero + Z_HIT_COUNT, ctr);
+    w->launches++;
+    return NP_OK;
+}
+template <int G>
+static int launch_epa(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevCounters* ctr)
+{
+    const int sm_shapes = shapes_in_smem(w) ? 1 : 0;
+    size_t smem = epa_smem<G>(w);
+    auto kern = k_epa<G, epa_fmax<G>(), 0, NP_NARROW_THREADS>;
+    int blocks = persistent_blocks(w, kern, smem, in.n, G);
+    kern<<<blocks, NP_NARROW_THREADS, smem, w->stream>>>(in, sview(w), sm_shapes, b.hit_list, b.zero + Z_HIT_COUNT, b.zero + Z_EPA_TICKET, b.hit_j, b.simplex,
+                                                        b.flags, b.contact, b.big_list, b.zero + Z_MID_COUNT, w->arena, ctr);
+    // overflow tiers (one warp per pair); both exit at once when their list is empty.  hit_list is free again by now.
+    auto mid = k_epa<32, NP_FMID, 1, NP_MID_THREADS>;
+    size_t msmem = shapes_smem(w) + sizeof(float) * (size_t)poly_words_fast(NP_FMID) * (NP_MID_THREADS / 32);
+    int mblocks = (int)std::min<long long>(w->sm_count * 2, std::max<long long>(1, ((long long)in.n * 32 + NP_MID_THREADS - 1) / NP_MID_THREADS));
+    mid<<<mblocks, NP_MID_THREADS, msmem, w->stream>>>(in, sview(w), sm_shapes, b.big_list, b.zero + Z_MID_COUNT, b.zero + Z_MID_TICKET, b.hit_j, b.simplex,
+                                                       b.flags, b.contact, b.hit_list, b.zero + Z_BIG_COUNT, w->arena, ctr);
+    auto big = k_epa<32, 64, 2, NP_MID_THREADS>;
+    int bblocks = std::min(w->arena.slots / (NP_MID_THREADS / 32), mblocks);
+    big<<<bblocks, NP_MID_THREADS, shapes_smem(w), w->stream>>>(in, sview(w), sm_shapes, b.hit_list, b.zero + Z_BIG_COUNT, b.zero + Z_BIG_TICKET, b.hit_j, b.simplex,
+                                                                b.flags, b.contact, nullptr, nullptr, w->arena, ctr);
+    w->launches += 3;
+    return NP_OK;
+}
+static void setup_kernels()
+{
+    // EPA keeps one polytope per group in shared memory next to the staged shape table: up to ~84 KB per block
+    const int bytes = 112 * 1024;
+    cudaFuncSetAttribute(k_epa<4, epa_fmax<4>(), 0, NP_NARROW_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_epa<8, epa_fmax<8>(), 0, NP_NARROW_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_epa<32, epa_fmax<32>(), 0, NP_NARROW_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_epa<32, NP_FMID, 1, NP_MID_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+static int launch_narrow(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevCounters* ctr)
+{
+    int r;
+    switch (pick_group(w, in.n, w->g_gjk_env, false)) {
+    case 1: r = launch_gjk<1>(w, in, b, ctr); break;
+    case 4: r = launch_gjk<4>(w, in, b, ctr); break;
+    case 8: r = launch_gjk<8>(w, in, b, ctr); break;
+    default: r = launch_gjk<32>(w, in, b, ctr); break;
+    }
+    if (r) return r;
+    switch (pick_group(w, in.n, w->g_epa_env, true)) {
+    case 1: r = launch_epa<1>(w, in, b, ctr); break;
+    case 4: r = launch_epa<4>(w, in, b, ctr); break;
+    case 8: r = launch_epa<8>(w, in, b, ctr); break;
+    default: r = launch_epa<32>(w, in, b, ctr); break;
+    }
+    return r;
+}
 
 // the kernels of one Physics_Update, enqueued on the world's stream (capturable)
 static int enqueue_step(np_world* w, float dt, bool timed)
@@ -210,12 +291,9 @@ static int enqueue_step(np_world* w, float dt, bool timed)
     // (grid broad-phase goes here)
     if (timed) CU(cudaEventRecord(w->ev[2], w->stream));
     CU(cudaMemsetAsync(w->d_zero, 0, sizeof(int) * (32 + 2 * (size_t)w->cap), w->stream));
-    int blocks = std::min(w->first_hit_blocks, (n + NP_NARROW_THREADS - 1) / NP_NARROW_THREADS);
-    if (shapes_in_smem(w))
-        k_first_hit<true><<<blocks, NP_NARROW_THREADS, sizeof(float4) * w->total_verts, w->stream>>>(s, sh, d_ticket(w), w->d_hit_j, w->d_contact, w->d_cflags, w->d_big_list, d_big_count(w), ctr);
-    else
-        k_first_hit<false><<<blocks, NP_NARROW_THREADS, 0, w->stream>>>(s, sh, d_ticket(w), w->d_hit_j, w->d_contact, w->d_cflags, w->d_big_list, d_big_count(w), ctr);
-    k_epa_big<<<(w->arena.slots + 63) / 64, 64, 0, w->stream>>>(s, sh, w->d_big_list, d_big_count(w), w->d_hit_j, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w->d_cflags, w->d_contact, w->arena);
+    NarrowIn in; memset(&in, 0, sizeof in); in.world = 1; in.n = n; in.s = s;
+    NarrowBufs nb = { w->d_zero, w->d_hit_j, w->d_cflags, w->d_contact, w->d_simplex, w->d_hit_list, w->d_big_list };
+    { int r = launch_narrow(w, in, nb, ctr); if (r) return r; }
     if (timed) CU(cudaEventRecord(w->ev[3], w->stream));
     k_count_incoming<<<b256, 256, 0, w->stream>>>(n, w->cap, w->d_hit_j, w->d_ints, d_inc_cnt(w));
     const int sb = (n + NP_SCAN_BLOCK - 1) / NP_SCAN_BLOCK;
@@ -225,6 +303,12 @@ static int enqueue_step(np_world* w, float dt, bool timed)
     k_fill_incoming<<<b256, 256, 0, w->stream>>>(n, w->cap, w->d_hit_j, w->d_ints, w->d_inc_off, d_cursor(w), w->d_inc);
     k_resolve<<<b256, 256, 0, w->stream>>>(s, w->d_hit_j, w->d_contact, w->d_inc_off, d_inc_cnt(w), w->d_inc);
     if (timed) CU(cudaEventRecord(w->ev[4], w->stream));
+    w->launches += 7;
+    if (w->snapshot_each_step) {
+        k_snapshot<<<b256, 256, 0, w->stream>>>(s, w->guid_base, w->snap_target ? (SnapObj*)w->snap_target : w->d_snap);
+        w->launches += 1;
+    }
+    if (timed) CU(cudaEventRecord(w->ev[5], w->stream));
     CU(cudaGetLastError());
     return NP_OK;
 }
@@ -252,6 +336,9 @@ np_world* np_world_create(int device)
         fail(NP_ERR_CUDA, "cannot create stream"); delete w; return nullptr;
     }
     for (auto& e : w->ev) cudaEventCreate(&e);
+    setup_kernels();
+    if (const char* e = getenv("NP_G_GJK")) w->g_gjk_env = atoi(e);
+    if (const char* e = getenv("NP_G_EPA")) w->g_epa_env = atoi(e);
     if (cudaMalloc((void**)&w->d_ctr, sizeof(DevCounters)) != cudaSuccess || ensure_arena(w) != NP_OK) { fail(NP_ERR_CUDA, "cannot allocate device scratch"); np_world_destroy(w); return nullptr; }
     cudaMemsetAsync(w->d_ctr, 0, sizeof(DevCounters), w->stream);
     return w;
@@ -262,8 +349,8 @@ void np_world_destroy(np_world* w)
     cudaSetDevice(w->device);
     if (w->stream) cudaStreamSynchronize(w->stream);
     drop_graph(w); free_store(w);
-    cudaFree(w->d_verts); cudaFree(w->d_soff); cudaFree(w->d_scnt); cudaFree(w->d_ctr);
-    cudaFree(w->arena.p); cudaFree(w->arena.A); cudaFree(w->arena.B); cudaFree(w->arena.fn); cudaFree(w->arena.fi); cudaFree(w->arena.edge);
+    cudaFree(w->d_verts); cudaFree(w->d_soff); cudaFree(w->d_scnt); cudaFree(w->d_ctr); cudaFree(w->d_flush);
+    cudaFree(w->arena.base);
     if (w->h_stage) cudaFreeHost(w->h_stage);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
@@ -279,6 +366,7 @@ int np_world_set_option(np_world* w, int option, int64_t value)
         w->broadphase = (int)value; drop_graph(w); return NP_OK;
     case NP_OPT_GRID_CELL: { uint32_t u = (uint32_t)value; memcpy(&w->grid_cell, &u, 4); return NP_OK; }
     case NP_OPT_COUNTERS: w->counters_on = value ? 1 : 0; drop_graph(w); return NP_OK;
+    case NP_OPT_SNAPSHOT_EACH_STEP: w->snapshot_each_step = value ? 1 : 0; drop_graph(w); return NP_OK;
     default: return fail(NP_ERR_INVALID, "unknown option");
     }
 }
@@ -526,6 +614,7 @@ int np_world_get_counters(np_world* w, np_counters* out)
     CU(cudaStreamSynchronize(w->stream));
     out->steps = w->steps; out->pair_tests = c.pair_tests; out->hits = c.hits; out->gjk_steps = c.gjk_steps; out->support_pairs = c.support_pairs;
     out->epa_iters = c.epa_iters; out->epa_tri_tests = c.epa_tri_tests; out->epa_overflow = c.epa_overflow; out->candidates = c.candidates;
+    out->support_verts = c.support_verts; out->kernel_launches = w->launches;
     return NP_OK;
 }
 int np_world_last_step_ms(np_world* w, float out[6])
@@ -536,8 +625,8 @@ int np_world_last_step_ms(np_world* w, float out[6])
     for (int k = 0; k < 6; k++) out[k] = 0.0f;
     if (w->steps == 0) return NP_OK;
     if (w->timed) {
-        for (int k = 0; k < 4; k++) CU(cudaEventElapsedTime(&out[k], w->ev[k], w->ev[k + 1]));
-        CU(cudaEventElapsedTime(&out[5], w->ev[0], w->ev[4]));
+        for (int k = 0; k < 5; k++) CU(cudaEventElapsedTime(&out[k], w->ev[k], w->ev[k + 1]));
+        CU(cudaEventElapsedTime(&out[5], w->ev[0], w->ev[5]));
     } else CU(cudaEventElapsedTime(&out[5], w->ev[0], w->ev[5]));
     return NP_OK;
 }
@@ -546,23 +635,25 @@ int np_world_last_step_ms(np_world* w, float out[6])
 static int run_pairs(np_world* w, int n, const int* d_sa, const float* d_pa, const int* d_sb, const float* d_pb, const float* d_xa, const float* d_xb,
                      int* d_hit, float4* d_out, float* kernel_ms)
 {
-    // scratch: ticket + big_count + big_list
-    int* d_scr = nullptr;
-    CU(cudaMallocAsync((void**)&d_scr, sizeof(int) * (32 + (size_t)n), w->stream));
-    CU(cudaMemsetAsync(d_scr, 0, sizeof(int) * 32, w->stream));
-    ShapeView sh = sview(w);
-    DevCounters* ctr = w->counters_on ? w->d_ctr : nullptr;
-    int blocks = std::max(1, std::min(w->pairs_blocks ? w->pairs_blocks : w->sm_count * 4, (n + NP_NARROW_THREADS - 1) / NP_NARROW_THREADS));
+    // scratch: counters | xfA | xfB (SoA) | simplex | hit_list | big_list
+    const size_t N = (size_t)n;
+    const size_t o_zero = 0, o_xa = 128, o_xb = o_xa + 4 * X_COUNT * N, o_sx = (o_xb + 4 * X_COUNT * N + 15) / 16 * 16, o_hl = o_sx + 96 * N, o_bl = o_hl + 4 * N, total = o_bl + 4 * N;
+    char* d = nullptr;
+    CU(cudaMallocAsync((void**)&d, total, w->stream));
+    CU(cudaMemsetAsync(d + o_zero, 0, 128, w->stream));
     if (kernel_ms) CU(cudaEventRecord(w->ev[0], w->stream));
-    if (shapes_in_smem(w))
-        k_pairs<true><<<blocks, NP_NARROW_THREADS, sizeof(float4) * w->total_verts, w->stream>>>(n, sh, d_sa, d_pa, d_sb, d_pb, d_xa, d_xb, d_scr, d_hit, d_out, d_scr + 32, d_scr + 1, ctr);
-    else
-        k_pairs<false><<<blocks, NP_NARROW_THREADS, 0, w->stream>>>(n, sh, d_sa, d_pa, d_sb, d_pb, d_xa, d_xb, d_scr, d_hit, d_out, d_scr + 32, d_scr + 1, ctr);
-    StoreView s = view(w);
-    k_epa_big<<<(w->arena.slots + 63) / 64, 64, 0, w->stream>>>(s, sh, d_scr + 32, d_scr + 1, nullptr, n, d_sa, d_pa, d_sb, d_pb, d_xa, d_xb, d_hit, d_out, w->arena);
+    const int b256 = (n + 255) / 256;
+    k_pose_xf<<<b256, 256, 0, w->stream>>>(n, d_pa, d_xa, (float*)(d + o_xa));
+    k_pose_xf<<<b256, 256, 0, w->stream>>>(n, d_pb, d_xb, (float*)(d + o_xb));
+    w->launches += 2;
+    NarrowIn in; memset(&in, 0, sizeof in); in.world = 0; in.n = n; in.s = view(w);
+    in.shape_a = d_sa; in.shape_b = d_sb; in.xf_a = (const float*)(d + o_xa); in.xf_b = (const float*)(d + o_xb);
+    NarrowBufs nb = { (int*)(d + o_zero), nullptr, d_hit, d_out, (float4*)(d + o_sx), (int*)(d + o_hl), (int*)(d + o_bl) };
+    int r = launch_narrow(w, in, nb, w->counters_on ? w->d_ctr : nullptr);
     if (kernel_ms) CU(cudaEventRecord(w->ev[5], w->stream));
     CU(cudaGetLastError());
-    CU(cudaFreeAsync(d_scr, w->stream));
+    CU(cudaFreeAsync(d, w->stream));
+    if (r) return r;
     if (kernel_ms) { CU(cudaStreamSynchronize(w->stream)); CU(cudaEventElapsedTime(kernel_ms, w->ev[0], w->ev[5])); }
     return NP_OK;
 }
@@ -665,8 +756,14 @@ int np_world_snapshot_device(np_world* w, void** d_ptr, size_t* bytes)
     if (!w || !d_ptr || !bytes) return fail(NP_ERR_INVALID, "bad arguments");
     int r = ensure_device(w); if (r) return r;
     int n = (int)w->bodies.size();
-    if (n > 0) { k_snapshot<<<(n + 255) / 256, 256, 0, w->stream>>>(view(w), 0u, w->d_snap); CU(cudaGetLastError()); }
+    if (n > 0) { k_snapshot<<<(n + 255) / 256, 256, 0, w->stream>>>(view(w), w->guid_base, w->d_snap); CU(cudaGetLastError()); w->launches++; }
     *d_ptr = w->d_snap; *bytes = sizeof(SnapObj) * (size_t)n;
+    return NP_OK;
+}
+int np_world_set_snapshot_target(np_world* w, void* d_dst, uint32_t guid_base)
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    w->snap_target = d_dst; w->guid_base = guid_base; drop_graph(w);
     return NP_OK;
 }
 int np_world_snapshot(np_world* w, np_snapshot_object* dst, int cap)
@@ -687,6 +784,15 @@ int np_device_free(np_world* w, void* p) { if (!w) return fail(NP_ERR_INVALID, "
 int np_device_upload(np_world* w, void* d_dst, const void* h_src, size_t bytes) { if (!w) return fail(NP_ERR_INVALID, "null world"); CU(cudaSetDevice(w->device)); CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, w->stream)); CU(cudaStreamSynchronize(w->stream)); return NP_OK; }
 int np_device_download(np_world* w, void* h_dst, const void* d_src, size_t bytes) { if (!w) return fail(NP_ERR_INVALID, "null world"); CU(cudaSetDevice(w->device)); CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, w->stream)); CU(cudaStreamSynchronize(w->stream)); return NP_OK; }
 void* np_world_stream(np_world* w) { return w ? (void*)w->stream : nullptr; }
+int np_device_flush_l2(np_world* w)
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    CU(cudaSetDevice(w->device));
+    const size_t bytes = 256u << 20;
+    if (!w->d_flush) CU(cudaMalloc(&w->d_flush, bytes));
+    CU(cudaMemsetAsync(w->d_flush, 0x5a, bytes, w->stream));
+    return NP_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ self tests
 int np_selftest_sincos_hash(np_world* w, uint32_t start, uint64_t count, uint64_t* hash_sin, uint64_t* hash_cos)
@@ -701,6 +807,27 @@ int np_selftest_sincos_hash(np_world* w, uint32_t start, uint64_t count, uint64_
     CU(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, w->stream)); CU(cudaFreeAsync(d, w->stream));
     CU(cudaStreamSynchronize(w->stream));
     *hash_sin = h[0]; *hash_cos = h[1];
+    return NP_OK;
+}
+int np_selftest_fp32_peak(np_world* w, float* tflops)
+{
+    if (!w || !tflops) return fail(NP_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(w->device));
+    float* d = nullptr; CU(cudaMallocAsync((void**)&d, 4, w->stream));
+    const int iters = 20000, blocks = w->sm_count * 8;
+    k_fp32_peak<<<blocks, 256, 0, w->stream>>>(100, d);                      // warm-up
+    float best = 0.0f;
+    for (int rep = 0; rep < 3; rep++) {
+        CU(cudaEventRecord(w->ev[0], w->stream));
+        k_fp32_peak<<<blocks, 256, 0, w->stream>>>(iters, d);
+        CU(cudaEventRecord(w->ev[5], w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+        float ms = 0.0f; CU(cudaEventElapsedTime(&ms, w->ev[0], w->ev[5]));
+        double flop = (double)blocks * 256.0 * iters * 16.0;
+        best = std::max(best, (float)(flop / (ms * 1e-3) / 1e12));
+    }
+    CU(cudaFreeAsync(d, w->stream)); CU(cudaGetLastError());
+    *tflops = best;
     return NP_OK;
 }
 int np_selftest_closest(np_world* w, int kind, const float* pts, int32_t* region, float uvw[3])

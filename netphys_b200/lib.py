@@ -40,7 +40,7 @@ class SnapshotObject(C.Structure):
 
 
 class Counters(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("steps", "pair_tests", "hits", "gjk_steps", "support_pairs", "epa_iters", "epa_tri_tests", "epa_overflow", "candidates")]
+    _fields_ = [(n, C.c_uint64) for n in ("steps", "pair_tests", "hits", "gjk_steps", "support_pairs", "epa_iters", "epa_tri_tests", "epa_overflow", "candidates", "support_verts", "kernel_launches")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -119,6 +119,9 @@ def load_library():
     L.np_device_upload.argtypes = [vp, vp, vp, C.c_size_t]
     L.np_device_download.argtypes = [vp, vp, vp, C.c_size_t]
     L.np_world_stream.restype = vp; L.np_world_stream.argtypes = [vp]
+    L.np_device_flush_l2.argtypes = [vp]
+    L.np_world_set_snapshot_target.argtypes = [vp, vp, C.c_uint32]
+    L.np_selftest_fp32_peak.argtypes = [vp, f32p]
     L.np_selftest_sincos_hash.argtypes = [vp, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.np_selftest_closest.argtypes = [vp, C.c_int, f32p, i32p, f32p]
     _LIB = L
@@ -154,7 +157,7 @@ class World:
     """np_world.  Mirrors the reference's implicit global world (engine/physics.cpp:9) as an explicit object."""
 
     EXACT, GRID = 0, 1
-    OPT_BROADPHASE, OPT_GRID_CELL, OPT_COUNTERS = 1, 2, 3
+    OPT_BROADPHASE, OPT_GRID_CELL, OPT_COUNTERS, OPT_SNAPSHOT_EACH_STEP = 1, 2, 3, 4
 
     def __init__(self, device=-1):
         self.L = load_library()
@@ -320,6 +323,12 @@ class World:
     def snapshot_device(self):
         p = C.c_void_p(); nb = C.c_size_t()
         self._ck(self.L.np_world_snapshot_device(self.w, C.byref(p), C.byref(nb))); return p.value, nb.value
+
+    def flush_l2(self): self._ck(self.L.np_device_flush_l2(self.w))
+    def set_snapshot_target(self, d_ptr, guid_base=0): self._ck(self.L.np_world_set_snapshot_target(self.w, d_ptr, guid_base))
+
+    def fp32_peak_tflops(self):
+        out = np.zeros(1, np.float32); self._ck(self.L.np_selftest_fp32_peak(self.w, _f(out))); return float(out[0])
 
     # -- self tests ------------------------------------------------------------------------------
     def sincos_hash(self, start, count):

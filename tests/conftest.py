@@ -1,0 +1,60 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def biteq(a, b):
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def assert_biteq(a, b, what=""):
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    assert a.shape == b.shape, "%s: shape %s vs %s" % (what, a.shape, b.shape)
+    bad = np.argwhere(a.view(np.uint32) != b.view(np.uint32))
+    assert len(bad) == 0, "%s: %d of %d floats differ, first at %s: got %r want %r" % (
+        what, len(bad), a.size, tuple(bad[0]), a[tuple(bad[0])], b[tuple(bad[0])])
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle.bind import Oracle
+    return Oracle()
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The reference's own engine, compiled in the dev container only (absent on the GPU box unless prebuilt)."""
+    from oracle.bind import Ref, ref_available
+    if not ref_available() and not os.path.isdir("/root/reference/engine"):
+        pytest.skip("oracle/_ref/libnetphys_ref.so not built and /root/reference absent")
+    return Ref()
+
+
+@pytest.fixture(scope="session")
+def npb():
+    import netphys_b200
+    return netphys_b200
+
+
+@pytest.fixture()
+def world(npb):
+    if npb.device_count() < 1:
+        pytest.fail("gpu test selected but no CUDA device is visible (netphys_b200 has no CPU path)")
+    w = npb.World(0)
+    yield w
+    w.close()
