@@ -13,15 +13,24 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _bits(a):
+    """float32 bit patterns with every NaN mapped to one canonical pattern: which NaN a 0/0 produces (x86 gives the
+    negative quiet NaN, the GPU 0x7fffffff) is not observable through the engine's API; NaN-ness is."""
+    a = np.ascontiguousarray(a, np.float32)
+    u = a.view(np.uint32).copy()
+    u[np.isnan(a)] = 0x7fc00000
+    return u
+
+
 def biteq(a, b):
     a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
-    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    return a.shape == b.shape and np.array_equal(_bits(a), _bits(b))
 
 
 def assert_biteq(a, b, what=""):
     a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
     assert a.shape == b.shape, "%s: shape %s vs %s" % (what, a.shape, b.shape)
-    bad = np.argwhere(a.view(np.uint32) != b.view(np.uint32))
+    bad = np.argwhere(_bits(a) != _bits(b))
     assert len(bad) == 0, "%s: %d of %d floats differ, first at %s: got %r want %r" % (
         what, len(bad), a.size, tuple(bad[0]), a[tuple(bad[0])], b[tuple(bad[0])])
 
