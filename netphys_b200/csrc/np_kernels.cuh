@@ -177,8 +177,11 @@ struct NarrowIn {
 //  For every hit the final simplex (A[4], B[4]) is written to simplex[item*6 .. +6) and the item is appended to hit_list.
 //  Persistent grid, warp-aggregated ticket counter, groups re-armed as soon as their item is resolved.
 // ---------------------------------------------------------------------------------------------------
+#ifndef NP_GJK_MINB
+#define NP_GJK_MINB 3
+#endif
 template <int G>
-__global__ void __launch_bounds__(NP_NARROW_THREADS, 4) k_gjk(NarrowIn in, ShapeView sh, int smem_shapes, int* __restrict__ ticket, int* __restrict__ hit_j,
+__global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn in, ShapeView sh, int smem_shapes, int* __restrict__ ticket, int* __restrict__ hit_j,
                                                           int* __restrict__ flags, float4* __restrict__ contact, float4* __restrict__ simplex,
                                                           int* __restrict__ hit_list, int* __restrict__ hit_count, DevCounters* ctr)
 {
@@ -228,9 +231,9 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, 4) k_gjk(NarrowIn in, Shape
                         if (in.world) hit_j[i] = j;
                         flags[i] = NP_PAIR_HIT | (m.seed_alive ? NP_PAIR_SEED_ALIVE : 0);
                         float4* o = simplex + (size_t)i * 6;
-                        o[0] = make_float4(m.A[0].x, m.A[0].y, m.A[0].z, m.A[1].x); o[1] = make_float4(m.A[1].y, m.A[1].z, m.A[2].x, m.A[2].y);
-                        o[2] = make_float4(m.A[2].z, m.A[3].x, m.A[3].y, m.A[3].z); o[3] = make_float4(m.B[0].x, m.B[0].y, m.B[0].z, m.B[1].x);
-                        o[4] = make_float4(m.B[1].y, m.B[1].z, m.B[2].x, m.B[2].y); o[5] = make_float4(m.B[2].z, m.B[3].x, m.B[3].y, m.B[3].z);
+                        o[0] = make_float4(m.A0.x, m.A0.y, m.A0.z, m.A1.x); o[1] = make_float4(m.A1.y, m.A1.z, m.A2.x, m.A2.y);
+                        o[2] = make_float4(m.A2.z, m.A3.x, m.A3.y, m.A3.z); o[3] = make_float4(m.B0.x, m.B0.y, m.B0.z, m.B1.x);
+                        o[4] = make_float4(m.B1.y, m.B1.z, m.B2.x, m.B2.y); o[5] = make_float4(m.B2.z, m.B3.x, m.B3.y, m.B3.z);
                         hit_list[atomicAdd(hit_count, 1)] = i;
                     }
                     have = false;
@@ -272,7 +275,7 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
     // polytope storage of this group: local memory (G = 1), shared memory, or the global arena (TIER 2)
     PolyLocal<LOCAL ? FMAX : 1> poly_local;
     PolyPtr poly_ptr;
-    constexpr bool FAST = TIER >= 1;
+    constexpr bool FAST = (TIER >= 1) || (G == 32);      // a full warp per pair: O(1)-per-edge horizon extraction
     if (TIER == 2) poly_ptr = poly_from(ar.base + (size_t)(blockIdx.x * GPB + gid) * poly_words_fast(NP_FBIG), NP_FBIG, true);
     else poly_ptr = poly_from((float*)(s_dyn + (smem_shapes ? sh.total_verts : 0)) + (size_t)gid * (FAST ? poly_words_fast(FMAX) : poly_words(FMAX)), FMAX, FAST);
     PairGeom g;

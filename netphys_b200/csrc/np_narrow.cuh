@@ -82,17 +82,18 @@ NP_D V3 support(const float4* __restrict__ v, int n, const float* R, V3 t, V3 d)
     return best;
 }
 
-NP_D V3 pick4(const V3* P, int k) { return k == 0 ? P[0] : (k == 1 ? P[1] : (k == 2 ? P[2] : P[3])); }
+NP_D V3 sel4(V3 a, V3 b, V3 c, V3 d, int k) { return k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d)); }
 
 // ---------------------------------------------------------------------------------------------------
 // GJK: DetectCollisionStep loop of DetectCollision (collision_detection.cpp:620-713), registers only.
 // One trip = one support pair, then the second half of step k (termination tests, push) and the first half
-// of step k+1 (solve, containment test, next direction).
+// of step k+1 (solve, containment test, next direction).  The simplex is kept in named scalars (never indexed
+// through a pointer) so that it cannot be demoted to local memory.
 // ---------------------------------------------------------------------------------------------------
 template <int G>
 struct GjkMachine {
     enum { RUN = 0, MISS = 1, HIT = 2 };
-    V3 P[4], A[4], B[4];
+    V3 P0, P1, P2, P3, A0, A1, A2, A3, B0, B1, B2, B3;
     V3 d;
     int nv, kn, k0, k1, k2;    // kn,k0..k2: vertices the last solve keeps (applied lazily, after the duplicate test)
     int steps, status, seed_alive;
@@ -110,12 +111,12 @@ struct GjkMachine {
         kn = nv; k0 = 0; k1 = 1; k2 = 2;
         if (nv == 2) {                                                                            // SolveLine :18-54
             float u;
-            int r = closest_line(P[0], P[1], &u);
+            int r = closest_line(P0, P1, &u);
             if (r == LINE_A) { kn = 1; }
             else if (r == LINE_B) { kn = 1; k0 = 1; }
         } else if (nv == 3) {                                                                     // SolveTriangle :56-118
             float u, v;
-            int r = closest_triangle(P[0], P[1], P[2], &u, &v);
+            int r = closest_triangle(P0, P1, P2, &u, &v);
             switch (r) {
             case TRI_A: kn = 1; break;
             case TRI_B: kn = 1; k0 = 1; break;
@@ -127,7 +128,7 @@ struct GjkMachine {
             }
         } else if (nv == 4) {                                                                     // SolveTetrahedron :121-259
             float u, v, w;
-            int r = closest_tetra(P[0], P[1], P[2], P[3], &u, &v, &w);
+            int r = closest_tetra(P0, P1, P2, P3, &u, &v, &w);
             switch (r) {
             case TET_A: kn = 1; break;
             case TET_B: kn = 1; k0 = 1; break;
@@ -147,12 +148,14 @@ struct GjkMachine {
             }
         }
         if (kn == 4) { status = HIT; return; }                                                    // :648-652 OVERLAP
-        V3 q0 = pick4(P, k0);
+        // most solves drop nothing (kn == nv): then the kept points are P0..P(kn-1) as they stand
+        const bool ident = (kn == nv);
+        V3 q0 = ident ? P0 : sel4(P0, P1, P2, P3, k0);
         if (kn == 1) d = dir1(q0);
         else {
-            V3 q1 = pick4(P, k1);
+            V3 q1 = ident ? P1 : sel4(P0, P1, P2, P3, k1);
             if (kn == 2) d = dir2(q0, q1);
-            else d = dir3(q0, q1, pick4(P, k2));
+            else d = dir3(q0, q1, ident ? P2 : sel4(P0, P1, P2, P3, k2));
         }
         if (feq(magsq(d), 0.0f)) status = MISS;                                                   // :655-658 NO_OVERLAP
     }
@@ -161,22 +164,23 @@ struct GjkMachine {
     {
         V3 sp = sub(sa, sb);
         if (dot(d, sp) < 0) { status = MISS; return; }                                            // :667
-        bool dup = false;
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (k < nv && veq(sa, A[k]) && veq(sb, B[k])) dup = true;                             // :674-680 against the PRE-solve points
+        // :674-680 the new support pair against the PRE-solve points
+        bool dup = (veq(sa, A0) && veq(sb, B0));
+        if (nv > 1) dup = dup || (veq(sa, A1) && veq(sb, B1));
+        if (nv > 2) dup = dup || (veq(sa, A2) && veq(sb, B2));
+        if (nv > 3) dup = dup || (veq(sa, A3) && veq(sb, B3));
         if (dup) { status = MISS; return; }
-        // the solve's order-preserving compaction, then push (:683-691)
-        V3 nP[3], nA[3], nB[3];
-        nP[0] = pick4(P, k0); nA[0] = pick4(A, k0); nB[0] = pick4(B, k0);
-        nP[1] = pick4(P, k1); nA[1] = pick4(A, k1); nB[1] = pick4(B, k1);
-        nP[2] = pick4(P, k2); nA[2] = pick4(A, k2); nB[2] = pick4(B, k2);
-#pragma unroll
-        for (int k = 0; k < 3; k++) { P[k] = nP[k]; A[k] = nA[k]; B[k] = nB[k]; }
-#pragma unroll
-        for (int k = 1; k < 4; k++)
-            if (k == kn) { P[k] = sp; A[k] = sa; B[k] = sb; }
-        if (k0 != 0) seed_alive = 0;             // the seed (p = B - A) can only ever sit at index 0
+        // the solve's order-preserving compaction (skipped when nothing was dropped), then push (:683-691)
+        if (kn != nv) {
+            V3 nP0 = sel4(P0, P1, P2, P3, k0), nA0 = sel4(A0, A1, A2, A3, k0), nB0 = sel4(B0, B1, B2, B3, k0);
+            V3 nP1 = sel4(P0, P1, P2, P3, k1), nA1 = sel4(A0, A1, A2, A3, k1), nB1 = sel4(B0, B1, B2, B3, k1);
+            V3 nP2 = sel4(P0, P1, P2, P3, k2), nA2 = sel4(A0, A1, A2, A3, k2), nB2 = sel4(B0, B1, B2, B3, k2);
+            P0 = nP0; A0 = nA0; B0 = nB0; P1 = nP1; A1 = nA1; B1 = nB1; P2 = nP2; A2 = nA2; B2 = nB2;
+            if (k0 != 0) seed_alive = 0;         // the seed (p = B - A) can only ever sit at index 0
+        }
+        if (kn == 1) { P1 = sp; A1 = sa; B1 = sb; }
+        else if (kn == 2) { P2 = sp; A2 = sa; B2 = sb; }
+        else { P3 = sp; A3 = sa; B3 = sb; }
         nv = kn + 1;
     }
 
@@ -186,7 +190,7 @@ struct GjkMachine {
         V3 sa = support<G>(g.va, g.na, g.Ra, g.ta, d);
         V3 sb = support<G>(g.vb, g.nb, g.Rb, g.tb, neg(d));
         st.support_pairs++; st.support_verts += (unsigned)(g.na + g.nb);
-        if (nv == 0) { A[0] = sa; B[0] = sb; P[0] = sub(sb, sa); nv = 1; }                        // :704  p = B - A
+        if (nv == 0) { A0 = sa; B0 = sb; P0 = sub(sb, sa); nv = 1; }                              // :704  p = B - A
         else consume(sa, sb);
         if (status == RUN) produce(st);
     }

@@ -196,7 +196,7 @@ static bool shapes_in_smem(np_world* w) { return w->total_verts <= NP_SMEM_VERTS
 // ---- narrow-phase launch plumbing -------------------------------------------------------------------------------
 static size_t shapes_smem(np_world* w) { return shapes_in_smem(w) ? sizeof(float4) * (size_t)w->total_verts : 0; }
 template <int G> constexpr int epa_fmax() { return G == 4 ? 32 : 64; }
-template <int G> static size_t epa_smem(np_world* w) { return shapes_smem(w) + (G > 1 ? sizeof(float) * (size_t)poly_words(epa_fmax<G>()) * (NP_NARROW_THREADS / G) : 0); }
+template <int G> static size_t epa_smem(np_world* w) { return shapes_smem(w) + (G > 1 ? sizeof(float) * (size_t)(G == 32 ? poly_words_fast(epa_fmax<G>()) : poly_words(epa_fmax<G>())) * (NP_NARROW_THREADS / G) : 0); }
 
 template <typename K>
 static int persistent_blocks(np_world* w, K kernel, size_t smem, long long items, int G)

@@ -56,7 +56,7 @@ assert SD_DTYPE.itemsize == C.sizeof(StaticPhysicsData) and COLLISION_DTYPE.item
 
 
 def library_path():
-    return os.path.join(HERE, "libnetphys_b200.so")
+    return os.environ.get("NETPHYS_B200_LIB", os.path.join(HERE, "libnetphys_b200.so"))   # override = tuning builds only
 
 
 def _declared_symbols():
