@@ -167,6 +167,7 @@ struct NarrowIn {
     StoreView s;
     const int* shape_a; const int* shape_b;      // pair mode
     const float* xf_a; const float* xf_b;        // pair mode: transforms, SoA [X_COUNT][n]
+    const int* cand; const int* cand_off; const int* cand_cnt;   // world mode with a broad phase: per-body ascending candidate lists (null = all j > i)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
     PairGeom g;
     PairStats st = { 0, 0, 0, 0, 0 };
     unsigned n_tests = 0, n_hits = 0;
-    int i = -1, j = 0, jend = 0;
+    int i = -1, j = 0, jend = 0, cbase = 0, c = 0, cn = 0;
     bool have = false, exhausted = false;
     const bool lead = glane<G>() == 0;
     const StoreView& s = in.s;
@@ -204,7 +205,8 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
             if (t < in.n) {
                 i = t;
                 if (in.world) {
-                    j = i + 1; jend = island_end[i];
+                    if (in.cand) { cbase = in.cand_off[i]; c = 0; jend = in.cand_cnt[i]; j = jend > 0 ? in.cand[cbase] : 0; if (jend > 0) jend = 0x7fffffff; cn = in.cand_cnt[i]; }
+                    else { j = i + 1; jend = island_end[i]; }
                     if (j < jend) {
                         load_xf(s.xf, s.cap, i, g.Ra, &g.ta);
                         int sa = shape_of[i]; g.va = verts + sh.off[sa]; g.na = sh.cnt[sa];
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
                         hit_list[atomicAdd(hit_count, 1)] = i;
                     }
                     have = false;
-                } else if (in.world && ++j < jend) {
+                } else if (in.world && (in.cand ? (++c < cn ? ((j = in.cand[cbase + c]), true) : false) : (++j < jend))) {
                     load_xf(s.xf, s.cap, j, g.Rb, &g.tb);
                     int sb = shape_of[j]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
                     m.begin();
@@ -350,6 +352,175 @@ __global__ void __launch_bounds__(256) k_pose_xf(int n, const float* __restrict_
 #pragma unroll
     for (int k = 0; k < 9; k++) out[(size_t)(X_R0 + k) * n + i] = R[k];
     out[(size_t)X_TX * n + i] = t.x; out[(size_t)X_TY * n + i] = t.y; out[(size_t)X_TZ * n + i] = t.z;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: uniform-grid broad phase (NP_BROADPHASE_GRID).  The reference has none (TODO at collision_detection.cpp:698,
+// todo.txt:7); candidates are the pairs i < j of one island whose world AABBs overlap, searched in ascending j.
+//   k_aabb        8 lanes per body: world-space AABB of its vertex list (world*p per vertex, as the support mapping does)
+//   k_grid_params cell edge h (option, or 2 x mean AABB extent), grid origin
+//   k_grid_count / k_grid_fill   counting sort of the bodies into hashed cells; bodies wider than h go to a 'large' list
+//   k_cand<FILL>  per body: count (FILL=0) then write (FILL=1) its candidates from the 27 neighbour cells + large bodies,
+//                 compacted through an exclusive prefix sum (k_scan_*), each body's segment sorted ascending
+// ---------------------------------------------------------------------------------------------------
+struct GridView {
+    float* aabb;          // [6][cap] min xyz, max xyz
+    int* cell;            // [cap] packed cell coordinates (10 bits each), -1 = large body
+    float* params;        // [0..2] origin, [3] h, [4] sum of extents (accumulated), [5..7] global min (as ordered ints)
+    int* bucket_cnt;      // [nbuckets]
+    int* bucket_off;      // [nbuckets]
+    int* bucket_cur;      // [nbuckets]
+    int* items;           // [cap] bodies grouped by bucket
+    int* large;           // [cap] large-body list
+    int* large_count;     // [1]
+    int* cand_cnt;        // [cap]
+    int* cand_off;        // [cap]
+    int* cand;            // [cand_cap]
+    int* error;           // [1] set when cand_cap is exceeded
+    int nbuckets, cand_cap;
+    float h_option;
+};
+NP_D int float_order(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }      // monotone float -> int
+NP_D float order_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void __launch_bounds__(256) k_aabb(StoreView s, ShapeView sh, GridView gv)
+{
+    constexpr int G = 8;
+    const int body = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gl = threadIdx.x & (G - 1);
+    const bool valid = body < s.n;
+    const int cap = s.cap;
+    float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    if (valid) {
+        float R[9]; V3 t;
+        load_xf(s.xf, cap, body, R, &t);
+        int shp = s.ints[I_SHAPE * cap + body];
+        const float4* v = sh.verts + sh.off[shp]; int n = sh.cnt[shp];
+        for (int k = gl; k < n; k += G) {
+            float4 q = v[k];
+            V3 wp = xf_point(R, t, mk(q.x, q.y, q.z));
+            lo[0] = fminf(lo[0], wp.x); lo[1] = fminf(lo[1], wp.y); lo[2] = fminf(lo[2], wp.z);
+            hi[0] = fmaxf(hi[0], wp.x); hi[1] = fmaxf(hi[1], wp.y); hi[2] = fmaxf(hi[2], wp.z);
+        }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o, G));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o, G));
+        }
+    }
+    if (valid && gl == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { gv.aabb[c * cap + body] = lo[c]; gv.aabb[(3 + c) * cap + body] = hi[c]; }
+        float ext = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
+        if (ext == ext && ext < INFINITY) atomicAdd(&gv.params[4], ext);
+#pragma unroll
+        for (int c = 0; c < 3; c++) if (lo[c] == lo[c]) atomicMin((int*)&gv.params[5 + c], float_order(lo[c]));
+    }
+}
+__global__ void k_grid_init(GridView gv)
+{
+    if (threadIdx.x < 5) gv.params[threadIdx.x] = 0.0f;
+    else if (threadIdx.x < 8) ((int*)gv.params)[threadIdx.x] = 0x7fffffff;
+    if (threadIdx.x == 8) { *gv.large_count = 0; }
+}
+__global__ void k_grid_params(int n, GridView gv)
+{
+    float h = gv.h_option > 0.0f ? gv.h_option : 2.0f * gv.params[4] / (float)(n > 0 ? n : 1);
+    if (!(h > 1e-20f)) h = 1.0f;
+    gv.params[3] = h;
+    for (int c = 0; c < 3; c++) gv.params[c] = order_float(((int*)gv.params)[5 + c]);
+}
+NP_D int cell_hash(int cx, int cy, int cz, int nbuckets) { return (int)(((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u) ^ ((unsigned)cz * 83492791u)) & (nbuckets - 1); }
+NP_D int clamp_cell(float x) { int c = (int)floorf(x); return c < 0 ? 0 : (c > 1023 ? 1023 : c); }
+__global__ void __launch_bounds__(256) k_grid_count(StoreView s, GridView gv)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    const int cap = s.cap;
+    const float h = gv.params[3];
+    float lo[3], hi[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { lo[c] = gv.aabb[c * cap + i]; hi[c] = gv.aabb[(3 + c) * cap + i]; }
+    float ext = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
+    if (!(ext <= h)) {                                   // wider than a cell (or NaN): brute-force list
+        gv.cell[i] = -1;
+        gv.large[atomicAdd(gv.large_count, 1)] = i;
+        return;
+    }
+    int cx = clamp_cell((0.5f * (lo[0] + hi[0]) - gv.params[0]) / h), cy = clamp_cell((0.5f * (lo[1] + hi[1]) - gv.params[1]) / h), cz = clamp_cell((0.5f * (lo[2] + hi[2]) - gv.params[2]) / h);
+    gv.cell[i] = cx | (cy << 10) | (cz << 20);
+    atomicAdd(&gv.bucket_cnt[cell_hash(cx, cy, cz, gv.nbuckets)], 1);
+}
+__global__ void __launch_bounds__(256) k_grid_fill(StoreView s, GridView gv)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    int c = gv.cell[i];
+    if (c < 0) return;
+    int b = cell_hash(c & 1023, (c >> 10) & 1023, (c >> 20) & 1023, gv.nbuckets);
+    gv.items[gv.bucket_off[b] + atomicAdd(&gv.bucket_cur[b], 1)] = i;
+}
+NP_D bool aabb_overlap(const float* aabb, int cap, int j, const float* lo, const float* hi)
+{
+    return hi[0] >= aabb[0 * cap + j] && aabb[3 * cap + j] >= lo[0] && hi[1] >= aabb[1 * cap + j] && aabb[4 * cap + j] >= lo[1] &&
+           hi[2] >= aabb[2 * cap + j] && aabb[5 * cap + j] >= lo[2];
+}
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, DevCounters* ctr)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    const int cap = s.cap;
+    const int jend = s.ints[I_ISLAND_END * cap + i];
+    float lo[3], hi[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { lo[c] = gv.aabb[c * cap + i]; hi[c] = gv.aabb[(3 + c) * cap + i]; }
+    int n = 0;
+    int* out = nullptr; int room = 0;
+    if (FILL) {
+        int off = gv.cand_off[i], cnt = gv.cand_cnt[i];
+        if (off + cnt > gv.cand_cap) { atomicExch(gv.error, 1); room = 0; } else room = cnt;
+        out = gv.cand + off;
+    }
+    const int ci = gv.cell[i];
+    if (ci < 0) {                                        // large body: every later body of the island
+        for (int j = i + 1; j < jend; j++)
+            if (aabb_overlap(gv.aabb, cap, j, lo, hi)) { if (FILL && n < room) out[n] = j; n++; }
+    } else {
+        const int cx = ci & 1023, cy = (ci >> 10) & 1023, cz = (ci >> 20) & 1023;
+        for (int dz = -1; dz <= 1; dz++) for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) {
+            int x = cx + dx, y = cy + dy, z = cz + dz;
+            if (x < 0 || y < 0 || z < 0 || x > 1023 || y > 1023 || z > 1023) continue;
+            const int want = x | (y << 10) | (z << 20);
+            const int b = cell_hash(x, y, z, gv.nbuckets);
+            const int o = gv.bucket_off[b], e = o + gv.bucket_cnt[b];
+            for (int q = o; q < e; q++) {
+                int j = gv.items[q];
+                if (j > i && j < jend && gv.cell[j] == want && aabb_overlap(gv.aabb, cap, j, lo, hi)) { if (FILL && n < room) out[n] = j; n++; }
+            }
+        }
+        const int nl = *gv.large_count;
+        for (int q = 0; q < nl; q++) {
+            int j = gv.large[q];
+            if (j > i && j < jend && aabb_overlap(gv.aabb, cap, j, lo, hi)) { if (FILL && n < room) out[n] = j; n++; }
+        }
+    }
+    if (!FILL) { gv.cand_cnt[i] = n; return; }
+    int m = n < room ? n : room;
+    for (int a = 1; a < m; a++) {                        // ascending j: the first-hit search walks candidates in the reference's order
+        int key = out[a], b = a - 1;
+        while (b >= 0 && out[b] > key) { out[b + 1] = out[b]; b--; }
+        out[b + 1] = key;
+    }
+    if (ctr) {
+        unsigned long long v = (unsigned long long)m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&ctr->candidates, v);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

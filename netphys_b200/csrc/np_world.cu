@@ -53,6 +53,8 @@ struct np_world {
     int* d_zero = nullptr;            // [tickets and counts (32 ints), inc_cnt[cap], cursor[cap]]  -- one memset per step
     int *d_inc_off = nullptr, *d_inc = nullptr, *d_sums = nullptr, *d_big_list = nullptr, *d_hit_list = nullptr;
     float4* d_simplex = nullptr;      // GJK result of every hit: A[4], B[4]
+    // grid broad phase (allocated on first use)
+    GridView grid = {}; int grid_cap = 0; int* d_grid_ints = nullptr; float* d_grid_f = nullptr;
     int max_verts = 0;                // largest shape
     int g_gjk_env = 0, g_epa_env = 0; // NP_G_GJK / NP_G_EPA overrides (tuning)
     DevCounters* d_ctr = nullptr;
@@ -118,6 +120,7 @@ static int upload_states(np_world* w, const np_body_state* in, int n)
     return NP_OK;
 }
 
+static int ensure_grid(np_world* w);
 static int ensure_device(np_world* w)
 {
     CU(cudaSetDevice(w->device));
@@ -157,7 +160,7 @@ static int ensure_device(np_world* w)
         CU(cudaMalloc((void**)&w->d_xf, sizeof(float) * X_COUNT * c)); CU(cudaMalloc((void**)&w->d_ints, sizeof(int) * I_COUNT * c));
         CU(cudaMalloc((void**)&w->d_hit_j, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_cflags, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_contact, sizeof(float4) * c));
         CU(cudaMalloc((void**)&w->d_zero, sizeof(int) * (32 + 2 * c))); CU(cudaMalloc((void**)&w->d_inc_off, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_inc, sizeof(int) * c));
-        CU(cudaMalloc((void**)&w->d_sums, sizeof(int) * (c / NP_SCAN_BLOCK + 2))); CU(cudaMalloc((void**)&w->d_big_list, sizeof(int) * c));
+        CU(cudaMalloc((void**)&w->d_sums, sizeof(int) * (4 * c / NP_SCAN_BLOCK + 2))); CU(cudaMalloc((void**)&w->d_big_list, sizeof(int) * c));
         CU(cudaMalloc((void**)&w->d_snap, sizeof(SnapObj) * c));
         CU(cudaMalloc((void**)&w->d_hit_list, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_simplex, sizeof(float4) * 6 * c));
         CU(cudaMemsetAsync(w->d_state, 0, sizeof(float) * S_COUNT * c, w->stream));
@@ -182,6 +185,7 @@ static int ensure_device(np_world* w)
     int r = upload_states(w, w->host_state.data(), n); if (r) return r;
     if (n > 0) { k_transforms<<<(n + 255) / 256, 256, 0, w->stream>>>(view(w)); CU(cudaGetLastError()); }
     w->dev_n = n; w->dev_state_valid = true; w->dirty_bodies = false;
+    if (w->broadphase == NP_BROADPHASE_GRID) { int rg = ensure_grid(w); if (rg) return rg; }
     return NP_OK;
 }
 static int ensure_arena(np_world* w)
@@ -277,33 +281,82 @@ static int launch_narrow(np_world* w, const NarrowIn& in, const NarrowBufs& b, D
     return r;
 }
 
+static void enqueue_scan(np_world* w, int n, const int* in, int* out)
+{
+    const int sb = (n + NP_SCAN_BLOCK - 1) / NP_SCAN_BLOCK;
+    k_scan_block_sums<<<sb, NP_SCAN_BLOCK, 0, w->stream>>>(n, in, w->d_sums);
+    k_scan_sums<<<1, 1024, 0, w->stream>>>(sb, w->d_sums);
+    k_scan_apply<<<sb, NP_SCAN_BLOCK, 0, w->stream>>>(n, in, w->d_sums, out);
+    w->launches += 3;
+}
+#define NP_CAND_PER_BODY 64
+static int ensure_grid(np_world* w)
+{
+    if (w->grid_cap == w->cap && w->d_grid_ints) return NP_OK;
+    cudaFree(w->d_grid_ints); cudaFree(w->d_grid_f); w->d_grid_ints = nullptr; w->d_grid_f = nullptr;
+    const size_t c = (size_t)w->cap;
+    int nb = 1024; while ((size_t)nb < 2 * c) nb <<= 1;
+    const size_t cand_cap = std::min<size_t>((size_t)NP_CAND_PER_BODY * c, (size_t)1 << 30);
+    // ints: cell[c] | bucket_cnt[nb] bucket_cur[nb] (zeroed together) | bucket_off[nb] | items[c] | large[c] | cand_cnt[c] | cand_off[c] | misc[32] | cand[cand_cap]
+    const size_t n_ints = c + 3 * (size_t)nb + 4 * c + 32 + cand_cap;
+    CU(cudaMalloc((void**)&w->d_grid_ints, sizeof(int) * n_ints));
+    CU(cudaMalloc((void**)&w->d_grid_f, sizeof(float) * (6 * c + 32)));
+    GridView& g = w->grid;
+    int* p = w->d_grid_ints;
+    g.cell = p; p += c; g.bucket_cnt = p; p += nb; g.bucket_cur = p; p += nb; g.bucket_off = p; p += nb; g.items = p; p += c; g.large = p; p += c;
+    g.cand_cnt = p; p += c; g.cand_off = p; p += c; g.large_count = p; g.error = p + 1; p += 32; g.cand = p;
+    g.aabb = w->d_grid_f; g.params = w->d_grid_f + 6 * c;
+    g.nbuckets = nb; g.cand_cap = (int)std::min<size_t>(cand_cap, 0x7fffffff);
+    CU(cudaMemsetAsync(g.large_count, 0, sizeof(int) * 32, w->stream));
+    w->grid_cap = w->cap;
+    return NP_OK;
+}
+// K2, enqueued between integrate and the narrow phase
+static int enqueue_grid(np_world* w, const StoreView& s, DevCounters* ctr)
+{
+    GridView& g = w->grid; g.h_option = w->grid_cell;
+    const int n = s.n, b256 = (n + 255) / 256;
+    k_grid_init<<<1, 32, 0, w->stream>>>(g);
+    CU(cudaMemsetAsync(g.bucket_cnt, 0, sizeof(int) * 2 * (size_t)g.nbuckets, w->stream));
+    k_aabb<<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), g);
+    k_grid_params<<<1, 1, 0, w->stream>>>(n, g);
+    k_grid_count<<<b256, 256, 0, w->stream>>>(s, g);
+    enqueue_scan(w, g.nbuckets, g.bucket_cnt, g.bucket_off);
+    k_grid_fill<<<b256, 256, 0, w->stream>>>(s, g);
+    k_cand<false><<<(n + 127) / 128, 128, 0, w->stream>>>(s, g, nullptr);
+    enqueue_scan(w, n, g.cand_cnt, g.cand_off);
+    k_cand<true><<<(n + 127) / 128, 128, 0, w->stream>>>(s, g, ctr);
+    w->launches += 7;
+    CU(cudaGetLastError());
+    return NP_OK;
+}
+
 // the kernels of one Physics_Update, enqueued on the world's stream (capturable)
 static int enqueue_step(np_world* w, float dt, bool timed)
 {
     const int n = (int)w->bodies.size();
     if (n == 0) return NP_OK;
-    StoreView s = view(w); ShapeView sh = sview(w);
+    StoreView s = view(w);
     DevCounters* ctr = w->counters_on ? w->d_ctr : nullptr;
     const int b256 = (n + 255) / 256;
     if (timed) CU(cudaEventRecord(w->ev[0], w->stream));
     k_integrate<<<b256, 256, 0, w->stream>>>(s, dt, 1);
+    w->launches += 1;
     if (timed) CU(cudaEventRecord(w->ev[1], w->stream));
-    // (grid broad-phase goes here)
+    if (w->broadphase == NP_BROADPHASE_GRID) { int r = enqueue_grid(w, s, ctr); if (r) return r; }
     if (timed) CU(cudaEventRecord(w->ev[2], w->stream));
     CU(cudaMemsetAsync(w->d_zero, 0, sizeof(int) * (32 + 2 * (size_t)w->cap), w->stream));
     NarrowIn in; memset(&in, 0, sizeof in); in.world = 1; in.n = n; in.s = s;
+    if (w->broadphase == NP_BROADPHASE_GRID) { in.cand = w->grid.cand; in.cand_off = w->grid.cand_off; in.cand_cnt = w->grid.cand_cnt; }
     NarrowBufs nb = { w->d_zero, w->d_hit_j, w->d_cflags, w->d_contact, w->d_simplex, w->d_hit_list, w->d_big_list };
     { int r = launch_narrow(w, in, nb, ctr); if (r) return r; }
     if (timed) CU(cudaEventRecord(w->ev[3], w->stream));
     k_count_incoming<<<b256, 256, 0, w->stream>>>(n, w->cap, w->d_hit_j, w->d_ints, d_inc_cnt(w));
-    const int sb = (n + NP_SCAN_BLOCK - 1) / NP_SCAN_BLOCK;
-    k_scan_block_sums<<<sb, NP_SCAN_BLOCK, 0, w->stream>>>(n, d_inc_cnt(w), w->d_sums);
-    k_scan_sums<<<1, 1024, 0, w->stream>>>(sb, w->d_sums);
-    k_scan_apply<<<sb, NP_SCAN_BLOCK, 0, w->stream>>>(n, d_inc_cnt(w), w->d_sums, w->d_inc_off);
+    enqueue_scan(w, n, d_inc_cnt(w), w->d_inc_off);
     k_fill_incoming<<<b256, 256, 0, w->stream>>>(n, w->cap, w->d_hit_j, w->d_ints, w->d_inc_off, d_cursor(w), w->d_inc);
     k_resolve<<<b256, 256, 0, w->stream>>>(s, w->d_hit_j, w->d_contact, w->d_inc_off, d_inc_cnt(w), w->d_inc);
     if (timed) CU(cudaEventRecord(w->ev[4], w->stream));
-    w->launches += 7;
+    w->launches += 3;
     if (w->snapshot_each_step) {
         k_snapshot<<<b256, 256, 0, w->stream>>>(s, w->guid_base, w->snap_target ? (SnapObj*)w->snap_target : w->d_snap);
         w->launches += 1;
@@ -349,7 +402,7 @@ void np_world_destroy(np_world* w)
     cudaSetDevice(w->device);
     if (w->stream) cudaStreamSynchronize(w->stream);
     drop_graph(w); free_store(w);
-    cudaFree(w->d_verts); cudaFree(w->d_soff); cudaFree(w->d_scnt); cudaFree(w->d_ctr); cudaFree(w->d_flush);
+    cudaFree(w->d_verts); cudaFree(w->d_soff); cudaFree(w->d_scnt); cudaFree(w->d_ctr); cudaFree(w->d_flush); cudaFree(w->d_grid_ints); cudaFree(w->d_grid_f);
     cudaFree(w->arena.base);
     if (w->h_stage) cudaFreeHost(w->h_stage);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
@@ -361,9 +414,8 @@ int np_world_set_option(np_world* w, int option, int64_t value)
     if (!w) return fail(NP_ERR_INVALID, "null world");
     switch (option) {
     case NP_OPT_BROADPHASE:
-        if (value == NP_BROADPHASE_GRID) return fail(NP_ERR_UNSUPPORTED, "NP_BROADPHASE_GRID is not available in this build");
-        if (value != NP_BROADPHASE_EXACT) return fail(NP_ERR_INVALID, "unknown broad-phase");
-        w->broadphase = (int)value; drop_graph(w); return NP_OK;
+        if (value != NP_BROADPHASE_EXACT && value != NP_BROADPHASE_GRID) return fail(NP_ERR_INVALID, "unknown broad-phase");
+        w->broadphase = (int)value; drop_graph(w); w->dirty_bodies = true; return NP_OK;
     case NP_OPT_GRID_CELL: { uint32_t u = (uint32_t)value; memcpy(&w->grid_cell, &u, 4); return NP_OK; }
     case NP_OPT_COUNTERS: w->counters_on = value ? 1 : 0; drop_graph(w); return NP_OK;
     case NP_OPT_SNAPSHOT_EACH_STEP: w->snapshot_each_step = value ? 1 : 0; drop_graph(w); return NP_OK;
@@ -372,7 +424,16 @@ int np_world_set_option(np_world* w, int option, int64_t value)
 }
 int np_world_begin_island(np_world* w) { if (!w) return fail(NP_ERR_INVALID, "null world"); if (!w->bodies.empty()) w->island++; return w->island; }
 int np_world_body_count(const np_world* w) { return w ? (int)w->bodies.size() : 0; }
-int np_world_synchronize(np_world* w) { if (!w) return fail(NP_ERR_INVALID, "null world"); CU(cudaSetDevice(w->device)); CU(cudaStreamSynchronize(w->stream)); return NP_OK; }
+static int check_grid_error(np_world* w)
+{
+    if (w->broadphase != NP_BROADPHASE_GRID || !w->d_grid_ints) return NP_OK;
+    int e = 0;
+    CU(cudaMemcpyAsync(&e, w->grid.error, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    if (e) return fail(NP_ERR_CAPACITY, "broad phase emitted more than NP_CAND_PER_BODY x capacity candidate pairs; raise the grid cell option or the capacity");
+    return NP_OK;
+}
+int np_world_synchronize(np_world* w) { if (!w) return fail(NP_ERR_INVALID, "null world"); CU(cudaSetDevice(w->device)); CU(cudaStreamSynchronize(w->stream)); return check_grid_error(w); }
 
 // ------------------------------------------------------------------------------------------------ shapes
 int np_shape_create_mesh(np_world* w, const float* xyz, int nverts)
@@ -576,6 +637,7 @@ int np_world_get_collisions(np_world* w, np_collision* out, int cap, int* count)
     *count = 0;
     int n = w->dev_n; if (!w->dev_state_valid || n == 0 || w->steps == 0) return NP_OK;
     CU(cudaSetDevice(w->device));
+    { int rg = check_grid_error(w); if (rg) return rg; }
     std::vector<int> hj(n), fl(n); std::vector<float4> cd(n);
     CU(cudaMemcpyAsync(hj.data(), w->d_hit_j, sizeof(int) * n, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaMemcpyAsync(fl.data(), w->d_cflags, sizeof(int) * n, cudaMemcpyDeviceToHost, w->stream));

@@ -270,3 +270,50 @@ def test_baseline_c3_1m_world_properties(world, oracle, npb):
         L = np.float32(L + np.float32(np.float32(g * np.float32(1.0)) * dt)); y = (y + np.float32(np.float32(L * np.float32(1.0)) * dt)).astype(np.float32)
     assert_biteq(st1[:, 1], y, "y after 2 steps")
     _check_first_hit_properties(world, oracle, sc, shapes, 300)
+
+
+# ---- NP_BROADPHASE_GRID (K2): the extension the reference only lists as a TODO -------------------------------------
+def _world_aabbs(oracle, shapes, body_shape, st):
+    """AABB of world*p over each body's vertices, float32, in the device's (= the reference support loop's) operation order."""
+    lo = np.zeros((len(st), 3), np.float32); hi = np.zeros((len(st), 3), np.float32)
+    for i in range(len(st)):
+        m = oracle.transform(st[i, 0:3], st[i, 3:6]).reshape(4, 4); p = shapes[body_shape[i]]
+        w = np.stack([((m[r, 0] * p[:, 0] + m[r, 1] * p[:, 1]) + m[r, 2] * p[:, 2]) + m[r, 3] for r in range(3)], axis=1).astype(np.float32)
+        lo[i] = w.min(axis=0); hi[i] = w.max(axis=0)
+    return lo, hi
+
+
+@pytest.mark.parametrize("n,spacing,with_ground,cell", [(1500, 0.9, True, 0.0), (3000, 1.1, False, 0.0), (800, 0.8, True, 1.5)])
+def test_grid_broadphase_candidate_parity(world, oracle, n, spacing, with_ground, cell):
+    """Candidate set == brute-force AABB overlap; per candidate pair the GJK/EPA result == the oracle's; first-hit order kept."""
+    sc = scenes.lattice_scene(n, spacing=spacing, seed=n, mix=(0.5, 0.2, 0.3))
+    if with_ground:   # a body much wider than a cell exercises the large-body list
+        sc["shape_specs"] = sc["shape_specs"] + [("box", 40.0, 40.0, 1.0)]
+        sc["sd"] = np.concatenate([sc["sd"], scenes.static_data((0, 0, 0), (5.0, -2.0, 5.0), (0, 0, 0), 0.0, 0.0)[None]]).astype(np.float32)
+        sc["body_shape"] = np.concatenate([sc["body_shape"], [len(sc["shape_specs"]) - 1]]).astype(np.int32)
+        sc["response"] = np.concatenate([sc["response"], [0]]).astype(np.int32)
+    shapes = scenes.resolve_specs(sc["shape_specs"], oracle)
+    world.set_option(world.OPT_BROADPHASE, world.GRID); world.set_option(world.OPT_COUNTERS, 1)
+    if cell: world.set_option(world.OPT_GRID_CELL, int(np.float32(cell).view(np.uint32)))
+    world.load_scene(sc)
+    ow = oracle.world(scenes.resolve(sc, oracle))
+    for step in range(2):
+        world.step(sc["dt"]); world.synchronize()
+        st = world.states(); a, b, d = world.collisions_as_arrays()
+        ow.step(sc["dt"]); assert_biteq(st, ow.state(), "state (collision independent in the reference: normals are never set)")
+        lo, hi = _world_aabbs(oracle, shapes, sc["body_shape"], st)
+        N = len(st); exp = []; ncand = 0
+        pose = np.concatenate([st[:, 0:3], st[:, 3:6]], axis=1)
+        for i in range(N):
+            js = np.arange(i + 1, N)
+            ov = np.all((hi[i] >= lo[js]) & (hi[js] >= lo[i]), axis=1)
+            js = js[ov]; ncand += len(js)
+            if len(js) == 0: continue
+            ho, oo, _ = oracle.detect_batch(shapes, sc["body_shape"][np.full(len(js), i)], np.repeat(pose[i][None], len(js), 0), sc["body_shape"][js], pose[js])
+            h = np.flatnonzero(ho)
+            if len(h): exp.append((i, js[h[0]], oo[h[0]]))
+        assert len(a) == len(exp), "collision count %d vs %d" % (len(a), len(exp))
+        assert np.array_equal(a, [e[0] for e in exp]) and np.array_equal(b, [e[1] for e in exp])
+        assert_biteq(d[:, 6:11], np.stack([e[2] for e in exp]), "CollisionData per candidate pair")
+        assert world.counters()["candidates"] == ncand * 1 + (0 if step == 0 else prev), "candidate set differs from brute-force AABB overlap"
+        prev = world.counters()["candidates"]
