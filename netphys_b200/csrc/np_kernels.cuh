@@ -281,7 +281,7 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
     if (TIER == 2) poly_ptr = poly_from(ar.base + (size_t)(blockIdx.x * GPB + gid) * poly_words_fast(NP_FBIG), NP_FBIG, true);
     else poly_ptr = poly_from((float*)(s_dyn + (smem_shapes ? sh.total_verts : 0)) + (size_t)gid * (FAST ? poly_words_fast(FMAX) : poly_words(FMAX)), FMAX, FAST);
     PairGeom g;
-    PairStats st = { 0, 0, 0, 0, 0 };
+    PairStats st = { 0, 0, 0, 0, 0 }, st0 = st;
     unsigned n_over = 0;
     const int total = *count;
     int item = -1;
@@ -312,6 +312,7 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
                 V3 B4[4] = { mk(q3.x, q3.y, q3.z), mk(q3.w, q4.x, q4.y), mk(q4.z, q4.w, q5.x), mk(q5.y, q5.z, q5.w) };
                 int seed = (flags[item] & NP_PAIR_SEED_ALIVE) ? 1 : 0;
                 if (LOCAL) ml.begin(poly_local, A4, B4, seed); else mp.begin(poly_ptr, A4, B4, seed);
+                st0 = st;
                 have = true;
             } else exhausted = true;
         }
@@ -326,7 +327,7 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
                     if (requeue) next_list[atomicAdd(next_count, 1)] = item;                       // flags/simplex stay for the re-run
                     else { flags[item] = fl & (NP_PAIR_HIT | NP_PAIR_SUCCESS | NP_PAIR_OVERFLOW); contact[item] = make_float4(pen.x, pen.y, pen.z, depth); }
                 }
-                if (requeue && TIER == 0) n_over++;
+                if (requeue) { st = st0; if (TIER == 0) n_over++; }      // the next tier re-runs the pair: count its work there, once
                 have = false;
             }
         }

@@ -59,14 +59,17 @@ template <int G> NP_D void gsync() { if (G > 1) __syncwarp(gmask<G>()); }
 template <int G>
 NP_D V3 support(const float4* __restrict__ v, int n, const float* R, V3 t, V3 d)
 {
-    V3 best = mk(0.0f, 0.0f, 0.0f);
+    // The scan only tracks (best dot, index); the winning world position is recomputed once at the end from the
+    // index -- the same world*p expression on the same operands, hence the same bits -- which also spares the
+    // cross-lane broadcast of the position.
     float bd = -INFINITY;
     int bi = 0x7fffffff;
+#pragma unroll 4
     for (int k = glane<G>(); k < n; k += G) {
         float4 q = v[k];
         V3 wp = xf_point(R, t, mk(q.x, q.y, q.z));
         float dp = dot(d, wp);
-        if (dp > bd) { bd = dp; best = wp; bi = k; }
+        if (dp > bd) { bd = dp; bi = k; }
     }
     if (G > 1) {
         const unsigned m = gmask<G>();
@@ -76,10 +79,10 @@ NP_D V3 support(const float4* __restrict__ v, int n, const float* R, V3 t, V3 d)
             int oi = __shfl_xor_sync(m, bi, o, G);
             if ((od > bd) || (od == bd && oi < bi)) { bd = od; bi = oi; }
         }
-        int owner = (bi == 0x7fffffff) ? 0 : (bi & (G - 1));
-        best.x = __shfl_sync(m, best.x, owner, G); best.y = __shfl_sync(m, best.y, owner, G); best.z = __shfl_sync(m, best.z, owner, G);
     }
-    return best;
+    if (bi == 0x7fffffff) return mk(0.0f, 0.0f, 0.0f);          // no vertex, or every dot product NaN / -inf
+    float4 q = v[bi];
+    return xf_point(R, t, mk(q.x, q.y, q.z));
 }
 
 NP_D V3 sel4(V3 a, V3 b, V3 c, V3 d, int k) { return k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d)); }

@@ -199,7 +199,7 @@ static bool shapes_in_smem(np_world* w) { return w->total_verts <= NP_SMEM_VERTS
 
 // ---- narrow-phase launch plumbing -------------------------------------------------------------------------------
 static size_t shapes_smem(np_world* w) { return shapes_in_smem(w) ? sizeof(float4) * (size_t)w->total_verts : 0; }
-template <int G> constexpr int epa_fmax() { return G == 4 ? 32 : 64; }
+template <int G> constexpr int epa_fmax() { return G == 4 ? 32 : (G == 32 ? 256 : 64); }
 template <int G> static size_t epa_smem(np_world* w) { return shapes_smem(w) + (G > 1 ? sizeof(float) * (size_t)(G == 32 ? poly_words_fast(epa_fmax<G>()) : poly_words(epa_fmax<G>())) * (NP_NARROW_THREADS / G) : 0); }
 
 template <typename K>
@@ -213,11 +213,12 @@ static int persistent_blocks(np_world* w, K kernel, size_t smem, long long items
 // group size: few items -> wide groups (latency, whole-GPU occupancy); many items -> narrow groups (throughput)
 static int pick_group(np_world* w, long long items, int env, bool epa)
 {
-    if (env == 1 || env == 4 || env == 8 || env == 32) return env;
-    const long long resident = (long long)w->sm_count * 2048;
-    if (items * 32 <= resident * 2) return 32;            // latency regime: a warp per pair still fills the GPU
-    if (items * 8 <= resident * 2) return 8;
-    return epa ? 4 : 1;                                   // throughput regime (measured: tools/sweep_g.sh)
+    if (env == 1 || env == 4 || env == 8 || env == 16 || env == 32) return env;
+    (void)w;
+    // measured on B200 (tools/sweep2.sh, tools/sweep_world.sh): below a few hundred thousand items the step is bound by the
+    // latency of its longest chains -> wide groups; above, by instruction throughput -> narrow groups
+    if (items <= 300000) return epa ? 32 : 8;
+    return epa ? 4 : 1;
 }
 struct NarrowBufs { int* zero; int* hit_j; int* flags; float4* contact; float4* simplex; int* hit_list; int* big_list; };
 
@@ -259,6 +260,7 @@ static void setup_kernels()
     const int bytes = 112 * 1024;
     cudaFuncSetAttribute(k_epa<4, epa_fmax<4>(), 0, NP_NARROW_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_epa<8, epa_fmax<8>(), 0, NP_NARROW_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_epa<16, epa_fmax<16>(), 0, NP_NARROW_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_epa<32, epa_fmax<32>(), 0, NP_NARROW_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_epa<32, NP_FMID, 1, NP_MID_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
@@ -269,6 +271,7 @@ static int launch_narrow(np_world* w, const NarrowIn& in, const NarrowBufs& b, D
     case 1: r = launch_gjk<1>(w, in, b, ctr); break;
     case 4: r = launch_gjk<4>(w, in, b, ctr); break;
     case 8: r = launch_gjk<8>(w, in, b, ctr); break;
+    case 16: r = launch_gjk<16>(w, in, b, ctr); break;
     default: r = launch_gjk<32>(w, in, b, ctr); break;
     }
     if (r) return r;
@@ -276,6 +279,7 @@ static int launch_narrow(np_world* w, const NarrowIn& in, const NarrowBufs& b, D
     case 1: r = launch_epa<1>(w, in, b, ctr); break;
     case 4: r = launch_epa<4>(w, in, b, ctr); break;
     case 8: r = launch_epa<8>(w, in, b, ctr); break;
+    case 16: r = launch_epa<16>(w, in, b, ctr); break;
     default: r = launch_epa<32>(w, in, b, ctr); break;
     }
     return r;

@@ -96,17 +96,25 @@ def test_detect_collision_single_and_edge_cases(world, oracle):
     assert len(hit) == 0
 
 
-def test_detect_collision_large_polytope_path(world, oracle):
-    """Pairs whose EPA polytope outgrows the in-kernel arena take the large-polytope path; results must not change."""
-    specs, sa, pa, sb, pb = scenes.random_pairs(150000, seed=4242, extent=0.6, mix=(0.0, 0.5, 0.5))
+@pytest.mark.parametrize("g_gjk,g_epa", [(1, 4), (4, 8), (8, 1), (16, 16), (32, 32)])
+def test_detect_collision_every_group_width_and_overflow_tier(npb, oracle, g_gjk, g_epa, monkeypatch):
+    """Every group width G of the GJK / EPA kernels gives the same bits, and pairs whose EPA polytope outgrows the
+    in-kernel arena (32 / 64 / 256 faces) are re-run in the overflow tiers without changing the result."""
+    monkeypatch.setenv("NP_G_GJK", str(g_gjk)); monkeypatch.setenv("NP_G_EPA", str(g_epa))       # tuning overrides, read at world creation
+    specs, sa, pa, sb, pb = scenes.random_pairs(120000, seed=4242, extent=0.6, mix=(0.0, 0.5, 0.5))
     shapes = scenes.resolve_specs(specs, oracle)
-    ids = np.array([world.create_mesh(s) for s in shapes], np.int32)
-    world.set_option(world.OPT_COUNTERS, 1)
-    hit, out = world.detect_batch(ids[sa], pa, ids[sb], pb)
     ho, oo, ctr = oracle.detect_batch(shapes, sa, pa, sb, pb, nthreads=8)
     assert ctr["epa_max_faces"] > 64, "workload no longer exercises the overflow path"
-    assert world.counters()["epa_overflow"] > 0
+    with npb.World(0) as w:
+        ids = np.array([w.create_mesh(s) for s in shapes], np.int32)
+        w.set_option(w.OPT_COUNTERS, 1)
+        hit, out = w.detect_batch(ids[sa], pa, ids[sb], pb)
+        if g_epa != 32:
+            assert w.counters()["epa_overflow"] > 0
+        c = w.counters()
     assert np.array_equal(hit, ho); assert_biteq(out, oo, "CollisionData incl. overflowed pairs")
+    assert c["pair_tests"] == len(sa) and c["hits"] == int(ho.sum()) and c["gjk_steps"] == ctr["gjk_steps"] and c["epa_iters"] == ctr["epa_iters"]
+    assert c["support_pairs"] == ctr["gjk_supports"] + ctr["epa_supports"] and c["epa_tri_tests"] == ctr["epa_tri_tests"]
 
 
 # ---- Physics_Update -----------------------------------------------------------------------------------------
