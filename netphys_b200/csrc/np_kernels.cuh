@@ -18,7 +18,7 @@ namespace np {
 enum { S_PX = 0, S_PY, S_PZ, S_RX, S_RY, S_RZ, S_LX, S_LY, S_LZ, S_HX, S_HY, S_HZ, S_COUNT };          // dynamic state
 enum { C_GX = 0, C_GY, C_GZ, C_MASS, C_ELAST, C_IINV0, C_COUNT = C_IINV0 + 9 };                       // per-body constants
 enum { X_R0 = 0, X_TX = 9, X_TY, X_TZ, X_COUNT };                                                      // transform
-enum { I_RESPONSE = 0, I_SHAPE, I_ISLAND_END, I_COUNT };
+enum { I_RESPONSE = 0, I_SHAPE, I_ISLAND_END, I_WVOFF, I_COUNT };     // I_WVOFF: first world vertex of the body in the per-step cache
 
 struct StoreView {
     int n, cap;
@@ -26,6 +26,7 @@ struct StoreView {
     const float* cst;  // [C_COUNT][cap]
     float* xf;         // [X_COUNT][cap]
     const int* ints;   // [I_COUNT][cap]
+    float4* wverts;    // world-space vertices of every body, rewritten each step by k_world_verts
 };
 struct ShapeView {
     const float4* verts;   // all shapes' local vertices, concatenated
@@ -181,14 +182,15 @@ struct NarrowIn {
 #ifndef NP_GJK_MINB
 #define NP_GJK_MINB 3
 #endif
-template <int G>
+template <int G, bool WORLD>
 __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn in, ShapeView sh, int smem_shapes, int* __restrict__ ticket, int* __restrict__ hit_j,
                                                           int* __restrict__ flags, float4* __restrict__ contact, float4* __restrict__ simplex,
                                                           int* __restrict__ hit_list, int* __restrict__ hit_count, DevCounters* ctr)
 {
     extern __shared__ float4 s_dyn[];
-    const float4* verts = stage_shapes(sh, s_dyn, smem_shapes != 0);
-    GjkMachine<G> m;
+    constexpr bool CACHED = WORLD && (G >= 8);      // wide groups read the per-step world-vertex cache (coalesced); narrow ones transform on the fly from shared memory
+    const float4* verts = CACHED ? nullptr : stage_shapes(sh, s_dyn, smem_shapes != 0);
+    GjkMachine<G, CACHED> m;
     PairGeom g;
     PairStats st = { 0, 0, 0, 0, 0 };
     unsigned n_tests = 0, n_hits = 0;
@@ -198,20 +200,26 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
     const StoreView& s = in.s;
     const int* shape_of = s.ints + I_SHAPE * s.cap;
     const int* island_end = s.ints + I_ISLAND_END * s.cap;
+    const int* wv_off = s.ints + I_WVOFF * s.cap;
     m.begin();
     for (;;) {
         int t = fetch_ticket<G>(ticket, !have && !exhausted);
         if (!have && !exhausted) {
             if (t < in.n) {
                 i = t;
-                if (in.world) {
+                if (WORLD) {
                     if (in.cand) { cbase = in.cand_off[i]; c = 0; jend = in.cand_cnt[i]; j = jend > 0 ? in.cand[cbase] : 0; if (jend > 0) jend = 0x7fffffff; cn = in.cand_cnt[i]; }
                     else { j = i + 1; jend = island_end[i]; }
                     if (j < jend) {
-                        load_xf(s.xf, s.cap, i, g.Ra, &g.ta);
-                        int sa = shape_of[i]; g.va = verts + sh.off[sa]; g.na = sh.cnt[sa];
-                        load_xf(s.xf, s.cap, j, g.Rb, &g.tb);
-                        int sb = shape_of[j]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
+                        if (CACHED) {
+                            g.va = s.wverts + wv_off[i]; g.na = sh.cnt[shape_of[i]];
+                            g.vb = s.wverts + wv_off[j]; g.nb = sh.cnt[shape_of[j]];
+                        } else {
+                            load_xf(s.xf, s.cap, i, g.Ra, &g.ta);
+                            int sa = shape_of[i]; g.va = verts + sh.off[sa]; g.na = sh.cnt[sa];
+                            load_xf(s.xf, s.cap, j, g.Rb, &g.tb);
+                            int sb = shape_of[j]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
+                        }
                         m.begin(); have = true;
                     } else if (lead) { hit_j[i] = -1; flags[i] = 0; }
                 } else {
@@ -225,12 +233,12 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
         if (!__any_sync(0xffffffffu, have)) { if (__all_sync(0xffffffffu, exhausted)) break; else continue; }
         if (have) {
             m.trip(g, st);
-            if (m.status != GjkMachine<G>::RUN) {
+            if (m.status != GjkMachine<G, CACHED>::RUN) {
                 n_tests++;
-                if (m.status == GjkMachine<G>::HIT) {
+                if (m.status == GjkMachine<G, CACHED>::HIT) {
                     n_hits++;
                     if (lead) {
-                        if (in.world) hit_j[i] = j;
+                        if (WORLD) hit_j[i] = j;
                         flags[i] = NP_PAIR_HIT | (m.seed_alive ? NP_PAIR_SEED_ALIVE : 0);
                         float4* o = simplex + (size_t)i * 6;
                         o[0] = make_float4(m.A0.x, m.A0.y, m.A0.z, m.A1.x); o[1] = make_float4(m.A1.y, m.A1.z, m.A2.x, m.A2.y);
@@ -239,12 +247,12 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
                         hit_list[atomicAdd(hit_count, 1)] = i;
                     }
                     have = false;
-                } else if (in.world && (in.cand ? (++c < cn ? ((j = in.cand[cbase + c]), true) : false) : (++j < jend))) {
-                    load_xf(s.xf, s.cap, j, g.Rb, &g.tb);
-                    int sb = shape_of[j]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
+                } else if (WORLD && (in.cand ? (++c < cn ? ((j = in.cand[cbase + c]), true) : false) : (++j < jend))) {
+                    if (CACHED) { g.vb = s.wverts + wv_off[j]; g.nb = sh.cnt[shape_of[j]]; }
+                    else { load_xf(s.xf, s.cap, j, g.Rb, &g.tb); int sb = shape_of[j]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb]; }
                     m.begin();
                 } else {
-                    if (lead) { if (in.world) hit_j[i] = -1; flags[i] = 0; if (!in.world) contact[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+                    if (lead) { if (WORLD) hit_j[i] = -1; flags[i] = 0; if (!WORLD) contact[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
                     have = false;
                 }
             }
@@ -263,14 +271,15 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
 // ---------------------------------------------------------------------------------------------------
 struct BigArena { float* base; int slots; };
 
-template <int G, int FMAX, int TIER, int THREADS>
+template <int G, int FMAX, int TIER, int THREADS, bool WORLD>
 __global__ void __launch_bounds__(THREADS, (THREADS == NP_NARROW_THREADS) ? 4 : 1)
 k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, const int* __restrict__ count, int* __restrict__ ticket,
       const int* __restrict__ hit_j, const float4* __restrict__ simplex, int* __restrict__ flags, float4* __restrict__ contact,
       int* __restrict__ next_list, int* __restrict__ next_count, BigArena ar, DevCounters* ctr)
 {
     extern __shared__ float4 s_dyn[];
-    const float4* verts = stage_shapes(sh, s_dyn, smem_shapes != 0);
+    constexpr bool CACHED = WORLD && (G >= 8);
+    const float4* verts = CACHED ? nullptr : stage_shapes(sh, s_dyn, smem_shapes != 0);
     constexpr int GPB = THREADS / G;                                // groups per block
     constexpr bool LOCAL = (G == 1 && TIER == 0);
     const int gid = threadIdx.x / G;
@@ -279,7 +288,7 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
     PolyPtr poly_ptr;
     constexpr bool FAST = (TIER >= 1) || (G == 32);      // a full warp per pair: O(1)-per-edge horizon extraction
     if (TIER == 2) poly_ptr = poly_from(ar.base + (size_t)(blockIdx.x * GPB + gid) * poly_words_fast(NP_FBIG), NP_FBIG, true);
-    else poly_ptr = poly_from((float*)(s_dyn + (smem_shapes ? sh.total_verts : 0)) + (size_t)gid * (FAST ? poly_words_fast(FMAX) : poly_words(FMAX)), FMAX, FAST);
+    else poly_ptr = poly_from((float*)(s_dyn + ((smem_shapes && !CACHED) ? sh.total_verts : 0)) + (size_t)gid * (FAST ? poly_words_fast(FMAX) : poly_words(FMAX)), FMAX, FAST);
     PairGeom g;
     PairStats st = { 0, 0, 0, 0, 0 }, st0 = st;
     unsigned n_over = 0;
@@ -288,19 +297,24 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
     bool have = false, exhausted = false;
     const bool lead = glane<G>() == 0;
     const StoreView& s = in.s;
-    EpaMachine<G, PolyLocal<LOCAL ? FMAX : 1>> ml;
-    EpaMachine<G, PolyPtr, FAST> mp;
+    EpaMachine<G, PolyLocal<LOCAL ? FMAX : 1>, false, CACHED> ml;
+    EpaMachine<G, PolyPtr, FAST, CACHED> mp;
     ml.done = true; mp.done = true;
     for (;;) {
         int t = fetch_ticket<G>(ticket, !have && !exhausted);
         if (!have && !exhausted) {
             if (t < total) {
                 item = list[t];
-                if (in.world) {
+                if (WORLD) {
                     int i = item, j = hit_j[i];
-                    load_xf(s.xf, s.cap, i, g.Ra, &g.ta); load_xf(s.xf, s.cap, j, g.Rb, &g.tb);
-                    int sa = s.ints[I_SHAPE * s.cap + i], sb = s.ints[I_SHAPE * s.cap + j];
-                    g.va = verts + sh.off[sa]; g.na = sh.cnt[sa]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
+                    if (CACHED) {
+                        g.va = s.wverts + s.ints[I_WVOFF * s.cap + i]; g.na = sh.cnt[s.ints[I_SHAPE * s.cap + i]];
+                        g.vb = s.wverts + s.ints[I_WVOFF * s.cap + j]; g.nb = sh.cnt[s.ints[I_SHAPE * s.cap + j]];
+                    } else {
+                        load_xf(s.xf, s.cap, i, g.Ra, &g.ta); load_xf(s.xf, s.cap, j, g.Rb, &g.tb);
+                        int sa = s.ints[I_SHAPE * s.cap + i], sb = s.ints[I_SHAPE * s.cap + j];
+                        g.va = verts + sh.off[sa]; g.na = sh.cnt[sa]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
+                    }
                 } else {
                     load_xf(in.xf_a, in.n, item, g.Ra, &g.ta); load_xf(in.xf_b, in.n, item, g.Rb, &g.tb);
                     int sa = in.shape_a[item], sb = in.shape_b[item];
@@ -358,7 +372,7 @@ __global__ void __launch_bounds__(256) k_pose_xf(int n, const float* __restrict_
 // ---------------------------------------------------------------------------------------------------
 // K2: uniform-grid broad phase (NP_BROADPHASE_GRID).  The reference has none (TODO at collision_detection.cpp:698,
 // todo.txt:7); candidates are the pairs i < j of one island whose world AABBs overlap, searched in ascending j.
-//   k_aabb        8 lanes per body: world-space AABB of its vertex list (world*p per vertex, as the support mapping does)
+//   k_world_verts<true>  K1b also reduces each body's world AABB
 //   k_grid_params cell edge h (option, or 2 x mean AABB extent), grid origin
 //   k_grid_count / k_grid_fill   counting sort of the bodies into hashed cells; bodies wider than h go to a 'large' list
 //   k_cand<FILL>  per body: count (FILL=0) then write (FILL=1) its candidates from the 27 neighbour cells + large bodies,
@@ -384,7 +398,11 @@ struct GridView {
 NP_D int float_order(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }      // monotone float -> int
 NP_D float order_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
-__global__ void __launch_bounds__(256) k_aabb(StoreView s, ShapeView sh, GridView gv)
+// K1b: world-space vertex cache (+ AABB for the grid).  8 lanes per body; world*p per vertex exactly as the support
+// mapping evaluates it (physics_util.cpp:17), so K3/K4 can take dot products of the cached vertices directly.
+// HBM: reads 48 B transform + the shape's local vertices (L2 resident), writes 16 B per vertex.
+template <bool AABB>
+__global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, GridView gv)
 {
     constexpr int G = 8;
     const int body = (blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -397,13 +415,18 @@ __global__ void __launch_bounds__(256) k_aabb(StoreView s, ShapeView sh, GridVie
         load_xf(s.xf, cap, body, R, &t);
         int shp = s.ints[I_SHAPE * cap + body];
         const float4* v = sh.verts + sh.off[shp]; int n = sh.cnt[shp];
+        float4* out = s.wverts + s.ints[I_WVOFF * cap + body];
         for (int k = gl; k < n; k += G) {
             float4 q = v[k];
             V3 wp = xf_point(R, t, mk(q.x, q.y, q.z));
-            lo[0] = fminf(lo[0], wp.x); lo[1] = fminf(lo[1], wp.y); lo[2] = fminf(lo[2], wp.z);
-            hi[0] = fmaxf(hi[0], wp.x); hi[1] = fmaxf(hi[1], wp.y); hi[2] = fmaxf(hi[2], wp.z);
+            out[k] = make_float4(wp.x, wp.y, wp.z, 0.0f);
+            if (AABB) {
+                lo[0] = fminf(lo[0], wp.x); lo[1] = fminf(lo[1], wp.y); lo[2] = fminf(lo[2], wp.z);
+                hi[0] = fmaxf(hi[0], wp.x); hi[1] = fmaxf(hi[1], wp.y); hi[2] = fmaxf(hi[2], wp.z);
+            }
         }
     }
+    if (!AABB) return;
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
 #pragma unroll
@@ -757,7 +780,7 @@ __global__ void k_selftest_support(ShapeView sh, int shape, const float* dir, co
 {
     float R[9]; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[3 * r + c] = xf16[4 * r + c];
     V3 t = mk(xf16[3], xf16[7], xf16[11]);
-    V3 r = support<1>(sh.verts + sh.off[shape], sh.cnt[shape], R, t, mk(dir[0], dir[1], dir[2]));
+    V3 r = support<1, false>(sh.verts + sh.off[shape], sh.cnt[shape], R, t, mk(dir[0], dir[1], dir[2]));
     out[0] = r.x; out[1] = r.y; out[2] = r.z;
 }
 

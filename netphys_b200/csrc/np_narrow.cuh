@@ -56,18 +56,19 @@ template <int G> NP_D void gsync() { if (G > 1) __syncwarp(gmask<G>()); }
 // PhysUtil_GetPointFurthestInDirection, physics_util.cpp:5-35: world*p per vertex, strict '>' from -inf, first
 // maximum wins, result starts at (0,0,0).  Lane l scans vertices l, l+G, ...; the cross-lane reduction prefers the
 // larger dot product and, on equal dot products, the lower vertex index.
-template <int G>
+template <int G, bool CACHED>
 NP_D V3 support(const float4* __restrict__ v, int n, const float* R, V3 t, V3 d)
 {
-    // The scan only tracks (best dot, index); the winning world position is recomputed once at the end from the
-    // index -- the same world*p expression on the same operands, hence the same bits -- which also spares the
-    // cross-lane broadcast of the position.
+    // CACHED: v holds the body's WORLD-space vertices, written once per step by k_world_verts with the very expression
+    // xf_point evaluates here, so both variants see the same bits.
+    // The scan only tracks (best dot, index); the winning world position is re-read / recomputed once at the end from the
+    // index -- same operands, same bits -- which also spares the cross-lane broadcast of the position.
     float bd = -INFINITY;
     int bi = 0x7fffffff;
 #pragma unroll 4
     for (int k = glane<G>(); k < n; k += G) {
         float4 q = v[k];
-        V3 wp = xf_point(R, t, mk(q.x, q.y, q.z));
+        V3 wp = CACHED ? mk(q.x, q.y, q.z) : xf_point(R, t, mk(q.x, q.y, q.z));
         float dp = dot(d, wp);
         if (dp > bd) { bd = dp; bi = k; }
     }
@@ -82,7 +83,7 @@ NP_D V3 support(const float4* __restrict__ v, int n, const float* R, V3 t, V3 d)
     }
     if (bi == 0x7fffffff) return mk(0.0f, 0.0f, 0.0f);          // no vertex, or every dot product NaN / -inf
     float4 q = v[bi];
-    return xf_point(R, t, mk(q.x, q.y, q.z));
+    return CACHED ? mk(q.x, q.y, q.z) : xf_point(R, t, mk(q.x, q.y, q.z));
 }
 
 NP_D V3 sel4(V3 a, V3 b, V3 c, V3 d, int k) { return k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d)); }
@@ -93,7 +94,7 @@ NP_D V3 sel4(V3 a, V3 b, V3 c, V3 d, int k) { return k == 0 ? a : (k == 1 ? b : 
 // of step k+1 (solve, containment test, next direction).  The simplex is kept in named scalars (never indexed
 // through a pointer) so that it cannot be demoted to local memory.
 // ---------------------------------------------------------------------------------------------------
-template <int G>
+template <int G, bool CACHED>
 struct GjkMachine {
     enum { RUN = 0, MISS = 1, HIT = 2 };
     V3 P0, P1, P2, P3, A0, A1, A2, A3, B0, B1, B2, B3;
@@ -190,8 +191,8 @@ struct GjkMachine {
     // call while status == RUN
     NP_D void trip(const PairGeom& g, PairStats& st)
     {
-        V3 sa = support<G>(g.va, g.na, g.Ra, g.ta, d);
-        V3 sb = support<G>(g.vb, g.nb, g.Rb, g.tb, neg(d));
+        V3 sa = support<G, CACHED>(g.va, g.na, g.Ra, g.ta, d);
+        V3 sb = support<G, CACHED>(g.vb, g.nb, g.Rb, g.tb, neg(d));
         st.support_pairs++; st.support_verts += (unsigned)(g.na + g.nb);
         if (nv == 0) { A0 = sa; B0 = sb; P0 = sub(sb, sa); nv = 1; }                              // :704  p = B - A
         else consume(sa, sb);
@@ -257,7 +258,7 @@ NP_D PolyPtr poly_from(float* base, int fmax, bool fast = false)
 // ---------------------------------------------------------------------------------------------------
 // EPA: FindIntersectionPoints on an origin-enclosing simplex (collision_detection.cpp:412-566)
 // ---------------------------------------------------------------------------------------------------
-template <int G, class Poly, bool FAST = false>
+template <int G, class Poly, bool FAST, bool CACHED>
 struct EpaMachine {
     int pnv, pnf, steps;
     V3 d;            // the stored normal of the closest face (the direction the polytope is pushed out along)
@@ -482,8 +483,8 @@ struct EpaMachine {
     {
         produce(poly, st);
         if (done) return;
-        V3 sa = support<G>(g.va, g.na, g.Ra, g.ta, d);
-        V3 sb = support<G>(g.vb, g.nb, g.Rb, g.tb, neg(d));
+        V3 sa = support<G, CACHED>(g.va, g.na, g.Ra, g.ta, d);
+        V3 sb = support<G, CACHED>(g.vb, g.nb, g.Rb, g.tb, neg(d));
         st.support_pairs++; st.support_verts += (unsigned)(g.na + g.nb);
         if constexpr (FAST) consume_fast(poly, sa, sb); else consume(poly, sa, sb);
     }

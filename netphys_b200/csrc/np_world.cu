@@ -53,6 +53,7 @@ struct np_world {
     int* d_zero = nullptr;            // [tickets and counts (32 ints), inc_cnt[cap], cursor[cap]]  -- one memset per step
     int *d_inc_off = nullptr, *d_inc = nullptr, *d_sums = nullptr, *d_big_list = nullptr, *d_hit_list = nullptr;
     float4* d_simplex = nullptr;      // GJK result of every hit: A[4], B[4]
+    float4* d_wverts = nullptr; size_t wverts_cap = 0;   // per-step world-vertex cache (K1b)
     // grid broad phase (allocated on first use)
     GridView grid = {}; int grid_cap = 0; int* d_grid_ints = nullptr; float* d_grid_f = nullptr;
     int max_verts = 0;                // largest shape
@@ -72,7 +73,7 @@ struct np_world {
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
-static StoreView view(np_world* w) { StoreView s; s.n = (int)w->bodies.size(); s.cap = w->cap; s.state = w->d_state; s.cst = w->d_cst; s.xf = w->d_xf; s.ints = w->d_ints; return s; }
+static StoreView view(np_world* w) { StoreView s; s.n = (int)w->bodies.size(); s.cap = w->cap; s.state = w->d_state; s.cst = w->d_cst; s.xf = w->d_xf; s.ints = w->d_ints; s.wverts = w->d_wverts; return s; }
 static ShapeView sview(np_world* w) { ShapeView s; s.verts = w->d_verts; s.off = w->d_soff; s.cnt = w->d_scnt; s.total_verts = w->total_verts; return s; }
 enum { Z_GJK_TICKET = 0, Z_HIT_COUNT, Z_EPA_TICKET, Z_MID_COUNT, Z_MID_TICKET, Z_BIG_COUNT, Z_BIG_TICKET };
 static int* d_inc_cnt(np_world* w) { return w->d_zero + 32; }
@@ -179,6 +180,16 @@ static int ensure_device(np_world* w)
         for (int k = 0; k < 9; k++) cst[(C_IINV0 + k) * cap + i] = sd.inverse_inertia_tensor[k];
         ints[I_RESPONSE * cap + i] = sd.collision_response; ints[I_SHAPE * cap + i] = w->bodies[i].shape; ints[I_ISLAND_END * cap + i] = island_end[i];
     }
+    size_t wv_total = 0;
+    for (int i = 0; i < n; i++) {
+        if (wv_total > 0x7fffffffu) return fail(NP_ERR_CAPACITY, "world-vertex cache exceeds 2^31 vertices");
+        ints[I_WVOFF * cap + i] = (int)wv_total; wv_total += w->shapes[w->bodies[i].shape].xyz.size() / 3;
+    }
+    if (wv_total > w->wverts_cap) {
+        cudaFree(w->d_wverts); w->d_wverts = nullptr;
+        w->wverts_cap = wv_total + wv_total / 4 + 1024;
+        CU(cudaMalloc((void**)&w->d_wverts, sizeof(float4) * w->wverts_cap));
+    }
     CU(cudaMemcpyAsync(w->d_cst, cst.data(), sizeof(float) * C_COUNT * cap, cudaMemcpyHostToDevice, w->stream));
     CU(cudaMemcpyAsync(w->d_ints, ints.data(), sizeof(int) * I_COUNT * cap, cudaMemcpyHostToDevice, w->stream));
     CU(cudaStreamSynchronize(w->stream));
@@ -200,7 +211,7 @@ static bool shapes_in_smem(np_world* w) { return w->total_verts <= NP_SMEM_VERTS
 // ---- narrow-phase launch plumbing -------------------------------------------------------------------------------
 static size_t shapes_smem(np_world* w) { return shapes_in_smem(w) ? sizeof(float4) * (size_t)w->total_verts : 0; }
 template <int G> constexpr int epa_fmax() { return G == 4 ? 32 : (G == 32 ? 256 : 64); }
-template <int G> static size_t epa_smem(np_world* w) { return shapes_smem(w) + (G > 1 ? sizeof(float) * (size_t)(G == 32 ? poly_words_fast(epa_fmax<G>()) : poly_words(epa_fmax<G>())) * (NP_NARROW_THREADS / G) : 0); }
+template <int G> static size_t epa_poly_smem() { return G > 1 ? sizeof(float) * (size_t)(G == 32 ? poly_words_fast(epa_fmax<G>()) : poly_words(epa_fmax<G>())) * (NP_NARROW_THREADS / G) : 0; }
 
 template <typename K>
 static int persistent_blocks(np_world* w, K kernel, size_t smem, long long items, int G)
@@ -213,7 +224,7 @@ static int persistent_blocks(np_world* w, K kernel, size_t smem, long long items
 // group size: few items -> wide groups (latency, whole-GPU occupancy); many items -> narrow groups (throughput)
 static int pick_group(np_world* w, long long items, int env, bool epa)
 {
-    if (env == 1 || env == 4 || env == 8 || env == 16 || env == 32) return env;
+    if (env >= 1 && env <= 32) return env;
     (void)w;
     // measured on B200 (tools/sweep2.sh, tools/sweep_world.sh): below a few hundred thousand items the step is bound by the
     // latency of its longest chains -> wide groups; above, by instruction throughput -> narrow groups
@@ -222,67 +233,70 @@ static int pick_group(np_world* w, long long items, int env, bool epa)
 }
 struct NarrowBufs { int* zero; int* hit_j; int* flags; float4* contact; float4* simplex; int* hit_list; int* big_list; };
 
-template <int G>
+template <int G, bool WORLD>
 static int launch_gjk(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevCounters* ctr)
 {
-    size_t smem = shapes_smem(w);
-    int blocks = persistent_blocks(w, k_gjk<G>, smem, in.n, G);
-    k_gjk<G><<<blocks, NP_NARROW_THREADS, smem, w->stream>>>(in, sview(w), shapes_in_smem(w) ? 1 : 0, b.zero + Z_GJK_TICKET, b.hit_j, b.flags, b.contact, b.simplex,
-                                                             b.hit_list, b.zero + Z_HIT_COUNT, ctr);
+    size_t smem = (WORLD && G >= 8) ? 0 : shapes_smem(w);
+    auto kern = k_gjk<G, WORLD>;
+    int blocks = persistent_blocks(w, kern, smem, in.n, G);
+    kern<<<blocks, NP_NARROW_THREADS, smem, w->stream>>>(in, sview(w), shapes_in_smem(w) ? 1 : 0, b.zero + Z_GJK_TICKET, b.hit_j, b.flags, b.contact, b.simplex,
+                                                        b.hit_list, b.zero + Z_HIT_COUNT, ctr);
     w->launches++;
     return NP_OK;
 }
-template <int G>
+template <int G, bool WORLD>
 static int launch_epa(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevCounters* ctr)
 {
     const int sm_shapes = shapes_in_smem(w) ? 1 : 0;
-    size_t smem = epa_smem<G>(w);
-    auto kern = k_epa<G, epa_fmax<G>(), 0, NP_NARROW_THREADS>;
+    const size_t sh_bytes = WORLD ? 0 : shapes_smem(w);      // the overflow tiers (G = 32) always read the cache in world mode
+    size_t smem = ((WORLD && G >= 8) ? 0 : shapes_smem(w)) + epa_poly_smem<G>();
+    auto kern = k_epa<G, epa_fmax<G>(), 0, NP_NARROW_THREADS, WORLD>;
     int blocks = persistent_blocks(w, kern, smem, in.n, G);
     kern<<<blocks, NP_NARROW_THREADS, smem, w->stream>>>(in, sview(w), sm_shapes, b.hit_list, b.zero + Z_HIT_COUNT, b.zero + Z_EPA_TICKET, b.hit_j, b.simplex,
                                                         b.flags, b.contact, b.big_list, b.zero + Z_MID_COUNT, w->arena, ctr);
     // overflow tiers (one warp per pair); both exit at once when their list is empty.  hit_list is free again by now.
-    auto mid = k_epa<32, NP_FMID, 1, NP_MID_THREADS>;
-    size_t msmem = shapes_smem(w) + sizeof(float) * (size_t)poly_words_fast(NP_FMID) * (NP_MID_THREADS / 32);
+    auto mid = k_epa<32, NP_FMID, 1, NP_MID_THREADS, WORLD>;
+    size_t msmem = sh_bytes + sizeof(float) * (size_t)poly_words_fast(NP_FMID) * (NP_MID_THREADS / 32);
     int mblocks = (int)std::min<long long>(w->sm_count * 2, std::max<long long>(1, ((long long)in.n * 32 + NP_MID_THREADS - 1) / NP_MID_THREADS));
     mid<<<mblocks, NP_MID_THREADS, msmem, w->stream>>>(in, sview(w), sm_shapes, b.big_list, b.zero + Z_MID_COUNT, b.zero + Z_MID_TICKET, b.hit_j, b.simplex,
                                                        b.flags, b.contact, b.hit_list, b.zero + Z_BIG_COUNT, w->arena, ctr);
-    auto big = k_epa<32, 64, 2, NP_MID_THREADS>;
+    auto big = k_epa<32, 64, 2, NP_MID_THREADS, WORLD>;
     int bblocks = std::min(w->arena.slots / (NP_MID_THREADS / 32), mblocks);
-    big<<<bblocks, NP_MID_THREADS, shapes_smem(w), w->stream>>>(in, sview(w), sm_shapes, b.hit_list, b.zero + Z_BIG_COUNT, b.zero + Z_BIG_TICKET, b.hit_j, b.simplex,
-                                                                b.flags, b.contact, nullptr, nullptr, w->arena, ctr);
+    big<<<bblocks, NP_MID_THREADS, sh_bytes, w->stream>>>(in, sview(w), sm_shapes, b.hit_list, b.zero + Z_BIG_COUNT, b.zero + Z_BIG_TICKET, b.hit_j, b.simplex,
+                                                          b.flags, b.contact, nullptr, nullptr, w->arena, ctr);
     w->launches += 3;
     return NP_OK;
 }
-static void setup_kernels()
+template <bool WORLD>
+static void setup_kernels_t()
 {
-    // EPA keeps one polytope per group in shared memory next to the staged shape table: up to ~84 KB per block
+    // EPA keeps one polytope per group in shared memory next to the staged shape table: up to ~105 KB per block
     const int bytes = 112 * 1024;
-    cudaFuncSetAttribute(k_epa<4, epa_fmax<4>(), 0, NP_NARROW_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(k_epa<8, epa_fmax<8>(), 0, NP_NARROW_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(k_epa<16, epa_fmax<16>(), 0, NP_NARROW_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(k_epa<32, epa_fmax<32>(), 0, NP_NARROW_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(k_epa<32, NP_FMID, 1, NP_MID_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_epa<4, epa_fmax<4>(), 0, NP_NARROW_THREADS, WORLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_epa<8, epa_fmax<8>(), 0, NP_NARROW_THREADS, WORLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_epa<32, epa_fmax<32>(), 0, NP_NARROW_THREADS, WORLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_epa<32, NP_FMID, 1, NP_MID_THREADS, WORLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+static void setup_kernels() { setup_kernels_t<true>(); setup_kernels_t<false>(); }
+// supported group widths: GJK {1, 8, 32}, EPA {1, 4, 8, 32} (other requests round to the nearest supported one)
+template <bool WORLD>
+static int launch_narrow_t(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevCounters* ctr)
+{
+    int r;
+    const int gg = pick_group(w, in.n, w->g_gjk_env, false), ge = pick_group(w, in.n, w->g_epa_env, true);
+    if (gg <= 1) r = launch_gjk<1, WORLD>(w, in, b, ctr);
+    else if (gg <= 8) r = launch_gjk<8, WORLD>(w, in, b, ctr);
+    else r = launch_gjk<32, WORLD>(w, in, b, ctr);
+    if (r) return r;
+    if (ge <= 1) r = launch_epa<1, WORLD>(w, in, b, ctr);
+    else if (ge <= 4) r = launch_epa<4, WORLD>(w, in, b, ctr);
+    else if (ge <= 8) r = launch_epa<8, WORLD>(w, in, b, ctr);
+    else r = launch_epa<32, WORLD>(w, in, b, ctr);
+    return r;
 }
 static int launch_narrow(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevCounters* ctr)
 {
-    int r;
-    switch (pick_group(w, in.n, w->g_gjk_env, false)) {
-    case 1: r = launch_gjk<1>(w, in, b, ctr); break;
-    case 4: r = launch_gjk<4>(w, in, b, ctr); break;
-    case 8: r = launch_gjk<8>(w, in, b, ctr); break;
-    case 16: r = launch_gjk<16>(w, in, b, ctr); break;
-    default: r = launch_gjk<32>(w, in, b, ctr); break;
-    }
-    if (r) return r;
-    switch (pick_group(w, in.n, w->g_epa_env, true)) {
-    case 1: r = launch_epa<1>(w, in, b, ctr); break;
-    case 4: r = launch_epa<4>(w, in, b, ctr); break;
-    case 8: r = launch_epa<8>(w, in, b, ctr); break;
-    case 16: r = launch_epa<16>(w, in, b, ctr); break;
-    default: r = launch_epa<32>(w, in, b, ctr); break;
-    }
-    return r;
+    return in.world ? launch_narrow_t<true>(w, in, b, ctr) : launch_narrow_t<false>(w, in, b, ctr);
 }
 
 static void enqueue_scan(np_world* w, int n, const int* in, int* out)
@@ -322,7 +336,7 @@ static int enqueue_grid(np_world* w, const StoreView& s, DevCounters* ctr)
     const int n = s.n, b256 = (n + 255) / 256;
     k_grid_init<<<1, 32, 0, w->stream>>>(g);
     CU(cudaMemsetAsync(g.bucket_cnt, 0, sizeof(int) * 2 * (size_t)g.nbuckets, w->stream));
-    k_aabb<<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), g);
+    k_world_verts<true><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), g);
     k_grid_params<<<1, 1, 0, w->stream>>>(n, g);
     k_grid_count<<<b256, 256, 0, w->stream>>>(s, g);
     enqueue_scan(w, g.nbuckets, g.bucket_cnt, g.bucket_off);
@@ -348,6 +362,7 @@ static int enqueue_step(np_world* w, float dt, bool timed)
     w->launches += 1;
     if (timed) CU(cudaEventRecord(w->ev[1], w->stream));
     if (w->broadphase == NP_BROADPHASE_GRID) { int r = enqueue_grid(w, s, ctr); if (r) return r; }
+    else { k_world_verts<false><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), w->grid); w->launches += 1; }
     if (timed) CU(cudaEventRecord(w->ev[2], w->stream));
     CU(cudaMemsetAsync(w->d_zero, 0, sizeof(int) * (32 + 2 * (size_t)w->cap), w->stream));
     NarrowIn in; memset(&in, 0, sizeof in); in.world = 1; in.n = n; in.s = s;
