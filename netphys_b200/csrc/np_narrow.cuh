@@ -285,6 +285,7 @@ struct EpaMachine {
     {
         pnv = 4; pnf = 4; steps = 0; flags = NP_PAIR_HIT; pen = mk(0.0f, 0.0f, 0.0f); depth = 0.0f; dist = 0.0f; done = false;
         d = mk(0.0f, 0.0f, 0.0f);
+        if constexpr (FAST) { for (int q = glane<G>(); q < NP_EPA_MAX_VERTS * NP_EPA_MAX_VERTS; q += G) poly.tab[q] = 0; }
         if (glane<G>() == 0) {
 #pragma unroll
             for (int k = 0; k < 4; k++) poly.setv(k, (k == 0 && seed_alive) ? sub(B4[0], A4[0]) : sub(A4[k], B4[k]), A4[k], B4[k]);
@@ -415,8 +416,6 @@ struct EpaMachine {
             if (veq(sa, poly.gA(i), NP_EPA_TOL) && veq(sb, poly.gB(i), NP_EPA_TOL)) found = true;
         found = __ballot_sync(m, found) != 0u;
         if (found) { converge(); return; }
-        constexpr int NV2 = NP_EPA_MAX_VERTS * NP_EPA_MAX_VERTS;
-        for (int q = gl; q < NV2; q += G) poly.tab[q] = 0;                  // low byte pair: added | cancelled << 8 ... kept as one u16 each below
         // pass 1: visibility, horizon tokens (3 per visible face, in face order), order-preserving compaction of the rest
         int keep = 0, ntok = 0;
         for (int base = 0; base < pnf; base += G) {
@@ -440,20 +439,31 @@ struct EpaMachine {
             keep += __popc(kmask);
             __syncwarp(m);
         }
-        // pass 2: replay the tokens; tab[a*24+b] = inserted (low byte) | cancelled (high byte) of directed edge (a,b)
-        // (a face contributes each directed edge at most once and nf <= fmax, but counts are bounded by 255 per direction
-        //  only for polytopes of up to 255 faces sharing an edge -- beyond that the pair is handed to the next tier)
+        // pass 2: replay the tokens in rounds of 32.  tab[a*24+b] = inserted (low byte) | cancelled (high byte) of directed
+        // edge (a,b); the table is all zero between expansions.  Tokens of one unordered vertex pair are handled, in order,
+        // by the lowest lane holding one of them (__match_any_sync); different pairs touch different entries.
         int bad = 0;
-        for (int t = 0; t < ntok; t++) {
-            uint16_t ed = poly.E(t);
-            int a = ed & 0xff, b = ed >> 8;
-            if ((((a ^ b) + 5 * (a & b)) & 31) != gl) continue;
-            uint16_t fw = poly.tab[a * NP_EPA_MAX_VERTS + b], rv = poly.tab[b * NP_EPA_MAX_VERTS + a];
-            if ((rv & 0xff) > (rv >> 8)) { poly.tab[b * NP_EPA_MAX_VERTS + a] = (uint16_t)(rv + 0x100); poly.seq[t] = 0xffff; }
-            else { poly.seq[t] = (uint16_t)(fw & 0xff); if ((fw & 0xff) == 0xff) bad = 1; poly.tab[a * NP_EPA_MAX_VERTS + b] = (uint16_t)(fw + 1); }
+        for (int base = 0; base < ntok; base += G) {
+            const int t = base + gl;
+            const bool tv = t < ntok;
+            const uint16_t ed = tv ? poly.E(t) : (uint16_t)0;
+            const int a0 = ed & 0xff, b0 = ed >> 8;
+            const unsigned key = tv ? (unsigned)((a0 < b0 ? a0 : b0) * NP_EPA_MAX_VERTS + (a0 < b0 ? b0 : a0)) : (0x10000u + (unsigned)gl);
+            unsigned peers = __match_any_sync(m, key);
+            if (tv && (__ffs(peers) - 1) == gl) {
+                while (peers) {
+                    const int bit = __ffs(peers) - 1; peers &= peers - 1;
+                    const int tt = base + bit;
+                    const uint16_t e2 = (bit == gl) ? ed : poly.E(tt);
+                    const int a = e2 & 0xff, b = e2 >> 8;
+                    uint16_t fw = poly.tab[a * NP_EPA_MAX_VERTS + b], rv = poly.tab[b * NP_EPA_MAX_VERTS + a];
+                    if ((rv & 0xff) > (rv >> 8)) { poly.tab[b * NP_EPA_MAX_VERTS + a] = (uint16_t)(rv + 0x100); poly.seq[tt] = 0xffff; }
+                    else { poly.seq[tt] = (uint16_t)(fw & 0xff); if ((fw & 0xff) == 0xff) bad = 1; poly.tab[a * NP_EPA_MAX_VERTS + b] = (uint16_t)(fw + 1); }
+                }
+            }
+            __syncwarp(m);
         }
         bad = __ballot_sync(m, bad != 0) != 0u;
-        __syncwarp(m);
         // pass 3: survivors in insertion order -> new faces
         int ne = 0;
         for (int base = 0; base < ntok; base += G) {
@@ -462,7 +472,7 @@ struct EpaMachine {
             if (t < ntok) { ed = poly.E(t); uint16_t s = poly.seq[t]; alive = (s != 0xffff) && (s >= (poly.tab[(ed & 0xff) * NP_EPA_MAX_VERTS + (ed >> 8)] >> 8)); }
             ne += __popc(__ballot_sync(m, alive));
         }
-        if (bad || keep + ne > poly.fmax) { flags |= NP_PAIR_OVERFLOW; done = true; return; }
+        if (bad || keep + ne > poly.fmax) { clear_table(poly, ntok); flags |= NP_PAIR_OVERFLOW; done = true; return; }
         if (gl == 0) poly.setv(pnv, sp, sa, sb);
         __syncwarp(m);
         int slot = keep;
@@ -474,8 +484,18 @@ struct EpaMachine {
             if (alive) add_face_at(poly, slot + __popc(am & ((1u << gl) - 1u)), ed & 0xff, ed >> 8, pnv);
             slot += __popc(am);
         }
+        clear_table(poly, ntok);
         pnf = keep + ne; pnv++;
         __syncwarp(m);
+    }
+    // leave the directed-edge table all zero again: only the entries this expansion touched
+    NP_D void clear_table(Poly& poly, int ntok)
+    {
+        __syncwarp(0xffffffffu);
+        for (int t = glane<G>(); t < ntok; t += G) {
+            uint16_t ed = poly.E(t); int a = ed & 0xff, b = ed >> 8;
+            poly.tab[a * NP_EPA_MAX_VERTS + b] = 0; poly.tab[b * NP_EPA_MAX_VERTS + a] = 0;
+        }
     }
 
     // call while !done: [closest face] -> [support pair] -> [convergence test / expansion]
