@@ -372,24 +372,26 @@ __global__ void __launch_bounds__(256) k_pose_xf(int n, const float* __restrict_
 // ---------------------------------------------------------------------------------------------------
 // K2: uniform-grid broad phase (NP_BROADPHASE_GRID).  The reference has none (TODO at collision_detection.cpp:698,
 // todo.txt:7); candidates are the pairs i < j of one island whose world AABBs overlap, searched in ascending j.
-//   k_world_verts<true>  K1b also reduces each body's world AABB
-//   k_grid_params cell edge h (option, or 2 x mean AABB extent), grid origin
-//   k_grid_count / k_grid_fill   counting sort of the bodies into hashed cells; bodies wider than h go to a 'large' list
-//   k_cand<FILL>  per body: count (FILL=0) then write (FILL=1) its candidates from the 27 neighbour cells + large bodies,
-//                 compacted through an exclusive prefix sum (k_scan_*), each body's segment sorted ascending
+//   k_world_verts<true>  K1b also reduces each body's world AABB (float4 lo/hi) and block-reduces the extent statistics
+//   k_grid_params        cell edge h = option, or the mean AABB extent; bodies wider than 4h are 'large' (brute force list)
+//   k_grid_count / k_grid_fill   counting sort of the small bodies into hashed cells (by AABB centre); max small extent H
+//   k_cand<false/true>   per body: count, then write, its candidates from the cells whose centres can hold a partner (+ the large
+//                        list); regions assigned by an exclusive prefix sum of the counts (k_scan_*), each sorted ascending
+// A partner j of i has |c_j - c_i| <= (e_i + e_j)/2 <= (e_i + H)/2 per axis, so only cells intersecting
+// [lo_i - H/2, hi_i + H/2] are visited: the visited volume follows the bodies' real extents, not the cell size.
 // ---------------------------------------------------------------------------------------------------
 struct GridView {
-    float* aabb;          // [6][cap] min xyz, max xyz
-    int* cell;            // [cap] packed cell coordinates (10 bits each), -1 = large body
-    float* params;        // [0..2] origin, [3] h, [4] sum of extents (accumulated), [5..7] global min (as ordered ints)
+    float4* aabb;         // [2*cap]: lo.xyz + packed cell (as int bits, -1 = large) | hi.xyz
+    float* params;        // [0..2] origin, [3] h, [4] sum of extents, [5..7] global min (ordered ints), [8] H (ordered int), [9] large threshold
     int* bucket_cnt;      // [nbuckets]
     int* bucket_off;      // [nbuckets]
     int* bucket_cur;      // [nbuckets]
     int* items;           // [cap] bodies grouped by bucket
     int* large;           // [cap] large-body list
     int* large_count;     // [1]
-    int* cand_cnt;        // [cap]
-    int* cand_off;        // [cap]
+    int* cand_cnt;        // [cap] actual candidates of body i
+    int* cand_ub;         // [cap] reserved entries of body i
+    int* cand_off;        // [cap] start of body i's region in cand
     int* cand;            // [cand_cap]
     int* error;           // [1] set when cand_cap is exceeded
     int nbuckets, cand_cap;
@@ -400,7 +402,7 @@ NP_D float order_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7ffffff
 
 // K1b: world-space vertex cache (+ AABB for the grid).  8 lanes per body; world*p per vertex exactly as the support
 // mapping evaluates it (physics_util.cpp:17), so K3/K4 can take dot products of the cached vertices directly.
-// HBM: reads 48 B transform + the shape's local vertices (L2 resident), writes 16 B per vertex.
+// HBM: reads 48 B transform + the shape's local vertices (L2 resident), writes 16 B per vertex (+ 32 B AABB).
 template <bool AABB>
 __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, GridView gv)
 {
@@ -435,26 +437,42 @@ __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, 
             hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o, G));
         }
     }
+    // per-body record, and block-level reduction of (sum of extents, global min corner): 4 atomics per BLOCK
+    float ext = 0.0f; int mn[3] = { 0x7fffffff, 0x7fffffff, 0x7fffffff };
     if (valid && gl == 0) {
+        gv.aabb[2 * body] = make_float4(lo[0], lo[1], lo[2], 0.0f); gv.aabb[2 * body + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+        float e = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
+        if (e == e && e < INFINITY) ext = e;
 #pragma unroll
-        for (int c = 0; c < 3; c++) { gv.aabb[c * cap + body] = lo[c]; gv.aabb[(3 + c) * cap + body] = hi[c]; }
-        float ext = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
-        if (ext == ext && ext < INFINITY) atomicAdd(&gv.params[4], ext);
+        for (int c = 0; c < 3; c++) if (lo[c] == lo[c]) mn[c] = float_order(lo[c]);
+    }
+    __shared__ float s_ext[8]; __shared__ int s_mn[8][3];
 #pragma unroll
-        for (int c = 0; c < 3; c++) if (lo[c] == lo[c]) atomicMin((int*)&gv.params[5 + c], float_order(lo[c]));
+    for (int o = 16; o > 0; o >>= 1) {
+        ext += __shfl_xor_sync(0xffffffffu, ext, o);
+#pragma unroll
+        for (int c = 0; c < 3; c++) mn[c] = min(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_ext[threadIdx.x >> 5] = ext; for (int c = 0; c < 3; c++) s_mn[threadIdx.x >> 5][c] = mn[c]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int wdx = 1; wdx < 8; wdx++) { ext += s_ext[wdx]; for (int c = 0; c < 3; c++) mn[c] = min(mn[c], s_mn[wdx][c]); }
+        if (ext != 0.0f) atomicAdd(&gv.params[4], ext);
+        for (int c = 0; c < 3; c++) if (mn[c] != 0x7fffffff) atomicMin((int*)&gv.params[5 + c], mn[c]);
     }
 }
 __global__ void k_grid_init(GridView gv)
 {
     if (threadIdx.x < 5) gv.params[threadIdx.x] = 0.0f;
     else if (threadIdx.x < 8) ((int*)gv.params)[threadIdx.x] = 0x7fffffff;
-    if (threadIdx.x == 8) { *gv.large_count = 0; }
+    else if (threadIdx.x == 8) ((int*)gv.params)[8] = float_order(0.0f);
+    if (threadIdx.x == 9) { *gv.large_count = 0; }
 }
 __global__ void k_grid_params(int n, GridView gv)
 {
-    float h = gv.h_option > 0.0f ? gv.h_option : 2.0f * gv.params[4] / (float)(n > 0 ? n : 1);
+    float h = gv.h_option > 0.0f ? gv.h_option : gv.params[4] / (float)(n > 0 ? n : 1);
     if (!(h > 1e-20f)) h = 1.0f;
-    gv.params[3] = h;
+    gv.params[3] = h; gv.params[9] = 4.0f * h;
     for (int c = 0; c < 3; c++) gv.params[c] = order_float(((int*)gv.params)[5 + c]);
 }
 NP_D int cell_hash(int cx, int cy, int cz, int nbuckets) { return (int)(((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u) ^ ((unsigned)cz * 83492791u)) & (nbuckets - 1); }
@@ -462,74 +480,95 @@ NP_D int clamp_cell(float x) { int c = (int)floorf(x); return c < 0 ? 0 : (c > 1
 __global__ void __launch_bounds__(256) k_grid_count(StoreView s, GridView gv)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s.n) return;
-    const int cap = s.cap;
-    const float h = gv.params[3];
-    float lo[3], hi[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) { lo[c] = gv.aabb[c * cap + i]; hi[c] = gv.aabb[(3 + c) * cap + i]; }
-    float ext = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
-    if (!(ext <= h)) {                                   // wider than a cell (or NaN): brute-force list
-        gv.cell[i] = -1;
-        gv.large[atomicAdd(gv.large_count, 1)] = i;
-        return;
+    float ext_small = 0.0f;
+    if (i < s.n) {
+        const float h = gv.params[3], big = gv.params[9];
+        float4 lo = gv.aabb[2 * i], hi = gv.aabb[2 * i + 1];
+        float ext = fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z));
+        int cell = -1;
+        if (!(ext <= big)) gv.large[atomicAdd(gv.large_count, 1)] = i;        // wider than 4 cells (or NaN): brute-force list
+        else {
+            int cx = clamp_cell((0.5f * (lo.x + hi.x) - gv.params[0]) / h), cy = clamp_cell((0.5f * (lo.y + hi.y) - gv.params[1]) / h), cz = clamp_cell((0.5f * (lo.z + hi.z) - gv.params[2]) / h);
+            cell = cx | (cy << 10) | (cz << 20);
+            atomicAdd(&gv.bucket_cnt[cell_hash(cx, cy, cz, gv.nbuckets)], 1);
+            ext_small = ext;
+        }
+        gv.aabb[2 * i].w = __int_as_float(cell);
     }
-    int cx = clamp_cell((0.5f * (lo[0] + hi[0]) - gv.params[0]) / h), cy = clamp_cell((0.5f * (lo[1] + hi[1]) - gv.params[1]) / h), cz = clamp_cell((0.5f * (lo[2] + hi[2]) - gv.params[2]) / h);
-    gv.cell[i] = cx | (cy << 10) | (cz << 20);
-    atomicAdd(&gv.bucket_cnt[cell_hash(cx, cy, cz, gv.nbuckets)], 1);
+    // H = largest extent among the small bodies: one atomic per block
+    __shared__ float s_e[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ext_small = fmaxf(ext_small, __shfl_xor_sync(0xffffffffu, ext_small, o));
+    if ((threadIdx.x & 31) == 0) s_e[threadIdx.x >> 5] = ext_small;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (int wdx = 1; wdx < 8; wdx++) ext_small = fmaxf(ext_small, s_e[wdx]); atomicMax((int*)&gv.params[8], float_order(ext_small)); }
 }
 __global__ void __launch_bounds__(256) k_grid_fill(StoreView s, GridView gv)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.n) return;
-    int c = gv.cell[i];
+    int c = __float_as_int(gv.aabb[2 * i].w);
     if (c < 0) return;
     int b = cell_hash(c & 1023, (c >> 10) & 1023, (c >> 20) & 1023, gv.nbuckets);
     gv.items[gv.bucket_off[b] + atomicAdd(&gv.bucket_cur[b], 1)] = i;
 }
-NP_D bool aabb_overlap(const float* aabb, int cap, int j, const float* lo, const float* hi)
+NP_D bool aabb_overlap(float4 lo, float4 hi, float4 jlo, float4 jhi)
 {
-    return hi[0] >= aabb[0 * cap + j] && aabb[3 * cap + j] >= lo[0] && hi[1] >= aabb[1 * cap + j] && aabb[4 * cap + j] >= lo[1] &&
-           hi[2] >= aabb[2 * cap + j] && aabb[5 * cap + j] >= lo[2];
+    return hi.x >= jlo.x && jhi.x >= lo.x && hi.y >= jlo.y && jhi.y >= lo.y && hi.z >= jlo.z && jhi.z >= lo.z;
 }
+// cells (by centre) that can hold a partner of the body with AABB [lo, hi]
+NP_D void cell_range(const GridView& gv, float4 lo, float4 hi, int* c0, int* c1)
+{
+    const float h = gv.params[3], half = 0.5f * order_float(((const int*)gv.params)[8]);
+    const float a[3] = { lo.x, lo.y, lo.z }, b[3] = { hi.x, hi.y, hi.z };
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        // The centre of a partner lies within r of this body's centre (plus a rounding margin); cells are assigned with the same
+        // monotone expression clamp_cell((centre - origin) / h), so evaluating it at the interval ends brackets every partner's cell.
+        float ctr = 0.5f * (a[c] + b[c]), r = 0.5f * (b[c] - a[c]) + half;
+        r += 1e-5f * (fabsf(ctr) + r + 1.0f);
+        c0[c] = clamp_cell((ctr - r - gv.params[c]) / h); c1[c] = clamp_cell((ctr + r - gv.params[c]) / h);
+    }
+}
+// FILL = false: count; FILL = true: write (same traversal), into the region the prefix sum of the counts assigns
 template <bool FILL>
 __global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, DevCounters* ctr)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.n) return;
-    const int cap = s.cap;
-    const int jend = s.ints[I_ISLAND_END * cap + i];
-    float lo[3], hi[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) { lo[c] = gv.aabb[c * cap + i]; hi[c] = gv.aabb[(3 + c) * cap + i]; }
-    int n = 0;
-    int* out = nullptr; int room = 0;
+    const int jend = s.ints[I_ISLAND_END * s.cap + i];
+    const float4 lo = gv.aabb[2 * i], hi = gv.aabb[2 * i + 1];
+    const int ci = __float_as_int(lo.w);
+    int n = 0, room = 0;
+    int* out = nullptr;
     if (FILL) {
-        int off = gv.cand_off[i], cnt = gv.cand_cnt[i];
-        if (off + cnt > gv.cand_cap) { atomicExch(gv.error, 1); room = 0; } else room = cnt;
+        int off = gv.cand_off[i]; room = gv.cand_cnt[i];
+        if ((long long)off + room > (long long)gv.cand_cap) { atomicExch(gv.error, 1); room = 0; }
         out = gv.cand + off;
     }
-    const int ci = gv.cell[i];
     if (ci < 0) {                                        // large body: every later body of the island
         for (int j = i + 1; j < jend; j++)
-            if (aabb_overlap(gv.aabb, cap, j, lo, hi)) { if (FILL && n < room) out[n] = j; n++; }
+            if (aabb_overlap(lo, hi, gv.aabb[2 * j], gv.aabb[2 * j + 1])) { if (FILL && n < room) out[n] = j; n++; }
     } else {
-        const int cx = ci & 1023, cy = (ci >> 10) & 1023, cz = (ci >> 20) & 1023;
-        for (int dz = -1; dz <= 1; dz++) for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) {
-            int x = cx + dx, y = cy + dy, z = cz + dz;
-            if (x < 0 || y < 0 || z < 0 || x > 1023 || y > 1023 || z > 1023) continue;
-            const int want = x | (y << 10) | (z << 20);
+        int c0[3], c1[3];
+        cell_range(gv, lo, hi, c0, c1);
+        for (int z = c0[2]; z <= c1[2]; z++) for (int y = c0[1]; y <= c1[1]; y++) for (int x = c0[0]; x <= c1[0]; x++) {
             const int b = cell_hash(x, y, z, gv.nbuckets);
-            const int o = gv.bucket_off[b], e = o + gv.bucket_cnt[b];
-            for (int q = o; q < e; q++) {
-                int j = gv.items[q];
-                if (j > i && j < jend && gv.cell[j] == want && aabb_overlap(gv.aabb, cap, j, lo, hi)) { if (FILL && n < room) out[n] = j; n++; }
+            const int cnt = gv.bucket_cnt[b];
+            if (cnt == 0) continue;
+            const int want = x | (y << 10) | (z << 20), o = gv.bucket_off[b];
+            for (int q = 0; q < cnt; q++) {
+                int j = gv.items[o + q];
+                if (j <= i || j >= jend) continue;
+                float4 jlo = gv.aabb[2 * j];
+                if (__float_as_int(jlo.w) != want) continue;                       // another cell hashed into this bucket
+                if (aabb_overlap(lo, hi, jlo, gv.aabb[2 * j + 1])) { if (FILL && n < room) out[n] = j; n++; }
             }
         }
         const int nl = *gv.large_count;
         for (int q = 0; q < nl; q++) {
             int j = gv.large[q];
-            if (j > i && j < jend && aabb_overlap(gv.aabb, cap, j, lo, hi)) { if (FILL && n < room) out[n] = j; n++; }
+            if (j > i && j < jend && aabb_overlap(lo, hi, gv.aabb[2 * j], gv.aabb[2 * j + 1])) { if (FILL && n < room) out[n] = j; n++; }
         }
     }
     if (!FILL) { gv.cand_cnt[i] = n; return; }

@@ -314,15 +314,15 @@ static int ensure_grid(np_world* w)
     const size_t c = (size_t)w->cap;
     int nb = 1024; while ((size_t)nb < 2 * c) nb <<= 1;
     const size_t cand_cap = std::min<size_t>((size_t)NP_CAND_PER_BODY * c, (size_t)1 << 30);
-    // ints: cell[c] | bucket_cnt[nb] bucket_cur[nb] (zeroed together) | bucket_off[nb] | items[c] | large[c] | cand_cnt[c] | cand_off[c] | misc[32] | cand[cand_cap]
-    const size_t n_ints = c + 3 * (size_t)nb + 4 * c + 32 + cand_cap;
+    // ints: bucket_cnt[nb] bucket_cur[nb] (zeroed together) | bucket_off[nb] | items[c] | large[c] | cand_cnt[c] | cand_ub[c] | cand_off[c] | misc[32] | cand[cand_cap]
+    const size_t n_ints = 3 * (size_t)nb + 5 * c + 32 + cand_cap;
     CU(cudaMalloc((void**)&w->d_grid_ints, sizeof(int) * n_ints));
-    CU(cudaMalloc((void**)&w->d_grid_f, sizeof(float) * (6 * c + 32)));
+    CU(cudaMalloc((void**)&w->d_grid_f, sizeof(float) * (8 * c + 32)));
     GridView& g = w->grid;
     int* p = w->d_grid_ints;
-    g.cell = p; p += c; g.bucket_cnt = p; p += nb; g.bucket_cur = p; p += nb; g.bucket_off = p; p += nb; g.items = p; p += c; g.large = p; p += c;
-    g.cand_cnt = p; p += c; g.cand_off = p; p += c; g.large_count = p; g.error = p + 1; p += 32; g.cand = p;
-    g.aabb = w->d_grid_f; g.params = w->d_grid_f + 6 * c;
+    g.bucket_cnt = p; p += nb; g.bucket_cur = p; p += nb; g.bucket_off = p; p += nb; g.items = p; p += c; g.large = p; p += c;
+    g.cand_cnt = p; p += c; g.cand_ub = p; p += c; g.cand_off = p; p += c; g.large_count = p; g.error = p + 1; p += 32; g.cand = p;
+    g.aabb = (float4*)w->d_grid_f; g.params = w->d_grid_f + 8 * c;
     g.nbuckets = nb; g.cand_cap = (int)std::min<size_t>(cand_cap, 0x7fffffff);
     CU(cudaMemsetAsync(g.large_count, 0, sizeof(int) * 32, w->stream));
     w->grid_cap = w->cap;
