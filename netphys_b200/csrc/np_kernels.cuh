@@ -397,8 +397,6 @@ struct GridView {
     int nbuckets, cand_cap;
     float h_option;
 };
-NP_D int float_order(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }      // monotone float -> int
-NP_D float order_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
 // K1b: world-space vertex cache (+ AABB for the grid).  8 lanes per body; world*p per vertex exactly as the support
 // mapping evaluates it (physics_util.cpp:17), so K3/K4 can take dot products of the cached vertices directly.

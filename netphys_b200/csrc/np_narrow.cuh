@@ -56,34 +56,48 @@ template <int G> NP_D void gsync() { if (G > 1) __syncwarp(gmask<G>()); }
 // PhysUtil_GetPointFurthestInDirection, physics_util.cpp:5-35: world*p per vertex, strict '>' from -inf, first
 // maximum wins, result starts at (0,0,0).  Lane l scans vertices l, l+G, ...; the cross-lane reduction prefers the
 // larger dot product and, on equal dot products, the lower vertex index.
+NP_D int float_order(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }      // monotone float -> int
+NP_D float order_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
 template <int G, bool CACHED>
 NP_D V3 support(const float4* __restrict__ v, int n, const float* R, V3 t, V3 d)
 {
     // CACHED: v holds the body's WORLD-space vertices, written once per step by k_world_verts with the very expression
     // xf_point evaluates here, so both variants see the same bits.
-    // The scan only tracks (best dot, index); the winning world position is re-read / recomputed once at the end from the
-    // index -- same operands, same bits -- which also spares the cross-lane broadcast of the position.
     float bd = -INFINITY;
     int bi = 0x7fffffff;
+    if (G == 1) {
+        // throughput regime: track (best dot, index) only and recompute the winner once -- same operands, same bits
+#pragma unroll 4
+        for (int k = 0; k < n; k++) {
+            float4 q = v[k];
+            V3 wp = CACHED ? mk(q.x, q.y, q.z) : xf_point(R, t, mk(q.x, q.y, q.z));
+            float dp = dot(d, wp);
+            if (dp > bd) { bd = dp; bi = k; }
+        }
+        if (bi == 0x7fffffff) return mk(0.0f, 0.0f, 0.0f);      // no vertex, or every dot product NaN / -inf
+        float4 q = v[bi];
+        return CACHED ? mk(q.x, q.y, q.z) : xf_point(R, t, mk(q.x, q.y, q.z));
+    }
+    // latency regime: each lane keeps its own winner; the cross-lane arg-max is two warp reductions (redux.sync) on an
+    // order-preserving integer image of the dot product (-0 folded into +0, as '>' does) and on the vertex index, then one
+    // broadcast of the owner's position.  Larger dot wins, lower index on ties == the reference's strict '>' scan.
+    V3 best = mk(0.0f, 0.0f, 0.0f);
 #pragma unroll 4
     for (int k = glane<G>(); k < n; k += G) {
         float4 q = v[k];
         V3 wp = CACHED ? mk(q.x, q.y, q.z) : xf_point(R, t, mk(q.x, q.y, q.z));
         float dp = dot(d, wp);
-        if (dp > bd) { bd = dp; bi = k; }
+        if (dp > bd) { bd = dp; bi = k; best = wp; }
     }
-    if (G > 1) {
-        const unsigned m = gmask<G>();
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-            float od = __shfl_xor_sync(m, bd, o, G);
-            int oi = __shfl_xor_sync(m, bi, o, G);
-            if ((od > bd) || (od == bd && oi < bi)) { bd = od; bi = oi; }
-        }
-    }
-    if (bi == 0x7fffffff) return mk(0.0f, 0.0f, 0.0f);          // no vertex, or every dot product NaN / -inf
-    float4 q = v[bi];
-    return CACHED ? mk(q.x, q.y, q.z) : xf_point(R, t, mk(q.x, q.y, q.z));
+    const unsigned m = gmask<G>();
+    const int key = float_order(bd + 0.0f);
+    const int kmax = __reduce_max_sync(m, key);
+    const unsigned imin = __reduce_min_sync(m, (key == kmax) ? (unsigned)bi : 0xffffffffu);
+    if (imin >= 0x7fffffffu) return mk(0.0f, 0.0f, 0.0f);
+    const int owner = (int)(imin & (unsigned)(G - 1));
+    best.x = __shfl_sync(m, best.x, owner, G); best.y = __shfl_sync(m, best.y, owner, G); best.z = __shfl_sync(m, best.z, owner, G);
+    return best;
 }
 
 NP_D V3 sel4(V3 a, V3 b, V3 c, V3 d, int k) { return k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d)); }
@@ -318,14 +332,13 @@ struct EpaMachine {
             float dsq = poly.D(f);
             if (dsq < best) { best = dsq; bi = f; }                                               // strict '<': first minimum wins
         }
-        if (G > 1) {
+        if (G > 1) {                             // smaller distance wins, lower face index on ties: two warp reductions
             const unsigned m = gmask<G>();
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) {
-                float od = __shfl_xor_sync(m, best, o, G);
-                int oi = __shfl_xor_sync(m, bi, o, G);
-                if ((od < best) || (od == best && oi < bi)) { best = od; bi = oi; }
-            }
+            const int key = float_order(best + 0.0f);
+            const int kmin = __reduce_min_sync(m, key);
+            bi = (int)__reduce_min_sync(m, (key == kmin) ? (unsigned)bi : 0xffffffffu);
+            best = order_float(kmin);
+            if ((unsigned)bi >= 0x7fffffffu) bi = 0x7fffffff;
         }
         if (bi == 0x7fffffff) bi = 0;            // every distance NaN: the reference's (zero-pinned) face_index stays 0
         st.epa_tri_tests += pnf;
