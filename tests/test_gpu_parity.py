@@ -325,3 +325,64 @@ def test_grid_broadphase_candidate_parity(world, oracle, n, spacing, with_ground
         assert_biteq(d[:, 6:11], np.stack([e[2] for e in exp]), "CollisionData per candidate pair")
         assert world.counters()["candidates"] == ncand * 1 + (0 if step == 0 else prev), "candidate set differs from brute-force AABB overlap"
         prev = world.counters()["candidates"]
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------------------
+def test_world_extreme_states(world, oracle):
+    """Huge / tiny / negative-zero Euler angles (both argument-reduction paths of sinf/cosf), NaN and inf positions,
+    a massless IMPULSE body (1/0 -> inf*0 -> NaN, physics.cpp:32) -- IEEE semantics must carry through identically."""
+    sc = scenes.lattice_scene(64, spacing=1.1, seed=5, mix=(0.4, 0.3, 0.3))
+    sd = sc["sd"]
+    sd[0, 6:9] = [500.0, -1.0e4, 3.0e5]; sd[1, 6:9] = [1e-20, -0.0, 119.99999]; sd[2, 6:9] = [120.0, 1e9, -3.3e38]
+    sd[3, 3:6] = [np.nan, 0.0, 0.0]; sd[4, 3:6] = [np.inf, 1.0, 1.0]; sd[5, 9] = 0.0          # massless, response stays IMPULSE
+    sd[6, 6:9] = [np.inf, 0.0, 0.0]; sd[7, 0:3] = [0.0, 0.0, 0.0]                               # no gravity: IsNone branch
+    world.set_option(world.OPT_COUNTERS, 1)
+    world.load_scene(sc); ow = oracle.world(scenes.resolve(sc, oracle))
+    for k in range(6):
+        world.step(sc["dt"]); ao, bo, do = ow.step(sc["dt"], True)
+        a, b, d = world.collisions_as_arrays()
+        assert np.array_equal(a, ao) and np.array_equal(b, bo), "collision list step %d" % k
+        assert_biteq(d, do, "collision data step %d" % k); assert_biteq(world.states(), ow.state(), "state step %d" % k)
+    assert world.counters()["pair_tests"] == ow.counters()[0]
+
+
+def test_many_shapes_global_table_and_empty_shape(world, oracle):
+    """More vertices than the shared-memory shape table holds (global-memory path) and a shape with no vertices
+    (support returns (0,0,0), physics_util.cpp:12)."""
+    rng = np.random.RandomState(3)
+    shapes = [scenes.random_hull(rng, nverts=64, radius=0.6) for _ in range(40)] + [np.zeros((0, 3), np.float32)]
+    n = 600
+    sc = scenes.lattice_scene(n, spacing=1.0, seed=8, mix=(1, 0, 0))
+    sc["shape_specs"] = [("mesh", s) for s in shapes]
+    sc["body_shape"] = rng.randint(0, len(shapes), size=n).astype(np.int32)
+    assert sum(len(s) for s in shapes) > 2048
+    world.load_scene(sc); ow = oracle.world(scenes.resolve(sc, oracle))
+    for k in range(3):
+        world.step(sc["dt"]); ao, bo, do = ow.step(sc["dt"], True)
+        a, b, d = world.collisions_as_arrays()
+        assert np.array_equal(a, ao) and np.array_equal(b, bo); assert_biteq(d, do, "collision data"); assert_biteq(world.states(), ow.state(), "state")
+    ids = np.arange(len(shapes), dtype=np.int32)
+    specs, sa, pa, sb, pb = scenes.random_pairs(20000, seed=12, extent=1.5, mix=tuple([1] * len(shapes)), shapes=sc["shape_specs"])
+    hit, out = world.detect_batch(ids[sa], pa, ids[sb], pb)
+    ho, oo, _ = oracle.detect_batch(shapes, sa, pa, sb, pb, nthreads=8)
+    assert np.array_equal(hit, ho); assert_biteq(out, oo, "pairs over 41 shapes")
+
+
+def test_grid_with_islands_and_graph_replay(world, oracle, npb):
+    """Grid broad phase + independent islands + step_n (CUDA graph) == the same stepped with plain launches."""
+    worlds = [scenes.lattice_scene(200, spacing=0.9, seed=300 + k, mix=(0.5, 0.2, 0.3)) for k in range(6)]
+    def build(w):
+        w.set_option(w.OPT_BROADPHASE, w.GRID)
+        for k, sc in enumerate(worlds):
+            if k: w.begin_island()
+            w.load_scene(sc)
+    build(world)
+    world.step_n(scenes.DT, 4); world.synchronize()
+    a1, b1, d1 = world.collisions_as_arrays(); st1 = world.states()
+    with npb.World(0) as w2:
+        build(w2)
+        for _ in range(4): w2.step(scenes.DT)
+        a2, b2, d2 = w2.collisions_as_arrays()
+        assert np.array_equal(a1, a2) and np.array_equal(b1, b2); assert_biteq(d1, d2, "collisions"); assert_biteq(st1, w2.states(), "state")
+    island = np.repeat(np.arange(6), 200)
+    assert np.all(island[a1] == island[b1]), "a collision crosses islands"
