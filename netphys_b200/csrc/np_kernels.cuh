@@ -78,6 +78,29 @@ __global__ void __launch_bounds__(256) k_integrate(StoreView s, float dt, int wr
     }
 }
 
+// host round trips move np_body_state[n] (array of structures, 48 B per body) as one contiguous copy; the transposition
+// to / from the component arrays happens here, on the device
+__global__ void __launch_bounds__(256) k_state_from_aos(int n, int cap, const float* __restrict__ aos, float* __restrict__ state)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4* p = reinterpret_cast<const float4*>(aos + 12 * (size_t)i);
+    float4 a = p[0], b = p[1], c = p[2];
+    const float v[12] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w };
+#pragma unroll
+    for (int k = 0; k < S_COUNT; k++) state[(size_t)k * cap + i] = v[k];
+}
+__global__ void __launch_bounds__(256) k_state_to_aos(int n, int cap, const float* __restrict__ state, float* __restrict__ aos)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < S_COUNT; k++) v[k] = state[(size_t)k * cap + i];
+    float4* p = reinterpret_cast<float4*>(aos + 12 * (size_t)i);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]); p[1] = make_float4(v[4], v[5], v[6], v[7]); p[2] = make_float4(v[8], v[9], v[10], v[11]);
+}
+
 // transforms only (used after np_body_set_state / before a standalone query on world bodies)
 __global__ void __launch_bounds__(256) k_transforms(StoreView s)
 {

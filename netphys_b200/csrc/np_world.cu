@@ -63,6 +63,7 @@ struct np_world {
     BigArena arena = {};
     // pinned staging for host round trips
     float* h_stage = nullptr; size_t h_stage_bytes = 0;
+    float* d_aos = nullptr; size_t d_aos_bytes = 0;   // device staging of np_body_state[n]
     // timing
     cudaEvent_t ev[6] = {};
     float last_ms[6] = {};
@@ -99,25 +100,40 @@ static int ensure_stage(np_world* w, size_t bytes)
 }
 static void drop_graph(np_world* w) { if (w->graph) { cudaGraphExecDestroy(w->graph); w->graph = nullptr; } }
 
-// state [12][cap] on the device  <->  np_body_state[n] on the host
+// state [12][cap] on the device  <->  np_body_state[n] on the host: one contiguous copy through pinned staging + a device transposition
+static int ensure_aos(np_world* w, size_t bytes)
+{
+    if (bytes <= w->d_aos_bytes) return NP_OK;
+    cudaFree(w->d_aos); w->d_aos = nullptr; w->d_aos_bytes = 0;
+    CU(cudaMalloc((void**)&w->d_aos, bytes));
+    w->d_aos_bytes = bytes;
+    return NP_OK;
+}
 static int download_states(np_world* w, np_body_state* out, int n)
 {
     if (n == 0) return NP_OK;
-    int r = ensure_stage(w, sizeof(float) * S_COUNT * (size_t)n); if (r) return r;
-    CU(cudaMemcpy2DAsync(w->h_stage, sizeof(float) * n, w->d_state, sizeof(float) * w->cap, sizeof(float) * n, S_COUNT, cudaMemcpyDeviceToHost, w->stream));
+    const size_t bytes = sizeof(float) * S_COUNT * (size_t)n;
+    int r = ensure_stage(w, bytes); if (r) return r;
+    r = ensure_aos(w, bytes); if (r) return r;
+    k_state_to_aos<<<(n + 255) / 256, 256, 0, w->stream>>>(n, w->cap, w->d_state, w->d_aos);
+    CU(cudaMemcpyAsync(w->h_stage, w->d_aos, bytes, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
-    float* o = (float*)out;
-    for (int c = 0; c < S_COUNT; c++) { const float* src = w->h_stage + (size_t)c * n; for (int i = 0; i < n; i++) o[(size_t)i * 12 + c] = src[i]; }
+    memcpy(out, w->h_stage, bytes);
+    w->launches++;
     return NP_OK;
 }
 static int upload_states(np_world* w, const np_body_state* in, int n)
 {
     if (n == 0) return NP_OK;
-    int r = ensure_stage(w, sizeof(float) * S_COUNT * (size_t)n); if (r) return r;
-    const float* s = (const float*)in;
-    for (int c = 0; c < S_COUNT; c++) { float* dst = w->h_stage + (size_t)c * n; for (int i = 0; i < n; i++) dst[i] = s[(size_t)i * 12 + c]; }
-    CU(cudaMemcpy2DAsync(w->d_state, sizeof(float) * w->cap, w->h_stage, sizeof(float) * n, sizeof(float) * n, S_COUNT, cudaMemcpyHostToDevice, w->stream));
-    CU(cudaStreamSynchronize(w->stream));   // the staging buffer is reused
+    const size_t bytes = sizeof(float) * S_COUNT * (size_t)n;
+    int r = ensure_stage(w, bytes); if (r) return r;
+    r = ensure_aos(w, bytes); if (r) return r;
+    CU(cudaStreamSynchronize(w->stream));                      // the staging buffer may still feed an earlier copy
+    memcpy(w->h_stage, in, bytes);
+    CU(cudaMemcpyAsync(w->d_aos, w->h_stage, bytes, cudaMemcpyHostToDevice, w->stream));
+    k_state_from_aos<<<(n + 255) / 256, 256, 0, w->stream>>>(n, w->cap, w->d_aos, w->d_state);
+    CU(cudaGetLastError());
+    w->launches++;
     return NP_OK;
 }
 
