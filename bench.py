@@ -31,6 +31,8 @@ WORKLOAD = ("C2 (BASELINE configs[1]): 10000 bodies in one world, unit boxes (8 
 F_SUPPORT_VERT, F_GJK_STEP, F_EPA_TRI, F_EPA_ITER = 27, 120, 110, 60
 # algorithmic bytes per body of the integrate+transform pass
 B_INTEGRATE = 48 + 56 + 36 + 48
+# DRAM traffic of the narrow-phase kernels in one C2 step, from the committed ncu capture (not measured live)
+NARROW_DRAM_BYTES_PER_STEP = 13.76e6 + 12.05e6
 
 
 def make_scene(rank=0):
@@ -236,7 +238,8 @@ def run_ours(args, rank, local_rank, world_size):
     ach_tf = flops / args.steps / (narrow_ms * 1e-3) / 1e12
     ach_gbs = BODIES * B_INTEGRATE / (integ_ms * 1e-3) / 1e9
     roof = {"bound": "fp32", "kernel": "k_gjk + k_epa (narrow phase: %.0f%% of the step)" % (100 * narrow_ms / float(np.mean(per[:, 5]))),
-            "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak if fp32_peak else None, "traffic": None,
+            "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak if fp32_peak else None,
+            "traffic": NARROW_DRAM_BYTES_PER_STEP, "traffic_source": "ncu --set full, dram__bytes_read+write of k_gjk + k_epa in one C2 step (profiles/r1_ncu_full_world_step.txt); the world-vertex cache alone is 13.6 MB",
             "peak_source": "measured in this run: non-FMA FADD/FMUL issue rate (np_selftest_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
             "algorithmic_flop_per_step": flops / args.steps}
     roof_hbm = {"bound": "hbm", "kernel": "k_integrate", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,

@@ -70,7 +70,7 @@ struct np_world {
     bool timed = false;
     unsigned long long steps = 0;
     // CUDA graph of one step (np_world_step_n)
-    cudaGraphExec_t graph = nullptr; float graph_dt = 0.0f;
+    cudaGraphExec_t graph = nullptr; float graph_dt = 0.0f; unsigned long long graph_launches = 0;
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -423,6 +423,7 @@ np_world* np_world_create(int device)
         fail(NP_ERR_CUDA, "cannot create stream"); delete w; return nullptr;
     }
     for (auto& e : w->ev) cudaEventCreate(&e);
+    { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { unsigned long long keep = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); } }   // scratch of pair-list queries stays cached
     setup_kernels();
     if (const char* e = getenv("NP_G_GJK")) w->g_gjk_env = atoi(e);
     if (const char* e = getenv("NP_G_EPA")) w->g_epa_env = atoi(e);
@@ -450,7 +451,7 @@ int np_world_set_option(np_world* w, int option, int64_t value)
     case NP_OPT_BROADPHASE:
         if (value != NP_BROADPHASE_EXACT && value != NP_BROADPHASE_GRID) return fail(NP_ERR_INVALID, "unknown broad-phase");
         w->broadphase = (int)value; drop_graph(w); w->dirty_bodies = true; return NP_OK;
-    case NP_OPT_GRID_CELL: { uint32_t u = (uint32_t)value; memcpy(&w->grid_cell, &u, 4); return NP_OK; }
+    case NP_OPT_GRID_CELL: { uint32_t u = (uint32_t)value; memcpy(&w->grid_cell, &u, 4); drop_graph(w); return NP_OK; }
     case NP_OPT_COUNTERS: w->counters_on = value ? 1 : 0; drop_graph(w); return NP_OK;
     case NP_OPT_SNAPSHOT_EACH_STEP: w->snapshot_each_step = value ? 1 : 0; drop_graph(w); return NP_OK;
     default: return fail(NP_ERR_INVALID, "unknown option");
@@ -640,8 +641,10 @@ int np_world_step_n(np_world* w, float dt, int steps)
     if (!w->graph || w->graph_dt != dt) {      // capture one step once, replay it `steps` times
         drop_graph(w);
         cudaGraph_t g = nullptr;
+        const unsigned long long l0 = w->launches;
         CU(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
         r = enqueue_step(w, dt, false);
+        w->graph_launches = w->launches - l0; w->launches = l0;        // counted per replay below
         cudaError_t e = cudaStreamEndCapture(w->stream, &g);
         if (r) { if (g) cudaGraphDestroy(g); return r; }
         if (e != cudaSuccess) return fail(NP_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
@@ -652,6 +655,7 @@ int np_world_step_n(np_world* w, float dt, int steps)
     }
     CU(cudaEventRecord(w->ev[0], w->stream));
     for (int i = 0; i < steps; i++) CU(cudaGraphLaunch(w->graph, w->stream));
+    w->launches += w->graph_launches * (unsigned long long)steps;
     CU(cudaEventRecord(w->ev[5], w->stream));
     w->timed = false; w->steps += (unsigned long long)steps;
     return NP_OK;

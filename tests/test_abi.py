@@ -65,3 +65,14 @@ def test_scene_generators_are_deterministic(npb):
     assert np.array_equal(pa, pa2) and np.array_equal(sb, sb2)
     sd = npb.lib.sd_rows_to_struct(a["sd"], a["response"])
     assert sd["mass"][0] == 1.0 and sd["collision_response"][5] == 1 and np.allclose(sd["inverse_inertia_tensor"][0][0], 6.0)
+
+
+def test_error_codes_without_device(npb):
+    """Argument validation happens before any device work: bad handles return NP_ERR_INVALID, never crash."""
+    L = npb.load_library()
+    assert L.np_world_body_count(None) == 0
+    assert L.np_world_step(None, 0.0) == -1 and L.np_world_synchronize(None) == -1
+    assert L.np_shape_create_box(None, 1.0, 1.0, 1.0) == -1
+    assert L.np_detect_collision_batch(None, 0, None, None, None, None, None, None) == -1
+    assert b"null" in L.np_last_error() or b"bad" in L.np_last_error()
+    L.np_world_destroy(None)                       # no-op
