@@ -34,7 +34,7 @@ typedef enum np_status {
     NP_ERR_NO_DEVICE = -2,   /* no CUDA device, or device is not sm_100 */
     NP_ERR_CUDA = -3,        /* a CUDA call failed; see np_last_error() */
     NP_ERR_CAPACITY = -4,    /* output buffer too small, or an internal hard cap was hit */
-    NP_ERR_UNSUPPORTED = -5  /* e.g. is3D == 0 (2-D mode), custom virtual PhysicsShape */
+    NP_ERR_UNSUPPORTED = -5  /* e.g. a custom virtual PhysicsShape */
 } np_status;
 
 /* COLLISION_RESPONSE, engine/physics.h:13-17 */
@@ -170,6 +170,9 @@ int np_detect_collision(np_world* w, int shape_a, const float a_transform[16], i
 /* n independent queries, host buffers; pose = position[3] rotation[3] -> GetTransform.  hit / out may be NULL. */
 int np_detect_collision_batch(np_world* w, int n, const int32_t* shape_a, const float* pose_a, const int32_t* shape_b,
                               const float* pose_b, int32_t* hit, np_collision_data* out);
+/* the same with is3D == false (engine/test_2d.cpp's mode: 3-point simplex, edge-based EPA, collision_detection.cpp:364-384,590-605) */
+int np_detect_collision_batch_2d(np_world* w, int n, const int32_t* shape_a, const float* pose_a, const int32_t* shape_b,
+                                 const float* pose_b, int32_t* hit, np_collision_data* out);
 /* same over device-resident buffers (SoA on the world's device); kernel_ms = device time of the GJK/EPA kernel */
 int np_detect_collision_batch_device(np_world* w, int n, const void* d_shape_a, const void* d_pose_a, const void* d_shape_b,
                                      const void* d_pose_b, void* d_hit, void* d_out, float* kernel_ms);

@@ -372,6 +372,102 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
     if (ctr) flush_stats<G>(ctr, st, 0u, 0u, n_over);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// 2-D mode (is3D == false) of DetectCollision: the test-only path of the reference (engine/test_2d.cpp) -- GJK that stops at a
+// 3-point simplex (collision_detection.cpp:648), the edge-based EPA (:364-384, :455-460) and the closest-edge answer for
+// separated shapes (:590-605).  One thread per pair; not a hot path.
+// ---------------------------------------------------------------------------------------------------
+struct Verts2D { V3 p[NP_EPA_MAX_VERTS], A[NP_EPA_MAX_VERTS], B[NP_EPA_MAX_VERTS]; int n; };
+// GetClosestEdgeToOrigin (:261-290); the indices default to 0 when no edge qualifies (zero-pinned uninitialised locals)
+NP_D void closest_edge2d(const Verts2D& s, float* distance, float* u, int* si, int* ei)
+{
+    float best = 3.402823466e+38f, bu = 0.0f; *si = 0; *ei = 0;
+    for (int i = 0; i < s.n; i++) {
+        int e = (i == s.n - 1) ? 0 : i + 1;
+        float iu; closest_line(s.p[i], s.p[e], &iu);
+        float dsq = magsq(add(s.p[i], mul(sub(s.p[e], s.p[i]), iu)));
+        if (dsq < best) { best = dsq; *si = i; *ei = e; bu = iu; }
+    }
+    *distance = sqrtf(best); *u = bu;
+}
+__global__ void __launch_bounds__(64) k_detect2d(int n, ShapeView sh, const int* __restrict__ shape_a, const int* __restrict__ shape_b,
+                                                const float* __restrict__ xf_a, const float* __restrict__ xf_b, int* __restrict__ flags, float4* __restrict__ contact)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    PairGeom g;
+    load_xf(xf_a, n, p, g.Ra, &g.ta); load_xf(xf_b, n, p, g.Rb, &g.tb);
+    g.va = sh.verts + sh.off[shape_a[p]]; g.na = sh.cnt[shape_a[p]]; g.vb = sh.verts + sh.off[shape_b[p]]; g.nb = sh.cnt[shape_b[p]];
+    Verts2D s;
+    s.n = 1;
+    s.A[0] = support<1, false>(g.va, g.na, g.Ra, g.ta, mk(1.0f, 1.0f, 1.0f));
+    s.B[0] = support<1, false>(g.vb, g.nb, g.Rb, g.tb, mk(-1.0f, -1.0f, -1.0f));
+    s.p[0] = sub(s.B[0], s.A[0]);                                                                 // :704
+    enum { CONT, OVERLAP, MISS };
+    int result = CONT, iter = 0;
+    while (result == CONT && iter++ < NP_GJK_MAX_STEPS) {                                          // DetectCollisionStep :620-692
+        V3 oA[3], oB[3]; const int nold = s.n;
+        for (int k = 0; k < nold; k++) { oA[k] = s.A[k]; oB[k] = s.B[k]; }
+        int kn = s.n, k0 = 0, k1 = 1;
+        if (s.n == 2) { float u; int r = closest_line(s.p[0], s.p[1], &u); if (r == LINE_A) kn = 1; else if (r == LINE_B) { kn = 1; k0 = 1; } }
+        else if (s.n == 3) {
+            float u, v; int r = closest_triangle(s.p[0], s.p[1], s.p[2], &u, &v);
+            switch (r) {
+            case TRI_A: kn = 1; break;
+            case TRI_B: kn = 1; k0 = 1; break;
+            case TRI_C: kn = 1; k0 = 2; break;
+            case TRI_AB: kn = 2; break;
+            case TRI_AC: kn = 2; k1 = 2; break;
+            case TRI_BC: kn = 2; k0 = 1; k1 = 2; break;
+            default: break;
+            }
+        }
+        if (kn < s.n) {
+            V3 p0 = s.p[k0], a0 = s.A[k0], b0 = s.B[k0], p1 = s.p[k1], a1 = s.A[k1], b1 = s.B[k1];
+            s.p[0] = p0; s.A[0] = a0; s.B[0] = b0; if (kn > 1) { s.p[1] = p1; s.A[1] = a1; s.B[1] = b1; }
+            s.n = kn;
+        }
+        if (s.n == 3) { result = OVERLAP; break; }                                                // :648 (!is3D && size == 3)
+        V3 d = s.n == 1 ? dir1(s.p[0]) : dir2(s.p[0], s.p[1]);
+        if (feq(magsq(d), 0.0f)) { result = MISS; break; }
+        V3 sa = support<1, false>(g.va, g.na, g.Ra, g.ta, d), sb = support<1, false>(g.vb, g.nb, g.Rb, g.tb, neg(d));
+        V3 sp = sub(sa, sb);
+        if (dot(d, sp) < 0) { result = MISS; break; }
+        bool dup = false;
+        for (int k = 0; k < nold; k++) if (veq(sa, oA[k]) && veq(sb, oB[k])) dup = true;
+        if (dup) { result = MISS; break; }
+        s.p[s.n] = sp; s.A[s.n] = sa; s.B[s.n] = sb; s.n++;
+    }
+    int fl = 0; V3 pen = mk(0.0f, 0.0f, 0.0f); float depth = 0.0f;
+    if (result == OVERLAP) {
+        fl |= NP_PAIR_HIT;
+        for (int it = 0; it < NP_EPA_MAX_STEPS; it++) {                                            // FindIntersectionPointsStep, 2-D branches
+            float distance, u; int ea, eb;
+            closest_edge2d(s, &distance, &u, &ea, &eb);
+            V3 a = s.p[ea], b = s.p[eb];
+            V3 cp = add(a, mul(sub(b, a), u)), edge = sub(b, a);
+            V3 nrm = mk(edge.y, -edge.x, 0.0f);
+            V3 normal = dot(cp, nrm) > 0.0f ? nrm : neg(nrm);
+            bool close = true;
+            if (distance > NP_EPA_TOL) {
+                V3 sa = support<1, false>(g.va, g.na, g.Ra, g.ta, normal), sb = support<1, false>(g.vb, g.nb, g.Rb, g.tb, neg(normal));
+                close = false;
+                for (int i = 0; i < s.n; i++) if (veq(sa, s.A[i], NP_EPA_TOL) && veq(sb, s.B[i], NP_EPA_TOL)) { close = true; break; }
+                if (!close) {                                                                     // simplex.h:59-75 insert before eb
+                    for (int i = s.n; i > eb; --i) { s.p[i] = s.p[i - 1]; s.A[i] = s.A[i - 1]; s.B[i] = s.B[i - 1]; }
+                    s.p[eb] = sub(sa, sb); s.A[eb] = sa; s.B[eb] = sb; s.n++;
+                }
+            }
+            if (close) { pen = neg(normalize(normal)); depth = distance; fl |= NP_PAIR_SUCCESS; break; }
+        }
+    } else if (s.n >= 2) {                                                                        // :590-605 separated: closest edge of the simplex
+        float distance, u; int si, ei;
+        closest_edge2d(s, &distance, &u, &si, &ei);
+        pen = add(s.p[si], mul(sub(s.p[ei], s.p[si]), u)); depth = distance; fl |= NP_PAIR_SUCCESS;
+    }
+    flags[p] = fl; contact[p] = make_float4(pen.x, pen.y, pen.z, depth);
+}
+
 // poses (position[3] rotation[3]) or row-major 4x4 matrices -> SoA transforms [X_COUNT][n]  (GetTransform, physics.h:70-76)
 __global__ void __launch_bounds__(256) k_pose_xf(int n, const float* __restrict__ pose, const float* __restrict__ xf16, float* __restrict__ out)
 {

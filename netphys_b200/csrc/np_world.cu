@@ -733,7 +733,7 @@ int np_world_last_step_ms(np_world* w, float out[6])
 
 // ------------------------------------------------------------------------------------------------ narrow phase
 static int run_pairs(np_world* w, int n, const int* d_sa, const float* d_pa, const int* d_sb, const float* d_pb, const float* d_xa, const float* d_xb,
-                     int* d_hit, float4* d_out, float* kernel_ms)
+                     int* d_hit, float4* d_out, float* kernel_ms, bool is2d = false)
 {
     // scratch: counters | xfA | xfB (SoA) | simplex | hit_list | big_list
     const size_t N = (size_t)n;
@@ -746,6 +746,12 @@ static int run_pairs(np_world* w, int n, const int* d_sa, const float* d_pa, con
     k_pose_xf<<<b256, 256, 0, w->stream>>>(n, d_pa, d_xa, (float*)(d + o_xa));
     k_pose_xf<<<b256, 256, 0, w->stream>>>(n, d_pb, d_xb, (float*)(d + o_xb));
     w->launches += 2;
+    if (is2d) {
+        k_detect2d<<<(n + 63) / 64, 64, 0, w->stream>>>(n, sview(w), d_sa, d_sb, (const float*)(d + o_xa), (const float*)(d + o_xb), d_hit, d_out);
+        w->launches += 1;
+        CU(cudaGetLastError()); CU(cudaFreeAsync(d, w->stream));
+        return NP_OK;
+    }
     NarrowIn in; memset(&in, 0, sizeof in); in.world = 0; in.n = n; in.s = view(w);
     in.shape_a = d_sa; in.shape_b = d_sb; in.xf_a = (const float*)(d + o_xa); in.xf_b = (const float*)(d + o_xb);
     NarrowBufs nb = { (int*)(d + o_zero), nullptr, d_hit, d_out, (float4*)(d + o_sx), (int*)(d + o_hl), (int*)(d + o_bl) };
@@ -774,8 +780,16 @@ static void expand_out(int n, const int* flags, const float4* cd, int32_t* hit, 
         }
     }
 }
+static int detect_batch_impl(np_world* w, int n, const int32_t* shape_a, const float* pose_a, const int32_t* shape_b, const float* pose_b,
+                             int32_t* hit, np_collision_data* out, bool is2d);
 int np_detect_collision_batch(np_world* w, int n, const int32_t* shape_a, const float* pose_a, const int32_t* shape_b, const float* pose_b,
                               int32_t* hit, np_collision_data* out)
+{ return detect_batch_impl(w, n, shape_a, pose_a, shape_b, pose_b, hit, out, false); }
+int np_detect_collision_batch_2d(np_world* w, int n, const int32_t* shape_a, const float* pose_a, const int32_t* shape_b, const float* pose_b,
+                                 int32_t* hit, np_collision_data* out)
+{ return detect_batch_impl(w, n, shape_a, pose_a, shape_b, pose_b, hit, out, true); }
+static int detect_batch_impl(np_world* w, int n, const int32_t* shape_a, const float* pose_a, const int32_t* shape_b, const float* pose_b,
+                             int32_t* hit, np_collision_data* out, bool is2d)
 {
     if (!w || n < 0 || (n > 0 && (!shape_a || !pose_a || !shape_b || !pose_b))) return fail(NP_ERR_INVALID, "bad arguments");
     if (n == 0) return NP_OK;
@@ -787,7 +801,7 @@ int np_detect_collision_batch(np_world* w, int n, const int32_t* shape_a, const 
     CU(cudaMallocAsync((void**)&d, total, w->stream));
     CU(cudaMemcpyAsync(d + o_sa, shape_a, 4 * N, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + o_sb, shape_b, 4 * N, cudaMemcpyHostToDevice, w->stream));
     CU(cudaMemcpyAsync(d + o_pa, pose_a, 24 * N, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + o_pb, pose_b, 24 * N, cudaMemcpyHostToDevice, w->stream));
-    r = run_pairs(w, n, (int*)(d + o_sa), (float*)(d + o_pa), (int*)(d + o_sb), (float*)(d + o_pb), nullptr, nullptr, (int*)(d + o_hit), (float4*)(d + o_out), nullptr);
+    r = run_pairs(w, n, (int*)(d + o_sa), (float*)(d + o_pa), (int*)(d + o_sb), (float*)(d + o_pb), nullptr, nullptr, (int*)(d + o_hit), (float4*)(d + o_out), nullptr, is2d);
     if (r) { cudaFreeAsync(d, w->stream); return r; }
     std::vector<int> fl(N); std::vector<float4> cd(N);
     CU(cudaMemcpyAsync(fl.data(), d + o_hit, 4 * N, cudaMemcpyDeviceToHost, w->stream)); CU(cudaMemcpyAsync(cd.data(), d + o_out, 16 * N, cudaMemcpyDeviceToHost, w->stream));
@@ -799,7 +813,6 @@ int np_detect_collision_batch(np_world* w, int n, const int32_t* shape_a, const 
 int np_detect_collision(np_world* w, int shape_a, const float a_transform[16], int shape_b, const float b_transform[16], int is3D, np_collision_data* out, int* hit)
 {
     if (!w || !a_transform || !b_transform) return fail(NP_ERR_INVALID, "bad arguments");
-    if (!is3D) return fail(NP_ERR_UNSUPPORTED, "2-D mode (is3D == false) is not implemented on the device");
     int32_t sa = shape_a, sb = shape_b;
     int r = check_shapes(w, 1, &sa, &sb); if (r) return r;
     r = ensure_device(w); if (r) return r;
@@ -807,7 +820,7 @@ int np_detect_collision(np_world* w, int shape_a, const float a_transform[16], i
     CU(cudaMallocAsync((void**)&d, 256, w->stream));
     CU(cudaMemcpyAsync(d, a_transform, 64, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + 64, b_transform, 64, cudaMemcpyHostToDevice, w->stream));
     CU(cudaMemcpyAsync(d + 128, &sa, 4, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + 132, &sb, 4, cudaMemcpyHostToDevice, w->stream));
-    r = run_pairs(w, 1, (int*)(d + 128), nullptr, (int*)(d + 132), nullptr, (float*)d, (float*)(d + 64), (int*)(d + 136), (float4*)(d + 144), nullptr);
+    r = run_pairs(w, 1, (int*)(d + 128), nullptr, (int*)(d + 132), nullptr, (float*)d, (float*)(d + 64), (int*)(d + 136), (float4*)(d + 144), nullptr, !is3D);
     if (r) { cudaFreeAsync(d, w->stream); return r; }
     int fl; float4 cd;
     CU(cudaMemcpyAsync(&fl, d + 136, 4, cudaMemcpyDeviceToHost, w->stream)); CU(cudaMemcpyAsync(&cd, d + 144, 16, cudaMemcpyDeviceToHost, w->stream));

@@ -111,6 +111,7 @@ def load_library():
     L.np_world_last_step_ms.argtypes = [vp, f32p]
     L.np_detect_collision.argtypes = [vp, C.c_int, f32p, C.c_int, f32p, C.c_int, C.POINTER(CollisionData), C.POINTER(C.c_int)]
     L.np_detect_collision_batch.argtypes = [vp, C.c_int, i32p, f32p, i32p, f32p, i32p, vp]
+    L.np_detect_collision_batch_2d.argtypes = [vp, C.c_int, i32p, f32p, i32p, f32p, i32p, vp]
     L.np_detect_collision_batch_device.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, f32p]
     L.np_world_snapshot.argtypes = [vp, vp, C.c_int]
     L.np_world_snapshot_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -291,11 +292,12 @@ class World:
         self._ck(self.L.np_detect_collision(self.w, sa, _f(np.ascontiguousarray(xa, np.float32)), sb, _f(np.ascontiguousarray(xb, np.float32)), int(is3d), C.byref(cd), C.byref(hit)))
         return hit.value, np.array(list(cd.penetration_direction) + [cd.depth, float(cd.success)], np.float32)
 
-    def detect_batch(self, sa, posea, sb, poseb):
+    def detect_batch(self, sa, posea, sb, poseb, is3d=True):
         sa = np.ascontiguousarray(sa, np.int32); sb = np.ascontiguousarray(sb, np.int32)
         posea = np.ascontiguousarray(posea, np.float32); poseb = np.ascontiguousarray(poseb, np.float32)
         n = len(sa); hit = np.zeros(n, np.int32); cd = np.zeros(n, COLLISION_DATA_DTYPE)
-        self._ck(self.L.np_detect_collision_batch(self.w, n, _i(sa), _f(posea), _i(sb), _f(poseb), _i(hit), cd.ctypes.data))
+        fn = self.L.np_detect_collision_batch if is3d else self.L.np_detect_collision_batch_2d
+        self._ck(fn(self.w, n, _i(sa), _f(posea), _i(sb), _f(poseb), _i(hit), cd.ctypes.data))
         out = np.zeros((n, 5), np.float32)
         out[:, 0:3] = cd["penetration_direction"]; out[:, 3] = cd["depth"]; out[:, 4] = cd["success"]
         return hit, out

@@ -90,8 +90,6 @@ def test_detect_collision_single_and_edge_cases(world, oracle):
         hit, out = world.detect_batch([box], pa, [box], pb); ho, oo, _ = oracle.detect_batch([bo], [0], pa, [0], pb)
         assert hit[0] == ho[0]
         assert np.array_equal(np.isnan(out), np.isnan(oo)); assert_biteq(np.nan_to_num(out), np.nan_to_num(oo), "edge pair")
-    with pytest.raises(Exception):
-        world.detect(sph, xa, brd, xb, is3d=False)                 # 2-D mode is not implemented: loud error, not a wrong answer
     hit, out = world.detect_batch(np.zeros(0, np.int32), np.zeros((0, 6), np.float32), np.zeros(0, np.int32), np.zeros((0, 6), np.float32))
     assert len(hit) == 0
 
@@ -386,3 +384,18 @@ def test_grid_with_islands_and_graph_replay(world, oracle, npb):
         assert np.array_equal(a1, a2) and np.array_equal(b1, b2); assert_biteq(d1, d2, "collisions"); assert_biteq(st1, w2.states(), "state")
     island = np.repeat(np.arange(6), 200)
     assert np.all(island[a1] == island[b1]), "a collision crosses islands"
+
+
+def test_detect_collision_2d_mode(world, oracle):
+    """is3D == false (engine/test_2d.cpp's mode) on the device == the oracle, per pair and through the single-query entry point."""
+    from test_oracle import _scene_2d
+    shapes, sa, pa, sb, pb = _scene_2d(np.random.RandomState(21), 6000)
+    ids = np.array([world.create_mesh(s) for s in shapes], np.int32)
+    hit, out = world.detect_batch(ids[sa], pa, ids[sb], pb, is3d=False)
+    for i in range(len(sa)):
+        ho, oo = oracle.detect(shapes[sa[i]], oracle.transform(pa[i, :3], pa[i, 3:]), shapes[sb[i]], oracle.transform(pb[i, :3], pb[i, 3:]), is3d=False)
+        assert hit[i] == ho, "pair %d" % i
+        assert_biteq(out[i], oo, "2-D CollisionData of pair %d" % i)
+    h1, o1 = world.detect(ids[0], oracle.transform(pa[5, :3], pa[5, 3:]), ids[1], oracle.transform(pb[5, :3], pb[5, 3:]), is3d=False)
+    h2, o2 = oracle.detect(shapes[0], oracle.transform(pa[5, :3], pa[5, 3:]), shapes[1], oracle.transform(pb[5, :3], pb[5, 3:]), is3d=False)
+    assert h1 == h2; assert_biteq(o1, o2, "single 2-D query")

@@ -158,3 +158,30 @@ def test_live_ref_world(oracle, ref):
         ar, br, dr = ref.step(sc["dt"], True); ao, bo, do = w.step(sc["dt"], True)
         assert np.array_equal(ar, ao) and np.array_equal(br, bo); assert_biteq(do, dr, "collisions step %d" % k)
         assert_biteq(w.state(), ref.state(), "state step %d" % k)
+
+
+def _scene_2d(rng, n):
+    """engine/test_2d.cpp:374-388: a triangle and a 5x5 square in the z = 0 plane, moved around in the plane."""
+    tri = np.array([[0, 1, 0], [4, 0, 0], [4, 2, 0]], np.float32); box = np.array([[0, 0, 0], [5, 0, 0], [5, 5, 0], [0, 5, 0]], np.float32)
+    hexa = np.array([[np.cos(a), np.sin(a), 0] for a in np.linspace(0, 2 * np.pi, 7)[:-1]], np.float32) * 1.5
+    pa = np.zeros((n, 6), np.float32); pb = np.zeros((n, 6), np.float32)
+    pa[:, 0:2] = rng.uniform(-4, 6, size=(n, 2)); pb[:, 0:2] = rng.uniform(-3, 3, size=(n, 2))
+    pa[:, 5] = rng.uniform(-np.pi, np.pi, size=n); pb[:, 5] = rng.uniform(-np.pi, np.pi, size=n)        # rotation about z keeps the plane
+    pa[0] = 0; pb[0] = 0                                                                                  # the harness' initial pose
+    return [tri, box, hexa], rng.randint(0, 3, size=n).astype(np.int32), pa, rng.randint(0, 3, size=n).astype(np.int32), pb
+
+
+def test_live_ref_2d_mode(oracle, ref):
+    """is3D == false (collision_detection.cpp:364-384, 455-460, 590-605, 648): oracle == compiled reference."""
+    shapes, sa, pa, sb, pb = _scene_2d(np.random.RandomState(21), 4000)
+    rid = [ref.mesh(s) for s in shapes]
+    nhit = 0
+    for i in range(len(sa)):
+        xa = oracle.transform(pa[i, :3], pa[i, 3:]); xb = oracle.transform(pb[i, :3], pb[i, 3:])
+        hr, outr = ref.detect(rid[sa[i]], xa, rid[sb[i]], xb, is3d=False)
+        ho, outo = oracle.detect(shapes[sa[i]], xa, shapes[sb[i]], xb, is3d=False)
+        assert hr == ho, "pair %d" % i
+        if outr[4] == 1 or outo[4] == 1:
+            assert_biteq(outo, outr, "2-D CollisionData of pair %d" % i)
+        nhit += hr
+    assert 0.05 < nhit / len(sa) < 0.95
