@@ -185,6 +185,18 @@ int np_world_snapshot_device(np_world* w, void** d_ptr, size_t* bytes);
  * guid_base is added to the body index (rank offset when worlds are sharded over GPUs). */
 int np_world_set_snapshot_target(np_world* w, void* d_dst, uint32_t guid_base);
 
+/* ---- command frames: netphys_server/world_s.cpp:12-108 (the step AFTER the path: what the server sends to clients) ---------- */
+/* World_S_Update(now): snapshot every body into a new command frame (ids count from 1) and drop frames older than 5000 ms
+ * (MAX_COMMAND_FRAME_TIME, world_s.cpp:21,57-68).  Returns the new frame id. */
+int np_world_record_frame(np_world* w, double time_ms);
+int np_world_frame_count(const np_world* w);
+/* World_S_FillWorldUpdateMessage / FillNewConnectionMessage + Packet::Serialize (common.h:77-93,130-163): writes the newest frame as
+ *   int32 packet_id | int32 data_size | int32 frame_id | float64 time_ms | int32 count | count x CommandFrameObject (36 B)
+ * packet_id: NP_PACKET_WORLD_STATE_UPDATE or NP_PACKET_NEW_CONNECTION.  Returns the bytes written, 0 when `cap` is too small or no frame exists. */
+#define NP_PACKET_WORLD_STATE_UPDATE 2342144
+#define NP_PACKET_NEW_CONNECTION 2342341
+int np_world_fill_packet(np_world* w, int packet_id, void* buffer, int cap);
+
 /* ---- device memory helpers for callers that keep buffers resident (bench, multi-GPU plumbing) ------- */
 void* np_device_alloc(np_world* w, size_t bytes);
 int np_device_free(np_world* w, void* p);

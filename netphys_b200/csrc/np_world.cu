@@ -26,6 +26,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 struct HostShape { std::vector<float> xyz; };
 struct HostBody { np_static_physics_data sd; int shape; int island; };
+struct CommandFrame { unsigned id; double time_ms; std::vector<np_snapshot_object> objects; };      // world_s.cpp:12-17
 
 struct np_world {
     int device = 0;
@@ -36,6 +37,7 @@ struct np_world {
     std::vector<HostBody> bodies;
     std::vector<np_body_state> host_state;   // authoritative until the first upload, refreshed on demand
     int island = 0;
+    std::vector<CommandFrame> frames; unsigned frame_counter = 1;      // world_s.cpp:19-21
     // options
     int broadphase = NP_BROADPHASE_EXACT;
     float grid_cell = 0.0f;
@@ -889,6 +891,36 @@ int np_world_snapshot(np_world* w, np_snapshot_object* dst, int cap)
     if (bytes) CU(cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
     return n;
+}
+
+// ------------------------------------------------------------------------------------------------ command frames (world_s.cpp)
+int np_world_record_frame(np_world* w, double time_ms)
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    CommandFrame f; f.id = w->frame_counter++; f.time_ms = time_ms;
+    f.objects.resize(w->bodies.size());
+    if (!f.objects.empty()) { int r = np_world_snapshot(w, f.objects.data(), (int)f.objects.size()); if (r < 0) return r; }
+    w->frames.push_back(std::move(f));
+    size_t drop = 0;                                          // erase old command frames, world_s.cpp:57-68
+    while (drop < w->frames.size() && !(time_ms - w->frames[drop].time_ms < 5000.0)) drop++;
+    if (drop) w->frames.erase(w->frames.begin(), w->frames.begin() + (long)drop);
+    return (int)(w->frame_counter - 1);
+}
+int np_world_frame_count(const np_world* w) { return w ? (int)w->frames.size() : 0; }
+int np_world_fill_packet(np_world* w, int packet_id, void* buffer, int cap)
+{
+    if (!w || !buffer) return fail(NP_ERR_INVALID, "bad arguments");
+    if (w->frames.empty()) return 0;                          // "Tried to send world state before any command frames were generated"
+    const CommandFrame& f = w->frames.back();
+    static_assert(sizeof(np_snapshot_object) == 36, "CommandFrameObject is 36 bytes");
+    const int count = (int)f.objects.size();
+    const long long data = 4 + 8 + 4 + 36LL * count, total = 8 + data;
+    if (total > cap) return 0;                                // Packet::Serialize returns 0 when the buffer is too small
+    char* p = (char*)buffer;
+    const int id = packet_id, size = (int)data, fid = (int)f.id;
+    memcpy(p, &id, 4); memcpy(p + 4, &size, 4); memcpy(p + 8, &fid, 4); memcpy(p + 12, &f.time_ms, 8); memcpy(p + 20, &count, 4);
+    if (count) memcpy(p + 24, f.objects.data(), 36 * (size_t)count);
+    return (int)total;
 }
 
 // ------------------------------------------------------------------------------------------------ device memory helpers

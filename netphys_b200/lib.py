@@ -121,6 +121,9 @@ def load_library():
     L.np_device_download.argtypes = [vp, vp, vp, C.c_size_t]
     L.np_world_stream.restype = vp; L.np_world_stream.argtypes = [vp]
     L.np_device_flush_l2.argtypes = [vp]
+    L.np_world_record_frame.argtypes = [vp, C.c_double]
+    L.np_world_frame_count.argtypes = [vp]
+    L.np_world_fill_packet.argtypes = [vp, C.c_int, vp, C.c_int]
     L.np_world_set_snapshot_target.argtypes = [vp, vp, C.c_uint32]
     L.np_selftest_fp32_peak.argtypes = [vp, f32p]
     L.np_selftest_sincos_hash.argtypes = [vp, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -327,6 +330,15 @@ class World:
         self._ck(self.L.np_world_snapshot_device(self.w, C.byref(p), C.byref(nb))); return p.value, nb.value
 
     def flush_l2(self): self._ck(self.L.np_device_flush_l2(self.w))
+    def record_frame(self, time_ms): return self._ck(self.L.np_world_record_frame(self.w, float(time_ms)))
+    def frame_count(self): return self.L.np_world_frame_count(self.w)
+
+    def fill_packet(self, packet_id=2342144, cap=None):
+        cap = cap if cap is not None else 24 + 36 * self.n
+        buf = np.zeros(max(cap, 1), np.uint8)
+        nb = self._ck(self.L.np_world_fill_packet(self.w, packet_id, buf.ctypes.data, cap))
+        return buf[:nb].tobytes()
+
     def set_snapshot_target(self, d_ptr, guid_base=0): self._ck(self.L.np_world_set_snapshot_target(self.w, d_ptr, guid_base))
 
     def fp32_peak_tflops(self):

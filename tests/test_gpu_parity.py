@@ -399,3 +399,24 @@ def test_detect_collision_2d_mode(world, oracle):
     h1, o1 = world.detect(ids[0], oracle.transform(pa[5, :3], pa[5, 3:]), ids[1], oracle.transform(pb[5, :3], pb[5, 3:]), is3d=False)
     h2, o2 = oracle.detect(shapes[0], oracle.transform(pa[5, :3], pa[5, 3:]), shapes[1], oracle.transform(pb[5, :3], pb[5, 3:]), is3d=False)
     assert h1 == h2; assert_biteq(o1, o2, "single 2-D query")
+
+
+def test_command_frames_and_wire_packet(world, oracle):
+    """netphys_server/world_s.cpp: the 5-second command-frame ring and the ClientWorldStateUpdatePacket wire layout."""
+    import struct
+    sc = scenes.few_boxes_scene(); world.load_scene(sc)
+    assert world.fill_packet() == b""                              # no frame yet
+    ids = []
+    for k in range(8):
+        world.step(sc["dt"]); ids.append(world.record_frame(1000.0 * k))
+    assert ids == list(range(1, 9))
+    assert world.frame_count() == 5                                # frames at 3000..7000 ms are younger than 5000 ms at now = 7000
+    pkt = world.fill_packet()
+    pid, size, fid = struct.unpack_from("<iii", pkt, 0); t, = struct.unpack_from("<d", pkt, 12); cnt, = struct.unpack_from("<i", pkt, 20)
+    assert (pid, fid, t, cnt) == (2342144, 8, 7000.0, world.n) and size == len(pkt) - 8 == 16 + 36 * cnt
+    objs = np.frombuffer(pkt, dtype=world.snapshot().dtype, offset=24, count=cnt)
+    snap = world.snapshot()
+    assert np.array_equal(objs["guid"], snap["guid"]); assert_biteq(objs["pos"], snap["pos"], "packet positions"); assert_biteq(objs["rot"], snap["rot"], "packet rotations")
+    assert np.frombuffer(pkt, np.uint8, offset=24 + 32, count=1)[0] == 1          # isEnabled: bool true + padding
+    assert world.fill_packet(cap=24 + 36 * cnt - 1) == b""         # Packet::Serialize refuses a short buffer
+    assert struct.unpack_from("<i", world.fill_packet(packet_id=2342341), 0)[0] == 2342341
