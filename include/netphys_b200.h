@@ -152,6 +152,15 @@ int np_world_set_states(np_world* w, const np_body_state* in, int n);
 /* ---- the step: Physics_Update, engine/physics.h:99-100 / physics.cpp:148-163 ----------------------- */
 int np_world_step(np_world* w, float dt);
 int np_world_step_n(np_world* w, float dt, int steps);    /* `steps` consecutive Physics_Update(dt) calls, one submission */
+/* One world, pair search sharded over processes (one per GPU).  Every process holds the whole world; this one runs GetCollisions'
+ * outer loop (physics.cpp:119) for bodies [first, first + count) only and writes their records into the caller's full-length device
+ * arrays: d_hit_j int32[n] (partner b, or -1), d_flags int32[n] (& 2 = CollisionData::success), d_contact float[4][n]
+ * (penetrationDirection.xyz, depth).  Per step:  np_world_step_begin (Physics::Update of every body + the owned part of
+ * GetCollisions)  ->  caller all-gathers the three arrays (NCCL; the step's only exchange)  ->  np_world_step_end (OnCollision over
+ * the complete list, snapshot).  State stays bit-identical on every process without being exchanged.  count < 0 = not sharded. */
+int np_world_set_shard(np_world* w, int first, int count, void* d_hit_j, void* d_flags, void* d_contact);
+int np_world_step_begin(np_world* w, float dt);
+int np_world_step_end(np_world* w);
 /* Physics::Update for every body only (physics.cpp:151-155), no collision phase */
 int np_world_integrate(np_world* w, float dt);
 /* collisions of the most recent step, in the reference's list order (ascending a) */

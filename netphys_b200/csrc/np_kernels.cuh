@@ -188,6 +188,7 @@ NP_D int fetch_ticket(int* counter, bool need)
 struct NarrowIn {
     int world;                 // 1: items are bodies of `s`; 0: items are pairs
     int n;                     // bodies or pairs
+    int first;                 // world mode: item t is body first + t (the shard of the pair search this process owns)
     StoreView s;
     const int* shape_a; const int* shape_b;      // pair mode
     const float* xf_a; const float* xf_b;        // pair mode: transforms, SoA [X_COUNT][n]
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
         int t = fetch_ticket<G>(ticket, !have && !exhausted);
         if (!have && !exhausted) {
             if (t < in.n) {
-                i = t;
+                i = WORLD ? t + in.first : t;
                 if (WORLD) {
                     if (in.cand) { cbase = in.cand_off[i]; c = 0; jend = in.cand_cnt[i]; j = jend > 0 ? in.cand[cbase] : 0; if (jend > 0) jend = 0x7fffffff; cn = in.cand_cnt[i]; }
                     else { j = i + 1; jend = island_end[i]; }
@@ -649,10 +650,11 @@ NP_D void cell_range(const GridView& gv, float4 lo, float4 hi, int* c0, int* c1)
 }
 // FILL = false: count; FILL = true: write (same traversal), into the region the prefix sum of the counts assigns
 template <bool FILL>
-__global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, DevCounters* ctr)
+__global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, int first, int count, DevCounters* ctr)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s.n) return;
+    if (i >= count) return;
+    i += first;
     const int jend = s.ints[I_ISLAND_END * s.cap + i];
     const float4 lo = gv.aabb[2 * i], hi = gv.aabb[2 * i + 1];
     const int ci = __float_as_int(lo.w);
@@ -714,7 +716,7 @@ __global__ void __launch_bounds__(256) k_count_incoming(int n, int cap, const in
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int b = hit_j[i];
-    if (b >= 0 && ints[I_RESPONSE * cap + b] == 1) atomicAdd(&cnt[b], 1);
+    if ((unsigned)b < (unsigned)n && ints[I_RESPONSE * cap + b] == 1) atomicAdd(&cnt[b], 1);      // (records may come from another process)
 }
 // exclusive scan of cnt[0..n) in three launches (per-block sums, scan of the sums, per-block scan + offset)
 #define NP_SCAN_BLOCK 1024
@@ -788,7 +790,7 @@ __global__ void __launch_bounds__(256) k_fill_incoming(int n, int cap, const int
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int b = hit_j[i];
-    if (b >= 0 && ints[I_RESPONSE * cap + b] == 1) inc[off[b] + atomicAdd(&cursor[b], 1)] = i;
+    if ((unsigned)b < (unsigned)n && ints[I_RESPONSE * cap + b] == 1) inc[off[b] + atomicAdd(&cursor[b], 1)] = i;
 }
 
 // Physics::ApplyImpulseResponse, physics.cpp:27-46

@@ -52,6 +52,10 @@ struct np_world {
     float4* d_verts = nullptr; int *d_soff = nullptr, *d_scnt = nullptr; int total_verts = 0;
     // per-step scratch
     int *d_hit_j = nullptr, *d_cflags = nullptr; float4* d_contact = nullptr;
+    // sharded pair search (np_world_set_shard): this process searches bodies [shard_first, shard_first + shard_count); the per-body
+    // collision records live in caller-provided buffers that the caller all-gathers between step_begin and step_end
+    int shard_first = 0, shard_count = -1; int *x_hit_j = nullptr, *x_cflags = nullptr; float4* x_contact = nullptr;
+    bool mid_step = false;
     int* d_zero = nullptr;            // [tickets and counts (32 ints), inc_cnt[cap], cursor[cap]]  -- one memset per step
     int *d_inc_off = nullptr, *d_inc = nullptr, *d_sums = nullptr, *d_big_list = nullptr, *d_hit_list = nullptr;
     float4* d_simplex = nullptr;      // GJK result of every hit: A[4], B[4]
@@ -79,6 +83,10 @@ struct np_world {
 static StoreView view(np_world* w) { StoreView s; s.n = (int)w->bodies.size(); s.cap = w->cap; s.state = w->d_state; s.cst = w->d_cst; s.xf = w->d_xf; s.ints = w->d_ints; s.wverts = w->d_wverts; return s; }
 static ShapeView sview(np_world* w) { ShapeView s; s.verts = w->d_verts; s.off = w->d_soff; s.cnt = w->d_scnt; s.total_verts = w->total_verts; return s; }
 enum { Z_GJK_TICKET = 0, Z_HIT_COUNT, Z_EPA_TICKET, Z_MID_COUNT, Z_MID_TICKET, Z_BIG_COUNT, Z_BIG_TICKET };
+static int* hitj(np_world* w) { return w->x_hit_j ? w->x_hit_j : w->d_hit_j; }
+static int* cflags(np_world* w) { return w->x_cflags ? w->x_cflags : w->d_cflags; }
+static float4* contacts(np_world* w) { return w->x_contact ? w->x_contact : w->d_contact; }
+static bool sharded(np_world* w) { return w->shard_count >= 0; }
 static int* d_inc_cnt(np_world* w) { return w->d_zero + 32; }
 static int* d_cursor(np_world* w) { return w->d_zero + 32 + w->cap; }
 
@@ -347,7 +355,7 @@ static int ensure_grid(np_world* w)
     return NP_OK;
 }
 // K2, enqueued between integrate and the narrow phase
-static int enqueue_grid(np_world* w, const StoreView& s, DevCounters* ctr)
+static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, DevCounters* ctr)
 {
     GridView& g = w->grid; g.h_option = w->grid_cell;
     const int n = s.n, b256 = (n + 255) / 256;
@@ -358,39 +366,57 @@ static int enqueue_grid(np_world* w, const StoreView& s, DevCounters* ctr)
     k_grid_count<<<b256, 256, 0, w->stream>>>(s, g);
     enqueue_scan(w, g.nbuckets, g.bucket_cnt, g.bucket_off);
     k_grid_fill<<<b256, 256, 0, w->stream>>>(s, g);
-    k_cand<false><<<(n + 127) / 128, 128, 0, w->stream>>>(s, g, nullptr);
-    enqueue_scan(w, n, g.cand_cnt, g.cand_off);
-    k_cand<true><<<(n + 127) / 128, 128, 0, w->stream>>>(s, g, ctr);
+    if (count > 0) {                 // candidates of the bodies this process searches (the whole world unless sharded)
+        k_cand<false><<<(count + 127) / 128, 128, 0, w->stream>>>(s, g, first, count, nullptr);
+        enqueue_scan(w, count, g.cand_cnt + first, g.cand_off + first);
+        k_cand<true><<<(count + 127) / 128, 128, 0, w->stream>>>(s, g, first, count, ctr);
+    }
     w->launches += 7;
     CU(cudaGetLastError());
     return NP_OK;
 }
 
-// the kernels of one Physics_Update, enqueued on the world's stream (capturable)
-static int enqueue_step(np_world* w, float dt, bool timed)
+// the kernels of one Physics_Update, enqueued on the world's stream (capturable), in two halves:
+//   search : integrate -> [grid] -> GJK/EPA first-hit search of bodies [first, first + count)      (physics.cpp:154-157)
+//   respond: OnCollision over every body's collisions -> snapshot                                  (physics.cpp:159-162)
+// A sharded world runs them as np_world_step_begin / np_world_step_end with the caller's all-gather of the collision
+// records in between; everything but the search itself is replicated and bit-identical on every process.
+static int enqueue_search(np_world* w, float dt, bool timed)
 {
     const int n = (int)w->bodies.size();
     if (n == 0) return NP_OK;
     StoreView s = view(w);
     DevCounters* ctr = w->counters_on ? w->d_ctr : nullptr;
     const int b256 = (n + 255) / 256;
+    const int first = sharded(w) ? w->shard_first : 0, count = sharded(w) ? w->shard_count : n;
     if (timed) CU(cudaEventRecord(w->ev[0], w->stream));
     k_integrate<<<b256, 256, 0, w->stream>>>(s, dt, 1);
     w->launches += 1;
     if (timed) CU(cudaEventRecord(w->ev[1], w->stream));
-    if (w->broadphase == NP_BROADPHASE_GRID) { int r = enqueue_grid(w, s, ctr); if (r) return r; }
+    if (w->broadphase == NP_BROADPHASE_GRID) { int r = enqueue_grid(w, s, first, count, ctr); if (r) return r; }
     else { k_world_verts<false><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), w->grid); w->launches += 1; }
     if (timed) CU(cudaEventRecord(w->ev[2], w->stream));
     CU(cudaMemsetAsync(w->d_zero, 0, sizeof(int) * (32 + 2 * (size_t)w->cap), w->stream));
-    NarrowIn in; memset(&in, 0, sizeof in); in.world = 1; in.n = n; in.s = s;
-    if (w->broadphase == NP_BROADPHASE_GRID) { in.cand = w->grid.cand; in.cand_off = w->grid.cand_off; in.cand_cnt = w->grid.cand_cnt; }
-    NarrowBufs nb = { w->d_zero, w->d_hit_j, w->d_cflags, w->d_contact, w->d_simplex, w->d_hit_list, w->d_big_list };
-    { int r = launch_narrow(w, in, nb, ctr); if (r) return r; }
+    if (count > 0) {
+        NarrowIn in; memset(&in, 0, sizeof in); in.world = 1; in.n = count; in.first = first; in.s = s;
+        if (w->broadphase == NP_BROADPHASE_GRID) { in.cand = w->grid.cand; in.cand_off = w->grid.cand_off; in.cand_cnt = w->grid.cand_cnt; }
+        NarrowBufs nb = { w->d_zero, hitj(w), cflags(w), contacts(w), w->d_simplex, w->d_hit_list, w->d_big_list };
+        int r = launch_narrow(w, in, nb, ctr); if (r) return r;
+    }
     if (timed) CU(cudaEventRecord(w->ev[3], w->stream));
-    k_count_incoming<<<b256, 256, 0, w->stream>>>(n, w->cap, w->d_hit_j, w->d_ints, d_inc_cnt(w));
+    CU(cudaGetLastError());
+    return NP_OK;
+}
+static int enqueue_respond(np_world* w, bool timed)
+{
+    const int n = (int)w->bodies.size();
+    if (n == 0) return NP_OK;
+    StoreView s = view(w);
+    const int b256 = (n + 255) / 256;
+    k_count_incoming<<<b256, 256, 0, w->stream>>>(n, w->cap, hitj(w), w->d_ints, d_inc_cnt(w));
     enqueue_scan(w, n, d_inc_cnt(w), w->d_inc_off);
-    k_fill_incoming<<<b256, 256, 0, w->stream>>>(n, w->cap, w->d_hit_j, w->d_ints, w->d_inc_off, d_cursor(w), w->d_inc);
-    k_resolve<<<b256, 256, 0, w->stream>>>(s, w->d_hit_j, w->d_contact, w->d_inc_off, d_inc_cnt(w), w->d_inc);
+    k_fill_incoming<<<b256, 256, 0, w->stream>>>(n, w->cap, hitj(w), w->d_ints, w->d_inc_off, d_cursor(w), w->d_inc);
+    k_resolve<<<b256, 256, 0, w->stream>>>(s, hitj(w), contacts(w), w->d_inc_off, d_inc_cnt(w), w->d_inc);
     if (timed) CU(cudaEventRecord(w->ev[4], w->stream));
     w->launches += 3;
     if (w->snapshot_each_step) {
@@ -400,6 +426,12 @@ static int enqueue_step(np_world* w, float dt, bool timed)
     if (timed) CU(cudaEventRecord(w->ev[5], w->stream));
     CU(cudaGetLastError());
     return NP_OK;
+}
+static int enqueue_step(np_world* w, float dt, bool timed)
+{
+    if (sharded(w)) return fail(NP_ERR_INVALID, "sharded world: step with np_world_step_begin / (all-gather) / np_world_step_end");
+    int r = enqueue_search(w, dt, timed); if (r) return r;
+    return enqueue_respond(w, timed);
 }
 
 // ------------------------------------------------------------------------------------------------ library
@@ -635,6 +667,45 @@ int np_world_step(np_world* w, float dt)
     w->timed = true; w->steps++;
     return NP_OK;
 }
+// Sharded pair search of ONE world across processes (BASELINE configs[4]).  Every process holds the whole world;
+// process r searches the first hit of bodies [first, first + count) only, and writes hit_j / flags / contact of those bodies into
+// the caller's full-length device arrays.  The caller all-gathers the three arrays (the one exchange of the step), then
+// np_world_step_end applies the impulse responses of the complete collision list on every process, which keeps the replicated
+// state bit-identical everywhere without exchanging it.
+int np_world_set_shard(np_world* w, int first, int count, void* d_hit_j, void* d_flags, void* d_contact)
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    if (w->mid_step) return fail(NP_ERR_INVALID, "np_world_set_shard between step_begin and step_end");
+    drop_graph(w);
+    if (count < 0) { w->shard_first = 0; w->shard_count = -1; w->x_hit_j = w->x_cflags = nullptr; w->x_contact = nullptr; return NP_OK; }
+    if (first < 0 || !d_hit_j || !d_flags || !d_contact) return fail(NP_ERR_INVALID, "bad shard (range or null collision arrays)");
+    w->shard_first = first; w->shard_count = count; w->x_hit_j = (int*)d_hit_j; w->x_cflags = (int*)d_flags; w->x_contact = (float4*)d_contact;
+    return NP_OK;
+}
+int np_world_step_begin(np_world* w, float dt)
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    if (w->mid_step) return fail(NP_ERR_INVALID, "np_world_step_begin called twice");
+    int r = ensure_device(w); if (r) return r;
+    const int n = (int)w->bodies.size();
+    if (sharded(w) && (long long)w->shard_first + w->shard_count > n) {      // ranks past the end own an empty or clipped range
+        if (w->shard_first > n) w->shard_first = n;
+        w->shard_count = n - w->shard_first;
+    }
+    r = enqueue_search(w, dt, true); if (r) return r;
+    w->mid_step = true;
+    return NP_OK;
+}
+int np_world_step_end(np_world* w)
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    if (!w->mid_step) return fail(NP_ERR_INVALID, "np_world_step_end without np_world_step_begin");
+    CU(cudaSetDevice(w->device));
+    w->mid_step = false;
+    int r = enqueue_respond(w, true); if (r) return r;
+    w->timed = true; w->steps++;
+    return NP_OK;
+}
 int np_world_step_n(np_world* w, float dt, int steps)
 {
     if (!w || steps < 0) return fail(NP_ERR_INVALID, "bad arguments");
@@ -679,9 +750,9 @@ int np_world_get_collisions(np_world* w, np_collision* out, int cap, int* count)
     CU(cudaSetDevice(w->device));
     { int rg = check_grid_error(w); if (rg) return rg; }
     std::vector<int> hj(n), fl(n); std::vector<float4> cd(n);
-    CU(cudaMemcpyAsync(hj.data(), w->d_hit_j, sizeof(int) * n, cudaMemcpyDeviceToHost, w->stream));
-    CU(cudaMemcpyAsync(fl.data(), w->d_cflags, sizeof(int) * n, cudaMemcpyDeviceToHost, w->stream));
-    CU(cudaMemcpyAsync(cd.data(), w->d_contact, sizeof(float4) * n, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaMemcpyAsync(hj.data(), hitj(w), sizeof(int) * n, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaMemcpyAsync(fl.data(), cflags(w), sizeof(int) * n, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaMemcpyAsync(cd.data(), contacts(w), sizeof(float4) * n, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
     int k = 0;
     for (int i = 0; i < n; i++) {

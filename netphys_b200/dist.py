@@ -39,3 +39,60 @@ class SnapshotExchange:
             return buf
         self.torch.distributed.all_gather_into_tensor(self.recv, buf)
         return self.recv
+
+
+def padded_shard(n_bodies, rank, world_size):
+    """Equal-length index ranges for the sharded pair search of ONE world: rank r searches bodies [first, first + count) where
+    every rank's slot is `slot` = ceil(n / world_size) long (the all-gather needs equal pieces); the last ranks may own fewer
+    (or no) bodies.  Returns (first, count, slot)."""
+    slot = max(1, -(-n_bodies // world_size))
+    first = min(n_bodies, rank * slot)
+    return first, min(n_bodies, first + slot) - first, slot
+
+
+class CollisionExchange:
+    """The one exchange of a sharded world step (np_world_set_shard / step_begin / step_end): all-gather, in place, of the three
+    per-body collision arrays -- hit_j int32, flags int32, contact float32[4] (= physics.h:26-31 Collision records, 24 bytes per
+    body) -- each rank contributing the slot of bodies it searched.  Tensors are CUDA for nccl, CPU for gloo."""
+
+    def __init__(self, n_bodies, device, world_size, rank):
+        import torch
+        self.torch = torch
+        self.world_size, self.rank = world_size, rank
+        self.first, self.count, self.slot = padded_shard(n_bodies, rank, world_size)
+        total = self.slot * world_size
+        self.hit_j = torch.full((total,), -1, dtype=torch.int32, device=device)
+        self.flags = torch.zeros(total, dtype=torch.int32, device=device)
+        self.contact = torch.zeros((total, 4), dtype=torch.float32, device=device)
+
+    def pointers(self):
+        return self.hit_j.data_ptr(), self.flags.data_ptr(), self.contact.data_ptr()
+
+    def exchange(self):
+        if self.world_size == 1:
+            return
+        lo, hi = self.rank * self.slot, (self.rank + 1) * self.slot
+        for t in (self.hit_j, self.flags, self.contact):
+            piece = t[lo:hi]
+            if not t.is_cuda:
+                piece = piece.clone()                   # gloo: no aliasing of input and output
+            self.torch.distributed.all_gather_into_tensor(t, piece)
+
+
+class ShardedWorld:
+    """One world whose pair search is split over the ranks of a torch.distributed group (BASELINE configs[4]).  Every rank loads
+    the same scene; `step` = step_begin -> CollisionExchange -> step_end, all enqueued on the world's own CUDA stream."""
+
+    def __init__(self, world, device, world_size, rank):
+        import torch
+        self.torch = torch
+        self.w = world
+        self.x = CollisionExchange(world.n, device, world_size, rank)
+        world.set_shard(self.x.first, self.x.count, *self.x.pointers())
+        self.stream = torch.cuda.ExternalStream(world.L.np_world_stream(world.w), device=device)
+
+    def step(self, dt):
+        self.w.step_begin(dt)
+        with self.torch.cuda.stream(self.stream):       # the collective is ordered after the search and before the response
+            self.x.exchange()
+        self.w.step_end()

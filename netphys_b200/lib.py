@@ -104,6 +104,9 @@ def load_library():
     L.np_world_set_states.argtypes = [vp, vp, C.c_int]
     L.np_world_step.argtypes = [vp, C.c_float]
     L.np_world_step_n.argtypes = [vp, C.c_float, C.c_int]
+    L.np_world_set_shard.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    L.np_world_step_begin.argtypes = [vp, C.c_float]
+    L.np_world_step_end.argtypes = [vp]
     L.np_world_integrate.argtypes = [vp, C.c_float]
     L.np_world_get_collisions.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
     L.np_world_step_host.argtypes = [vp, C.c_float, vp, vp, C.c_int]
@@ -265,6 +268,14 @@ class World:
     def set_option(self, opt, value): self._ck(self.L.np_world_set_option(self.w, opt, int(value)))
     def step(self, dt): self._ck(self.L.np_world_step(self.w, float(np.float32(dt))))
     def step_n(self, dt, steps): self._ck(self.L.np_world_step_n(self.w, float(np.float32(dt)), steps))
+
+    def set_shard(self, first, count, d_hit_j=0, d_flags=0, d_contact=0):
+        """Search only bodies [first, first + count) (count < 0: whole world); records go to the given full-length device arrays."""
+        self._ck(self.L.np_world_set_shard(self.w, first, count, d_hit_j or None, d_flags or None, d_contact or None))
+
+    def step_begin(self, dt): self._ck(self.L.np_world_step_begin(self.w, float(np.float32(dt))))
+
+    def step_end(self): self._ck(self.L.np_world_step_end(self.w))
     def integrate(self, dt): self._ck(self.L.np_world_integrate(self.w, float(np.float32(dt))))
     def synchronize(self): self._ck(self.L.np_world_synchronize(self.w))
 

@@ -1,0 +1,99 @@
+"""GPU suite: ONE world whose pair search is sharded over R processes (np_world_set_shard / step_begin / step_end,
+SURVEY 8(e)-2).  R worlds on one GPU stand in for the R ranks and the host plays the all-gather; the NCCL version of the same
+exchange is netphys_b200.dist.ShardedWorld (exercised by bench.py under torchrun, and by tests/test_dist.py on gloo)."""
+import numpy as np
+import pytest
+
+from netphys_b200 import scenes
+from netphys_b200.dist import padded_shard
+from conftest import assert_biteq
+
+pytestmark = pytest.mark.gpu
+
+
+class _Rank:
+    def __init__(self, npb, sc, n_ranks, rank, mode):
+        self.w = w = npb.World(0)
+        w.set_option(w.OPT_BROADPHASE, mode); w.set_option(w.OPT_COUNTERS, 1)
+        w.load_scene(sc)
+        self.first, self.count, self.slot = padded_shard(w.n, rank, n_ranks)
+        self.total = self.slot * n_ranks
+        self.d = [w.dev_alloc(4 * self.total), w.dev_alloc(4 * self.total), w.dev_alloc(16 * self.total)]
+        w.set_shard(self.first, self.count, *self.d)
+
+    def my_records(self):
+        out = [np.zeros(self.slot, np.int32), np.zeros(self.slot, np.int32), np.zeros((self.slot, 4), np.float32)]
+        for a, p, width in zip(out, self.d, (4, 4, 16)):
+            self.w.dev_download(a, p + width * self.first if self.count else p)      # an empty tail rank contributes padding
+        return out
+
+    def receive(self, gathered):
+        for a, p in zip(gathered, self.d):
+            self.w.dev_upload(p, a)
+
+
+def _sharded_steps(npb, sc, n_ranks, mode, steps, check):
+    ranks = [_Rank(npb, sc, n_ranks, r, mode) for r in range(n_ranks)]
+    try:
+        for k in range(steps):
+            for r in ranks: r.w.step_begin(sc["dt"])
+            pieces = [r.my_records() for r in ranks]
+            gathered = [np.concatenate([p[c] for p in pieces]) for c in range(3)]
+            for r in ranks: r.receive(gathered)
+            for r in ranks: r.w.step_end()
+            check(k, ranks)
+        return [r.w.counters() for r in ranks]
+    finally:
+        for r in ranks: r.w.close()
+
+
+@pytest.mark.parametrize("n,n_ranks", [(700, 2), (1001, 3), (5, 8)])
+def test_sharded_exact_world_equals_reference_on_every_rank(npb, oracle, n, n_ranks):
+    sc = scenes.lattice_scene(n, spacing=1.1, seed=n, mix=(0.5, 0.3, 0.2))
+    ow = oracle.world(scenes.resolve(sc, oracle))
+
+    def check(k, ranks):
+        ao, bo, do = ow.step(sc["dt"], True); so = ow.state()
+        for r in ranks:
+            a, b, d = r.w.collisions_as_arrays()
+            assert np.array_equal(a, ao) and np.array_equal(b, bo), "collision list, step %d" % k
+            assert_biteq(d, do, "collision data, step %d" % k); assert_biteq(r.w.states(), so, "replicated state, step %d" % k)
+
+    ctrs = _sharded_steps(npb, sc, n_ranks, 0, 8, check)
+    pt, hits, _ = ow.counters()
+    assert sum(c["pair_tests"] for c in ctrs) == pt and sum(c["hits"] for c in ctrs) == hits, "the ranks together ran the reference's DetectCollision calls, once each"
+    if n >= 100:
+        assert max(c["pair_tests"] for c in ctrs) < 0.75 * pt, "the search is not actually split"
+
+
+def test_sharded_grid_world_equals_unsharded(npb):
+    sc = scenes.lattice_scene(1500, spacing=0.9, seed=3, mix=(0.5, 0.2, 0.3))
+    with npb.World(0) as one:
+        one.set_option(one.OPT_BROADPHASE, one.GRID); one.load_scene(sc)
+
+        def check(k, ranks):
+            one.step(sc["dt"]); a1, b1, d1 = one.collisions_as_arrays(); s1 = one.states()
+            assert len(a1) > 50
+            for r in ranks:
+                a, b, d = r.w.collisions_as_arrays()
+                assert np.array_equal(a, a1) and np.array_equal(b, b1); assert_biteq(d, d1, "collision data"); assert_biteq(r.w.states(), s1, "state")
+
+        _sharded_steps(npb, sc, 3, one.GRID, 4, check)
+
+
+def test_shard_api_errors(npb):
+    sc = scenes.lattice_scene(64, spacing=1.2, seed=1)
+    with npb.World(0) as w:
+        w.load_scene(sc)
+        with pytest.raises(npb.NetphysError): w.step_end()                                   # no step in flight
+        d = [w.dev_alloc(4 * 64), w.dev_alloc(4 * 64), w.dev_alloc(16 * 64)]
+        with pytest.raises(npb.NetphysError): w.set_shard(0, 32, d[0], 0, d[2])             # missing array
+        w.dev_upload(d[0], np.full(64, -1, np.int32)); w.dev_upload(d[1], np.zeros(64, np.int32)); w.dev_upload(d[2], np.zeros((64, 4), np.float32))
+        w.set_shard(0, 32, *d)
+        with pytest.raises(npb.NetphysError): w.step(sc["dt"])                               # a sharded world cannot run the monolithic step
+        w.step_begin(sc["dt"])
+        with pytest.raises(npb.NetphysError): w.step_begin(sc["dt"])
+        with pytest.raises(npb.NetphysError): w.set_shard(0, -1)
+        w.step_end()
+        w.set_shard(0, -1)                                                            # back to a whole-world search
+        w.step(sc["dt"]); w.synchronize()
