@@ -295,14 +295,14 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
 // ---------------------------------------------------------------------------------------------------
 struct BigArena { float* base; int slots; };
 
-template <int G, int FMAX, int TIER, int THREADS, bool WORLD>
+template <int G, int FMAX, int TIER, int THREADS, bool WORLD, bool CACHED = (WORLD && G >= 8)>
 __global__ void __launch_bounds__(THREADS, (THREADS == NP_NARROW_THREADS) ? 4 : 1)
 k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, const int* __restrict__ count, int* __restrict__ ticket,
       const int* __restrict__ hit_j, const float4* __restrict__ simplex, int* __restrict__ flags, float4* __restrict__ contact,
       int* __restrict__ next_list, int* __restrict__ next_count, BigArena ar, DevCounters* ctr)
 {
     extern __shared__ float4 s_dyn[];
-    constexpr bool CACHED = WORLD && (G >= 8);
+    // CACHED: read the per-step world-vertex cache (wide groups; large worlds skip the cache and transform on the fly, np_world.cu)
     const float4* verts = CACHED ? nullptr : stage_shapes(sh, s_dyn, smem_shapes != 0);
     constexpr int GPB = THREADS / G;                                // groups per block
     constexpr bool LOCAL = (G == 1 && TIER == 0);
@@ -521,7 +521,7 @@ struct GridView {
 // K1b: world-space vertex cache (+ AABB for the grid).  8 lanes per body; world*p per vertex exactly as the support
 // mapping evaluates it (physics_util.cpp:17), so K3/K4 can take dot products of the cached vertices directly.
 // HBM: reads 48 B transform + the shape's local vertices (L2 resident), writes 16 B per vertex (+ 32 B AABB).
-template <bool AABB>
+template <bool AABB, bool WRITE = true>
 __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, GridView gv)
 {
     constexpr int G = 8;
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, 
         for (int k = gl; k < n; k += G) {
             float4 q = v[k];
             V3 wp = xf_point(R, t, mk(q.x, q.y, q.z));
-            out[k] = make_float4(wp.x, wp.y, wp.z, 0.0f);
+            if (WRITE) out[k] = make_float4(wp.x, wp.y, wp.z, 0.0f);
             if (AABB) {
                 lo[0] = fminf(lo[0], wp.x); lo[1] = fminf(lo[1], wp.y); lo[2] = fminf(lo[2], wp.z);
                 hi[0] = fmaxf(hi[0], wp.x); hi[1] = fmaxf(hi[1], wp.y); hi[2] = fmaxf(hi[2], wp.z);

@@ -269,23 +269,24 @@ static int launch_gjk(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevC
     w->launches++;
     return NP_OK;
 }
-template <int G, bool WORLD>
+// TC: the overflow tiers (one warp per pair) read the world-vertex cache -- world mode, when this step built it (wants_cache)
+template <int G, bool WORLD, bool TC>
 static int launch_epa(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevCounters* ctr)
 {
     const int sm_shapes = shapes_in_smem(w) ? 1 : 0;
-    const size_t sh_bytes = WORLD ? 0 : shapes_smem(w);      // the overflow tiers (G = 32) always read the cache in world mode
+    const size_t sh_bytes = TC ? 0 : shapes_smem(w);
     size_t smem = ((WORLD && G >= 8) ? 0 : shapes_smem(w)) + epa_poly_smem<G>();
     auto kern = k_epa<G, epa_fmax<G>(), 0, NP_NARROW_THREADS, WORLD>;
     int blocks = persistent_blocks(w, kern, smem, in.n, G);
     kern<<<blocks, NP_NARROW_THREADS, smem, w->stream>>>(in, sview(w), sm_shapes, b.hit_list, b.zero + Z_HIT_COUNT, b.zero + Z_EPA_TICKET, b.hit_j, b.simplex,
                                                         b.flags, b.contact, b.big_list, b.zero + Z_MID_COUNT, w->arena, ctr);
     // overflow tiers (one warp per pair); both exit at once when their list is empty.  hit_list is free again by now.
-    auto mid = k_epa<32, NP_FMID, 1, NP_MID_THREADS, WORLD>;
+    auto mid = k_epa<32, NP_FMID, 1, NP_MID_THREADS, WORLD, TC>;
     size_t msmem = sh_bytes + sizeof(float) * (size_t)poly_words_fast(NP_FMID) * (NP_MID_THREADS / 32);
     int mblocks = (int)std::min<long long>(w->sm_count * 2, std::max<long long>(1, ((long long)in.n * 32 + NP_MID_THREADS - 1) / NP_MID_THREADS));
     mid<<<mblocks, NP_MID_THREADS, msmem, w->stream>>>(in, sview(w), sm_shapes, b.big_list, b.zero + Z_MID_COUNT, b.zero + Z_MID_TICKET, b.hit_j, b.simplex,
                                                        b.flags, b.contact, b.hit_list, b.zero + Z_BIG_COUNT, w->arena, ctr);
-    auto big = k_epa<32, 64, 2, NP_MID_THREADS, WORLD>;
+    auto big = k_epa<32, 64, 2, NP_MID_THREADS, WORLD, TC>;
     int bblocks = std::min(w->arena.slots / (NP_MID_THREADS / 32), mblocks);
     big<<<bblocks, NP_MID_THREADS, sh_bytes, w->stream>>>(in, sview(w), sm_shapes, b.hit_list, b.zero + Z_BIG_COUNT, b.zero + Z_BIG_TICKET, b.hit_j, b.simplex,
                                                           b.flags, b.contact, nullptr, nullptr, w->arena, ctr);
@@ -300,7 +301,8 @@ static void setup_kernels_t()
     cudaFuncSetAttribute(k_epa<4, epa_fmax<4>(), 0, NP_NARROW_THREADS, WORLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_epa<8, epa_fmax<8>(), 0, NP_NARROW_THREADS, WORLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_epa<32, epa_fmax<32>(), 0, NP_NARROW_THREADS, WORLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(k_epa<32, NP_FMID, 1, NP_MID_THREADS, WORLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_epa<32, NP_FMID, 1, NP_MID_THREADS, WORLD, WORLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_epa<32, NP_FMID, 1, NP_MID_THREADS, WORLD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 static void setup_kernels() { setup_kernels_t<true>(); setup_kernels_t<false>(); }
 // supported group widths: GJK {1, 8, 32}, EPA {1, 4, 8, 32} (other requests round to the nearest supported one)
@@ -313,11 +315,17 @@ static int launch_narrow_t(np_world* w, const NarrowIn& in, const NarrowBufs& b,
     else if (gg <= 8) r = launch_gjk<8, WORLD>(w, in, b, ctr);
     else r = launch_gjk<32, WORLD>(w, in, b, ctr);
     if (r) return r;
-    if (ge <= 1) r = launch_epa<1, WORLD>(w, in, b, ctr);
-    else if (ge <= 4) r = launch_epa<4, WORLD>(w, in, b, ctr);
-    else if (ge <= 8) r = launch_epa<8, WORLD>(w, in, b, ctr);
-    else r = launch_epa<32, WORLD>(w, in, b, ctr);
+    // narrow main kernels (G < 8) transform on the fly; when GJK is narrow too nothing needs the cache and the step does not build it
+    if (ge <= 1) r = (WORLD && gg >= 8) ? launch_epa<1, WORLD, WORLD>(w, in, b, ctr) : launch_epa<1, WORLD, false>(w, in, b, ctr);
+    else if (ge <= 4) r = (WORLD && gg >= 8) ? launch_epa<4, WORLD, WORLD>(w, in, b, ctr) : launch_epa<4, WORLD, false>(w, in, b, ctr);
+    else if (ge <= 8) r = launch_epa<8, WORLD, WORLD>(w, in, b, ctr);
+    else r = launch_epa<32, WORLD, WORLD>(w, in, b, ctr);
     return r;
+}
+// does a world-mode search over `items` bodies read the world-vertex cache?  (same decision as launch_narrow_t)
+static bool wants_cache(np_world* w, long long items)
+{
+    return items > 0 && (pick_group(w, items, w->g_gjk_env, false) >= 8 || pick_group(w, items, w->g_epa_env, true) >= 8);
 }
 static int launch_narrow(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevCounters* ctr)
 {
@@ -355,13 +363,14 @@ static int ensure_grid(np_world* w)
     return NP_OK;
 }
 // K2, enqueued between integrate and the narrow phase
-static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, DevCounters* ctr)
+static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, bool cache, DevCounters* ctr)
 {
     GridView& g = w->grid; g.h_option = w->grid_cell;
     const int n = s.n, b256 = (n + 255) / 256;
     k_grid_init<<<1, 32, 0, w->stream>>>(g);
     CU(cudaMemsetAsync(g.bucket_cnt, 0, sizeof(int) * 2 * (size_t)g.nbuckets, w->stream));
-    k_world_verts<true><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), g);
+    if (cache) k_world_verts<true, true><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), g);
+    else k_world_verts<true, false><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), g);
     k_grid_params<<<1, 1, 0, w->stream>>>(n, g);
     k_grid_count<<<b256, 256, 0, w->stream>>>(s, g);
     enqueue_scan(w, g.nbuckets, g.bucket_cnt, g.bucket_off);
@@ -393,8 +402,9 @@ static int enqueue_search(np_world* w, float dt, bool timed)
     k_integrate<<<b256, 256, 0, w->stream>>>(s, dt, 1);
     w->launches += 1;
     if (timed) CU(cudaEventRecord(w->ev[1], w->stream));
-    if (w->broadphase == NP_BROADPHASE_GRID) { int r = enqueue_grid(w, s, first, count, ctr); if (r) return r; }
-    else { k_world_verts<false><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), w->grid); w->launches += 1; }
+    const bool cache = wants_cache(w, count);
+    if (w->broadphase == NP_BROADPHASE_GRID) { int r = enqueue_grid(w, s, first, count, cache, ctr); if (r) return r; }
+    else if (cache) { k_world_verts<false><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), w->grid); w->launches += 1; }
     if (timed) CU(cudaEventRecord(w->ev[2], w->stream));
     CU(cudaMemsetAsync(w->d_zero, 0, sizeof(int) * (32 + 2 * (size_t)w->cap), w->stream));
     if (count > 0) {
