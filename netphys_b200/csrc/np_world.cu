@@ -275,10 +275,18 @@ static int launch_epa(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevC
 {
     const int sm_shapes = shapes_in_smem(w) ? 1 : 0;
     const size_t sh_bytes = TC ? 0 : shapes_smem(w);
-    size_t smem = ((WORLD && G >= 8) ? 0 : shapes_smem(w)) + epa_poly_smem<G>();
     auto kern = k_epa<G, epa_fmax<G>(), 0, NP_NARROW_THREADS, WORLD>;
+    size_t smem = ((WORLD && G >= 8) ? 0 : shapes_smem(w)) + epa_poly_smem<G>();
+    int stage = sm_shapes;
+    if (smem > epa_poly_smem<G>() && !getenv("NP_EPA_STAGE")) {          // the shape table is staged next to the polytopes only while it costs no resident block
+        int with = 0, without = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with, kern, NP_NARROW_THREADS, smem) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&without, kern, NP_NARROW_THREADS, epa_poly_smem<G>()) == cudaSuccess && without > with) {
+            stage = 0; smem = epa_poly_smem<G>();
+        } else cudaGetLastError();
+    }
     int blocks = persistent_blocks(w, kern, smem, in.n, G);
-    kern<<<blocks, NP_NARROW_THREADS, smem, w->stream>>>(in, sview(w), sm_shapes, b.hit_list, b.zero + Z_HIT_COUNT, b.zero + Z_EPA_TICKET, b.hit_j, b.simplex,
+    kern<<<blocks, NP_NARROW_THREADS, smem, w->stream>>>(in, sview(w), stage, b.hit_list, b.zero + Z_HIT_COUNT, b.zero + Z_EPA_TICKET, b.hit_j, b.simplex,
                                                         b.flags, b.contact, b.big_list, b.zero + Z_MID_COUNT, w->arena, ctr);
     // overflow tiers (one warp per pair); both exit at once when their list is empty.  hit_list is free again by now.
     auto mid = k_epa<32, NP_FMID, 1, NP_MID_THREADS, WORLD, TC>;
