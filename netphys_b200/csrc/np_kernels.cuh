@@ -203,6 +203,15 @@ struct NarrowIn {
 //  For every hit the final simplex (A[4], B[4]) is written to simplex[item*6 .. +6) and the item is appended to hit_list.
 //  Persistent grid, warp-aggregated ticket counter, groups re-armed as soon as their item is resolved.
 // ---------------------------------------------------------------------------------------------------
+#ifdef NP_TIMELINE
+__device__ unsigned long long g_tl[8 * 65536];     // per body (debug builds): see tools/dbg_timeline.py
+NP_D unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define NP_TL(i, k) do { if ((i) < 65536) g_tl[8 * (i) + (k)] = gtime(); } while (0)
+#define NP_TLV(i, k, v) do { if ((i) < 65536) g_tl[8 * (i) + (k)] = (unsigned long long)(v); } while (0)
+#else
+#define NP_TL(i, k) do { } while (0)
+#define NP_TLV(i, k, v) do { } while (0)
+#endif
 #ifndef NP_GJK_MINB
 #define NP_GJK_MINB 3
 #endif
@@ -231,6 +240,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
         if (!have && !exhausted) {
             if (t < in.n) {
                 i = WORLD ? t + in.first : t;
+                if (WORLD && lead) { NP_TL(i, 0); NP_TLV(i, 2, 0); NP_TLV(i, 3, 0); }
                 if (WORLD) {
                     if (in.cand) { cbase = in.cand_off[i]; c = 0; jend = in.cand_cnt[i]; j = jend > 0 ? in.cand[cbase] : 0; if (jend > 0) jend = 0x7fffffff; cn = in.cand_cnt[i]; }
                     else { j = i + 1; jend = island_end[i]; }
@@ -257,11 +267,15 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
         if (!__any_sync(0xffffffffu, have)) { if (__all_sync(0xffffffffu, exhausted)) break; else continue; }
         if (have) {
             m.trip(g, st);
+#ifdef NP_TIMELINE
+            if (WORLD && lead && i < 65536) g_tl[8 * i + 2]++;
+#endif
             if (m.status != GjkMachine<G, CACHED>::RUN) {
                 n_tests++;
                 if (m.status == GjkMachine<G, CACHED>::HIT) {
                     n_hits++;
                     if (lead) {
+                        if (WORLD) { NP_TL(i, 1); NP_TLV(i, 7, (g.na << 16) | g.nb); }
                         if (WORLD) hit_j[i] = j;
                         flags[i] = NP_PAIR_HIT | (m.seed_alive ? NP_PAIR_SEED_ALIVE : 0);
                         float4* o = simplex + (size_t)i * 6;
@@ -277,6 +291,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
                     m.begin();
                 } else {
                     if (lead) { if (WORLD) hit_j[i] = -1; flags[i] = 0; if (!WORLD) contact[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+                    if (WORLD && lead) NP_TL(i, 1);
                     have = false;
                 }
             }
@@ -349,17 +364,19 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
                 V3 A4[4] = { mk(q0.x, q0.y, q0.z), mk(q0.w, q1.x, q1.y), mk(q1.z, q1.w, q2.x), mk(q2.y, q2.z, q2.w) };
                 V3 B4[4] = { mk(q3.x, q3.y, q3.z), mk(q3.w, q4.x, q4.y), mk(q4.z, q4.w, q5.x), mk(q5.y, q5.z, q5.w) };
                 int seed = (flags[item] & NP_PAIR_SEED_ALIVE) ? 1 : 0;
-                if (LOCAL) ml.begin(poly_local, A4, B4, seed); else mp.begin(poly_ptr, A4, B4, seed);
+                if constexpr (LOCAL) ml.begin(poly_local, A4, B4, seed); else mp.begin(poly_ptr, A4, B4, seed);
                 st0 = st;
                 have = true;
+                if (WORLD && lead) NP_TL(item, 4);
             } else exhausted = true;
         }
         if (!__any_sync(0xffffffffu, have)) { if (__all_sync(0xffffffffu, exhausted)) break; else continue; }
         if (have) {
             bool done; int fl; V3 pen; float depth;
-            if (LOCAL) { ml.trip(g, poly_local, st); done = ml.done; fl = ml.flags; pen = ml.pen; depth = ml.depth; }
+            if constexpr (LOCAL) { ml.trip(g, poly_local, st); done = ml.done; fl = ml.flags; pen = ml.pen; depth = ml.depth; }
             else { mp.trip(g, poly_ptr, st); done = mp.done; fl = mp.flags; pen = mp.pen; depth = mp.depth; }
             if (done) {
+                if (WORLD && lead) { NP_TL(item, 5); NP_TLV(item, 6, LOCAL ? ml.steps : mp.steps); }
                 const bool requeue = (fl & NP_PAIR_OVERFLOW) && TIER < 2;
                 if (lead) {
                     if (requeue) next_list[atomicAdd(next_count, 1)] = item;                       // flags/simplex stay for the re-run

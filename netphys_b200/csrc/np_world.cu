@@ -269,12 +269,29 @@ static int launch_gjk(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevC
     w->launches++;
     return NP_OK;
 }
-// TC: the overflow tiers (one warp per pair) read the world-vertex cache -- world mode, when this step built it (wants_cache)
+// EPA overflow tiers (one warp per pair) over big_list; both exit at once when their list is empty.  hit_list is free again by then.
+// TC: they read the world-vertex cache -- world mode, when this step built it (wants_cache)
+template <bool WORLD, bool TC>
+static int launch_epa_tiers(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevCounters* ctr)
+{
+    const int sm_shapes = shapes_in_smem(w) ? 1 : 0;
+    const size_t sh_bytes = TC ? 0 : shapes_smem(w);
+    auto mid = k_epa<32, NP_FMID, 1, NP_MID_THREADS, WORLD, TC>;
+    size_t msmem = sh_bytes + sizeof(float) * (size_t)poly_words_fast(NP_FMID) * (NP_MID_THREADS / 32);
+    int mblocks = (int)std::min<long long>(w->sm_count * 2, std::max<long long>(1, ((long long)in.n * 32 + NP_MID_THREADS - 1) / NP_MID_THREADS));
+    mid<<<mblocks, NP_MID_THREADS, msmem, w->stream>>>(in, sview(w), sm_shapes, b.big_list, b.zero + Z_MID_COUNT, b.zero + Z_MID_TICKET, b.hit_j, b.simplex,
+                                                       b.flags, b.contact, b.hit_list, b.zero + Z_BIG_COUNT, w->arena, ctr);
+    auto big = k_epa<32, 64, 2, NP_MID_THREADS, WORLD, TC>;
+    int bblocks = std::min(w->arena.slots / (NP_MID_THREADS / 32), mblocks);
+    big<<<bblocks, NP_MID_THREADS, sh_bytes, w->stream>>>(in, sview(w), sm_shapes, b.hit_list, b.zero + Z_BIG_COUNT, b.zero + Z_BIG_TICKET, b.hit_j, b.simplex,
+                                                          b.flags, b.contact, nullptr, nullptr, w->arena, ctr);
+    w->launches += 2;
+    return NP_OK;
+}
 template <int G, bool WORLD, bool TC>
 static int launch_epa(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevCounters* ctr)
 {
     const int sm_shapes = shapes_in_smem(w) ? 1 : 0;
-    const size_t sh_bytes = TC ? 0 : shapes_smem(w);
     auto kern = k_epa<G, epa_fmax<G>(), 0, NP_NARROW_THREADS, WORLD>;
     size_t smem = ((WORLD && G >= 8) ? 0 : shapes_smem(w)) + epa_poly_smem<G>();
     int stage = sm_shapes;
@@ -288,18 +305,8 @@ static int launch_epa(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevC
     int blocks = persistent_blocks(w, kern, smem, in.n, G);
     kern<<<blocks, NP_NARROW_THREADS, smem, w->stream>>>(in, sview(w), stage, b.hit_list, b.zero + Z_HIT_COUNT, b.zero + Z_EPA_TICKET, b.hit_j, b.simplex,
                                                         b.flags, b.contact, b.big_list, b.zero + Z_MID_COUNT, w->arena, ctr);
-    // overflow tiers (one warp per pair); both exit at once when their list is empty.  hit_list is free again by now.
-    auto mid = k_epa<32, NP_FMID, 1, NP_MID_THREADS, WORLD, TC>;
-    size_t msmem = sh_bytes + sizeof(float) * (size_t)poly_words_fast(NP_FMID) * (NP_MID_THREADS / 32);
-    int mblocks = (int)std::min<long long>(w->sm_count * 2, std::max<long long>(1, ((long long)in.n * 32 + NP_MID_THREADS - 1) / NP_MID_THREADS));
-    mid<<<mblocks, NP_MID_THREADS, msmem, w->stream>>>(in, sview(w), sm_shapes, b.big_list, b.zero + Z_MID_COUNT, b.zero + Z_MID_TICKET, b.hit_j, b.simplex,
-                                                       b.flags, b.contact, b.hit_list, b.zero + Z_BIG_COUNT, w->arena, ctr);
-    auto big = k_epa<32, 64, 2, NP_MID_THREADS, WORLD, TC>;
-    int bblocks = std::min(w->arena.slots / (NP_MID_THREADS / 32), mblocks);
-    big<<<bblocks, NP_MID_THREADS, sh_bytes, w->stream>>>(in, sview(w), sm_shapes, b.hit_list, b.zero + Z_BIG_COUNT, b.zero + Z_BIG_TICKET, b.hit_j, b.simplex,
-                                                          b.flags, b.contact, nullptr, nullptr, w->arena, ctr);
-    w->launches += 3;
-    return NP_OK;
+    w->launches += 1;
+    return launch_epa_tiers<WORLD, TC>(w, in, b, ctr);
 }
 template <bool WORLD>
 static void setup_kernels_t()
@@ -1064,6 +1071,14 @@ int np_selftest_fp32_peak(np_world* w, float* tflops)
     *tflops = best;
     return NP_OK;
 }
+#ifdef NP_TIMELINE
+int np_debug_dump(np_world* w, unsigned long long* out, int n)
+{
+    CU(cudaSetDevice(w->device)); CU(cudaStreamSynchronize(w->stream));
+    CU(cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 8 * (size_t)std::min(n, 65536)));
+    return NP_OK;
+}
+#endif
 int np_selftest_closest(np_world* w, int kind, const float* pts, int32_t* region, float uvw[3])
 {
     if (!w || kind < 2 || kind > 4 || !pts || !region || !uvw) return fail(NP_ERR_INVALID, "bad arguments");

@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of tuning builds: world 10k (C2), world 1M (C3 mix), pairs box / mix
+# A/B of tuning builds: world 10k (C2), world 1M (C3 mix), pairs box / mix; then overflow counters
 for lib in "$@"; do
   echo "== $lib"
   export NETPHYS_B200_LIB=$PWD/netphys_b200/$lib
@@ -7,4 +7,5 @@ for lib in "$@"; do
   python tools/prof_world.py 1000000 4 c3 | tail -1
   python tools/prof_pairs.py box 1000000 3 | tail -1
   python tools/prof_pairs.py mix 1000000 3 | tail -1
+  NP_COUNT=1 python tools/prof_pairs.py mix 1000000 1 | tail -1 | grep -o "'hits': [0-9]*\|'epa_overflow': [0-9]*" | paste - -
 done
