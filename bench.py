@@ -325,6 +325,12 @@ def run_ours(args, rank, local_rank, world_size):
                 tot = float(np.mean(ms4[:, 5]))
                 extra["worlds_4096x256"] = {"workload": "BASELINE configs[3] on one GPU: 4096 independent 256-body worlds (islands) in one store, box/icosphere",
                                             "value": 4096 * 256 / (tot * 1e-3), "unit": "body-steps/s", "ms_per_step": tot}
+            with W(local_rank, variant="fma") as w5:             # the same C2 world on the FMA-contracted build (poses within 1e-5 relative)
+                w5.load_scene(scene)
+                for _ in range(3): w5.step(dt)
+                ms5 = np.array([(w5.flush_l2(), w5.step(dt), w5.last_step_ms())[2] for _ in range(10)])
+                extra["c2_fma_build"] = {"workload": "the headline world on libnetphys_b200_fma.so (-fmad=true; not bit-exact: tests/test_gpu_fma.py holds it to 1e-5 relative on poses)",
+                                         "value": BODIES / (float(np.mean(ms5[:, 5])) * 1e-3), "unit": "body-steps/s", "ms_per_step": float(np.mean(ms5[:, 5]))}
         except Exception as e:                                   # never lose the headline line to an auxiliary leg
             extra["error"] = repr(e)
     # ---- CPU baseline on this box's host cores (bounded sample) ---------------------------------------------------------

@@ -55,10 +55,6 @@ SNAPSHOT_DTYPE = np.dtype([("guid", "<u4"), ("pos", "<f4", 3), ("rot", "<f4", 4)
 assert SD_DTYPE.itemsize == C.sizeof(StaticPhysicsData) and COLLISION_DTYPE.itemsize == C.sizeof(Collision) and SNAPSHOT_DTYPE.itemsize == 36
 
 
-def library_path():
-    return os.environ.get("NETPHYS_B200_LIB", os.path.join(HERE, "libnetphys_b200.so"))   # override = tuning builds only
-
-
 def _declared_symbols():
     """Every function include/netphys_b200.h declares (the boundary the library must export)."""
     text = open(os.path.join(ROOT, "include", "netphys_b200.h")).read()
@@ -67,14 +63,21 @@ def _declared_symbols():
 
 
 DECLARED_SYMBOLS = _declared_symbols()
-_LIB = None
+_LIBS = {}
 
 
-def load_library():
-    global _LIB
-    if _LIB is not None:
-        return _LIB
-    path = library_path()
+def library_path(variant="exact"):
+    """exact: the parity build (-fmad=false, bit-identical to the reference).  fma: the same sources with FMA contraction
+    (-fmad=true), whose poses stay within 1e-5 relative of the reference (tests/test_gpu_fma.py)."""
+    if variant == "fma":
+        return os.path.join(HERE, "libnetphys_b200_fma.so")
+    return os.environ.get("NETPHYS_B200_LIB", os.path.join(HERE, "libnetphys_b200.so"))   # override = tuning builds only
+
+
+def load_library(variant="exact"):
+    path = library_path(variant)
+    if path in _LIBS:
+        return _LIBS[path]
     if not os.path.exists(path):
         raise NetphysError("%s is not built -- run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
                            "netphys_b200 has no CPU fallback." % path)
@@ -131,7 +134,7 @@ def load_library():
     L.np_selftest_fp32_peak.argtypes = [vp, f32p]
     L.np_selftest_sincos_hash.argtypes = [vp, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.np_selftest_closest.argtypes = [vp, C.c_int, f32p, i32p, f32p]
-    _LIB = L
+    _LIBS[path] = L
     return L
 
 
@@ -166,8 +169,8 @@ class World:
     EXACT, GRID = 0, 1
     OPT_BROADPHASE, OPT_GRID_CELL, OPT_COUNTERS, OPT_SNAPSHOT_EACH_STEP = 1, 2, 3, 4
 
-    def __init__(self, device=-1):
-        self.L = load_library()
+    def __init__(self, device=-1, variant="exact"):
+        self.L = load_library(variant)
         self.w = self.L.np_world_create(device)
         if not self.w:
             raise NetphysError("np_world_create failed: %s" % self.L.np_last_error().decode())

@@ -9,12 +9,13 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_library_exports_every_declared_symbol(npb):
-    L = npb.load_library()
+@pytest.mark.parametrize("variant", ["exact", "fma"])
+def test_library_exports_every_declared_symbol(npb, variant):
+    L = npb.load_library(variant)
     assert len(npb.DECLARED_SYMBOLS) >= 40
     missing = [s for s in npb.DECLARED_SYMBOLS if not hasattr(L, s)]
     assert not missing, missing
-    out = subprocess.run(["nm", "-D", "--defined-only", npb.library_path()], capture_output=True, text=True).stdout
+    out = subprocess.run(["nm", "-D", "--defined-only", npb.library_path(variant)], capture_output=True, text=True).stdout
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l and l.split()[-1].startswith("np_")}
     assert exported == set(npb.DECLARED_SYMBOLS), (exported ^ set(npb.DECLARED_SYMBOLS))
     assert L.np_abi_version() == 1
