@@ -149,6 +149,15 @@ int np_body_apply_impulse_response(np_world* w, int body, const np_collision_dat
 int np_world_get_states(np_world* w, np_body_state* out, int cap);                        /* all bodies, creation order */
 int np_world_set_states(np_world* w, const np_body_state* in, int n);
 
+/* ---- adapter extension: what an ODE-shaped World facade (netphys_common/world.h:8-28; include/netphys/world.h) needs beyond the
+ * engine's API.  NOT reference semantics -- engine/ has gravity only (physics.cpp:178-181) -- defined here and mirrored by the oracle:
+ * a force acts during the next step only, as L += F*dt right after the gravity term of Physics::Update (calls accumulate, F = sum);
+ * a disabled body is not integrated (it still collides) and reports isEnabled = 0 in the snapshot (world_s.cpp:48). */
+int np_body_add_force(np_world* w, int body, const float f[3]);                          /* dBodyAddForce, netphys_common/player.cpp:38 */
+int np_body_set_enabled(np_world* w, int body, int enabled);                             /* dBodyEnable / dBodyDisable */
+int np_body_is_enabled(np_world* w, int body);                                           /* dBodyIsEnabled, netphys_server/world_s.cpp:48 */
+int np_world_clear_bodies(np_world* w);                                                  /* World::Reset, netphys_common/world.cpp:129-141: drops every body, keeps the shapes */
+
 /* ---- the step: Physics_Update, engine/physics.h:99-100 / physics.cpp:148-163 ----------------------- */
 int np_world_step(np_world* w, float dt);
 int np_world_step_n(np_world* w, float dt, int steps);    /* `steps` consecutive Physics_Update(dt) calls, one submission */

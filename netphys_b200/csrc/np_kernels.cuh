@@ -27,6 +27,7 @@ struct StoreView {
     float* xf;         // [X_COUNT][cap]
     const int* ints;   // [I_COUNT][cap]
     float4* wverts;    // world-space vertices of every body, rewritten each step by k_world_verts
+    float* ext;        // adapter extension, null unless used: [4][cap] = one-step external force xyz (np_body_add_force), enabled flag
 };
 struct ShapeView {
     const float4* verts;   // all shapes' local vertices, concatenated
@@ -42,23 +43,35 @@ struct DevCounters {       // mirrors np_counters (all uint64)
 // K1: integrate + transform.  HBM-bound: per body 12 state floats + 14 constants read, 9 state floats +
 // 12 transform floats written.
 // ---------------------------------------------------------------------------------------------------
+// EXT (worlds that used np_body_add_force / np_body_set_enabled; not reference semantics): a disabled body is not integrated; a
+// pending external force adds L += F*dt right after the gravity term and is consumed.
+template <bool EXT>
 __global__ void __launch_bounds__(256) k_integrate(StoreView s, float dt, int write_xf)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.n) return;
     const int cap = s.cap;
     float* st = s.state; const float* c = s.cst;
+    const bool enabled = !EXT || s.ext[3 * (size_t)cap + i] != 0.0f;
     V3 pos = mk(st[S_PX * cap + i], st[S_PY * cap + i], st[S_PZ * cap + i]);
     V3 rot = mk(st[S_RX * cap + i], st[S_RY * cap + i], st[S_RZ * cap + i]);
     V3 L = mk(st[S_LX * cap + i], st[S_LY * cap + i], st[S_LZ * cap + i]);
     V3 H = mk(st[S_HX * cap + i], st[S_HY * cap + i], st[S_HZ * cap + i]);
     V3 g = mk(c[C_GX * cap + i], c[C_GY * cap + i], c[C_GZ * cap + i]);
     float mass = c[C_MASS * cap + i];
-    if (!is_none(g)) {                                                                            // physics.cpp:178-181
+    if (enabled && !is_none(g)) {                                                                 // physics.cpp:178-181
         L = add(L, mul(mul(g, mass), dt));
         st[S_LX * cap + i] = L.x; st[S_LY * cap + i] = L.y; st[S_LZ * cap + i] = L.z;
     }
-    if (!feq(mass, 0.0f)) {                                                                       // :184-193
+    if (EXT && enabled) {
+        V3 f = mk(s.ext[i], s.ext[(size_t)cap + i], s.ext[2 * (size_t)cap + i]);
+        if (f.x != 0.0f || f.y != 0.0f || f.z != 0.0f) {
+            L = add(L, mul(f, dt));
+            st[S_LX * cap + i] = L.x; st[S_LY * cap + i] = L.y; st[S_LZ * cap + i] = L.z;
+            s.ext[i] = 0.0f; s.ext[(size_t)cap + i] = 0.0f; s.ext[2 * (size_t)cap + i] = 0.0f;
+        }
+    }
+    if (enabled && !feq(mass, 0.0f)) {                                                            // :184-193
         float iinv[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) iinv[k] = c[(C_IINV0 + k) * cap + i];
@@ -862,6 +875,12 @@ __global__ void __launch_bounds__(256) k_resolve(StoreView s, const int* __restr
     st[S_HX * cap + k] = H.x; st[S_HY * cap + k] = H.y; st[S_HZ * cap + k] = H.z;
 }
 
+// np_body_add_force / np_body_set_enabled on one body
+__global__ void k_ext_one(float* ext, int cap, int i, int what, float x, float y, float z)
+{
+    if (what == 0) { ext[i] = ext[i] + x; ext[(size_t)cap + i] = ext[(size_t)cap + i] + y; ext[2 * (size_t)cap + i] = ext[2 * (size_t)cap + i] + z; }
+    else ext[3 * (size_t)cap + i] = x;
+}
 // stand-alone ApplyImpulseResponse / GetTransform on one body (API completeness; not on the step path)
 __global__ void k_impulse_one(StoreView s, int k, V3 r, float depth, V3 n)
 {
@@ -906,7 +925,7 @@ __global__ void __launch_bounds__(256) k_snapshot(StoreView s, uint32_t guid_bas
     o.rot[1] = sx * cy * cz - cx * sy * sz;
     o.rot[2] = cx * sy * cz + sx * cy * sz;
     o.rot[3] = cx * cy * sz - sx * sy * cz;
-    o.enabled = 1u;
+    o.enabled = (s.ext && s.ext[3 * (size_t)cap + i] == 0.0f) ? 0u : 1u;                          // dBodyIsEnabled, world_s.cpp:48
     out[i] = o;
 }
 

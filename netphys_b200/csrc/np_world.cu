@@ -25,7 +25,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
     } while (0)
 
 struct HostShape { std::vector<float> xyz; };
-struct HostBody { np_static_physics_data sd; int shape; int island; };
+struct HostBody { np_static_physics_data sd; int shape; int island; int enabled = 1; };
 struct CommandFrame { unsigned id; double time_ms; std::vector<np_snapshot_object> objects; };      // world_s.cpp:12-17
 
 struct np_world {
@@ -60,6 +60,7 @@ struct np_world {
     int *d_inc_off = nullptr, *d_inc = nullptr, *d_sums = nullptr, *d_big_list = nullptr, *d_hit_list = nullptr;
     float4* d_simplex = nullptr;      // GJK result of every hit: A[4], B[4]
     float4* d_wverts = nullptr; size_t wverts_cap = 0;   // per-step world-vertex cache (K1b)
+    float* d_ext = nullptr;           // adapter extension, allocated on first use: [4][cap] external force xyz + enabled flag
     // grid broad phase (allocated on first use)
     GridView grid = {}; int grid_cap = 0; int* d_grid_ints = nullptr; float* d_grid_f = nullptr;
     int max_verts = 0;                // largest shape
@@ -80,7 +81,7 @@ struct np_world {
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
-static StoreView view(np_world* w) { StoreView s; s.n = (int)w->bodies.size(); s.cap = w->cap; s.state = w->d_state; s.cst = w->d_cst; s.xf = w->d_xf; s.ints = w->d_ints; s.wverts = w->d_wverts; return s; }
+static StoreView view(np_world* w) { StoreView s; s.n = (int)w->bodies.size(); s.cap = w->cap; s.state = w->d_state; s.cst = w->d_cst; s.xf = w->d_xf; s.ints = w->d_ints; s.wverts = w->d_wverts; s.ext = w->d_ext; return s; }
 static ShapeView sview(np_world* w) { ShapeView s; s.verts = w->d_verts; s.off = w->d_soff; s.cnt = w->d_scnt; s.total_verts = w->total_verts; return s; }
 enum { Z_GJK_TICKET = 0, Z_HIT_COUNT, Z_EPA_TICKET, Z_MID_COUNT, Z_MID_TICKET, Z_BIG_COUNT, Z_BIG_TICKET };
 static int* hitj(np_world* w) { return w->x_hit_j ? w->x_hit_j : w->d_hit_j; }
@@ -148,6 +149,20 @@ static int upload_states(np_world* w, const np_body_state* in, int n)
 }
 
 static int ensure_grid(np_world* w);
+// adapter extension storage: forces start at zero, the enabled row comes from the host mirror
+static int ensure_ext(np_world* w, const std::vector<float>* keep_forces = nullptr, int keep_cap = 0)
+{
+    if (w->d_ext) return NP_OK;
+    drop_graph(w);
+    const size_t cap = (size_t)w->cap;
+    std::vector<float> h(4 * cap, 0.0f);
+    for (size_t i = 0; i < cap; i++) h[3 * cap + i] = (i < w->bodies.size() && !w->bodies[i].enabled) ? 0.0f : 1.0f;
+    if (keep_forces) for (int r = 0; r < 3; r++) for (int i = 0; i < keep_cap && (size_t)i < cap; i++) h[r * cap + i] = (*keep_forces)[(size_t)r * keep_cap + i];
+    CU(cudaMalloc((void**)&w->d_ext, sizeof(float) * 4 * cap));
+    CU(cudaMemcpyAsync(w->d_ext, h.data(), sizeof(float) * 4 * cap, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return NP_OK;
+}
 static int ensure_device(np_world* w)
 {
     CU(cudaSetDevice(w->device));
@@ -177,6 +192,13 @@ static int ensure_device(np_world* w)
     if (w->dev_state_valid && w->dev_n > 0) {   // bodies were added after stepping: keep what the device has
         int r = download_states(w, w->host_state.data(), w->dev_n); if (r) return r;
     }
+    std::vector<float> old_ext; int old_cap = 0;
+    if (n > w->cap && w->d_ext) {               // the store is about to be reallocated: carry pending forces over
+        old_cap = w->cap; old_ext.resize(4 * (size_t)old_cap);
+        CU(cudaMemcpyAsync(old_ext.data(), w->d_ext, sizeof(float) * 4 * (size_t)old_cap, cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+        cudaFree(w->d_ext); w->d_ext = nullptr;
+    }
     if (n > w->cap) {
         free_store(w);
         int cap = std::max(1024, (n + 1023) / 1024 * 1024);
@@ -193,6 +215,13 @@ static int ensure_device(np_world* w)
         CU(cudaMemsetAsync(w->d_state, 0, sizeof(float) * S_COUNT * c, w->stream));
         CU(cudaMemsetAsync(w->d_hit_j, 0xff, sizeof(int) * c, w->stream)); CU(cudaMemsetAsync(w->d_cflags, 0, sizeof(int) * c, w->stream));
         CU(cudaMemsetAsync(w->d_contact, 0, sizeof(float4) * c, w->stream));
+    }
+    if (old_cap) { int re = ensure_ext(w, &old_ext, old_cap); if (re) return re; }
+    else if (w->d_ext) {                        // bodies were added: their enabled flags
+        std::vector<float> en((size_t)w->cap, 1.0f);
+        for (int i = 0; i < n; i++) en[i] = w->bodies[i].enabled ? 1.0f : 0.0f;
+        CU(cudaMemcpyAsync(w->d_ext + 3 * (size_t)w->cap, en.data(), sizeof(float) * (size_t)w->cap, cudaMemcpyHostToDevice, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
     }
     const size_t cap = (size_t)w->cap;
     // constants + ints, SoA
@@ -414,7 +443,7 @@ static int enqueue_search(np_world* w, float dt, bool timed)
     const int b256 = (n + 255) / 256;
     const int first = sharded(w) ? w->shard_first : 0, count = sharded(w) ? w->shard_count : n;
     if (timed) CU(cudaEventRecord(w->ev[0], w->stream));
-    k_integrate<<<b256, 256, 0, w->stream>>>(s, dt, 1);
+    if (s.ext) k_integrate<true><<<b256, 256, 0, w->stream>>>(s, dt, 1); else k_integrate<false><<<b256, 256, 0, w->stream>>>(s, dt, 1);
     w->launches += 1;
     if (timed) CU(cudaEventRecord(w->ev[1], w->stream));
     const bool cache = wants_cache(w, count);
@@ -495,7 +524,7 @@ void np_world_destroy(np_world* w)
     if (!w) return;
     cudaSetDevice(w->device);
     if (w->stream) cudaStreamSynchronize(w->stream);
-    drop_graph(w); free_store(w);
+    drop_graph(w); free_store(w); cudaFree(w->d_ext);
     cudaFree(w->d_verts); cudaFree(w->d_soff); cudaFree(w->d_scnt); cudaFree(w->d_ctr); cudaFree(w->d_flush); cudaFree(w->d_grid_ints); cudaFree(w->d_grid_f);
     cudaFree(w->arena.base);
     if (w->h_stage) cudaFreeHost(w->h_stage);
@@ -650,6 +679,41 @@ int np_body_reset(np_world* w, int body)                                        
     memcpy(st.position, w->bodies[body].sd.initial_position, 12); memcpy(st.rotation, w->bodies[body].sd.initial_rotation, 12);
     return np_body_set_state(w, body, &st);
 }
+// ---- adapter extension for an ODE-shaped World facade (include/netphys/world.h).  Not reference semantics: the engine
+// has gravity only (physics.cpp:178-181).
+int np_body_add_force(np_world* w, int body, const float f[3])                            // dBodyAddForce, netphys_common/player.cpp:38
+{
+    int r = check_body(w, body); if (r) return r;
+    if (!f) return fail(NP_ERR_INVALID, "null force");
+    r = ensure_device(w); if (r) return r;
+    r = ensure_ext(w); if (r) return r;
+    k_ext_one<<<1, 1, 0, w->stream>>>(w->d_ext, w->cap, body, 0, f[0], f[1], f[2]);
+    CU(cudaGetLastError());
+    return NP_OK;
+}
+int np_body_set_enabled(np_world* w, int body, int enabled)                               // dBodyEnable / dBodyDisable
+{
+    int r = check_body(w, body); if (r) return r;
+    w->bodies[body].enabled = enabled ? 1 : 0;
+    r = ensure_device(w); if (r) return r;
+    r = ensure_ext(w); if (r) return r;
+    k_ext_one<<<1, 1, 0, w->stream>>>(w->d_ext, w->cap, body, 1, enabled ? 1.0f : 0.0f, 0.0f, 0.0f);
+    CU(cudaGetLastError());
+    return NP_OK;
+}
+int np_body_is_enabled(np_world* w, int body) { int r = check_body(w, body); if (r) return r; return w->bodies[body].enabled; }   // dBodyIsEnabled, world_s.cpp:48
+int np_world_clear_bodies(np_world* w)                                                    // World::Reset, netphys_common/world.cpp:129-141
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    if (w->mid_step) return fail(NP_ERR_INVALID, "np_world_clear_bodies between step_begin and step_end");
+    CU(cudaSetDevice(w->device)); CU(cudaStreamSynchronize(w->stream));
+    drop_graph(w);
+    w->bodies.clear(); w->host_state.clear(); w->island = 0;
+    w->dirty_bodies = true; w->dev_state_valid = false; w->dev_n = 0;
+    if (w->d_ext) { cudaFree(w->d_ext); w->d_ext = nullptr; }
+    w->shard_first = 0; w->shard_count = -1; w->x_hit_j = w->x_cflags = nullptr; w->x_contact = nullptr;
+    return NP_OK;
+}
 int np_world_get_states(np_world* w, np_body_state* out, int cap)
 {
     if (!w || !out) return fail(NP_ERR_INVALID, "bad arguments");
@@ -763,7 +827,7 @@ int np_world_integrate(np_world* w, float dt)
     if (!w) return fail(NP_ERR_INVALID, "null world");
     int r = ensure_device(w); if (r) return r;
     int n = (int)w->bodies.size(); if (n == 0) return NP_OK;
-    k_integrate<<<(n + 255) / 256, 256, 0, w->stream>>>(view(w), dt, 1);
+    if (w->d_ext) k_integrate<true><<<(n + 255) / 256, 256, 0, w->stream>>>(view(w), dt, 1); else k_integrate<false><<<(n + 255) / 256, 256, 0, w->stream>>>(view(w), dt, 1);
     CU(cudaGetLastError());
     return NP_OK;
 }

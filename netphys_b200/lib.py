@@ -107,6 +107,8 @@ def load_library(variant="exact"):
     L.np_world_set_states.argtypes = [vp, vp, C.c_int]
     L.np_world_step.argtypes = [vp, C.c_float]
     L.np_world_step_n.argtypes = [vp, C.c_float, C.c_int]
+    L.np_body_add_force.argtypes = [vp, C.c_int, vp]; L.np_body_set_enabled.argtypes = [vp, C.c_int, C.c_int]
+    L.np_body_is_enabled.argtypes = [vp, C.c_int]; L.np_world_clear_bodies.argtypes = [vp]
     L.np_world_set_shard.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.np_world_step_begin.argtypes = [vp, C.c_float]
     L.np_world_step_end.argtypes = [vp]
@@ -275,6 +277,15 @@ class World:
     def set_shard(self, first, count, d_hit_j=0, d_flags=0, d_contact=0):
         """Search only bodies [first, first + count) (count < 0: whole world); records go to the given full-length device arrays."""
         self._ck(self.L.np_world_set_shard(self.w, first, count, d_hit_j or None, d_flags or None, d_contact or None))
+
+    def add_force(self, body, f):
+        f = np.ascontiguousarray(f, np.float32); self._ck(self.L.np_body_add_force(self.w, body, f.ctypes.data))
+
+    def set_enabled(self, body, enabled): self._ck(self.L.np_body_set_enabled(self.w, body, int(bool(enabled))))
+
+    def is_enabled(self, body): return bool(self._ck(self.L.np_body_is_enabled(self.w, body)))
+
+    def clear_bodies(self): self._ck(self.L.np_world_clear_bodies(self.w))
 
     def step_begin(self, dt): self._ck(self.L.np_world_step_begin(self.w, float(np.float32(dt))))
 

@@ -65,6 +65,8 @@ class Oracle:
         L.npo_world_add_shape.argtypes = [C.c_void_p, f32p, C.c_int]
         L.npo_world_add_body.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int]
         L.npo_world_count.argtypes = [C.c_void_p]
+        L.npo_world_add_force.argtypes = [C.c_void_p, C.c_int, f32p]; L.npo_world_add_force.restype = None
+        L.npo_world_set_enabled.argtypes = [C.c_void_p, C.c_int, C.c_int]; L.npo_world_set_enabled.restype = None
         L.npo_world_get_state.argtypes = [C.c_void_p, f32p]
         L.npo_world_set_state.argtypes = [C.c_void_p, f32p]
         L.npo_world_step.argtypes = [C.c_void_p, C.c_float, i32p, i32p, f32p, C.c_int]
@@ -171,6 +173,12 @@ class OracleWorld:
         out = np.zeros((self.n, 12), np.float32)
         self.o.L.npo_world_get_state(self.w, _f(out))
         return out
+
+    def add_force(self, body, f):
+        self.o.L.npo_world_add_force(self.w, int(body), _f(f32(f)))
+
+    def set_enabled(self, body, enabled):
+        self.o.L.npo_world_set_enabled(self.w, int(body), int(bool(enabled)))
 
     def set_state(self, st):
         self.o.L.npo_world_set_state(self.w, _f(f32(st)))

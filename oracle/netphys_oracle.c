@@ -652,6 +652,8 @@ typedef struct {
     int response;
     int shape;
     v3 pos, rot, L, H;
+    /* adapter extension (no counterpart in engine/): a one-step external force and an enable flag, see npo_world_add_force */
+    v3 force; int disabled;
 } body;
 typedef struct { float* xyz; int n; } shape;
 struct npo_world {
@@ -688,6 +690,10 @@ int npo_world_add_body(npo_world* w, int shp, const float* sd, int response)    
     return w->nb++;
 }
 int npo_world_count(const npo_world* w) { return w->nb; }
+/* Adapter extension for the ODE-shaped World facade; the reference engine has gravity only.  The force acts during
+ * the next step only, as L += F*dt right after the gravity term of Physics::Update; a disabled body is not integrated. */
+void npo_world_add_force(npo_world* w, int i, const float* f) { if (i >= 0 && i < w->nb) w->b[i].force = v_add(w->b[i].force, v_ld(f)); }
+void npo_world_set_enabled(npo_world* w, int i, int enabled) { if (i >= 0 && i < w->nb) w->b[i].disabled = !enabled; }
 void npo_world_get_state(const npo_world* w, float* o)
 { for (int i = 0; i < w->nb; i++) { v_st(o + 12 * i, w->b[i].pos); v_st(o + 12 * i + 3, w->b[i].rot); v_st(o + 12 * i + 6, w->b[i].L); v_st(o + 12 * i + 9, w->b[i].H); } }
 void npo_world_set_state(npo_world* w, const float* in)
@@ -697,7 +703,12 @@ void npo_world_counters(const npo_world* w, long long* pt, long long* hits, npo_
 
 static void body_update(body* b, float dt)                                               /* physics.cpp:175-194 */
 {
+    if (b->disabled) return;                                                             /* extension: dBodyIsEnabled == 0 */
     if (!v_isnone(b->gravity)) b->L = v_add(b->L, v_mul(v_mul(b->gravity, b->mass), dt));
+    if (b->force.x != 0.0f || b->force.y != 0.0f || b->force.z != 0.0f) {                /* extension: dBodyAddForce, consumed by this step */
+        b->L = v_add(b->L, v_mul(b->force, dt));
+        b->force.x = b->force.y = b->force.z = 0.0f;
+    }
     if (!feq(b->mass, 0.0f, TOL_DEFAULT)) {
         v3 v = v_mul(b->L, 1.0f / b->mass);
         v3 w = m3_mul(&b->inv_inertia, b->H);

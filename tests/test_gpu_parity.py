@@ -420,3 +420,49 @@ def test_command_frames_and_wire_packet(world, oracle):
     assert np.frombuffer(pkt, np.uint8, offset=24 + 32, count=1)[0] == 1          # isEnabled: bool true + padding
     assert world.fill_packet(cap=24 + 36 * cnt - 1) == b""         # Packet::Serialize refuses a short buffer
     assert struct.unpack_from("<i", world.fill_packet(packet_id=2342341), 0)[0] == 2342341
+
+
+def test_adapter_extension_forces_enable_and_clear(world, oracle, npb):
+    """np_body_add_force / np_body_set_enabled / np_world_clear_bodies (the ODE-facade hooks; this project's extension, mirrored by
+    the oracle): accumulation order, one-step lifetime, pending forces surviving a store reallocation, graph replay, the snapshot flag."""
+    rng = np.random.default_rng(11)
+    sc = scenes.lattice_scene(900, spacing=1.2, seed=5, mix=(0.5, 0.3, 0.2))
+    ids = world.load_scene(sc); ow = oracle.world(scenes.resolve(sc, oracle))
+    n = 900
+    for k in range(12):
+        for body in rng.integers(0, n, 40):
+            f = rng.uniform(-50, 50, 3).astype(np.float32)
+            world.add_force(int(body), f); ow.add_force(int(body), f)
+        if k == 3:
+            for body in (5, 17, 400): world.set_enabled(body, False); ow.set_enabled(body, False)
+        if k == 7:
+            world.set_enabled(17, True); ow.set_enabled(17, True)
+        if k == 5:        # grow the store past its capacity with forces pending: 900 -> 2300 bodies
+            extra = scenes.lattice_scene(1400, spacing=1.2, seed=6)
+            ex = scenes.resolve(extra, oracle)
+            eids = np.array([world.create_sphere(s[1]) if s[0] == "sphere" else world.create_box(*s[1:]) for s in extra["shape_specs"]], np.int32)
+            world.create_bodies(eids[extra["body_shape"]], npb.lib.sd_rows_to_struct(extra["sd"], extra["response"]))
+            import ctypes as C
+            fp = lambda a: np.ascontiguousarray(a, np.float32).ctypes.data_as(C.POINTER(C.c_float))
+            sh0 = [ow.o.L.npo_world_add_shape(ow.w, fp(s), len(s)) for s in ex["shapes"]]
+            for i in range(1400):
+                ow.o.L.npo_world_add_body(ow.w, sh0[int(extra["body_shape"][i])], fp(extra["sd"][i]), int(extra["response"][i]))
+            ow.n = n = 2300
+        if k == 9: world.step_n(sc["dt"], 1)          # the captured graph consumes the pending forces too
+        else: world.step(sc["dt"])
+        ow.step(sc["dt"])
+        assert_biteq(world.states(), ow.state(), "state, step %d" % k)
+    snap = world.snapshot()
+    assert list(np.flatnonzero(snap["is_enabled"] == 0)) == [5, 400] and world.is_enabled(17) and not world.is_enabled(5)
+    world.step(sc["dt"]); ow.step(sc["dt"])          # no force added: nothing lingers
+    assert_biteq(world.states(), ow.state(), "state after the forces were consumed")
+    world.clear_bodies()
+    assert world.n == 0 and len(world.collisions()) == 0
+    world.step(sc["dt"])                              # an empty world steps
+    few = scenes.few_boxes_scene(); shapes = scenes.resolve(few, oracle)
+    fids = np.array([world.create_sphere(s[1]) if s[0] == "sphere" else world.create_box(*s[1:]) for s in few["shape_specs"]], np.int32)
+    world.create_bodies(fids[few["body_shape"]], npb.lib.sd_rows_to_struct(few["sd"], few["response"]))
+    ow2 = oracle.world(shapes)
+    for k in range(5):
+        world.step(few["dt"]); ow2.step(few["dt"])
+    assert_biteq(world.states(), ow2.state(), "a world rebuilt after np_world_clear_bodies")
