@@ -351,6 +351,18 @@ def run_ours(args, rank, local_rank, world_size):
                                            "value": 1e6 / (tot * 1e-3), "unit": "body-steps/s", "ms_per_step": tot,
                                            "k_integrate": {"bound": "hbm", "achieved": 1e6 * B_INTEGRATE / (integ * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                                            "frac": 1e6 * B_INTEGRATE / (integ * 1e-3) / 1e9 / hbm_peak, "ms": integ}}
+            with W(local_rank) as w6:                            # configs[2] as worded: the same 1M world behind the uniform-grid broad phase
+                w6.set_option(W.OPT_BROADPHASE, W.GRID); w6.set_option(W.OPT_COUNTERS, 1)
+                w6.load_scene(big)
+                for _ in range(3): w6.step(big["dt"])
+                g0 = w6.counters()
+                ms6 = np.array([(w6.flush_l2(), w6.step(big["dt"]), w6.last_step_ms())[2] for _ in range(5)])
+                g1 = w6.counters()
+                tot = float(np.mean(ms6[:, 5])); bp = float(np.mean(ms6[:, 1])); cands = (g1["candidates"] - g0["candidates"]) / 5
+                extra["world_1m_mixed_grid"] = {"workload": "BASELINE configs[2]: the same 1 000 000 bodies with NP_BROADPHASE_GRID (AABB culling changes the collision list: the reference has no broad phase, DESIGN.md section 7)",
+                                                "value": 1e6 / (tot * 1e-3), "unit": "body-steps/s", "ms_per_step": tot, "broadphase_ms": bp, "narrow_ms": float(np.mean(ms6[:, 2])),
+                                                "candidate_pairs_per_step": cands, "pair_tests_per_step": (g1["pair_tests"] - g0["pair_tests"]) / 5,
+                                                "candidate_pairs_per_sec_broadphase": cands / (bp * 1e-3)}
             wsc = scenes.lattice_scene(256, spacing=1.2, seed=1000)
             with W(local_rank) as w4:
                 ids = np.array([w4.create_box(1.0, 1.0, 1.0), w4.create_sphere(0.5)], np.int32)
