@@ -544,7 +544,8 @@ struct GridView {
     int* cand_off;        // [cap] start of body i's region in cand
     int* cand;            // [cand_cap]
     int* error;           // [1] set when cand_cap is exceeded
-    int nbuckets, cand_cap;
+    int* spill_cursor;    // [1] next free entry of the spill region of cand (reset to cap * NP_CAND_SLOTS every step)
+    int nbuckets, cand_cap, spill_base;
     float h_option;
 };
 
@@ -614,7 +615,7 @@ __global__ void k_grid_init(GridView gv)
     if (threadIdx.x < 5) gv.params[threadIdx.x] = 0.0f;
     else if (threadIdx.x < 8) ((int*)gv.params)[threadIdx.x] = 0x7fffffff;
     else if (threadIdx.x == 8) ((int*)gv.params)[8] = float_order(0.0f);
-    if (threadIdx.x == 9) { *gv.large_count = 0; }
+    if (threadIdx.x == 9) { *gv.large_count = 0; *gv.spill_cursor = gv.spill_base; }
 }
 __global__ void k_grid_params(int n, GridView gv)
 {
@@ -678,26 +679,18 @@ NP_D void cell_range(const GridView& gv, float4 lo, float4 hi, int* c0, int* c1)
         c0[c] = clamp_cell((ctr - r - gv.params[c]) / h); c1[c] = clamp_cell((ctr + r - gv.params[c]) / h);
     }
 }
-// FILL = false: count; FILL = true: write (same traversal), into the region the prefix sum of the counts assigns
-template <bool FILL>
-__global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, int first, int count, DevCounters* ctr)
+// One traversal per body: the first NP_CAND_SLOTS candidates go to the body's own slot block cand[i * NP_CAND_SLOTS ..]; a body with more
+// (a few percent; the ground slab) reserves room in the spill region behind the slot blocks and walks its cells a second time.
+// Each list is then sorted ascending: the first-hit search walks candidates in the reference's order.
+#define NP_CAND_SLOTS 16
+template <bool STORE>
+NP_D int cand_walk(const StoreView& s, const GridView& gv, int i, int jend, float4 lo, float4 hi, int* out, int room)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    i += first;
-    const int jend = s.ints[I_ISLAND_END * s.cap + i];
-    const float4 lo = gv.aabb[2 * i], hi = gv.aabb[2 * i + 1];
     const int ci = __float_as_int(lo.w);
-    int n = 0, room = 0;
-    int* out = nullptr;
-    if (FILL) {
-        int off = gv.cand_off[i]; room = gv.cand_cnt[i];
-        if ((long long)off + room > (long long)gv.cand_cap) { atomicExch(gv.error, 1); room = 0; }
-        out = gv.cand + off;
-    }
+    int n = 0;
     if (ci < 0) {                                        // large body: every later body of the island
         for (int j = i + 1; j < jend; j++)
-            if (aabb_overlap(lo, hi, gv.aabb[2 * j], gv.aabb[2 * j + 1])) { if (FILL && n < room) out[n] = j; n++; }
+            if (aabb_overlap(lo, hi, gv.aabb[2 * j], gv.aabb[2 * j + 1])) { if (STORE && n < room) out[n] = j; n++; }
     } else {
         int c0[3], c1[3];
         cell_range(gv, lo, hi, c0, c1);
@@ -711,24 +704,42 @@ __global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, int firs
                 if (j <= i || j >= jend) continue;
                 float4 jlo = gv.aabb[2 * j];
                 if (__float_as_int(jlo.w) != want) continue;                       // another cell hashed into this bucket
-                if (aabb_overlap(lo, hi, jlo, gv.aabb[2 * j + 1])) { if (FILL && n < room) out[n] = j; n++; }
+                if (aabb_overlap(lo, hi, jlo, gv.aabb[2 * j + 1])) { if (STORE && n < room) out[n] = j; n++; }
             }
         }
         const int nl = *gv.large_count;
         for (int q = 0; q < nl; q++) {
             int j = gv.large[q];
-            if (j > i && j < jend && aabb_overlap(lo, hi, gv.aabb[2 * j], gv.aabb[2 * j + 1])) { if (FILL && n < room) out[n] = j; n++; }
+            if (j > i && j < jend && aabb_overlap(lo, hi, gv.aabb[2 * j], gv.aabb[2 * j + 1])) { if (STORE && n < room) out[n] = j; n++; }
         }
     }
-    if (!FILL) { gv.cand_cnt[i] = n; return; }
-    int m = n < room ? n : room;
-    for (int a = 1; a < m; a++) {                        // ascending j: the first-hit search walks candidates in the reference's order
-        int key = out[a], b = a - 1;
-        while (b >= 0 && out[b] > key) { out[b + 1] = out[b]; b--; }
-        out[b + 1] = key;
+    return n;
+}
+__global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, int first, int count, DevCounters* ctr)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = 0;
+    if (i < count) {
+        i += first;
+        const int jend = s.ints[I_ISLAND_END * s.cap + i];
+        const float4 lo = gv.aabb[2 * i], hi = gv.aabb[2 * i + 1];
+        int* out = gv.cand + (size_t)i * NP_CAND_SLOTS;
+        int off = i * NP_CAND_SLOTS;
+        n = cand_walk<true>(s, gv, i, jend, lo, hi, out, NP_CAND_SLOTS);
+        if (n > NP_CAND_SLOTS) {
+            off = atomicAdd(gv.spill_cursor, n);
+            if ((long long)off + n > (long long)gv.cand_cap) { atomicExch(gv.error, 1); n = 0; }
+            else { out = gv.cand + off; cand_walk<true>(s, gv, i, jend, lo, hi, out, n); }
+        }
+        gv.cand_cnt[i] = n; gv.cand_off[i] = off;
+        for (int a = 1; a < n; a++) {                    // ascending j
+            int key = out[a], b = a - 1;
+            while (b >= 0 && out[b] > key) { out[b + 1] = out[b]; b--; }
+            out[b + 1] = key;
+        }
     }
     if (ctr) {
-        unsigned long long v = (unsigned long long)m;
+        unsigned long long v = (unsigned long long)n;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if ((threadIdx.x & 31) == 0 && v) atomicAdd(&ctr->candidates, v);

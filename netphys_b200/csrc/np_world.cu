@@ -399,9 +399,10 @@ static int ensure_grid(np_world* w)
     GridView& g = w->grid;
     int* p = w->d_grid_ints;
     g.bucket_cnt = p; p += nb; g.bucket_cur = p; p += nb; g.bucket_off = p; p += nb; g.items = p; p += c; g.large = p; p += c;
-    g.cand_cnt = p; p += c; g.cand_ub = p; p += c; g.cand_off = p; p += c; g.large_count = p; g.error = p + 1; p += 32; g.cand = p;
+    g.cand_cnt = p; p += c; g.cand_ub = p; p += c; g.cand_off = p; p += c; g.large_count = p; g.error = p + 1; g.spill_cursor = p + 2; p += 32; g.cand = p;
     g.aabb = (float4*)w->d_grid_f; g.params = w->d_grid_f + 8 * c;
-    g.nbuckets = nb; g.cand_cap = (int)std::min<size_t>(cand_cap, 0x7fffffff);
+    g.nbuckets = nb; g.cand_cap = (int)std::min<size_t>(cand_cap, 0x7fffffff); g.spill_base = (int)std::min<size_t>(c * NP_CAND_SLOTS, 0x7fffffff);
+    if (g.spill_base >= g.cand_cap) return fail(NP_ERR_CAPACITY, "world too large for the grid broad phase's candidate store");
     CU(cudaMemsetAsync(g.large_count, 0, sizeof(int) * 32, w->stream));
     w->grid_cap = w->cap;
     return NP_OK;
@@ -420,11 +421,10 @@ static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, b
     enqueue_scan(w, g.nbuckets, g.bucket_cnt, g.bucket_off);
     k_grid_fill<<<b256, 256, 0, w->stream>>>(s, g);
     if (count > 0) {                 // candidates of the bodies this process searches (the whole world unless sharded)
-        k_cand<false><<<(count + 127) / 128, 128, 0, w->stream>>>(s, g, first, count, nullptr);
-        enqueue_scan(w, count, g.cand_cnt + first, g.cand_off + first);
-        k_cand<true><<<(count + 127) / 128, 128, 0, w->stream>>>(s, g, first, count, ctr);
+        k_cand<<<(count + 127) / 128, 128, 0, w->stream>>>(s, g, first, count, ctr);
+        w->launches += 1;
     }
-    w->launches += 7;
+    w->launches += 5;
     CU(cudaGetLastError());
     return NP_OK;
 }
