@@ -525,8 +525,8 @@ __global__ void __launch_bounds__(256) k_pose_xf(int n, const float* __restrict_
 //   k_world_verts<true>  K1b also reduces each body's world AABB (float4 lo/hi) and block-reduces the extent statistics
 //   k_grid_params        cell edge h = option, or the mean AABB extent; bodies wider than 4h are 'large' (brute force list)
 //   k_grid_count / k_grid_fill   counting sort of the small bodies into hashed cells (by AABB centre); max small extent H
-//   k_cand<false/true>   per body: count, then write, its candidates from the cells whose centres can hold a partner (+ the large
-//                        list); regions assigned by an exclusive prefix sum of the counts (k_scan_*), each sorted ascending
+//   k_cand               per body: its candidates from the cells whose centres can hold a partner (+ the large list), one walk
+//                        into the body's slot block (a second one into the spill region when it has more), sorted ascending
 // A partner j of i has |c_j - c_i| <= (e_i + e_j)/2 <= (e_i + H)/2 per axis, so only cells intersecting
 // [lo_i - H/2, hi_i + H/2] are visited: the visited volume follows the bodies' real extents, not the cell size.
 // ---------------------------------------------------------------------------------------------------
@@ -540,7 +540,7 @@ struct GridView {
     int* large;           // [cap] large-body list
     int* large_count;     // [1]
     int* cand_cnt;        // [cap] actual candidates of body i
-    int* cand_ub;         // [cap] reserved entries of body i
+    int* cand_ub;         // [cap] (unused)
     int* cand_off;        // [cap] start of body i's region in cand
     int* cand;            // [cand_cap]
     int* error;           // [1] set when cand_cap is exceeded
