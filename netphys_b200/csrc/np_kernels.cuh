@@ -228,7 +228,7 @@ NP_D unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0
 #ifndef NP_GJK_MINB
 #define NP_GJK_MINB 3
 #endif
-template <int G, bool WORLD>
+template <int G, bool WORLD, bool COOP = false>
 __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn in, ShapeView sh, int smem_shapes, int* __restrict__ ticket, int* __restrict__ hit_j,
                                                           int* __restrict__ flags, float4* __restrict__ contact, float4* __restrict__ simplex,
                                                           int* __restrict__ hit_list, int* __restrict__ hit_count, DevCounters* ctr)
@@ -278,8 +278,13 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
             } else exhausted = true;
         }
         if (!__any_sync(0xffffffffu, have)) { if (__all_sync(0xffffffffu, exhausted)) break; else continue; }
+        if constexpr (COOP) {                            // G = 1, mixed shape sizes: large shapes' supports by the whole warp (support_coop)
+            static_assert(!COOP || G == 1, "cooperative supports are for the thread-per-pair kernel");
+            const V3 sa = support_coop<1>(have, g.va, g.na, g.Ra, g.ta, m.d);
+            const V3 sb = support_coop<1>(have, g.vb, g.nb, g.Rb, g.tb, neg(m.d));
+            if (have) m.trip_with(g, sa, sb, st);
+        } else if (have) m.trip(g, st);
         if (have) {
-            m.trip(g, st);
 #ifdef NP_TIMELINE
             if (WORLD && lead && i < 65536) g_tl[8 * i + 2]++;
 #endif

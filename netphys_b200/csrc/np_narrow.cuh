@@ -100,6 +100,56 @@ NP_D V3 support(const float4* __restrict__ v, int n, const float* R, V3 t, V3 d)
     return best;
 }
 
+// Thread-per-pair kernels: the lanes of a warp hold different pairs, and a per-lane vertex loop runs as long as the LARGEST shape in
+// the warp (a 162-vertex sphere next to 8-vertex boxes: 22 % of the lanes active, measured).  Lanes whose shape has at least
+// NP_COOP_MIN vertices are therefore served one after the other by the whole warp -- their arguments broadcast, the vertices strided
+// over 32 lanes, the same order-preserving arg-max as support<32> -- unless so many lanes are large that the plain loop is cheaper.
+// Small shapes keep the per-lane loop.  Must be called by all 32 lanes; `want` says whether this lane needs a result.
+#ifndef NP_COOP_MIN
+#define NP_COOP_MIN 48
+#endif
+// G lanes per pair: `want` is uniform inside a group and the result goes to all of its lanes.  With a plain loop the warp pays
+// n/G iterations whenever any group is large; served by the warp a large group costs n/32 iterations plus ~50 instructions of
+// broadcast and reduction, so the warp serves them only while at most 20/G groups are large.  (Used with G = 1: in the EPA kernel,
+// G = 4, the same change measured 2 % slower -- supports are not what its warps wait for.)
+template <int G>
+NP_D V3 support_coop(bool want, const float4* __restrict__ v, int n, const float* R, V3 t, V3 d)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = (int)(threadIdx.x & 31u);
+    V3 res = mk(0.0f, 0.0f, 0.0f);
+    bool served = false;
+    unsigned big = __ballot_sync(full, want && glane<G>() == 0 && n >= NP_COOP_MIN);
+    if (__popc(big) <= 20 / G) {
+        while (big) {
+            const int src = __ffs(big) - 1; big &= big - 1;
+            const float4* sv = (const float4*)__shfl_sync(full, (unsigned long long)v, src);
+            const int sn = __shfl_sync(full, n, src);
+            float sR[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) sR[k] = __shfl_sync(full, R[k], src);
+            const V3 st = mk(__shfl_sync(full, t.x, src), __shfl_sync(full, t.y, src), __shfl_sync(full, t.z, src));
+            const V3 sd = mk(__shfl_sync(full, d.x, src), __shfl_sync(full, d.y, src), __shfl_sync(full, d.z, src));
+            float bd = -INFINITY; int bi = 0x7fffffff; V3 best = mk(0.0f, 0.0f, 0.0f);
+#pragma unroll 2
+            for (int k = lane; k < sn; k += 32) {
+                float4 q = sv[k];
+                V3 wp = xf_point(sR, st, mk(q.x, q.y, q.z));
+                float dp = dot(sd, wp);
+                if (dp > bd) { bd = dp; bi = k; best = wp; }
+            }
+            const int key = float_order(bd + 0.0f);
+            const int kmax = __reduce_max_sync(full, key);
+            const unsigned imin = __reduce_min_sync(full, (key == kmax) ? (unsigned)bi : 0xffffffffu);
+            const int owner = (int)(imin & 31u);
+            best.x = __shfl_sync(full, best.x, owner); best.y = __shfl_sync(full, best.y, owner); best.z = __shfl_sync(full, best.z, owner);
+            if ((lane & ~(G - 1)) == src) { res = (imin >= 0x7fffffffu) ? mk(0.0f, 0.0f, 0.0f) : best; served = true; }
+        }
+    }
+    if (want && !served) res = support<G, false>(v, n, R, t, d);
+    return res;
+}
+
 NP_D V3 sel4(V3 a, V3 b, V3 c, V3 d, int k) { return k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d)); }
 
 // ---------------------------------------------------------------------------------------------------
@@ -200,6 +250,15 @@ struct GjkMachine {
         else if (kn == 2) { P2 = sp; A2 = sa; B2 = sb; }
         else { P3 = sp; A3 = sa; B3 = sb; }
         nv = kn + 1;
+    }
+
+    // a trip whose support pair was evaluated by the caller (support_coop); call while status == RUN
+    NP_D void trip_with(const PairGeom& g, V3 sa, V3 sb, PairStats& st)
+    {
+        st.support_pairs++; st.support_verts += (unsigned)(g.na + g.nb);
+        if (nv == 0) { A0 = sa; B0 = sb; P0 = sub(sb, sa); nv = 1; }                              // :704  p = B - A
+        else consume(sa, sb);
+        if (status == RUN) produce(st);
     }
 
     // call while status == RUN

@@ -65,6 +65,7 @@ struct np_world {
     GridView grid = {}; int grid_cap = 0; int* d_grid_ints = nullptr; float* d_grid_f = nullptr;
     int max_verts = 0;                // largest shape
     int g_gjk_env = 0, g_epa_env = 0; // NP_G_GJK / NP_G_EPA overrides (tuning)
+    bool coop = false; int coop_env = -1;   // large and small shapes mixed: warp-cooperative supports in the narrow kernels (NP_COOP=0/1 overrides)
     DevCounters* d_ctr = nullptr;
     SnapObj* d_snap = nullptr;
     BigArena arena = {};
@@ -235,6 +236,11 @@ static int ensure_device(np_world* w)
         for (int k = 0; k < 9; k++) cst[(C_IINV0 + k) * cap + i] = sd.inverse_inertia_tensor[k];
         ints[I_RESPONSE * cap + i] = sd.collision_response; ints[I_SHAPE * cap + i] = w->bodies[i].shape; ints[I_ISLAND_END * cap + i] = island_end[i];
     }
+    {   // large and small shapes side by side (and the large ones a minority): the thread-per-pair kernels serve large supports warp-wide
+        long long big = 0;
+        for (int i = 0; i < n; i++) big += (w->shapes[w->bodies[i].shape].xyz.size() / 3 >= NP_COOP_MIN) ? 1 : 0;
+        w->coop = w->coop_env >= 0 ? w->coop_env != 0 : (big > 0 && big * 100 <= (long long)n * 35);
+    }
     size_t wv_total = 0;
     for (int i = 0; i < n; i++) {
         if (wv_total > 0x7fffffffu) return fail(NP_ERR_CAPACITY, "world-vertex cache exceeds 2^31 vertices");
@@ -292,6 +298,7 @@ static int launch_gjk(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevC
 {
     size_t smem = (WORLD && G >= 8) ? 0 : shapes_smem(w);
     auto kern = k_gjk<G, WORLD>;
+    if constexpr (G == 1 && WORLD) { if (w->coop) kern = k_gjk<G, WORLD, true>; }
     int blocks = persistent_blocks(w, kern, smem, in.n, G);
     kern<<<blocks, NP_NARROW_THREADS, smem, w->stream>>>(in, sview(w), shapes_in_smem(w) ? 1 : 0, b.zero + Z_GJK_TICKET, b.hit_j, b.flags, b.contact, b.simplex,
                                                         b.hit_list, b.zero + Z_HIT_COUNT, ctr);
@@ -514,6 +521,7 @@ np_world* np_world_create(int device)
     { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { unsigned long long keep = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); } }   // scratch of pair-list queries stays cached
     setup_kernels();
     if (const char* e = getenv("NP_G_GJK")) w->g_gjk_env = atoi(e);
+    if (const char* e = getenv("NP_COOP")) w->coop_env = atoi(e);
     if (const char* e = getenv("NP_G_EPA")) w->g_epa_env = atoi(e);
     if (cudaMalloc((void**)&w->d_ctr, sizeof(DevCounters)) != cudaSuccess || ensure_arena(w) != NP_OK) { fail(NP_ERR_CUDA, "cannot allocate device scratch"); np_world_destroy(w); return nullptr; }
     cudaMemsetAsync(w->d_ctr, 0, sizeof(DevCounters), w->stream);

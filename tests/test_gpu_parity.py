@@ -466,3 +466,34 @@ def test_adapter_extension_forces_enable_and_clear(world, oracle, npb):
     for k in range(5):
         world.step(few["dt"]); ow2.step(few["dt"])
     assert_biteq(world.states(), ow2.state(), "a world rebuilt after np_world_clear_bodies")
+
+
+@pytest.mark.parametrize("g_gjk,g_epa,coop,grid", [(1, 4, 1, 0), (1, 4, 0, 0), (1, 1, 1, 1), (32, 8, 0, 0), (1, 4, 1, 1)])
+def test_world_step_every_kernel_configuration(npb, oracle, g_gjk, g_epa, coop, grid, monkeypatch):
+    """World mode with the kernels a LARGE world selects (thread-per-body GJK, 4-lane EPA, warp-cooperative supports for the large
+    shapes of a mixed population), forced onto a world small enough for the oracle: collision list, contact data, state and counters."""
+    monkeypatch.setenv("NP_G_GJK", str(g_gjk)); monkeypatch.setenv("NP_G_EPA", str(g_epa)); monkeypatch.setenv("NP_COOP", str(coop))
+    sc = scenes.lattice_scene(2500, spacing=1.1, seed=77, mix=(0.6, 0.25, 0.15))
+    with npb.World(0) as w:
+        w.set_option(w.OPT_COUNTERS, 1)
+        if grid: w.set_option(w.OPT_BROADPHASE, w.GRID)
+        w.load_scene(sc)
+        ow = oracle.world(scenes.resolve(sc, oracle))
+        monkeypatch.delenv("NP_G_GJK"); monkeypatch.delenv("NP_G_EPA"); monkeypatch.delenv("NP_COOP")   # (read at world creation)
+        if True:
+            for k in range(5):
+                w.step(sc["dt"])
+                a, b, d = w.collisions_as_arrays()
+                if not grid:
+                    ao, bo, do = ow.step(sc["dt"], True)
+                    assert np.array_equal(a, ao) and np.array_equal(b, bo), "collision list step %d" % k
+                    assert_biteq(d, do, "collision data step %d" % k); assert_biteq(w.states(), ow.state(), "state step %d" % k)
+            if grid:                                      # grid mode has no oracle list: the default kernels in grid mode are the reference
+                with npb.World(0) as ref:
+                    ref.set_option(ref.OPT_BROADPHASE, ref.GRID); ref.load_scene(sc)
+                    for k in range(5): ref.step(sc["dt"])
+                    a2, b2, d2 = ref.collisions_as_arrays()
+                    assert np.array_equal(a, a2) and np.array_equal(b, b2); assert_biteq(d, d2, "collision data"); assert_biteq(w.states(), ref.states(), "state")
+            else:
+                pt, hits, _ = ow.counters(); c = w.counters()
+                assert c["pair_tests"] == pt and c["hits"] == hits
