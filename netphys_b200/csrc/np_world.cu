@@ -149,6 +149,21 @@ static int upload_states(np_world* w, const np_body_state* in, int n)
     return NP_OK;
 }
 
+// device arrays of a store of `c` bodies (w->cap is already set); on failure the caller frees whatever was allocated
+static int alloc_store(np_world* w, size_t c)
+{
+    CU(cudaMalloc((void**)&w->d_state, sizeof(float) * S_COUNT * c)); CU(cudaMalloc((void**)&w->d_cst, sizeof(float) * C_COUNT * c));
+    CU(cudaMalloc((void**)&w->d_xf, sizeof(float) * X_COUNT * c)); CU(cudaMalloc((void**)&w->d_ints, sizeof(int) * I_COUNT * c));
+    CU(cudaMalloc((void**)&w->d_hit_j, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_cflags, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_contact, sizeof(float4) * c));
+    CU(cudaMalloc((void**)&w->d_zero, sizeof(int) * (32 + 2 * c))); CU(cudaMalloc((void**)&w->d_inc_off, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_inc, sizeof(int) * c));
+    CU(cudaMalloc((void**)&w->d_sums, sizeof(int) * (4 * c / NP_SCAN_BLOCK + 2))); CU(cudaMalloc((void**)&w->d_big_list, sizeof(int) * c));
+    CU(cudaMalloc((void**)&w->d_snap, sizeof(SnapObj) * c));
+    CU(cudaMalloc((void**)&w->d_hit_list, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_simplex, sizeof(float4) * 6 * c));
+    CU(cudaMemsetAsync(w->d_state, 0, sizeof(float) * S_COUNT * c, w->stream));
+    CU(cudaMemsetAsync(w->d_hit_j, 0xff, sizeof(int) * c, w->stream)); CU(cudaMemsetAsync(w->d_cflags, 0, sizeof(int) * c, w->stream));
+    CU(cudaMemsetAsync(w->d_contact, 0, sizeof(float4) * c, w->stream));
+    return NP_OK;
+}
 static int ensure_grid(np_world* w);
 // adapter extension storage: forces start at zero, the enabled row comes from the host mirror
 static int ensure_ext(np_world* w, const std::vector<float>* keep_forces = nullptr, int keep_cap = 0)
@@ -206,16 +221,8 @@ static int ensure_device(np_world* w)
         if (n > 4096) cap = std::max(cap, (int)std::min<long long>((long long)n * 5 / 4, 1LL << 30) / 1024 * 1024 + 1024);
         w->cap = cap;
         size_t c = (size_t)cap;
-        CU(cudaMalloc((void**)&w->d_state, sizeof(float) * S_COUNT * c)); CU(cudaMalloc((void**)&w->d_cst, sizeof(float) * C_COUNT * c));
-        CU(cudaMalloc((void**)&w->d_xf, sizeof(float) * X_COUNT * c)); CU(cudaMalloc((void**)&w->d_ints, sizeof(int) * I_COUNT * c));
-        CU(cudaMalloc((void**)&w->d_hit_j, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_cflags, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_contact, sizeof(float4) * c));
-        CU(cudaMalloc((void**)&w->d_zero, sizeof(int) * (32 + 2 * c))); CU(cudaMalloc((void**)&w->d_inc_off, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_inc, sizeof(int) * c));
-        CU(cudaMalloc((void**)&w->d_sums, sizeof(int) * (4 * c / NP_SCAN_BLOCK + 2))); CU(cudaMalloc((void**)&w->d_big_list, sizeof(int) * c));
-        CU(cudaMalloc((void**)&w->d_snap, sizeof(SnapObj) * c));
-        CU(cudaMalloc((void**)&w->d_hit_list, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_simplex, sizeof(float4) * 6 * c));
-        CU(cudaMemsetAsync(w->d_state, 0, sizeof(float) * S_COUNT * c, w->stream));
-        CU(cudaMemsetAsync(w->d_hit_j, 0xff, sizeof(int) * c, w->stream)); CU(cudaMemsetAsync(w->d_cflags, 0, sizeof(int) * c, w->stream));
-        CU(cudaMemsetAsync(w->d_contact, 0, sizeof(float4) * c, w->stream));
+        int ra = alloc_store(w, c);
+        if (ra) { free_store(w); w->dev_state_valid = false; w->dev_n = 0; return ra; }      // the bodies stay on the host; a later call retries
     }
     if (old_cap) { int re = ensure_ext(w, &old_ext, old_cap); if (re) return re; }
     else if (w->d_ext) {                        // bodies were added: their enabled flags
@@ -490,6 +497,7 @@ static int enqueue_respond(np_world* w, bool timed)
 }
 static int enqueue_step(np_world* w, float dt, bool timed)
 {
+    if (w->mid_step) return fail(NP_ERR_INVALID, "a step is open: np_world_step_begin must be closed by np_world_step_end");
     if (sharded(w)) return fail(NP_ERR_INVALID, "sharded world: step with np_world_step_begin / (all-gather) / np_world_step_end");
     int r = enqueue_search(w, dt, timed); if (r) return r;
     return enqueue_respond(w, timed);
