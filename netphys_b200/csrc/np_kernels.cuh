@@ -18,7 +18,7 @@ namespace np {
 enum { S_PX = 0, S_PY, S_PZ, S_RX, S_RY, S_RZ, S_LX, S_LY, S_LZ, S_HX, S_HY, S_HZ, S_COUNT };          // dynamic state
 enum { C_GX = 0, C_GY, C_GZ, C_MASS, C_ELAST, C_IINV0, C_COUNT = C_IINV0 + 9 };                       // per-body constants
 enum { X_R0 = 0, X_TX = 9, X_TY, X_TZ, X_COUNT };                                                      // transform
-enum { I_RESPONSE = 0, I_SHAPE, I_ISLAND_END, I_WVOFF, I_COUNT };     // I_WVOFF: first world vertex of the body in the per-step cache
+enum { I_RESPONSE = 0, I_SHAPE, I_ISLAND_END, I_WVOFF, I_ORDER, I_COUNT };     // I_WVOFF: first world vertex of the body in the per-step cache; I_ORDER: search order (bodies grouped by shape)
 
 struct StoreView {
     int n, cap;
@@ -202,6 +202,10 @@ struct NarrowIn {
     int world;                 // 1: items are bodies of `s`; 0: items are pairs
     int n;                     // bodies or pairs
     int first;                 // world mode: item t is body first + t (the shard of the pair search this process owns)
+    int ordered;               // world mode: item t is body ints[I_ORDER][first + t] -- the searched range visited grouped by shape.  The
+                               // persistent kernels hand out items in order, so at any moment every warp of the GPU works on the same
+                               // shape and its lanes run support loops of one length, however they were refilled.  (Grouping inside
+                               // windows smaller than the ~70 k items in flight does nothing: measured.)  Any order gives the same results.
     StoreView s;
     const int* shape_a; const int* shape_b;      // pair mode
     const float* xf_a; const float* xf_b;        // pair mode: transforms, SoA [X_COUNT][n]
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
         int t = fetch_ticket<G>(ticket, !have && !exhausted);
         if (!have && !exhausted) {
             if (t < in.n) {
-                i = WORLD ? t + in.first : t;
+                i = WORLD ? (in.ordered ? s.ints[I_ORDER * s.cap + in.first + t] : t + in.first) : t;
                 if (WORLD && lead) { NP_TL(i, 0); NP_TLV(i, 2, 0); NP_TLV(i, 3, 0); }
                 if (WORLD) {
                     if (in.cand) { cbase = in.cand_off[i]; c = 0; jend = in.cand_cnt[i]; j = jend > 0 ? in.cand[cbase] : 0; if (jend > 0) jend = 0x7fffffff; cn = in.cand_cnt[i]; }

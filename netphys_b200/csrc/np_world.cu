@@ -65,6 +65,7 @@ struct np_world {
     GridView grid = {}; int grid_cap = 0; int* d_grid_ints = nullptr; float* d_grid_f = nullptr;
     int max_verts = 0;                // largest shape
     int g_gjk_env = 0, g_epa_env = 0; // NP_G_GJK / NP_G_EPA overrides (tuning)
+    int order_on = 1; bool order_dirty = true;   // NP_ORDER=0: search bodies in index order (tuning)
     bool coop = false; int coop_env = -1;   // large and small shapes mixed: warp-cooperative supports in the narrow kernels (NP_COOP=0/1 overrides)
     DevCounters* d_ctr = nullptr;
     SnapObj* d_snap = nullptr;
@@ -165,6 +166,27 @@ static int alloc_store(np_world* w, size_t c)
     return NP_OK;
 }
 static int ensure_grid(np_world* w);
+// search order of the range this process searches (the whole world unless sharded): grouped by shape, stable; see NarrowIn::ordered
+static int upload_order(np_world* w)
+{
+    const int n = (int)w->bodies.size();
+    w->order_dirty = false;
+    if (n == 0 || !w->d_ints) return NP_OK;
+    int f = w->shard_count >= 0 ? std::min(w->shard_first, n) : 0, c = w->shard_count >= 0 ? std::min(w->shard_count, n - f) : n;
+    std::vector<int> ord(n);
+    for (int i = 0; i < n; i++) ord[i] = i;
+    // secondary key: the shape of the first partner the exact search will test (body i + 1 of the same island), so that both sides match
+    const bool pairkey = w->broadphase == NP_BROADPHASE_EXACT;
+    auto key = [&](int a) {
+        long long k = (long long)w->bodies[a].shape << 32;
+        if (pairkey && a + 1 < n && w->bodies[a + 1].island == w->bodies[a].island) k |= (unsigned)(w->bodies[a + 1].shape + 1);
+        return k;
+    };
+    std::stable_sort(ord.begin() + f, ord.begin() + f + c, [&](int a, int b) { return key(a) < key(b); });
+    CU(cudaMemcpyAsync(w->d_ints + (size_t)I_ORDER * w->cap, ord.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return NP_OK;
+}
 // adapter extension storage: forces start at zero, the enabled row comes from the host mirror
 static int ensure_ext(np_world* w, const std::vector<float>* keep_forces = nullptr, int keep_cap = 0)
 {
@@ -203,7 +225,7 @@ static int ensure_device(np_world* w)
         CU(cudaStreamSynchronize(w->stream));
         w->dirty_shapes = false;
     }
-    if (!w->dirty_bodies) return NP_OK;
+    if (!w->dirty_bodies) return w->order_dirty ? upload_order(w) : NP_OK;
     drop_graph(w);
     if (w->dev_state_valid && w->dev_n > 0) {   // bodies were added after stepping: keep what the device has
         int r = download_states(w, w->host_state.data(), w->dev_n); if (r) return r;
@@ -264,6 +286,7 @@ static int ensure_device(np_world* w)
     int r = upload_states(w, w->host_state.data(), n); if (r) return r;
     if (n > 0) { k_transforms<<<(n + 255) / 256, 256, 0, w->stream>>>(view(w)); CU(cudaGetLastError()); }
     w->dev_n = n; w->dev_state_valid = true; w->dirty_bodies = false;
+    { int ro = upload_order(w); if (ro) return ro; }
     if (w->broadphase == NP_BROADPHASE_GRID) { int rg = ensure_grid(w); if (rg) return rg; }
     return NP_OK;
 }
@@ -467,6 +490,7 @@ static int enqueue_search(np_world* w, float dt, bool timed)
     CU(cudaMemsetAsync(w->d_zero, 0, sizeof(int) * (32 + 2 * (size_t)w->cap), w->stream));
     if (count > 0) {
         NarrowIn in; memset(&in, 0, sizeof in); in.world = 1; in.n = count; in.first = first; in.s = s;
+        in.ordered = w->order_on;
         if (w->broadphase == NP_BROADPHASE_GRID) { in.cand = w->grid.cand; in.cand_off = w->grid.cand_off; in.cand_cnt = w->grid.cand_cnt; }
         NarrowBufs nb = { w->d_zero, hitj(w), cflags(w), contacts(w), w->d_simplex, w->d_hit_list, w->d_big_list };
         int r = launch_narrow(w, in, nb, ctr); if (r) return r;
@@ -530,6 +554,7 @@ np_world* np_world_create(int device)
     setup_kernels();
     if (const char* e = getenv("NP_G_GJK")) w->g_gjk_env = atoi(e);
     if (const char* e = getenv("NP_COOP")) w->coop_env = atoi(e);
+    if (const char* e = getenv("NP_ORDER")) w->order_on = atoi(e) != 0;
     if (const char* e = getenv("NP_G_EPA")) w->g_epa_env = atoi(e);
     if (cudaMalloc((void**)&w->d_ctr, sizeof(DevCounters)) != cudaSuccess || ensure_arena(w) != NP_OK) { fail(NP_ERR_CUDA, "cannot allocate device scratch"); np_world_destroy(w); return nullptr; }
     cudaMemsetAsync(w->d_ctr, 0, sizeof(DevCounters), w->stream);
@@ -781,7 +806,7 @@ int np_world_set_shard(np_world* w, int first, int count, void* d_hit_j, void* d
 {
     if (!w) return fail(NP_ERR_INVALID, "null world");
     if (w->mid_step) return fail(NP_ERR_INVALID, "np_world_set_shard between step_begin and step_end");
-    drop_graph(w);
+    drop_graph(w); w->order_dirty = true;
     if (count < 0) { w->shard_first = 0; w->shard_count = -1; w->x_hit_j = w->x_cflags = nullptr; w->x_contact = nullptr; return NP_OK; }
     if (first < 0 || !d_hit_j || !d_flags || !d_contact) return fail(NP_ERR_INVALID, "bad shard (range or null collision arrays)");
     w->shard_first = first; w->shard_count = count; w->x_hit_j = (int*)d_hit_j; w->x_cflags = (int*)d_flags; w->x_contact = (float4*)d_contact;
