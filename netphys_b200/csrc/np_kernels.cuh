@@ -232,6 +232,7 @@ NP_D unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0
 #ifndef NP_GJK_MINB
 #define NP_GJK_MINB 3
 #endif
+#define NP_HIT_CLASSES 4
 template <int G, bool WORLD, bool COOP = false>
 __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn in, ShapeView sh, int smem_shapes, int* __restrict__ ticket, int* __restrict__ hit_j,
                                                           int* __restrict__ flags, float4* __restrict__ contact, float4* __restrict__ simplex,
@@ -304,7 +305,10 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
                         o[0] = make_float4(m.A0.x, m.A0.y, m.A0.z, m.A1.x); o[1] = make_float4(m.A1.y, m.A1.z, m.A2.x, m.A2.y);
                         o[2] = make_float4(m.A2.z, m.A3.x, m.A3.y, m.A3.z); o[3] = make_float4(m.B0.x, m.B0.y, m.B0.z, m.B1.x);
                         o[4] = make_float4(m.B1.y, m.B1.z, m.B2.x, m.B2.y); o[5] = make_float4(m.B2.z, m.B3.x, m.B3.y, m.B3.z);
-                        hit_list[atomicAdd(hit_count, 1)] = i;
+                        // hits are filed by the shape sizes of the pair (NP_HIT_CLASSES lists of in.n entries each), so that the groups
+                        // of an EPA warp run support loops of one length
+                        const int cls = (g.na >= NP_COOP_MIN ? 2 : 0) + (g.nb >= NP_COOP_MIN ? 1 : 0);
+                        hit_list[(size_t)cls * in.n + atomicAdd(hit_count + cls, 1)] = i;
                     }
                     have = false;
                 } else if (WORLD && (in.cand ? (++c < cn ? ((j = in.cand[cbase + c]), true) : false) : (++j < jend))) {
@@ -353,7 +357,13 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
     PairGeom g;
     PairStats st = { 0, 0, 0, 0, 0 }, st0 = st;
     unsigned n_over = 0;
-    const int total = *count;
+    // TIER 0 reads the GJK hits, NP_HIT_CLASSES lists of in.n entries (see k_gjk); the overflow tiers read one plain list
+    int cum[NP_HIT_CLASSES];
+    int total = 0;
+    if (TIER == 0) {
+#pragma unroll
+        for (int k = 0; k < NP_HIT_CLASSES; k++) { total += count[k]; cum[k] = total; }
+    } else total = *count;
     int item = -1;
     bool have = false, exhausted = false;
     const bool lead = glane<G>() == 0;
@@ -365,7 +375,12 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
         int t = fetch_ticket<G>(ticket, !have && !exhausted);
         if (!have && !exhausted) {
             if (t < total) {
-                item = list[t];
+                if (TIER == 0) {
+                    int k = 0, base = 0;
+#pragma unroll
+                    for (int q = 0; q < NP_HIT_CLASSES - 1; q++) if (t >= cum[q]) { k = q + 1; base = cum[q]; }
+                    item = list[(size_t)k * in.n + (t - base)];
+                } else item = list[t];
                 if (WORLD) {
                     int i = item, j = hit_j[i];
                     if (CACHED) {

@@ -85,7 +85,7 @@ struct np_world {
 // ------------------------------------------------------------------------------------------------ helpers
 static StoreView view(np_world* w) { StoreView s; s.n = (int)w->bodies.size(); s.cap = w->cap; s.state = w->d_state; s.cst = w->d_cst; s.xf = w->d_xf; s.ints = w->d_ints; s.wverts = w->d_wverts; s.ext = w->d_ext; return s; }
 static ShapeView sview(np_world* w) { ShapeView s; s.verts = w->d_verts; s.off = w->d_soff; s.cnt = w->d_scnt; s.total_verts = w->total_verts; return s; }
-enum { Z_GJK_TICKET = 0, Z_HIT_COUNT, Z_EPA_TICKET, Z_MID_COUNT, Z_MID_TICKET, Z_BIG_COUNT, Z_BIG_TICKET };
+enum { Z_GJK_TICKET = 0, Z_EPA_TICKET, Z_MID_COUNT, Z_MID_TICKET, Z_BIG_COUNT, Z_BIG_TICKET, Z_HIT_COUNT = 8 /* NP_HIT_CLASSES counters */ };
 static int* hitj(np_world* w) { return w->x_hit_j ? w->x_hit_j : w->d_hit_j; }
 static int* cflags(np_world* w) { return w->x_cflags ? w->x_cflags : w->d_cflags; }
 static float4* contacts(np_world* w) { return w->x_contact ? w->x_contact : w->d_contact; }
@@ -159,7 +159,7 @@ static int alloc_store(np_world* w, size_t c)
     CU(cudaMalloc((void**)&w->d_zero, sizeof(int) * (32 + 2 * c))); CU(cudaMalloc((void**)&w->d_inc_off, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_inc, sizeof(int) * c));
     CU(cudaMalloc((void**)&w->d_sums, sizeof(int) * (4 * c / NP_SCAN_BLOCK + 2))); CU(cudaMalloc((void**)&w->d_big_list, sizeof(int) * c));
     CU(cudaMalloc((void**)&w->d_snap, sizeof(SnapObj) * c));
-    CU(cudaMalloc((void**)&w->d_hit_list, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_simplex, sizeof(float4) * 6 * c));
+    CU(cudaMalloc((void**)&w->d_hit_list, sizeof(int) * NP_HIT_CLASSES * c)); CU(cudaMalloc((void**)&w->d_simplex, sizeof(float4) * 6 * c));
     CU(cudaMemsetAsync(w->d_state, 0, sizeof(float) * S_COUNT * c, w->stream));
     CU(cudaMemsetAsync(w->d_hit_j, 0xff, sizeof(int) * c, w->stream)); CU(cudaMemsetAsync(w->d_cflags, 0, sizeof(int) * c, w->stream));
     CU(cudaMemsetAsync(w->d_contact, 0, sizeof(float4) * c, w->stream));
@@ -940,7 +940,7 @@ static int run_pairs(np_world* w, int n, const int* d_sa, const float* d_pa, con
 {
     // scratch: counters | xfA | xfB (SoA) | simplex | hit_list | big_list
     const size_t N = (size_t)n;
-    const size_t o_zero = 0, o_xa = 128, o_xb = o_xa + 4 * X_COUNT * N, o_sx = (o_xb + 4 * X_COUNT * N + 15) / 16 * 16, o_hl = o_sx + 96 * N, o_bl = o_hl + 4 * N, total = o_bl + 4 * N;
+    const size_t o_zero = 0, o_xa = 128, o_xb = o_xa + 4 * X_COUNT * N, o_sx = (o_xb + 4 * X_COUNT * N + 15) / 16 * 16, o_hl = o_sx + 96 * N, o_bl = o_hl + 4 * NP_HIT_CLASSES * N, total = o_bl + 4 * N;
     char* d = nullptr;
     CU(cudaMallocAsync((void**)&d, total, w->stream));
     CU(cudaMemsetAsync(d + o_zero, 0, 128, w->stream));
