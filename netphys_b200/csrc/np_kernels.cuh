@@ -209,6 +209,7 @@ struct NarrowIn {
     StoreView s;
     const int* shape_a; const int* shape_b;      // pair mode
     const float* xf_a; const float* xf_b;        // pair mode: transforms, SoA [X_COUNT][n]
+    const int* order;                            // pair mode: item t is pair order[t] (pairs grouped by shape-size class, k_pair_order), or null
     const int* cand; const int* cand_off; const int* cand_cnt;   // world mode with a broad phase: per-body ascending candidate lists (null = all j > i)
 };
 
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
         int t = fetch_ticket<G>(ticket, !have && !exhausted);
         if (!have && !exhausted) {
             if (t < in.n) {
-                i = WORLD ? (in.ordered ? s.ints[I_ORDER * s.cap + in.first + t] : t + in.first) : t;
+                i = WORLD ? (in.ordered ? s.ints[I_ORDER * s.cap + in.first + t] : t + in.first) : (in.order ? in.order[t] : t);
                 if (WORLD && lead) { NP_TL(i, 0); NP_TLV(i, 2, 0); NP_TLV(i, 3, 0); }
                 if (WORLD) {
                     if (in.cand) { cbase = in.cand_off[i]; c = 0; jend = in.cand_cnt[i]; j = jend > 0 ? in.cand[cbase] : 0; if (jend > 0) jend = 0x7fffffff; cn = in.cand_cnt[i]; }
@@ -425,6 +426,33 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
         }
     }
     if (ctr) flush_stats<G>(ctr, st, 0u, 0u, n_over);
+}
+
+// Pair lists arrive in the caller's order; for the thread-per-pair kernels the pairs are visited grouped by the vertex-count classes of
+// their two shapes (small <= 12 < medium < NP_COOP_MIN <= large: 9 classes), for the reason given at NarrowIn::ordered.  Counting sort:
+// k_pair_order<false> counts, k_pair_order<true> scatters (order inside a class is arbitrary; results do not depend on it).
+NP_D int size_class(int nverts) { return nverts <= 12 ? 0 : (nverts < NP_COOP_MIN ? 1 : 2); }
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_pair_order(int n, ShapeView sh, const int* __restrict__ shape_a, const int* __restrict__ shape_b, int* __restrict__ counts /* [9] then cursors [9] */, int* __restrict__ order)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int key = -1;
+    if (p < n) key = size_class(sh.cnt[shape_a[p]]) * 3 + size_class(sh.cnt[shape_b[p]]);
+    if (SCATTER && __any_sync(0xffffffffu, key >= 0 && counts[key] == n)) {   // one class holds every pair: keep the caller's (coalesced) order
+        if (p < n) order[p] = p;
+        return;
+    }
+    // one atomic per class per warp
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
+    int base = 0;
+    if (key >= 0 && lane == leader) base = atomicAdd(counts + (SCATTER ? 9 : 0) + key, __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (SCATTER && key >= 0) {
+        int off = 0;
+        for (int k = 0; k < key; k++) off += counts[k];
+        order[off + base + rank] = p;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -85,7 +85,7 @@ struct np_world {
 // ------------------------------------------------------------------------------------------------ helpers
 static StoreView view(np_world* w) { StoreView s; s.n = (int)w->bodies.size(); s.cap = w->cap; s.state = w->d_state; s.cst = w->d_cst; s.xf = w->d_xf; s.ints = w->d_ints; s.wverts = w->d_wverts; s.ext = w->d_ext; return s; }
 static ShapeView sview(np_world* w) { ShapeView s; s.verts = w->d_verts; s.off = w->d_soff; s.cnt = w->d_scnt; s.total_verts = w->total_verts; return s; }
-enum { Z_GJK_TICKET = 0, Z_EPA_TICKET, Z_MID_COUNT, Z_MID_TICKET, Z_BIG_COUNT, Z_BIG_TICKET, Z_HIT_COUNT = 8 /* NP_HIT_CLASSES counters */ };
+enum { Z_GJK_TICKET = 0, Z_EPA_TICKET, Z_MID_COUNT, Z_MID_TICKET, Z_BIG_COUNT, Z_BIG_TICKET, Z_HIT_COUNT = 8 /* NP_HIT_CLASSES counters */, Z_PAIR_CLASS = 12 /* 9 counts + 9 cursors */ };
 static int* hitj(np_world* w) { return w->x_hit_j ? w->x_hit_j : w->d_hit_j; }
 static int* cflags(np_world* w) { return w->x_cflags ? w->x_cflags : w->d_cflags; }
 static float4* contacts(np_world* w) { return w->x_contact ? w->x_contact : w->d_contact; }
@@ -940,7 +940,7 @@ static int run_pairs(np_world* w, int n, const int* d_sa, const float* d_pa, con
 {
     // scratch: counters | xfA | xfB (SoA) | simplex | hit_list | big_list
     const size_t N = (size_t)n;
-    const size_t o_zero = 0, o_xa = 128, o_xb = o_xa + 4 * X_COUNT * N, o_sx = (o_xb + 4 * X_COUNT * N + 15) / 16 * 16, o_hl = o_sx + 96 * N, o_bl = o_hl + 4 * NP_HIT_CLASSES * N, total = o_bl + 4 * N;
+    const size_t o_zero = 0, o_xa = 128, o_xb = o_xa + 4 * X_COUNT * N, o_sx = (o_xb + 4 * X_COUNT * N + 15) / 16 * 16, o_hl = o_sx + 96 * N, o_bl = o_hl + 4 * NP_HIT_CLASSES * N, o_or = o_bl + 4 * N, total = o_or + 4 * N;
     char* d = nullptr;
     CU(cudaMallocAsync((void**)&d, total, w->stream));
     CU(cudaMemsetAsync(d + o_zero, 0, 128, w->stream));
@@ -957,6 +957,13 @@ static int run_pairs(np_world* w, int n, const int* d_sa, const float* d_pa, con
     }
     NarrowIn in; memset(&in, 0, sizeof in); in.world = 0; in.n = n; in.s = view(w);
     in.shape_a = d_sa; in.shape_b = d_sb; in.xf_a = (const float*)(d + o_xa); in.xf_b = (const float*)(d + o_xb);
+    if (w->order_on && pick_group(w, n, w->g_gjk_env, false) == 1 && w->shapes.size() > 1) {     // thread-per-pair regime, more than one shape
+        int* cnts = (int*)(d + o_zero) + Z_PAIR_CLASS;
+        k_pair_order<false><<<b256, 256, 0, w->stream>>>(n, sview(w), d_sa, d_sb, cnts, nullptr);
+        k_pair_order<true><<<b256, 256, 0, w->stream>>>(n, sview(w), d_sa, d_sb, cnts, (int*)(d + o_or));
+        in.order = (const int*)(d + o_or);
+        w->launches += 2;
+    }
     NarrowBufs nb = { (int*)(d + o_zero), nullptr, d_hit, d_out, (float4*)(d + o_sx), (int*)(d + o_hl), (int*)(d + o_bl) };
     int r = launch_narrow(w, in, nb, w->counters_on ? w->d_ctr : nullptr);
     if (kernel_ms) CU(cudaEventRecord(w->ev[5], w->stream));
