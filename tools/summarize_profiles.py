@@ -5,7 +5,7 @@ rows = [r for r in csv.reader(open("gpurun_out/prof_launches.csv")) if len(r) > 
 hdr = rows[0]; ik, iv, iid = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("ID")
 L = [(int(r[iid]), r[ik].split("(")[0].replace("void ", ""), float(r[iv].replace(",", ""))) for r in rows[1:]]
 # one timed world step = launches between two consecutive k_integrate after the warm-up
-starts = [i for i, l in enumerate(L) if l[1] == "k_integrate"]
+starts = [i for i, l in enumerate(L) if l[1].startswith("k_integrate")]
 with open("profiles/%s_launches_bench.txt" % tag, "w") as f:
     f.write("# ncu --metrics gpu__time_duration.sum --clock-control none : python bench.py --steps 3 --warmup 3  (per-launch times are cold-cache and serialised)\n")
     if len(starts) > 5:
