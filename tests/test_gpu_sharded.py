@@ -97,3 +97,28 @@ def test_shard_api_errors(npb):
         w.step_end()
         w.set_shard(0, -1)                                                            # back to a whole-world search
         w.step(sc["dt"]); w.synchronize()
+
+
+def test_shard_changes_between_steps_and_bodies_added(npb, oracle):
+    """The searched range may change between steps and bodies may be added: the search order is rebuilt for the range, results stay
+    the reference's.  One world plays both ranks in turn (two half searches per step into the same arrays)."""
+    sc = scenes.lattice_scene(1200, spacing=1.1, seed=9, mix=(0.5, 0.3, 0.2))
+    ow = oracle.world(scenes.resolve(sc, oracle))
+    with npb.World(0) as w, npb.World(0) as w2:
+        for x in (w, w2): x.load_scene(sc)
+        n = w.n
+        d = [w.dev_alloc(4 * 4096), w.dev_alloc(4 * 4096), w.dev_alloc(16 * 4096)]
+        d2 = [w2.dev_alloc(4 * 4096), w2.dev_alloc(4 * 4096), w2.dev_alloc(16 * 4096)]
+        for k in range(6):
+            cut = [n // 2, n // 3, 1, n - 1, n // 2, 700][k]                   # a different split every step
+            w.set_shard(0, cut, *d); w2.set_shard(cut, n - cut, *d2)
+            w.step_begin(sc["dt"]); w2.step_begin(sc["dt"])
+            for width, p, p2 in zip((4, 4, 16), d, d2):                        # the host plays the all-gather
+                a = np.zeros(width // 4 * cut, np.int32); b = np.zeros(width // 4 * (n - cut), np.int32)
+                w.dev_download(a, p); w2.dev_download(b, p2 + width * cut)
+                w.dev_upload(p + width * cut, b); w2.dev_upload(p2, a)
+            w.step_end(); w2.step_end()
+            ao, bo, do = ow.step(sc["dt"], True)
+            for x in (w, w2):
+                a, b, dd = x.collisions_as_arrays()
+                assert np.array_equal(a, ao) and np.array_equal(b, bo); assert_biteq(dd, do, "collision data"); assert_biteq(x.states(), ow.state(), "state step %d" % k)
