@@ -343,12 +343,18 @@ def run_ours(args, rank, local_rank, world_size):
         try:
             big = scenes.lattice_scene(1_000_000, spacing=1.3, seed=43, mix=(0.7, 0.2, 0.1))
             with W(local_rank) as w3:
+                w3.set_option(W.OPT_COUNTERS, 1)
                 w3.load_scene(big)
                 for _ in range(3): w3.step(big["dt"])
+                k0 = w3.counters()
                 ms3 = np.array([(w3.flush_l2(), w3.step(big["dt"]), w3.last_step_ms())[2] for _ in range(5)])
-                tot = float(np.mean(ms3[:, 5])); integ = float(np.mean(ms3[:, 0]))
+                k1 = w3.counters()
+                tot = float(np.mean(ms3[:, 5])); integ = float(np.mean(ms3[:, 0])); nar = float(np.mean(ms3[:, 2]))
+                f3, _ = narrow_flops(k0, k1)
                 extra["world_1m_mixed"] = {"workload": "BASELINE configs[2] size: 1 000 000 bodies (70% box, 20% icosphere, 10% 16-vertex hull), one world, exact pair search",
                                            "value": 1e6 / (tot * 1e-3), "unit": "body-steps/s", "ms_per_step": tot,
+                                           "narrow_phase": {"bound": "fp32", "ms": nar, "achieved": f3 / 5 / (nar * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                                                            "frac": f3 / 5 / (nar * 1e-3) / 1e12 / fp32_peak if fp32_peak else None, "pair_tests_per_step": (k1["pair_tests"] - k0["pair_tests"]) / 5},
                                            "k_integrate": {"bound": "hbm", "achieved": 1e6 * B_INTEGRATE / (integ * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                                            "frac": 1e6 * B_INTEGRATE / (integ * 1e-3) / 1e9 / hbm_peak, "ms": integ}}
             with W(local_rank) as w6:                            # configs[2] as worded: the same 1M world behind the uniform-grid broad phase
@@ -360,7 +366,9 @@ def run_ours(args, rank, local_rank, world_size):
                 g1 = w6.counters()
                 tot = float(np.mean(ms6[:, 5])); bp = float(np.mean(ms6[:, 1])); cands = (g1["candidates"] - g0["candidates"]) / 5
                 extra["world_1m_mixed_grid"] = {"workload": "BASELINE configs[2]: the same 1 000 000 bodies with NP_BROADPHASE_GRID (AABB culling changes the collision list: the reference has no broad phase, DESIGN.md section 7)",
-                                                "value": 1e6 / (tot * 1e-3), "unit": "body-steps/s", "ms_per_step": tot, "broadphase_ms": bp, "narrow_ms": float(np.mean(ms6[:, 2])),
+                                                "value": 1e6 / (tot * 1e-3), "unit": "body-steps/s", "ms_per_step": tot,
+                                           "narrow_phase": {"bound": "fp32", "ms": nar, "achieved": f3 / 5 / (nar * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                                                            "frac": f3 / 5 / (nar * 1e-3) / 1e12 / fp32_peak if fp32_peak else None, "pair_tests_per_step": (k1["pair_tests"] - k0["pair_tests"]) / 5}, "broadphase_ms": bp, "narrow_ms": float(np.mean(ms6[:, 2])),
                                                 "candidate_pairs_per_step": cands, "pair_tests_per_step": (g1["pair_tests"] - g0["pair_tests"]) / 5,
                                                 "candidate_pairs_per_sec_broadphase": cands / (bp * 1e-3)}
             wsc = scenes.lattice_scene(256, spacing=1.2, seed=1000)
