@@ -804,12 +804,15 @@ __global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, int firs
 // frozen CollisionData, so per body the sequence is: every collision (i, k) with hit_j[i] == k in ascending
 // i (all of them precede k's own entry in the list because i < k), then k's own collision (k, hit_j[k]).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_count_incoming(int n, int cap, const int* __restrict__ hit_j, const int* __restrict__ ints, int* __restrict__ cnt)
+// Two launches.  k_link threads every collision (i, k) onto an intrusive list per hit body k (head[k], next[i]; 0 = end, entries are
+// i + 1; head is zeroed with the step's counters); k_resolve walks k's list in ascending i -- the lists are short (one or two entries,
+// rarely more), so the next-smallest entry is found by re-walking -- then applies k's own collision, and packs the snapshot record.
+__global__ void __launch_bounds__(256) k_link(int n, int cap, const int* __restrict__ hit_j, const int* __restrict__ ints, int* __restrict__ head, int* __restrict__ next)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int b = hit_j[i];
-    if ((unsigned)b < (unsigned)n && ints[I_RESPONSE * cap + b] == 1) atomicAdd(&cnt[b], 1);      // (records may come from another process)
+    if ((unsigned)b < (unsigned)n && ints[I_RESPONSE * cap + b] == 1) next[i] = atomicExch(&head[b], i + 1);      // (records may come from another process)
 }
 // exclusive scan of cnt[0..n) in three launches (per-block sums, scan of the sums, per-block scan + offset)
 #define NP_SCAN_BLOCK 1024
@@ -877,15 +880,6 @@ __global__ void __launch_bounds__(NP_SCAN_BLOCK) k_scan_apply(int n, const int* 
     __syncthreads();
     if (i < n) out[i] = sums[blockIdx.x] + warp_tot[wid] + x - v;
 }
-__global__ void __launch_bounds__(256) k_fill_incoming(int n, int cap, const int* __restrict__ hit_j, const int* __restrict__ ints,
-                                                      const int* __restrict__ off, int* __restrict__ cursor, int* __restrict__ inc)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int b = hit_j[i];
-    if ((unsigned)b < (unsigned)n && ints[I_RESPONSE * cap + b] == 1) inc[off[b] + atomicAdd(&cursor[b], 1)] = i;
-}
-
 // Physics::ApplyImpulseResponse, physics.cpp:27-46
 NP_D void impulse(V3& pos, V3& L, V3& H, float mass, float elast, const float* iinv, V3 r, float cdepth, V3 n)
 {
@@ -900,42 +894,59 @@ NP_D void impulse(V3& pos, V3& L, V3& H, float mass, float elast, const float* i
     float adjust = cdepth * 1.01f;
     pos = add(pos, mul(n, adjust));
 }
+struct SnapObj { uint32_t guid; float pos[3]; float rot[4]; uint32_t enabled; };
+// CommandFrameObject of body i (netphys_server/world_s.cpp:37-48): position, quaternion (w,x,y,z) of the Euler rotation, isEnabled
+NP_D SnapObj snap_of(const StoreView& s, int i, V3 pos, uint32_t guid_base)
+{
+    const int cap = s.cap;
+    float hx = s.state[S_RX * cap + i] * 0.5f, hy = s.state[S_RY * cap + i] * 0.5f, hz = s.state[S_RZ * cap + i] * 0.5f;
+    float sx, cx, sy, cy, sz, cz;
+    np_sincosf(hx, &sx, &cx); np_sincosf(hy, &sy, &cy); np_sincosf(hz, &sz, &cz);
+    SnapObj o;
+    o.guid = guid_base + (uint32_t)i;
+    o.pos[0] = pos.x; o.pos[1] = pos.y; o.pos[2] = pos.z;
+    o.rot[0] = cx * cy * cz + sx * sy * sz;
+    o.rot[1] = sx * cy * cz - cx * sy * sz;
+    o.rot[2] = cx * sy * cz + sx * cy * sz;
+    o.rot[3] = cx * cy * sz - sx * sy * cz;
+    o.enabled = (s.ext && s.ext[3 * (size_t)cap + i] == 0.0f) ? 0u : 1u;                          // dBodyIsEnabled, world_s.cpp:48
+    return o;
+}
 __global__ void __launch_bounds__(256) k_resolve(StoreView s, const int* __restrict__ hit_j, const float4* __restrict__ contact,
-                                                const int* __restrict__ inc_off, const int* __restrict__ inc_cnt, int* __restrict__ inc)
+                                                const int* __restrict__ head, const int* __restrict__ next, SnapObj* __restrict__ snap, uint32_t guid_base)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= s.n) return;
     const int cap = s.cap;
-    if (s.ints[I_RESPONSE * cap + k] != 1) return;
-    int own = hit_j[k], ninc = inc_cnt[k];
-    if (own < 0 && ninc == 0) return;
     float* st = s.state; const float* c = s.cst;
     V3 pos = mk(st[S_PX * cap + k], st[S_PY * cap + k], st[S_PZ * cap + k]);
-    V3 L = mk(st[S_LX * cap + k], st[S_LY * cap + k], st[S_LZ * cap + k]);
-    V3 H = mk(st[S_HX * cap + k], st[S_HY * cap + k], st[S_HZ * cap + k]);
-    float mass = c[C_MASS * cap + k], elast = c[C_ELAST * cap + k];
-    float iinv[9];
+    const int own = hit_j[k], first = head[k];
+    if (s.ints[I_RESPONSE * cap + k] == 1 && ((unsigned)own < (unsigned)s.n || first != 0)) {
+        V3 L = mk(st[S_LX * cap + k], st[S_LY * cap + k], st[S_LZ * cap + k]);
+        V3 H = mk(st[S_HX * cap + k], st[S_HY * cap + k], st[S_HZ * cap + k]);
+        float mass = c[C_MASS * cap + k], elast = c[C_ELAST * cap + k];
+        float iinv[9];
 #pragma unroll
-    for (int q = 0; q < 9; q++) iinv[q] = c[(C_IINV0 + q) * cap + k];
-    // CollisionData::a_normal / b_normal are never written by the reference (collision_detection.cpp:533-543)
-    const V3 a_normal = mk(0.0f, 0.0f, 0.0f), b_normal = mk(0.0f, 0.0f, 0.0f);
-    int* seg = inc + inc_off[k];
-    for (int a = 1; a < ninc; a++) {                     // the fill order is arbitrary: restore ascending i
-        int key = seg[a], b = a - 1;
-        while (b >= 0 && seg[b] > key) { seg[b + 1] = seg[b]; b--; }
-        seg[b + 1] = key;
+        for (int q = 0; q < 9; q++) iinv[q] = c[(C_IINV0 + q) * cap + k];
+        // CollisionData::a_normal / b_normal are never written by the reference (collision_detection.cpp:533-543)
+        const V3 a_normal = mk(0.0f, 0.0f, 0.0f), b_normal = mk(0.0f, 0.0f, 0.0f);
+        for (int last = -1;;) {                              // k is `b` of collision (i, k), ascending i: normal = a_normal (physics.cpp:109)
+            int best = 0x7fffffff;
+            for (int e = first; e != 0; e = next[e - 1]) { int i = e - 1; if (i > last && i < best) best = i; }
+            if (best == 0x7fffffff) break;
+            float4 cd = contact[best];
+            impulse(pos, L, H, mass, elast, iinv, mk(cd.x, cd.y, cd.z), cd.w, a_normal);
+            last = best;
+        }
+        if ((unsigned)own < (unsigned)s.n) {                 // k is `a` of its own collision: normal = b_normal (physics.cpp:99)
+            float4 cd = contact[k];
+            impulse(pos, L, H, mass, elast, iinv, mk(cd.x, cd.y, cd.z), cd.w, b_normal);
+        }
+        st[S_PX * cap + k] = pos.x; st[S_PY * cap + k] = pos.y; st[S_PZ * cap + k] = pos.z;
+        st[S_LX * cap + k] = L.x; st[S_LY * cap + k] = L.y; st[S_LZ * cap + k] = L.z;
+        st[S_HX * cap + k] = H.x; st[S_HY * cap + k] = H.y; st[S_HZ * cap + k] = H.z;
     }
-    for (int a = 0; a < ninc; a++) {                     // k is `b` of collision (i, k): normal = a_normal (physics.cpp:109)
-        float4 cd = contact[seg[a]];
-        impulse(pos, L, H, mass, elast, iinv, mk(cd.x, cd.y, cd.z), cd.w, a_normal);
-    }
-    if (own >= 0) {                                      // k is `a` of its own collision: normal = b_normal (physics.cpp:99)
-        float4 cd = contact[k];
-        impulse(pos, L, H, mass, elast, iinv, mk(cd.x, cd.y, cd.z), cd.w, b_normal);
-    }
-    st[S_PX * cap + k] = pos.x; st[S_PY * cap + k] = pos.y; st[S_PZ * cap + k] = pos.z;
-    st[S_LX * cap + k] = L.x; st[S_LY * cap + k] = L.y; st[S_LZ * cap + k] = L.z;
-    st[S_HX * cap + k] = H.x; st[S_HY * cap + k] = H.y; st[S_HZ * cap + k] = H.z;
+    if (snap) snap[k] = snap_of(s, k, pos, guid_base);
 }
 
 // np_body_add_force / np_body_set_enabled on one body
@@ -972,24 +983,12 @@ __global__ void k_transform_one(StoreView s, int i, float* out16)
 // K6: replication snapshot.  One 36-byte CommandFrameObject per body (netphys_common/common.h:120-127):
 // guid, pos[3], rot[4] (quaternion of the Euler XYZ rotation R = Rz*Ry*Rx), isEnabled.
 // ---------------------------------------------------------------------------------------------------
-struct SnapObj { uint32_t guid; float pos[3]; float rot[4]; uint32_t enabled; };
 __global__ void __launch_bounds__(256) k_snapshot(StoreView s, uint32_t guid_base, SnapObj* __restrict__ out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.n) return;
     const int cap = s.cap;
-    float hx = s.state[S_RX * cap + i] * 0.5f, hy = s.state[S_RY * cap + i] * 0.5f, hz = s.state[S_RZ * cap + i] * 0.5f;
-    float sx, cx, sy, cy, sz, cz;
-    np_sincosf(hx, &sx, &cx); np_sincosf(hy, &sy, &cy); np_sincosf(hz, &sz, &cz);
-    SnapObj o;
-    o.guid = guid_base + (uint32_t)i;
-    o.pos[0] = s.state[S_PX * cap + i]; o.pos[1] = s.state[S_PY * cap + i]; o.pos[2] = s.state[S_PZ * cap + i];
-    o.rot[0] = cx * cy * cz + sx * sy * sz;
-    o.rot[1] = sx * cy * cz - cx * sy * sz;
-    o.rot[2] = cx * sy * cz + sx * cy * sz;
-    o.rot[3] = cx * cy * sz - sx * sy * cz;
-    o.enabled = (s.ext && s.ext[3 * (size_t)cap + i] == 0.0f) ? 0u : 1u;                          // dBodyIsEnabled, world_s.cpp:48
-    out[i] = o;
+    out[i] = snap_of(s, i, mk(s.state[S_PX * cap + i], s.state[S_PY * cap + i], s.state[S_PZ * cap + i]), guid_base);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -56,7 +56,7 @@ struct np_world {
     // collision records live in caller-provided buffers that the caller all-gathers between step_begin and step_end
     int shard_first = 0, shard_count = -1; int *x_hit_j = nullptr, *x_cflags = nullptr; float4* x_contact = nullptr;
     bool mid_step = false;
-    int* d_zero = nullptr;            // [tickets and counts (32 ints), inc_cnt[cap], cursor[cap]]  -- one memset per step
+    int* d_zero = nullptr;            // [tickets and counts (32 ints), head[cap] of the incoming-collision lists]  -- one memset per step
     int *d_inc_off = nullptr, *d_inc = nullptr, *d_sums = nullptr, *d_big_list = nullptr, *d_hit_list = nullptr;
     float4* d_simplex = nullptr;      // GJK result of every hit: A[4], B[4]
     float4* d_wverts = nullptr; size_t wverts_cap = 0;   // per-step world-vertex cache (K1b)
@@ -487,7 +487,7 @@ static int enqueue_search(np_world* w, float dt, bool timed)
     if (w->broadphase == NP_BROADPHASE_GRID) { int r = enqueue_grid(w, s, first, count, cache, ctr); if (r) return r; }
     else if (cache) { k_world_verts<false><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), w->grid); w->launches += 1; }
     if (timed) CU(cudaEventRecord(w->ev[2], w->stream));
-    CU(cudaMemsetAsync(w->d_zero, 0, sizeof(int) * (32 + 2 * (size_t)w->cap), w->stream));
+    CU(cudaMemsetAsync(w->d_zero, 0, sizeof(int) * (32 + (size_t)w->cap), w->stream));        // counters, tickets and the incoming-list heads
     if (count > 0) {
         NarrowIn in; memset(&in, 0, sizeof in); in.world = 1; in.n = count; in.first = first; in.s = s;
         in.ordered = w->order_on;
@@ -505,16 +505,11 @@ static int enqueue_respond(np_world* w, bool timed)
     if (n == 0) return NP_OK;
     StoreView s = view(w);
     const int b256 = (n + 255) / 256;
-    k_count_incoming<<<b256, 256, 0, w->stream>>>(n, w->cap, hitj(w), w->d_ints, d_inc_cnt(w));
-    enqueue_scan(w, n, d_inc_cnt(w), w->d_inc_off);
-    k_fill_incoming<<<b256, 256, 0, w->stream>>>(n, w->cap, hitj(w), w->d_ints, w->d_inc_off, d_cursor(w), w->d_inc);
-    k_resolve<<<b256, 256, 0, w->stream>>>(s, hitj(w), contacts(w), w->d_inc_off, d_inc_cnt(w), w->d_inc);
+    SnapObj* snap = w->snapshot_each_step ? (w->snap_target ? (SnapObj*)w->snap_target : w->d_snap) : nullptr;
+    k_link<<<b256, 256, 0, w->stream>>>(n, w->cap, hitj(w), w->d_ints, d_inc_cnt(w), w->d_inc);
+    k_resolve<<<b256, 256, 0, w->stream>>>(s, hitj(w), contacts(w), d_inc_cnt(w), w->d_inc, snap, w->guid_base);      // + the snapshot record
     if (timed) CU(cudaEventRecord(w->ev[4], w->stream));
-    w->launches += 3;
-    if (w->snapshot_each_step) {
-        k_snapshot<<<b256, 256, 0, w->stream>>>(s, w->guid_base, w->snap_target ? (SnapObj*)w->snap_target : w->d_snap);
-        w->launches += 1;
-    }
+    w->launches += 2;
     if (timed) CU(cudaEventRecord(w->ev[5], w->stream));
     CU(cudaGetLastError());
     return NP_OK;
