@@ -97,7 +97,9 @@ typedef enum np_option {
     NP_OPT_BROADPHASE = 1,        /* np_broadphase */
     NP_OPT_GRID_CELL = 2,         /* float bits: grid cell edge; 0 = auto (largest AABB extent) */
     NP_OPT_COUNTERS = 3,          /* 1 = accumulate pair-test / hit / iteration counters (np_world_get_counters) */
-    NP_OPT_SNAPSHOT_EACH_STEP = 4 /* 1 = np_world_step also packs the replication snapshot (world_s.cpp:23-51) */
+    NP_OPT_SNAPSHOT_EACH_STEP = 4,/* 1 = np_world_step also packs the replication snapshot (world_s.cpp:23-51) */
+    NP_OPT_PHASE_TIMING = 5       /* 1 = time the phases of every step with CUDA events (np_world_last_step_ms [0..4]); the events cost a few
+                                     microseconds each, so a step runs faster without them.  The total [5] is always measured. */
 } np_option;
 
 typedef struct np_counters {
@@ -178,8 +180,8 @@ int np_world_get_collisions(np_world* w, np_collision* out, int cap, int* count)
  * step, download all states into `out`.  Copies are inside the call. */
 int np_world_step_host(np_world* w, float dt, const np_body_state* in, np_body_state* out, int n);
 int np_world_get_counters(np_world* w, np_counters* out);
-/* device time (ms, CUDA events on the world's stream) of the kernels of the most recent np_world_step[_n]:
- * [0] integrate+transform, [1] broad-phase, [2] narrow-phase (GJK+EPA), [3] resolve, [4] snapshot, [5] total */
+/* device time (ms, CUDA events on the world's stream) of the kernels of the most recent step: [5] total; with NP_OPT_PHASE_TIMING also
+ * [0] integrate+transform, [1] broad-phase / world-vertex cache, [2] narrow-phase (GJK+EPA), [3] response (+ snapshot record), [4] - */
 int np_world_last_step_ms(np_world* w, float out[6]);
 
 /* ---- narrow phase: DetectCollision, engine/physics.h:103-110 --------------------------------------- */

@@ -26,6 +26,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 struct HostShape { std::vector<float> xyz; };
 struct HostBody { np_static_physics_data sd; int shape; int island; int enabled = 1; };
+struct StepGraph { uint32_t dt_bits; void* snap; uint32_t guid; cudaGraphExec_t exec; unsigned long long launches; };   // one captured Physics_Update
 struct CommandFrame { unsigned id; double time_ms; std::vector<np_snapshot_object> objects; };      // world_s.cpp:12-17
 
 struct np_world {
@@ -79,7 +80,8 @@ struct np_world {
     bool timed = false;
     unsigned long long steps = 0;
     // CUDA graph of one step (np_world_step_n)
-    cudaGraphExec_t graph = nullptr; float graph_dt = 0.0f; unsigned long long graph_launches = 0;
+    std::vector<StepGraph> graphs; int graph_on = 1; bool capturing = false;
+    int phase_timing = 0;             // NP_OPT_PHASE_TIMING: per-phase events inside the step (they cost ~4 us each)      // np_world_step replays a captured step (NP_GRAPH=0: plain launches)
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -111,7 +113,7 @@ static int ensure_stage(np_world* w, size_t bytes)
     w->h_stage_bytes = bytes;
     return NP_OK;
 }
-static void drop_graph(np_world* w) { if (w->graph) { cudaGraphExecDestroy(w->graph); w->graph = nullptr; } }
+static void drop_graph(np_world* w) { for (auto& g : w->graphs) cudaGraphExecDestroy(g.exec); w->graphs.clear(); }
 
 // state [12][cap] on the device  <->  np_body_state[n] on the host: one contiguous copy through pinned staging + a device transposition
 static int ensure_aos(np_world* w, size_t bytes)
@@ -479,14 +481,14 @@ static int enqueue_search(np_world* w, float dt, bool timed)
     DevCounters* ctr = w->counters_on ? w->d_ctr : nullptr;
     const int b256 = (n + 255) / 256;
     const int first = sharded(w) ? w->shard_first : 0, count = sharded(w) ? w->shard_count : n;
-    if (timed) CU(cudaEventRecord(w->ev[0], w->stream));
+    if (timed && !w->capturing) CU(cudaEventRecord(w->ev[0], w->stream));
     if (s.ext) k_integrate<true><<<b256, 256, 0, w->stream>>>(s, dt, 1); else k_integrate<false><<<b256, 256, 0, w->stream>>>(s, dt, 1);
     w->launches += 1;
-    if (timed) CU(cudaEventRecord(w->ev[1], w->stream));
+    if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[1], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     const bool cache = wants_cache(w, count);
     if (w->broadphase == NP_BROADPHASE_GRID) { int r = enqueue_grid(w, s, first, count, cache, ctr); if (r) return r; }
     else if (cache) { k_world_verts<false><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), w->grid); w->launches += 1; }
-    if (timed) CU(cudaEventRecord(w->ev[2], w->stream));
+    if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[2], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     CU(cudaMemsetAsync(w->d_zero, 0, sizeof(int) * (32 + (size_t)w->cap), w->stream));        // counters, tickets and the incoming-list heads
     if (count > 0) {
         NarrowIn in; memset(&in, 0, sizeof in); in.world = 1; in.n = count; in.first = first; in.s = s;
@@ -495,7 +497,7 @@ static int enqueue_search(np_world* w, float dt, bool timed)
         NarrowBufs nb = { w->d_zero, hitj(w), cflags(w), contacts(w), w->d_simplex, w->d_hit_list, w->d_big_list };
         int r = launch_narrow(w, in, nb, ctr); if (r) return r;
     }
-    if (timed) CU(cudaEventRecord(w->ev[3], w->stream));
+    if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[3], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     CU(cudaGetLastError());
     return NP_OK;
 }
@@ -508,9 +510,9 @@ static int enqueue_respond(np_world* w, bool timed)
     SnapObj* snap = w->snapshot_each_step ? (w->snap_target ? (SnapObj*)w->snap_target : w->d_snap) : nullptr;
     k_link<<<b256, 256, 0, w->stream>>>(n, w->cap, hitj(w), w->d_ints, d_inc_cnt(w), w->d_inc);
     k_resolve<<<b256, 256, 0, w->stream>>>(s, hitj(w), contacts(w), d_inc_cnt(w), w->d_inc, snap, w->guid_base);      // + the snapshot record
-    if (timed) CU(cudaEventRecord(w->ev[4], w->stream));
+    if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[4], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     w->launches += 2;
-    if (timed) CU(cudaEventRecord(w->ev[5], w->stream));
+    if (timed && !w->capturing) CU(cudaEventRecord(w->ev[5], w->stream));
     CU(cudaGetLastError());
     return NP_OK;
 }
@@ -549,6 +551,7 @@ np_world* np_world_create(int device)
     setup_kernels();
     if (const char* e = getenv("NP_G_GJK")) w->g_gjk_env = atoi(e);
     if (const char* e = getenv("NP_COOP")) w->coop_env = atoi(e);
+    if (const char* e = getenv("NP_GRAPH")) w->graph_on = atoi(e) != 0;
     if (const char* e = getenv("NP_ORDER")) w->order_on = atoi(e) != 0;
     if (const char* e = getenv("NP_G_EPA")) w->g_epa_env = atoi(e);
     if (cudaMalloc((void**)&w->d_ctr, sizeof(DevCounters)) != cudaSuccess || ensure_arena(w) != NP_OK) { fail(NP_ERR_CUDA, "cannot allocate device scratch"); np_world_destroy(w); return nullptr; }
@@ -578,6 +581,7 @@ int np_world_set_option(np_world* w, int option, int64_t value)
     case NP_OPT_GRID_CELL: { uint32_t u = (uint32_t)value; memcpy(&w->grid_cell, &u, 4); drop_graph(w); return NP_OK; }
     case NP_OPT_COUNTERS: w->counters_on = value ? 1 : 0; drop_graph(w); return NP_OK;
     case NP_OPT_SNAPSHOT_EACH_STEP: w->snapshot_each_step = value ? 1 : 0; drop_graph(w); return NP_OK;
+    case NP_OPT_PHASE_TIMING: w->phase_timing = value ? 1 : 0; drop_graph(w); return NP_OK;
     default: return fail(NP_ERR_INVALID, "unknown option");
     }
 }
@@ -784,11 +788,49 @@ int np_body_get_transform(np_world* w, int body, float out16[16])               
 }
 
 // ------------------------------------------------------------------------------------------------ step
+// One captured Physics_Update per (dt, snapshot target): with thousands of bodies a step is a dozen kernels of a few microseconds and
+// the launch gaps of plain submission cost as much as the kernels (measured 0.31 -> 0.26 ms per step on the 10 k-body world).  The
+// phase events are recorded inside the graph, so np_world_last_step_ms keeps its breakdown.
+static int get_step_graph(np_world* w, float dt, StepGraph** out)
+{
+    uint32_t bits; memcpy(&bits, &dt, 4);
+    for (auto& g : w->graphs) if (g.dt_bits == bits && g.snap == w->snap_target && g.guid == w->guid_base) { *out = &g; return NP_OK; }
+    if (w->graphs.size() >= 4) { cudaGraphExecDestroy(w->graphs.front().exec); w->graphs.erase(w->graphs.begin()); }
+    cudaGraph_t g = nullptr;
+    const unsigned long long l0 = w->launches;
+    CU(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
+    w->capturing = true;                                                  // (phase events become external event-record nodes)
+    int r = enqueue_step(w, dt, true);
+    w->capturing = false;
+    StepGraph sg = { bits, w->snap_target, w->guid_base, nullptr, w->launches - l0 };
+    w->launches = l0;                                                     // counted per replay
+    cudaError_t e = cudaStreamEndCapture(w->stream, &g);
+    if (r) { if (g) cudaGraphDestroy(g); return r; }
+    if (e != cudaSuccess) return fail(NP_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&sg.exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(NP_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    w->graphs.push_back(sg);
+    *out = &w->graphs.back();
+    return NP_OK;
+}
+static int step_once(np_world* w, float dt)
+{
+    if (!w->graph_on || sharded(w) || w->mid_step) return enqueue_step(w, dt, true);
+    StepGraph* g = nullptr;
+    int r = get_step_graph(w, dt, &g); if (r) return r;
+    CU(cudaEventRecord(w->ev[0], w->stream));
+    CU(cudaGraphLaunch(g->exec, w->stream));
+    CU(cudaEventRecord(w->ev[5], w->stream));
+    w->launches += g->launches;
+    return NP_OK;
+}
 int np_world_step(np_world* w, float dt)
 {
     if (!w) return fail(NP_ERR_INVALID, "null world");
     int r = ensure_device(w); if (r) return r;
-    r = enqueue_step(w, dt, true); if (r) return r;
+    if (w->bodies.empty()) return NP_OK;
+    r = step_once(w, dt); if (r) return r;
     w->timed = true; w->steps++;
     return NP_OK;
 }
@@ -836,26 +878,8 @@ int np_world_step_n(np_world* w, float dt, int steps)
     if (!w || steps < 0) return fail(NP_ERR_INVALID, "bad arguments");
     int r = ensure_device(w); if (r) return r;
     if (w->bodies.empty() || steps == 0) return NP_OK;
-    if (!w->graph || w->graph_dt != dt) {      // capture one step once, replay it `steps` times
-        drop_graph(w);
-        cudaGraph_t g = nullptr;
-        const unsigned long long l0 = w->launches;
-        CU(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
-        r = enqueue_step(w, dt, false);
-        w->graph_launches = w->launches - l0; w->launches = l0;        // counted per replay below
-        cudaError_t e = cudaStreamEndCapture(w->stream, &g);
-        if (r) { if (g) cudaGraphDestroy(g); return r; }
-        if (e != cudaSuccess) return fail(NP_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-        e = cudaGraphInstantiate(&w->graph, g, 0);
-        cudaGraphDestroy(g);
-        if (e != cudaSuccess) { w->graph = nullptr; return fail(NP_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
-        w->graph_dt = dt;
-    }
-    CU(cudaEventRecord(w->ev[0], w->stream));
-    for (int i = 0; i < steps; i++) CU(cudaGraphLaunch(w->graph, w->stream));
-    w->launches += w->graph_launches * (unsigned long long)steps;
-    CU(cudaEventRecord(w->ev[5], w->stream));
-    w->timed = false; w->steps += (unsigned long long)steps;
+    for (int i = 0; i < steps; i++) { r = step_once(w, dt); if (r) return r; }
+    w->timed = true; w->steps += (unsigned long long)steps;                // (the phase events are those of the last step)
     return NP_OK;
 }
 int np_world_integrate(np_world* w, float dt)
@@ -899,8 +923,8 @@ int np_world_step_host(np_world* w, float dt, const np_body_state* in, np_body_s
     if (!w || !out || n != (int)w->bodies.size()) return fail(NP_ERR_INVALID, "bad arguments");
     int r = ensure_device(w); if (r) return r;
     if (in) { r = upload_states(w, in, n); if (r) return r; }
-    r = enqueue_step(w, dt, false); if (r) return r;
-    w->timed = false; w->steps++;
+    r = step_once(w, dt); if (r) return r;
+    w->timed = true; w->steps++;
     return download_states(w, out, n);
 }
 int np_world_get_counters(np_world* w, np_counters* out)
@@ -922,7 +946,7 @@ int np_world_last_step_ms(np_world* w, float out[6])
     CU(cudaStreamSynchronize(w->stream));
     for (int k = 0; k < 6; k++) out[k] = 0.0f;
     if (w->steps == 0) return NP_OK;
-    if (w->timed) {
+    if (w->timed && w->phase_timing) {
         for (int k = 0; k < 5; k++) CU(cudaEventElapsedTime(&out[k], w->ev[k], w->ev[k + 1]));
         CU(cudaEventElapsedTime(&out[5], w->ev[0], w->ev[5]));
     } else CU(cudaEventElapsedTime(&out[5], w->ev[0], w->ev[5]));
@@ -1081,7 +1105,7 @@ int np_world_snapshot_device(np_world* w, void** d_ptr, size_t* bytes)
 int np_world_set_snapshot_target(np_world* w, void* d_dst, uint32_t guid_base)
 {
     if (!w) return fail(NP_ERR_INVALID, "null world");
-    w->snap_target = d_dst; w->guid_base = guid_base; drop_graph(w);
+    w->snap_target = d_dst; w->guid_base = guid_base;          // (captured steps are keyed by the target)
     return NP_OK;
 }
 int np_world_snapshot(np_world* w, np_snapshot_object* dst, int cap)

@@ -169,7 +169,7 @@ class World:
     """np_world.  Mirrors the reference's implicit global world (engine/physics.cpp:9) as an explicit object."""
 
     EXACT, GRID = 0, 1
-    OPT_BROADPHASE, OPT_GRID_CELL, OPT_COUNTERS, OPT_SNAPSHOT_EACH_STEP = 1, 2, 3, 4
+    OPT_BROADPHASE, OPT_GRID_CELL, OPT_COUNTERS, OPT_SNAPSHOT_EACH_STEP, OPT_PHASE_TIMING = 1, 2, 3, 4, 5
 
     def __init__(self, device=-1, variant="exact"):
         self.L = load_library(variant)

@@ -10,6 +10,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 sc = scenes.lattice_scene(n, spacing=1.2, seed=42)
 with npb.World(0) as w:
     w.set_option(w.OPT_COUNTERS, 1)
+    w.set_option(w.OPT_PHASE_TIMING, 1)
     w.load_scene(sc)
     for k in range(5): w.step(sc["dt"])
     print("step ms", np.round(w.last_step_ms(), 4))

@@ -8,7 +8,7 @@ spacing = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 sc = scenes.lattice_scene(n, spacing=spacing, seed=43, mix=(0.7, 0.2, 0.1))
 for mode in (1, 0):
     with npb.World(0) as w:
-        w.set_option(w.OPT_BROADPHASE, mode); w.set_option(w.OPT_COUNTERS, 1)
+        w.set_option(w.OPT_BROADPHASE, mode); w.set_option(w.OPT_PHASE_TIMING, 1); w.set_option(w.OPT_COUNTERS, 1)
         w.load_scene(sc)
         for k in range(4):
             w.step(sc["dt"]); ms = w.last_step_ms()

@@ -10,6 +10,7 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 mix = {"c2": (0.5, 0.5, 0.0), "c3": (0.7, 0.2, 0.1), "box": (1, 0, 0)}[sys.argv[3] if len(sys.argv) > 3 else "c2"]
 sc = scenes.lattice_scene(n, spacing=1.2, seed=42, mix=mix)
 with npb.World(0) as w:
+    w.set_option(w.OPT_PHASE_TIMING, 1)
     w.load_scene(sc)
     for k in range(steps):
         w.step(sc["dt"])

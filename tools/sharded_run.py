@@ -28,6 +28,7 @@ W = npb.World
 with W(lr) as w, W(lr) as ref:
     for x in (w, ref):
         if grid: x.set_option(W.OPT_BROADPHASE, W.GRID)
+        x.set_option(W.OPT_PHASE_TIMING, 1)
         x.load_scene(sc)
     sw = ShardedWorld(w, torch.device("cuda", lr), ws, rank)
     dt = sc["dt"]
