@@ -58,7 +58,7 @@ struct np_world {
     int shard_first = 0, shard_count = -1; int *x_hit_j = nullptr, *x_cflags = nullptr; float4* x_contact = nullptr;
     bool mid_step = false;
     int* d_zero = nullptr;            // [tickets and counts (32 ints), head[cap] of the incoming-collision lists]  -- one memset per step
-    int *d_inc_off = nullptr, *d_inc = nullptr, *d_sums = nullptr, *d_big_list = nullptr, *d_hit_list = nullptr;
+    int *d_inc = nullptr /* next[] of the incoming-collision lists */, *d_sums = nullptr, *d_big_list = nullptr, *d_hit_list = nullptr;
     float4* d_simplex = nullptr;      // GJK result of every hit: A[4], B[4]
     float4* d_wverts = nullptr; size_t wverts_cap = 0;   // per-step world-vertex cache (K1b)
     float* d_ext = nullptr;           // adapter extension, allocated on first use: [4][cap] external force xyz + enabled flag
@@ -93,15 +93,14 @@ static int* cflags(np_world* w) { return w->x_cflags ? w->x_cflags : w->d_cflags
 static float4* contacts(np_world* w) { return w->x_contact ? w->x_contact : w->d_contact; }
 static bool sharded(np_world* w) { return w->shard_count >= 0; }
 static int* d_inc_cnt(np_world* w) { return w->d_zero + 32; }
-static int* d_cursor(np_world* w) { return w->d_zero + 32 + w->cap; }
 
 static void free_store(np_world* w)
 {
     cudaFree(w->d_state); cudaFree(w->d_cst); cudaFree(w->d_xf); cudaFree(w->d_ints);
     cudaFree(w->d_hit_j); cudaFree(w->d_cflags); cudaFree(w->d_contact); cudaFree(w->d_zero);
-    cudaFree(w->d_inc_off); cudaFree(w->d_inc); cudaFree(w->d_sums); cudaFree(w->d_big_list); cudaFree(w->d_snap); cudaFree(w->d_hit_list); cudaFree(w->d_simplex);
+    cudaFree(w->d_inc); cudaFree(w->d_sums); cudaFree(w->d_big_list); cudaFree(w->d_snap); cudaFree(w->d_hit_list); cudaFree(w->d_simplex);
     w->d_state = w->d_cst = w->d_xf = nullptr; w->d_ints = nullptr; w->d_hit_j = w->d_cflags = nullptr; w->d_contact = nullptr;
-    w->d_zero = w->d_inc_off = w->d_inc = w->d_sums = w->d_big_list = w->d_hit_list = nullptr; w->d_snap = nullptr; w->d_simplex = nullptr;
+    w->d_zero = w->d_inc = w->d_sums = w->d_big_list = w->d_hit_list = nullptr; w->d_snap = nullptr; w->d_simplex = nullptr;
     w->cap = 0;
 }
 static int ensure_stage(np_world* w, size_t bytes)
@@ -158,7 +157,7 @@ static int alloc_store(np_world* w, size_t c)
     CU(cudaMalloc((void**)&w->d_state, sizeof(float) * S_COUNT * c)); CU(cudaMalloc((void**)&w->d_cst, sizeof(float) * C_COUNT * c));
     CU(cudaMalloc((void**)&w->d_xf, sizeof(float) * X_COUNT * c)); CU(cudaMalloc((void**)&w->d_ints, sizeof(int) * I_COUNT * c));
     CU(cudaMalloc((void**)&w->d_hit_j, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_cflags, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_contact, sizeof(float4) * c));
-    CU(cudaMalloc((void**)&w->d_zero, sizeof(int) * (32 + 2 * c))); CU(cudaMalloc((void**)&w->d_inc_off, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_inc, sizeof(int) * c));
+    CU(cudaMalloc((void**)&w->d_zero, sizeof(int) * (32 + c))); CU(cudaMalloc((void**)&w->d_inc, sizeof(int) * c));
     CU(cudaMalloc((void**)&w->d_sums, sizeof(int) * (4 * c / NP_SCAN_BLOCK + 2))); CU(cudaMalloc((void**)&w->d_big_list, sizeof(int) * c));
     CU(cudaMalloc((void**)&w->d_snap, sizeof(SnapObj) * c));
     CU(cudaMalloc((void**)&w->d_hit_list, sizeof(int) * NP_HIT_CLASSES * c)); CU(cudaMalloc((void**)&w->d_simplex, sizeof(float4) * 6 * c));
@@ -295,7 +294,7 @@ static int ensure_device(np_world* w)
 static int ensure_arena(np_world* w)
 {
     if (w->arena.base) return NP_OK;
-    w->arena.slots = w->sm_count * 2 * (NP_MID_THREADS / 32);             // one slot per warp of the TIER 2 launch
+    w->arena.slots = 128;             // one slot (an 8192-face polytope, 263 KB) per warp of the TIER 2 launch: polytopes beyond 1024 faces are pathological
     CU(cudaMalloc((void**)&w->arena.base, sizeof(float) * (size_t)poly_words_fast(NP_FBIG) * w->arena.slots));
     return NP_OK;
 }
