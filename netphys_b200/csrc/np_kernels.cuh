@@ -4,8 +4,8 @@
 //   K3  k_gjk<G>             GJK: GetCollisions' ordered first-hit search (physics.cpp:116-145) or an explicit pair list
 //   K4  k_epa<G,FMAX,BIG>    EPA over the hits (collision_detection.cpp:412-566); BIG = large-polytope re-run
 //   K0  k_pose_xf            GetTransform for pair-list queries
-//   K5  k_count_incoming / k_fill_incoming / k_resolve   OnCollision + ApplyImpulseResponse (physics.cpp:27-114)
-//   K6  k_snapshot           CommandFrameObject packing                 (netphys_server/world_s.cpp:23-51)
+//   K5  k_link / k_resolve   OnCollision + ApplyImpulseResponse (physics.cpp:27-114), + the snapshot record of the step
+//   K6  k_snapshot           CommandFrameObject packing on demand       (netphys_server/world_s.cpp:23-51)
 //
 // HBM layout: structure-of-arrays by COMPONENT, every array `cap` floats long (cap a multiple of 32), so a
 // warp reading component c of 32 consecutive bodies issues one fully coalesced 128-byte request.
