@@ -536,26 +536,24 @@ struct EpaMachine {
             __syncwarp(m);
         }
         bad = __ballot_sync(m, bad != 0) != 0u;
-        // pass 3: survivors in insertion order -> new faces
+        // pass 3: survivors, in insertion order, compacted into the (already consumed) head of seq[]; then one new face per survivor.
+        // AddFace is the long dependent chain of the expansion (normalise + closest point on the triangle), so it runs
+        // ceil(survivors / 32) times, not once per round of tokens.
         int ne = 0;
         for (int base = 0; base < ntok; base += G) {
             const int t = base + gl;
             bool alive = false; uint16_t ed = 0;
             if (t < ntok) { ed = poly.E(t); uint16_t s = poly.seq[t]; alive = (s != 0xffff) && (s >= (poly.tab[(ed & 0xff) * NP_EPA_MAX_VERTS + (ed >> 8)] >> 8)); }
-            ne += __popc(__ballot_sync(m, alive));
+            const unsigned am = __ballot_sync(m, alive);
+            __syncwarp(m);                                                       // every lane has read its seq[t]: positions <= t may be overwritten
+            if (alive) poly.seq[ne + __popc(am & ((1u << gl) - 1u))] = ed;
+            ne += __popc(am);
+            __syncwarp(m);
         }
         if (bad || keep + ne > poly.fmax) { clear_table(poly, ntok); flags |= NP_PAIR_OVERFLOW; done = true; return; }
         if (gl == 0) poly.setv(pnv, sp, sa, sb);
         __syncwarp(m);
-        int slot = keep;
-        for (int base = 0; base < ntok; base += G) {
-            const int t = base + gl;
-            bool alive = false; uint16_t ed = 0;
-            if (t < ntok) { ed = poly.E(t); uint16_t s = poly.seq[t]; alive = (s != 0xffff) && (s >= (poly.tab[(ed & 0xff) * NP_EPA_MAX_VERTS + (ed >> 8)] >> 8)); }
-            const unsigned am = __ballot_sync(m, alive);
-            if (alive) add_face_at(poly, slot + __popc(am & ((1u << gl) - 1u)), ed & 0xff, ed >> 8, pnv);
-            slot += __popc(am);
-        }
+        for (int e = gl; e < ne; e += G) { const uint16_t ed = poly.seq[e]; add_face_at(poly, keep + e, ed & 0xff, ed >> 8, pnv); }
         clear_table(poly, ntok);
         pnf = keep + ne; pnv++;
         __syncwarp(m);
