@@ -415,6 +415,9 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
             else { mp.trip(g, poly_ptr, st); done = mp.done; fl = mp.flags; pen = mp.pen; depth = mp.depth; }
             if (done) {
                 if (WORLD && lead) { NP_TL(item, 5); NP_TLV(item, 6, LOCAL ? ml.steps : mp.steps); }
+#ifdef NP_TIMELINE
+                if (WORLD && lead && !LOCAL && item < 65536) { g_tl[8 * item + 0] = mp.cyc[0]; g_tl[8 * item + 1] = mp.cyc[1]; g_tl[8 * item + 2] = mp.cyc[2]; g_tl[8 * item + 3] = mp.cyc[3]; g_tl[8 * item + 7] = mp.pnf; }
+#endif
                 const bool requeue = (fl & NP_PAIR_OVERFLOW) && TIER < 2;
                 if (lead) {
                     if (requeue) next_list[atomicAdd(next_count, 1)] = item;                       // flags/simplex stay for the re-run

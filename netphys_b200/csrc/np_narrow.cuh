@@ -338,6 +338,9 @@ struct EpaMachine {
     float dist;
     int flags; V3 pen; float depth;
     bool done;
+#ifdef NP_TIMELINE
+    long long cyc[4];      // produce | supports | consume up to the token replay | survivors + new faces
+#endif
 
     // Simplex::AddFace, simplex.h:37-53 (called by one lane per face).  Also evaluates, once, what every later
     // GetClosestTriangleToOrigin scan (:300-318) would recompute for this face: the squared distance of its closest
@@ -357,6 +360,9 @@ struct EpaMachine {
     NP_D void begin(Poly& poly, const V3* A4, const V3* B4, int seed_alive)
     {
         pnv = 4; pnf = 4; steps = 0; flags = NP_PAIR_HIT; pen = mk(0.0f, 0.0f, 0.0f); depth = 0.0f; dist = 0.0f; done = false;
+#ifdef NP_TIMELINE
+        cyc[0] = cyc[1] = cyc[2] = cyc[3] = 0;
+#endif
         d = mk(0.0f, 0.0f, 0.0f);
         if constexpr (FAST) { for (int q = glane<G>(); q < NP_EPA_MAX_VERTS * NP_EPA_MAX_VERTS; q += G) poly.tab[q] = 0; }
         if (glane<G>() == 0) {
@@ -536,6 +542,9 @@ struct EpaMachine {
             __syncwarp(m);
         }
         bad = __ballot_sync(m, bad != 0) != 0u;
+#ifdef NP_TIMELINE
+        const long long cp3 = clock64();
+#endif
         // pass 3: survivors, in insertion order, compacted into the (already consumed) head of seq[]; then one new face per survivor.
         // AddFace is the long dependent chain of the expansion (normalise + closest point on the triangle), so it runs
         // ceil(survivors / 32) times, not once per round of tokens.
@@ -554,6 +563,9 @@ struct EpaMachine {
         if (gl == 0) poly.setv(pnv, sp, sa, sb);
         __syncwarp(m);
         for (int e = gl; e < ne; e += G) { const uint16_t ed = poly.seq[e]; add_face_at(poly, keep + e, ed & 0xff, ed >> 8, pnv); }
+#ifdef NP_TIMELINE
+        cyc[3] += clock64() - cp3;
+#endif
         clear_table(poly, ntok);
         pnf = keep + ne; pnv++;
         __syncwarp(m);
@@ -571,12 +583,24 @@ struct EpaMachine {
     // call while !done: [closest face] -> [support pair] -> [convergence test / expansion]
     NP_D void trip(const PairGeom& g, Poly& poly, PairStats& st)
     {
+#ifdef NP_TIMELINE
+        long long c0 = clock64();
+#endif
         produce(poly, st);
+#ifdef NP_TIMELINE
+        long long c1 = clock64(); cyc[0] += c1 - c0;
+#endif
         if (done) return;
         V3 sa = support<G, CACHED>(g.va, g.na, g.Ra, g.ta, d);
         V3 sb = support<G, CACHED>(g.vb, g.nb, g.Rb, g.tb, neg(d));
+#ifdef NP_TIMELINE
+        long long c2 = clock64(); cyc[1] += c2 - c1;
+#endif
         st.support_pairs++; st.support_verts += (unsigned)(g.na + g.nb);
         if constexpr (FAST) consume_fast(poly, sa, sb); else consume(poly, sa, sb);
+#ifdef NP_TIMELINE
+        cyc[2] += clock64() - c2;
+#endif
     }
 };
 
