@@ -494,7 +494,14 @@ struct EpaMachine {
             if (veq(sa, poly.gA(i), NP_EPA_TOL) && veq(sb, poly.gB(i), NP_EPA_TOL)) found = true;
         found = __ballot_sync(m, found) != 0u;
         if (found) { converge(); return; }
-        // pass 1: visibility, horizon tokens (3 per visible face, in face order), order-preserving compaction of the rest
+        // pass 1: visibility, horizon tokens (3 per visible face, in face order), order-preserving compaction of the rest.  The directed
+        // edges of the removed faces are also marked in a 24x24 bit table: as long as none occurs twice, UniqueEdges keeps exactly the
+        // edges whose reverse is not an edge of a removed face, in token order -- whichever of the two came first, the later one erases
+        // the earlier and is not added -- and the replay of pass 2 is not needed.
+        uint32_t* bits = (uint32_t*)(poly.tab + NP_EPA_MAX_VERTS * NP_EPA_MAX_VERTS);      // the unused half of the counter-table area
+        if (gl < (NP_EPA_MAX_VERTS * NP_EPA_MAX_VERTS + 31) / 32) bits[gl] = 0u;
+        __syncwarp(m);
+        bool dup = false;
         int keep = 0, ntok = 0;
         for (int base = 0; base < pnf; base += G) {
             const int f = base + gl;
@@ -507,6 +514,10 @@ struct EpaMachine {
                 int t = ntok + 3 * __popc(vmask & ((1u << gl) - 1u));
                 int v0 = idx & 0xff, v1 = (idx >> 8) & 0xff, v2 = (idx >> 16) & 0xff;
                 if (t + 2 < poly.emax) { poly.setE(t, (uint16_t)(v0 | (v1 << 8))); poly.setE(t + 1, (uint16_t)(v1 | (v2 << 8))); poly.setE(t + 2, (uint16_t)(v2 | (v0 << 8))); }
+                const int e0 = v0 * NP_EPA_MAX_VERTS + v1, e1 = v1 * NP_EPA_MAX_VERTS + v2, e2 = v2 * NP_EPA_MAX_VERTS + v0;
+                dup |= (atomicOr(&bits[e0 >> 5], 1u << (e0 & 31)) >> (e0 & 31)) & 1u;
+                dup |= (atomicOr(&bits[e1 >> 5], 1u << (e1 & 31)) >> (e1 & 31)) & 1u;
+                dup |= (atomicOr(&bits[e2 >> 5], 1u << (e2 & 31)) >> (e2 & 31)) & 1u;
             }
             ntok += 3 * __popc(vmask);
             __syncwarp(m);
@@ -520,8 +531,9 @@ struct EpaMachine {
         // pass 2: replay the tokens in rounds of 32.  tab[a*24+b] = inserted (low byte) | cancelled (high byte) of directed
         // edge (a,b); the table is all zero between expansions.  Tokens of one unordered vertex pair are handled, in order,
         // by the lowest lane holding one of them (__match_any_sync); different pairs touch different entries.
+        const bool replay = __ballot_sync(m, dup) != 0u;        // a directed edge occurred twice: the order of the erasures matters
         int bad = 0;
-        for (int base = 0; base < ntok; base += G) {
+        for (int base = 0; replay && base < ntok; base += G) {
             const int t = base + gl;
             const bool tv = t < ntok;
             const uint16_t ed = tv ? poly.E(t) : (uint16_t)0;
@@ -552,21 +564,25 @@ struct EpaMachine {
         for (int base = 0; base < ntok; base += G) {
             const int t = base + gl;
             bool alive = false; uint16_t ed = 0;
-            if (t < ntok) { ed = poly.E(t); uint16_t s = poly.seq[t]; alive = (s != 0xffff) && (s >= (poly.tab[(ed & 0xff) * NP_EPA_MAX_VERTS + (ed >> 8)] >> 8)); }
+            if (t < ntok) {
+                ed = poly.E(t);
+                if (replay) { uint16_t s = poly.seq[t]; alive = (s != 0xffff) && (s >= (poly.tab[(ed & 0xff) * NP_EPA_MAX_VERTS + (ed >> 8)] >> 8)); }
+                else { const int r = (ed >> 8) * NP_EPA_MAX_VERTS + (ed & 0xff); alive = ((bits[r >> 5] >> (r & 31)) & 1u) == 0u; }
+            }
             const unsigned am = __ballot_sync(m, alive);
             __syncwarp(m);                                                       // every lane has read its seq[t]: positions <= t may be overwritten
             if (alive) poly.seq[ne + __popc(am & ((1u << gl) - 1u))] = ed;
             ne += __popc(am);
             __syncwarp(m);
         }
-        if (bad || keep + ne > poly.fmax) { clear_table(poly, ntok); flags |= NP_PAIR_OVERFLOW; done = true; return; }
+        if (bad || keep + ne > poly.fmax) { if (replay) clear_table(poly, ntok); flags |= NP_PAIR_OVERFLOW; done = true; return; }
         if (gl == 0) poly.setv(pnv, sp, sa, sb);
         __syncwarp(m);
         for (int e = gl; e < ne; e += G) { const uint16_t ed = poly.seq[e]; add_face_at(poly, keep + e, ed & 0xff, ed >> 8, pnv); }
 #ifdef NP_TIMELINE
         cyc[3] += clock64() - cp3;
 #endif
-        clear_table(poly, ntok);
+        if (replay) clear_table(poly, ntok);
         pnf = keep + ne; pnv++;
         __syncwarp(m);
     }
