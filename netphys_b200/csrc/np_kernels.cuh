@@ -260,6 +260,9 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
             if (t < in.n) {
                 i = WORLD ? (in.ordered ? s.ints[I_ORDER * s.cap + in.first + t] : t + in.first) : (in.order ? in.order[t] : t);
                 if (WORLD && lead) { NP_TL(i, 0); NP_TLV(i, 2, 0); NP_TLV(i, 3, 0); }
+#ifdef NP_TIMELINE
+                m.cyc[0] = m.cyc[1] = m.cyc[2] = 0;
+#endif
                 if (WORLD) {
                     if (in.cand) { cbase = in.cand_off[i]; c = 0; jend = in.cand_cnt[i]; j = jend > 0 ? in.cand[cbase] : 0; if (jend > 0) jend = 0x7fffffff; cn = in.cand_cnt[i]; }
                     else { j = i + 1; jend = island_end[i]; }
@@ -300,6 +303,9 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
                     n_hits++;
                     if (lead) {
                         if (WORLD) { NP_TL(i, 1); NP_TLV(i, 7, (g.na << 16) | g.nb); }
+#ifdef NP_TIMELINE
+                        if (WORLD && i < 65536) { g_tl[8 * i + 3] = (unsigned long long)m.cyc[0]; g_tl[8 * i + 4] = (unsigned long long)m.cyc[1]; g_tl[8 * i + 5] = (unsigned long long)m.cyc[2]; }
+#endif
                         if (WORLD) hit_j[i] = j;
                         flags[i] = NP_PAIR_HIT | (m.seed_alive ? NP_PAIR_SEED_ALIVE : 0);
                         float4* o = simplex + (size_t)i * 6;
@@ -405,7 +411,9 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
                 if constexpr (LOCAL) ml.begin(poly_local, A4, B4, seed); else mp.begin(poly_ptr, A4, B4, seed);
                 st0 = st;
                 have = true;
+#ifndef NP_TL_GJK
                 if (WORLD && lead) NP_TL(item, 4);
+#endif
             } else exhausted = true;
         }
         if (!__any_sync(0xffffffffu, have)) { if (__all_sync(0xffffffffu, exhausted)) break; else continue; }
@@ -414,8 +422,10 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
             if constexpr (LOCAL) { ml.trip(g, poly_local, st); done = ml.done; fl = ml.flags; pen = ml.pen; depth = ml.depth; }
             else { mp.trip(g, poly_ptr, st); done = mp.done; fl = mp.flags; pen = mp.pen; depth = mp.depth; }
             if (done) {
+#ifndef NP_TL_GJK
                 if (WORLD && lead) { NP_TL(item, 5); NP_TLV(item, 6, LOCAL ? ml.steps : mp.steps); }
-#ifdef NP_TIMELINE
+#endif
+#if defined(NP_TIMELINE) && !defined(NP_TL_GJK)      // (-DNP_TL_GJK keeps the GJK stamps of tools/gjk_cycles.py instead)
                 if (WORLD && lead && !LOCAL && item < 65536) { g_tl[8 * item + 0] = mp.cyc[0]; g_tl[8 * item + 1] = mp.cyc[1]; g_tl[8 * item + 2] = mp.cyc[2]; g_tl[8 * item + 3] = mp.cyc[3]; g_tl[8 * item + 7] = mp.pnf; }
 #endif
                 const bool requeue = (fl & NP_PAIR_OVERFLOW) && TIER < 2;

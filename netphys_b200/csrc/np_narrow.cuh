@@ -79,25 +79,25 @@ NP_D V3 support(const float4* __restrict__ v, int n, const float* R, V3 t, V3 d)
         float4 q = v[bi];
         return CACHED ? mk(q.x, q.y, q.z) : xf_point(R, t, mk(q.x, q.y, q.z));
     }
-    // latency regime: each lane keeps its own winner; the cross-lane arg-max is two warp reductions (redux.sync) on an
-    // order-preserving integer image of the dot product (-0 folded into +0, as '>' does) and on the vertex index, then one
-    // broadcast of the owner's position.  Larger dot wins, lower index on ties == the reference's strict '>' scan.
-    V3 best = mk(0.0f, 0.0f, 0.0f);
+    // latency regime: each lane tracks (best dot, index) only -- the loop is the longest dependent stretch of a trip (half of its cycles,
+    // tools/gjk_cycles.py), so it carries as few instructions per vertex as possible.  The cross-lane arg-max is two warp reductions
+    // (redux.sync) on an order-preserving integer image of the dot product (-0 folded into +0, as '>' does) and on the vertex index:
+    // larger dot wins, lower index on ties == the reference's strict '>' scan.  The winner's position is then re-read (one broadcast
+    // load) and, where the vertices are shape-local, transformed again: same operands, same bits.
 #pragma unroll 4
     for (int k = glane<G>(); k < n; k += G) {
         float4 q = v[k];
         V3 wp = CACHED ? mk(q.x, q.y, q.z) : xf_point(R, t, mk(q.x, q.y, q.z));
         float dp = dot(d, wp);
-        if (dp > bd) { bd = dp; bi = k; best = wp; }
+        if (dp > bd) { bd = dp; bi = k; }
     }
     const unsigned m = gmask<G>();
     const int key = float_order(bd + 0.0f);
     const int kmax = __reduce_max_sync(m, key);
     const unsigned imin = __reduce_min_sync(m, (key == kmax) ? (unsigned)bi : 0xffffffffu);
     if (imin >= 0x7fffffffu) return mk(0.0f, 0.0f, 0.0f);
-    const int owner = (int)(imin & (unsigned)(G - 1));
-    best.x = __shfl_sync(m, best.x, owner, G); best.y = __shfl_sync(m, best.y, owner, G); best.z = __shfl_sync(m, best.z, owner, G);
-    return best;
+    const float4 q = v[imin];
+    return CACHED ? mk(q.x, q.y, q.z) : xf_point(R, t, mk(q.x, q.y, q.z));
 }
 
 // Thread-per-pair kernels: the lanes of a warp hold different pairs, and a per-lane vertex loop runs as long as the LARGEST shape in
@@ -130,20 +130,22 @@ NP_D V3 support_coop(bool want, const float4* __restrict__ v, int n, const float
             for (int k = 0; k < 9; k++) sR[k] = __shfl_sync(full, R[k], src);
             const V3 st = mk(__shfl_sync(full, t.x, src), __shfl_sync(full, t.y, src), __shfl_sync(full, t.z, src));
             const V3 sd = mk(__shfl_sync(full, d.x, src), __shfl_sync(full, d.y, src), __shfl_sync(full, d.z, src));
-            float bd = -INFINITY; int bi = 0x7fffffff; V3 best = mk(0.0f, 0.0f, 0.0f);
+            float bd = -INFINITY; int bi = 0x7fffffff;
 #pragma unroll 2
             for (int k = lane; k < sn; k += 32) {
                 float4 q = sv[k];
                 V3 wp = xf_point(sR, st, mk(q.x, q.y, q.z));
                 float dp = dot(sd, wp);
-                if (dp > bd) { bd = dp; bi = k; best = wp; }
+                if (dp > bd) { bd = dp; bi = k; }
             }
             const int key = float_order(bd + 0.0f);
             const int kmax = __reduce_max_sync(full, key);
             const unsigned imin = __reduce_min_sync(full, (key == kmax) ? (unsigned)bi : 0xffffffffu);
-            const int owner = (int)(imin & 31u);
-            best.x = __shfl_sync(full, best.x, owner); best.y = __shfl_sync(full, best.y, owner); best.z = __shfl_sync(full, best.z, owner);
-            if ((lane & ~(G - 1)) == src) { res = (imin >= 0x7fffffffu) ? mk(0.0f, 0.0f, 0.0f) : best; served = true; }
+            if ((lane & ~(G - 1)) == src) {
+                if (imin >= 0x7fffffffu) res = mk(0.0f, 0.0f, 0.0f);
+                else { const float4 q = sv[imin]; res = xf_point(sR, st, mk(q.x, q.y, q.z)); }
+                served = true;
+            }
         }
     }
     if (want && !served) res = support<G, false>(v, n, R, t, d);
@@ -165,6 +167,9 @@ struct GjkMachine {
     V3 d;
     int nv, kn, k0, k1, k2;    // kn,k0..k2: vertices the last solve keeps (applied lazily, after the duplicate test)
     int steps, status, seed_alive;
+#ifdef NP_TIMELINE
+    long long cyc[3];      // supports | consume | produce (accumulated over the body's whole search, reset by the kernel)
+#endif
 
     NP_D void begin()
     {
@@ -264,12 +269,24 @@ struct GjkMachine {
     // call while status == RUN
     NP_D void trip(const PairGeom& g, PairStats& st)
     {
+#ifdef NP_TIMELINE
+        const long long c0 = clock64();
+#endif
         V3 sa = support<G, CACHED>(g.va, g.na, g.Ra, g.ta, d);
         V3 sb = support<G, CACHED>(g.vb, g.nb, g.Rb, g.tb, neg(d));
+#ifdef NP_TIMELINE
+        const long long c1 = clock64(); cyc[0] += c1 - c0;
+#endif
         st.support_pairs++; st.support_verts += (unsigned)(g.na + g.nb);
         if (nv == 0) { A0 = sa; B0 = sb; P0 = sub(sb, sa); nv = 1; }                              // :704  p = B - A
         else consume(sa, sb);
+#ifdef NP_TIMELINE
+        const long long c2 = clock64(); cyc[1] += c2 - c1;
+#endif
         if (status == RUN) produce(st);
+#ifdef NP_TIMELINE
+        cyc[2] += clock64() - c2;
+#endif
     }
 };
 
