@@ -1,9 +1,11 @@
 // netphys_b200/csrc/np_kernels.cuh -- CUDA kernels (sm_100a) of the per-step rigid-body path.
 //
 //   K1  k_integrate          Physics::Update + GetTransform             (physics.cpp:175-194, physics.h:70-76)
-//   K3  k_gjk<G>             GJK: GetCollisions' ordered first-hit search (physics.cpp:116-145) or an explicit pair list
-//   K4  k_epa<G,FMAX,BIG>    EPA over the hits (collision_detection.cpp:412-566); BIG = large-polytope re-run
-//   K0  k_pose_xf            GetTransform for pair-list queries
+//   K1b k_world_verts        per-step world-vertex cache (+ AABBs for the grid), only when a kernel of the step reads it
+//   K2  k_grid_*, k_cand     uniform-grid broad phase (NP_BROADPHASE_GRID; the reference has none)
+//   K3  k_gjk<G,WORLD,COOP>  GJK: GetCollisions' ordered first-hit search (physics.cpp:116-145) or an explicit pair list
+//   K4  k_epa<G,FMAX,TIER,..> EPA over the hits (collision_detection.cpp:412-566); TIER 1/2 = large-polytope re-runs
+//   K0  k_pose_xf, k_pair_order   GetTransform and the visiting order for pair-list queries
 //   K5  k_link / k_resolve   OnCollision + ApplyImpulseResponse (physics.cpp:27-114), + the snapshot record of the step
 //   K6  k_snapshot           CommandFrameObject packing on demand       (netphys_server/world_s.cpp:23-51)
 //

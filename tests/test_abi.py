@@ -77,3 +77,17 @@ def test_error_codes_without_device(npb):
     assert L.np_detect_collision_batch(None, 0, None, None, None, None, None, None) == -1
     assert b"null" in L.np_last_error() or b"bad" in L.np_last_error()
     L.np_world_destroy(None)                       # no-op
+
+
+def test_python_constants_match_the_header(npb):
+    """The ctypes view mirrors the header's enums by hand: keep them in step."""
+    import re
+    text = open(os.path.join(ROOT, "include", "netphys_b200.h")).read()
+    enum = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(NP_[A-Z0-9_]+)\s*=\s*(-?\d+)", text)}
+    W = npb.World
+    assert (W.OPT_BROADPHASE, W.OPT_GRID_CELL, W.OPT_COUNTERS, W.OPT_SNAPSHOT_EACH_STEP, W.OPT_PHASE_TIMING) == \
+        tuple(enum[k] for k in ("NP_OPT_BROADPHASE", "NP_OPT_GRID_CELL", "NP_OPT_COUNTERS", "NP_OPT_SNAPSHOT_EACH_STEP", "NP_OPT_PHASE_TIMING"))
+    assert (W.EXACT, W.GRID) == (enum["NP_BROADPHASE_EXACT"], enum["NP_BROADPHASE_GRID"])
+    assert enum["NP_OK"] == 0 and enum["NP_ERR_NO_DEVICE"] == -2
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(NP_PACKET_[A-Z_]+)\s+(\d+)", text)}
+    assert defs == {"NP_PACKET_WORLD_STATE_UPDATE": 2342144, "NP_PACKET_NEW_CONNECTION": 2342341}
