@@ -222,6 +222,10 @@ void* np_device_alloc(np_world* w, size_t bytes);
 int np_device_free(np_world* w, void* p);
 int np_device_upload(np_world* w, void* d_dst, const void* h_src, size_t bytes);
 int np_device_download(np_world* w, void* h_dst, const void* d_src, size_t bytes);
+/* page-locked host buffers: np_world_step_host / get_states / set_states copy straight to and from them (any other host pointer is
+ * staged through an internal pinned buffer with one extra memcpy each way) */
+void* np_host_alloc(np_world* w, size_t bytes);
+int np_host_free(np_world* w, void* p);
 void* np_world_stream(np_world* w);                                        /* cudaStream_t */
 /* benchmarking hygiene: overwrite a 256 MiB scratch on the world's stream so the next step starts with a cold L2 */
 int np_device_flush_l2(np_world* w);

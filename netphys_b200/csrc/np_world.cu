@@ -60,7 +60,7 @@ struct np_world {
     int* d_zero = nullptr;            // [tickets and counts (32 ints), head[cap] of the incoming-collision lists]  -- one memset per step
     int *d_inc = nullptr /* next[] of the incoming-collision lists */, *d_sums = nullptr, *d_big_list = nullptr, *d_hit_list = nullptr;
     float4* d_simplex = nullptr;      // GJK result of every hit: A[4], B[4]
-    float4* d_wverts = nullptr; size_t wverts_cap = 0;   // per-step world-vertex cache (K1b)
+    float4* d_wverts = nullptr; size_t wverts_cap = 0, wv_total = 0;   // per-step world-vertex cache (K1b), allocated on first use (ensure_cache)
     float* d_ext = nullptr;           // adapter extension, allocated on first use: [4][cap] external force xyz + enabled flag
     // grid broad phase (allocated on first use)
     GridView grid = {}; int grid_cap = 0; int* d_grid_ints = nullptr; float* d_grid_f = nullptr;
@@ -123,16 +123,25 @@ static int ensure_aos(np_world* w, size_t bytes)
     w->d_aos_bytes = bytes;
     return NP_OK;
 }
+// page-locked host memory (np_host_alloc, cudaHostRegister, cudaMallocHost) is copied to / from directly; pageable memory goes
+// through the world's pinned staging buffer
+static bool host_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
 static int download_states(np_world* w, np_body_state* out, int n)
 {
     if (n == 0) return NP_OK;
     const size_t bytes = sizeof(float) * S_COUNT * (size_t)n;
-    int r = ensure_stage(w, bytes); if (r) return r;
+    const bool direct = host_pinned(out);
+    int r = direct ? NP_OK : ensure_stage(w, bytes); if (r) return r;
     r = ensure_aos(w, bytes); if (r) return r;
     k_state_to_aos<<<(n + 255) / 256, 256, 0, w->stream>>>(n, w->cap, w->d_state, w->d_aos);
-    CU(cudaMemcpyAsync(w->h_stage, w->d_aos, bytes, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaMemcpyAsync(direct ? (void*)out : (void*)w->h_stage, w->d_aos, bytes, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
-    memcpy(out, w->h_stage, bytes);
+    if (!direct) memcpy(out, w->h_stage, bytes);
     w->launches++;
     return NP_OK;
 }
@@ -140,11 +149,14 @@ static int upload_states(np_world* w, const np_body_state* in, int n)
 {
     if (n == 0) return NP_OK;
     const size_t bytes = sizeof(float) * S_COUNT * (size_t)n;
-    int r = ensure_stage(w, bytes); if (r) return r;
+    const bool direct = host_pinned(in);
+    int r = direct ? NP_OK : ensure_stage(w, bytes); if (r) return r;
     r = ensure_aos(w, bytes); if (r) return r;
-    CU(cudaStreamSynchronize(w->stream));                      // the staging buffer may still feed an earlier copy
-    memcpy(w->h_stage, in, bytes);
-    CU(cudaMemcpyAsync(w->d_aos, w->h_stage, bytes, cudaMemcpyHostToDevice, w->stream));
+    if (!direct) {
+        CU(cudaStreamSynchronize(w->stream));                  // the staging buffer may still feed an earlier copy
+        memcpy(w->h_stage, in, bytes);
+    }
+    CU(cudaMemcpyAsync(w->d_aos, direct ? (const void*)in : (const void*)w->h_stage, bytes, cudaMemcpyHostToDevice, w->stream));
     k_state_from_aos<<<(n + 255) / 256, 256, 0, w->stream>>>(n, w->cap, w->d_aos, w->d_state);
     CU(cudaGetLastError());
     w->launches++;
@@ -276,11 +288,7 @@ static int ensure_device(np_world* w)
         if (wv_total > 0x7fffffffu) return fail(NP_ERR_CAPACITY, "world-vertex cache exceeds 2^31 vertices");
         ints[I_WVOFF * cap + i] = (int)wv_total; wv_total += w->shapes[w->bodies[i].shape].xyz.size() / 3;
     }
-    if (wv_total > w->wverts_cap) {
-        cudaFree(w->d_wverts); w->d_wverts = nullptr;
-        w->wverts_cap = wv_total + wv_total / 4 + 1024;
-        CU(cudaMalloc((void**)&w->d_wverts, sizeof(float4) * w->wverts_cap));
-    }
+    w->wv_total = wv_total;               // the cache itself is allocated by ensure_cache, only for steps whose kernels read it
     CU(cudaMemcpyAsync(w->d_cst, cst.data(), sizeof(float) * C_COUNT * cap, cudaMemcpyHostToDevice, w->stream));
     CU(cudaMemcpyAsync(w->d_ints, ints.data(), sizeof(int) * I_COUNT * cap, cudaMemcpyHostToDevice, w->stream));
     CU(cudaStreamSynchronize(w->stream));
@@ -408,6 +416,20 @@ static int launch_narrow_t(np_world* w, const NarrowIn& in, const NarrowBufs& b,
 static bool wants_cache(np_world* w, long long items)
 {
     return items > 0 && (pick_group(w, items, w->g_gjk_env, false) >= 8 || pick_group(w, items, w->g_epa_env, true) >= 8);
+}
+// the world-vertex cache is allocated the first time a step's kernels read it (never inside a stream capture); on failure nothing changes
+static int ensure_cache(np_world* w)
+{
+    const int n = (int)w->bodies.size();
+    const long long count = w->shard_count >= 0 ? w->shard_count : n;
+    if (!wants_cache(w, count) || w->wv_total <= w->wverts_cap) return NP_OK;
+    drop_graph(w);
+    CU(cudaStreamSynchronize(w->stream));
+    cudaFree(w->d_wverts); w->d_wverts = nullptr; w->wverts_cap = 0;
+    const size_t want = w->wv_total + w->wv_total / 4 + 1024;
+    CU(cudaMalloc((void**)&w->d_wverts, sizeof(float4) * want));
+    w->wverts_cap = want;
+    return NP_OK;
 }
 static int launch_narrow(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevCounters* ctr)
 {
@@ -563,6 +585,8 @@ void np_world_destroy(np_world* w)
     cudaSetDevice(w->device);
     if (w->stream) cudaStreamSynchronize(w->stream);
     drop_graph(w); free_store(w); cudaFree(w->d_ext);
+    cudaFree(w->d_wverts); w->d_wverts = nullptr; w->wverts_cap = 0;
+    cudaFree(w->d_aos); w->d_aos = nullptr; w->d_aos_bytes = 0;
     cudaFree(w->d_verts); cudaFree(w->d_soff); cudaFree(w->d_scnt); cudaFree(w->d_ctr); cudaFree(w->d_flush); cudaFree(w->d_grid_ints); cudaFree(w->d_grid_f);
     cudaFree(w->arena.base);
     if (w->h_stage) cudaFreeHost(w->h_stage);
@@ -592,6 +616,7 @@ static int check_grid_error(np_world* w)
     int e = 0;
     CU(cudaMemcpyAsync(&e, w->grid.error, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
+    if (e) CU(cudaMemsetAsync(w->grid.error, 0, sizeof(int), w->stream));      // reported once; the flag then starts over
     if (e) return fail(NP_ERR_CAPACITY, "broad phase emitted more than NP_CAND_PER_BODY x capacity candidate pairs; raise the grid cell option or the capacity");
     return NP_OK;
 }
@@ -750,6 +775,7 @@ int np_world_clear_bodies(np_world* w)                                          
     w->bodies.clear(); w->host_state.clear(); w->island = 0;
     w->dirty_bodies = true; w->dev_state_valid = false; w->dev_n = 0;
     if (w->d_ext) { cudaFree(w->d_ext); w->d_ext = nullptr; }
+    cudaFree(w->d_wverts); w->d_wverts = nullptr; w->wverts_cap = 0; w->wv_total = 0;
     w->shard_first = 0; w->shard_count = -1; w->x_hit_j = w->x_cflags = nullptr; w->x_contact = nullptr;
     return NP_OK;
 }
@@ -828,6 +854,7 @@ int np_world_step(np_world* w, float dt)
 {
     if (!w) return fail(NP_ERR_INVALID, "null world");
     int r = ensure_device(w); if (r) return r;
+    r = ensure_cache(w); if (r) return r;
     if (w->bodies.empty()) return NP_OK;
     r = step_once(w, dt); if (r) return r;
     w->timed = true; w->steps++;
@@ -853,6 +880,7 @@ int np_world_step_begin(np_world* w, float dt)
     if (!w) return fail(NP_ERR_INVALID, "null world");
     if (w->mid_step) return fail(NP_ERR_INVALID, "np_world_step_begin called twice");
     int r = ensure_device(w); if (r) return r;
+    r = ensure_cache(w); if (r) return r;
     const int n = (int)w->bodies.size();
     if (sharded(w) && (long long)w->shard_first + w->shard_count > n) {      // ranks past the end own an empty or clipped range
         if (w->shard_first > n) w->shard_first = n;
@@ -876,6 +904,7 @@ int np_world_step_n(np_world* w, float dt, int steps)
 {
     if (!w || steps < 0) return fail(NP_ERR_INVALID, "bad arguments");
     int r = ensure_device(w); if (r) return r;
+    r = ensure_cache(w); if (r) return r;
     if (w->bodies.empty() || steps == 0) return NP_OK;
     for (int i = 0; i < steps; i++) { r = step_once(w, dt); if (r) return r; }
     w->timed = true; w->steps += (unsigned long long)steps;                // (the phase events are those of the last step)
@@ -921,6 +950,7 @@ int np_world_step_host(np_world* w, float dt, const np_body_state* in, np_body_s
 {
     if (!w || !out || n != (int)w->bodies.size()) return fail(NP_ERR_INVALID, "bad arguments");
     int r = ensure_device(w); if (r) return r;
+    r = ensure_cache(w); if (r) return r;
     if (in) { r = upload_states(w, in, n); if (r) return r; }
     r = step_once(w, dt); if (r) return r;
     w->timed = true; w->steps++;
@@ -1154,6 +1184,8 @@ void* np_device_alloc(np_world* w, size_t bytes) { if (!w) return nullptr; void*
 int np_device_free(np_world* w, void* p) { if (!w) return fail(NP_ERR_INVALID, "null world"); CU(cudaSetDevice(w->device)); CU(cudaStreamSynchronize(w->stream)); CU(cudaFree(p)); return NP_OK; }
 int np_device_upload(np_world* w, void* d_dst, const void* h_src, size_t bytes) { if (!w) return fail(NP_ERR_INVALID, "null world"); CU(cudaSetDevice(w->device)); CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, w->stream)); CU(cudaStreamSynchronize(w->stream)); return NP_OK; }
 int np_device_download(np_world* w, void* h_dst, const void* d_src, size_t bytes) { if (!w) return fail(NP_ERR_INVALID, "null world"); CU(cudaSetDevice(w->device)); CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, w->stream)); CU(cudaStreamSynchronize(w->stream)); return NP_OK; }
+void* np_host_alloc(np_world* w, size_t bytes) { if (!w) return nullptr; void* p = nullptr; if (cudaSetDevice(w->device) != cudaSuccess || cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { fail(NP_ERR_CUDA, "cudaMallocHost failed"); return nullptr; } return p; }
+int np_host_free(np_world* w, void* p) { if (!w) return fail(NP_ERR_INVALID, "null world"); CU(cudaSetDevice(w->device)); CU(cudaStreamSynchronize(w->stream)); CU(cudaFreeHost(p)); return NP_OK; }
 void* np_world_stream(np_world* w) { return w ? (void*)w->stream : nullptr; }
 int np_device_flush_l2(np_world* w)
 {

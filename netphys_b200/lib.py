@@ -127,6 +127,8 @@ def load_library(variant="exact"):
     L.np_device_free.argtypes = [vp, vp]
     L.np_device_upload.argtypes = [vp, vp, vp, C.c_size_t]
     L.np_device_download.argtypes = [vp, vp, vp, C.c_size_t]
+    L.np_host_alloc.restype = vp; L.np_host_alloc.argtypes = [vp, C.c_size_t]
+    L.np_host_free.argtypes = [vp, vp]
     L.np_world_stream.restype = vp; L.np_world_stream.argtypes = [vp]
     L.np_device_flush_l2.argtypes = [vp]
     L.np_world_record_frame.argtypes = [vp, C.c_double]
@@ -340,6 +342,22 @@ class World:
     def dev_free(self, p): self._ck(self.L.np_device_free(self.w, p))
     def dev_upload(self, p, arr): arr = np.ascontiguousarray(arr); self._ck(self.L.np_device_upload(self.w, p, arr.ctypes.data, arr.nbytes))
     def dev_download(self, arr, p): self._ck(self.L.np_device_download(self.w, arr.ctypes.data, p, arr.nbytes))
+
+    def host_array(self, shape, dtype=np.float32):
+        """numpy array backed by page-locked host memory (np_host_alloc); free with host_free(arr) before the world closes."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = self.L.np_host_alloc(self.w, nbytes)
+        if not p:
+            raise NetphysError(self.L.np_last_error().decode())
+        buf = (C.c_char * nbytes).from_address(p)
+        arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        arr[...] = 0
+        self._pinned = getattr(self, "_pinned", {}); self._pinned[arr.ctypes.data] = p
+        return arr
+
+    def host_free(self, arr):
+        p = getattr(self, "_pinned", {}).pop(arr.ctypes.data, None)
+        if p: self._ck(self.L.np_host_free(self.w, p))
 
     def detect_batch_device(self, n, d_sa, d_pa, d_sb, d_pb, d_hit, d_out, timed=True):
         ms = C.c_float(0.0)

@@ -11,18 +11,28 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_the_contract_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, NP_BENCH_BODIES="20000")                 # the default (1 000 000 bodies, ~7 s per CPU step) is for the GPU box
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["metric"] == "body_steps_per_sec" and d["unit"] == "body-steps/s" and d["higher_is_better"] is True
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["value"] > 1e4 and d["ms_per_step"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "10000 bodies" in d["config"]["workload"]
+    assert "20000 mixed convex bodies" in d["config"]["workload"] and d["config"]["bodies_per_gpu"] == 20000
+    # both arms print the SAME config dict (the driver compares them)
+    sys.path.insert(0, ROOT)
+    os.environ["NP_BENCH_BODIES"] = "20000"
+    try:
+        import importlib, bench
+        importlib.reload(bench)
+        assert d["config"] == bench.CONFIG
+    finally:
+        del os.environ["NP_BENCH_BODIES"]
 
 
 def test_reference_arm_other_ranks_stay_silent():
-    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", NP_BENCH_BODIES="20000")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
 
