@@ -20,13 +20,13 @@ namespace np {
 enum { S_PX = 0, S_PY, S_PZ, S_RX, S_RY, S_RZ, S_LX, S_LY, S_LZ, S_HX, S_HY, S_HZ, S_COUNT };          // dynamic state
 enum { C_GX = 0, C_GY, C_GZ, C_MASS, C_ELAST, C_IINV0, C_COUNT = C_IINV0 + 9 };                       // per-body constants
 enum { X_R0 = 0, X_TX = 9, X_TY, X_TZ, X_COUNT };                                                      // transform
-enum { I_RESPONSE = 0, I_SHAPE, I_ISLAND_END, I_WVOFF, I_ORDER, I_COUNT };     // I_WVOFF: first world vertex of the body in the per-step cache; I_ORDER: search order (bodies grouped by shape)
+enum { I_RESPONSE = 0, I_SHAPE, I_ISLAND_END, I_WVOFF, I_ORDER, I_WVOFF_BIG, I_COUNT };     // I_WVOFF: first world vertex of the body in the per-step cache (I_WVOFF_BIG: in the cache of large bodies only, -1 for small ones); I_ORDER: search order (bodies grouped by shape)
 
 struct StoreView {
     int n, cap;
     float* state;      // [S_COUNT][cap]
     const float* cst;  // [C_COUNT][cap]
-    float* xf;         // [X_COUNT][cap]
+    float* xf;         // [cap][X_COUNT]: one body's transform is 48 contiguous bytes (3 float4) -- written coalesced by K1, gathered per pair by K3/K4
     const int* ints;   // [I_COUNT][cap]
     float4* wverts;    // world-space vertices of every body, rewritten each step by k_world_verts
     float* ext;        // adapter extension, null unless used: [4][cap] = one-step external force xyz (np_body_add_force), enabled flag
@@ -40,6 +40,21 @@ struct ShapeView {
 struct DevCounters {       // mirrors np_counters (all uint64)
     unsigned long long steps, pair_tests, hits, gjk_steps, support_pairs, epa_iters, epa_tri_tests, epa_overflow, candidates, support_verts;
 };
+
+// transform of body i: R[9] then t, 12 floats = 3 float4 (`stride` is kept in the signature for the callers; unused)
+NP_D void store_xf(float* __restrict__ xf, int i, const float* R, V3 t)
+{
+    float4* p = reinterpret_cast<float4*>(xf) + 3 * (size_t)i;
+    p[0] = make_float4(R[0], R[1], R[2], R[3]); p[1] = make_float4(R[4], R[5], R[6], R[7]); p[2] = make_float4(R[8], t.x, t.y, t.z);
+}
+NP_D void load_xf(const float* __restrict__ xf, int stride, int i, float* R, V3* t)
+{
+    (void)stride;
+    const float4* p = reinterpret_cast<const float4*>(xf) + 3 * (size_t)i;
+    const float4 a = p[0], b = p[1], c = p[2];
+    R[0] = a.x; R[1] = a.y; R[2] = a.z; R[3] = a.w; R[4] = b.x; R[5] = b.y; R[6] = b.z; R[7] = b.w; R[8] = c.x;
+    *t = mk(c.y, c.z, c.w);
+}
 
 // ---------------------------------------------------------------------------------------------------
 // K1: integrate + transform.  HBM-bound: per body 12 state floats + 14 constants read, 9 state floats +
@@ -87,9 +102,7 @@ __global__ void __launch_bounds__(256) k_integrate(StoreView s, float dt, int wr
     if (write_xf) {
         float R[9]; V3 t;
         make_transform(pos, rot, R, &t);
-#pragma unroll
-        for (int k = 0; k < 9; k++) s.xf[(X_R0 + k) * cap + i] = R[k];
-        s.xf[X_TX * cap + i] = t.x; s.xf[X_TY * cap + i] = t.y; s.xf[X_TZ * cap + i] = t.z;
+        store_xf(s.xf, i, R, t);
     }
 }
 
@@ -126,9 +139,7 @@ __global__ void __launch_bounds__(256) k_transforms(StoreView s)
     V3 rot = mk(s.state[S_RX * cap + i], s.state[S_RY * cap + i], s.state[S_RZ * cap + i]);
     float R[9]; V3 t;
     make_transform(pos, rot, R, &t);
-#pragma unroll
-    for (int k = 0; k < 9; k++) s.xf[(X_R0 + k) * cap + i] = R[k];
-    s.xf[X_TX * cap + i] = t.x; s.xf[X_TY * cap + i] = t.y; s.xf[X_TZ * cap + i] = t.z;
+    store_xf(s.xf, i, R, t);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -140,12 +151,6 @@ __global__ void __launch_bounds__(256) k_transforms(StoreView s)
 #define NP_MID_THREADS 64
 #define NP_FBIG 8192                // faces per warp in the global-memory last-resort arena (hard cap; beyond it success = false)
 
-NP_D void load_xf(const float* __restrict__ xf, int stride, int i, float* R, V3* t)
-{
-#pragma unroll
-    for (int k = 0; k < 9; k++) R[k] = xf[(size_t)(X_R0 + k) * stride + i];
-    *t = mk(xf[(size_t)X_TX * stride + i], xf[(size_t)X_TY * stride + i], xf[(size_t)X_TZ * stride + i]);
-}
 NP_D const float4* stage_shapes(const ShapeView& sh, float4* smem, bool use_smem)
 {
     if (!use_smem) return sh.verts;
@@ -210,7 +215,7 @@ struct NarrowIn {
                                // windows smaller than the ~70 k items in flight does nothing: measured.)  Any order gives the same results.
     StoreView s;
     const int* shape_a; const int* shape_b;      // pair mode
-    const float* xf_a; const float* xf_b;        // pair mode: transforms, SoA [X_COUNT][n]
+    const float* xf_a; const float* xf_b;        // pair mode: transforms [n][X_COUNT]
     const int* order;                            // pair mode: item t is pair order[t] (pairs grouped by shape-size class, k_pair_order), or null
     const int* cand; const int* cand_off; const int* cand_cnt;   // world mode with a broad phase: per-body ascending candidate lists (null = all j > i)
 };
@@ -333,6 +338,183 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
         }
     }
     if (ctr) flush_stats<G>(ctr, st, n_tests, n_hits, 0u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3, thread per item, second generation (the throughput regime: hundreds of thousands of bodies or pairs).  Same persistent
+// ticketed loop and the same results as k_gjk<1>, but
+//   * the simplex lives in shared memory (GjkS): ~100 registers instead of 150, 4-5 resident blocks per SM instead of 3;
+//   * COOP: supports of large shapes are served by the whole warp (support_coop1), CBIG: from the per-step cache of the large
+//     bodies' world vertices (k_world_verts<.., 2>) -- a large body then never loads its transform at all;
+//   * transforms are gathered as 3 float4 per body (AoS) instead of 12 strided scalars.
+// ---------------------------------------------------------------------------------------------------
+#ifndef NP_GJK1_MINB
+#define NP_GJK1_MINB 4
+#endif
+template <bool WORLD, bool COOP, bool CBIG>
+__global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK1_MINB) k_gjk1(NarrowIn in, ShapeView sh, int smem_shapes, int* __restrict__ ticket, int* __restrict__ hit_j,
+                                                           int* __restrict__ flags, float4* __restrict__ contact, float4* __restrict__ simplex,
+                                                           int* __restrict__ hit_list, int* __restrict__ hit_count, DevCounters* ctr)
+{
+    static_assert(!CBIG || (WORLD && COOP), "the large-body vertex cache serves the cooperative supports of a world step");
+    extern __shared__ float4 s_dyn[];
+    const float4* verts = stage_shapes(sh, s_dyn, smem_shapes != 0);
+    GjkS m;
+    m.sm = reinterpret_cast<float*>(s_dyn + (smem_shapes ? sh.total_verts : 0)) + threadIdx.x;
+    m.stride = NP_NARROW_THREADS;
+    PairGeom g;
+    PairStats st = { 0, 0, 0, 0, 0 };
+    unsigned n_tests = 0, n_hits = 0;
+    int i = -1, j = 0, jend = 0, cbase = 0, c = 0, cn = 0;
+    bool have = false, exhausted = false;
+    const StoreView& s = in.s;
+    const int* shape_of = s.ints + I_SHAPE * s.cap;
+    const int* island_end = s.ints + I_ISLAND_END * s.cap;
+    const int* wv_big = s.ints + I_WVOFF_BIG * s.cap;
+    // geometry of one side: a large body reads its cached world vertices (CBIG), anything else its shape-local vertices + transform
+    auto arm_a = [&](int body) {
+        const int sa = shape_of[body]; g.na = sh.cnt[sa];
+        if (CBIG && g.na >= NP_COOP_MIN) g.va = s.wverts + wv_big[body];
+        else { g.va = verts + sh.off[sa]; load_xf(s.xf, s.cap, body, g.Ra, &g.ta); }
+    };
+    auto arm_b = [&](int body) {
+        const int sb = shape_of[body]; g.nb = sh.cnt[sb];
+        if (CBIG && g.nb >= NP_COOP_MIN) g.vb = s.wverts + wv_big[body];
+        else { g.vb = verts + sh.off[sb]; load_xf(s.xf, s.cap, body, g.Rb, &g.tb); }
+    };
+    m.begin();
+    for (;;) {
+        int t = fetch_ticket<1>(ticket, !have && !exhausted);
+        if (!have && !exhausted) {
+            if (t < in.n) {
+                i = WORLD ? (in.ordered ? s.ints[I_ORDER * s.cap + in.first + t] : t + in.first) : (in.order ? in.order[t] : t);
+                if (WORLD) {
+                    if (in.cand) { cbase = in.cand_off[i]; c = 0; cn = in.cand_cnt[i]; j = cn > 0 ? in.cand[cbase] : 0; jend = cn > 0 ? 0x7fffffff : 0; }
+                    else { j = i + 1; jend = island_end[i]; }
+                    if (j < jend) { arm_a(i); arm_b(j); m.begin(); have = true; }
+                    else { hit_j[i] = -1; flags[i] = 0; }
+                } else {
+                    load_xf(in.xf_a, in.n, i, g.Ra, &g.ta); load_xf(in.xf_b, in.n, i, g.Rb, &g.tb);
+                    int sa = in.shape_a[i], sb = in.shape_b[i];
+                    g.va = verts + sh.off[sa]; g.na = sh.cnt[sa]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
+                    m.begin(); have = true;
+                }
+            } else exhausted = true;
+        }
+        if (!__any_sync(0xffffffffu, have)) { if (__all_sync(0xffffffffu, exhausted)) break; else continue; }
+        V3 sa, sb;
+        if constexpr (COOP) {
+            sa = support_coop1<CBIG>(have, g.va, g.na, g.Ra, g.ta, m.d);
+            sb = support_coop1<CBIG>(have, g.vb, g.nb, g.Rb, g.tb, neg(m.d));
+        } else if (have) {
+            sa = support<1, false>(g.va, g.na, g.Ra, g.ta, m.d);
+            sb = support<1, false>(g.vb, g.nb, g.Rb, g.tb, neg(m.d));
+        }
+        if (have) {
+            m.trip_with(g.na + g.nb, sa, sb, st);
+            if (m.status != GjkS::RUN) {
+                n_tests++;
+                if (m.status == GjkS::HIT) {
+                    n_hits++;
+                    if (WORLD) hit_j[i] = j;
+                    flags[i] = NP_PAIR_HIT | (m.seed_alive ? NP_PAIR_SEED_ALIVE : 0);
+                    m.write_hit(simplex + (size_t)i * 6);
+                    const int cls = (g.na >= NP_COOP_MIN ? 2 : 0) + (g.nb >= NP_COOP_MIN ? 1 : 0);
+                    {   // one atomic per class among the lanes that hit in this trip (opportunistic warp aggregation)
+                        const unsigned act = __activemask(), peers = __match_any_sync(act, cls);
+                        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+                        int pos = 0;
+                        if (lane == leader) pos = atomicAdd(hit_count + cls, __popc(peers));
+                        pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1u));
+                        hit_list[(size_t)cls * in.n + pos] = i;
+                    }
+                    have = false;
+                } else if (WORLD && (in.cand ? (++c < cn ? ((j = in.cand[cbase + c]), true) : false) : (++j < jend))) {
+                    arm_b(j); m.begin();
+                } else {
+                    if (WORLD) hit_j[i] = -1;
+                    flags[i] = 0;
+                    if (!WORLD) contact[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    have = false;
+                }
+            }
+        }
+    }
+    if (ctr) flush_stats<1>(ctr, st, n_tests, n_hits, 0u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4a: the first EPA iteration's first half, one THREAD per hit.  Most hits of the reference's GJK are degenerate simplices (the
+// B - A seed, collision_detection.cpp:704, makes it report ~70 % of separated pairs): their closest face is within 0.01 of the
+// origin and FindIntersectionPointsStep converges at :424 before any support is taken.  In the group kernels those hits held a
+// group for one trip while its neighbours ran 41-iteration support loops (ncu: 8 of 32 lanes active in k_epa<4>).  Here every
+// thread runs the same straight-line code -- SetupForEPA's four faces (simplex.h:29-53), the closest-face scan (:292-325), the
+// distance test (:424) -- answers the converged hits, and files the others (same four size classes) for k_epa, which starts them
+// over from the simplex.
+// ---------------------------------------------------------------------------------------------------
+template <bool WORLD>
+__global__ void __launch_bounds__(256) k_epa_first(int n_items, const int* __restrict__ list, const int* __restrict__ count, const float4* __restrict__ simplex,
+                                                  int* __restrict__ flags, float4* __restrict__ contact, int* __restrict__ next_list, int* __restrict__ next_count, DevCounters* ctr)
+{
+    int cum[NP_HIT_CLASSES]; int total = 0;
+#pragma unroll
+    for (int k = 0; k < NP_HIT_CLASSES; k++) { total += count[k]; cum[k] = total; }
+    unsigned n_conv = 0;
+    const int lane = threadIdx.x & 31;
+    for (int tb = blockIdx.x * blockDim.x + (threadIdx.x & ~31); tb < total; tb += gridDim.x * blockDim.x) {      // warp-uniform trip count
+        const int t = tb + lane;
+        const bool valid = t < total;
+        int k = 0, item = 0; bool conv = true;
+        if (valid) {
+            int base = 0;
+#pragma unroll
+            for (int q = 0; q < NP_HIT_CLASSES - 1; q++) if (t >= cum[q]) { k = q + 1; base = cum[q]; }
+            item = list[(size_t)k * n_items + (t - base)];
+            const float4* o = simplex + (size_t)item * 6;
+            const float4 q0 = o[0], q1 = o[1], q2 = o[2], q3 = o[3], q4 = o[4], q5 = o[5];
+            const V3 A0 = mk(q0.x, q0.y, q0.z), A1 = mk(q0.w, q1.x, q1.y), A2 = mk(q1.z, q1.w, q2.x), A3 = mk(q2.y, q2.z, q2.w);
+            const V3 B0 = mk(q3.x, q3.y, q3.z), B1 = mk(q3.w, q4.x, q4.y), B2 = mk(q4.z, q4.w, q5.x), B3 = mk(q5.y, q5.z, q5.w);
+            const int fl = flags[item];
+            const V3 P0 = (fl & NP_PAIR_SEED_ALIVE) ? sub(B0, A0) : sub(A0, B0), P1 = sub(A1, B1), P2 = sub(A2, B2), P3 = sub(A3, B3);
+            float best = 3.402823466e+38f; V3 bn = mk(0.0f, 0.0f, 0.0f); bool any = false; V3 n0 = bn;
+#pragma unroll
+            for (int f = 0; f < 4; f++) {                                             // faces 012, 023, 310, 132
+                const V3 a = f == 0 ? P0 : (f == 1 ? P0 : (f == 2 ? P3 : P1));
+                const V3 b = f == 0 ? P1 : (f == 1 ? P2 : (f == 2 ? P1 : P3));
+                const V3 cc = f == 0 ? P2 : (f == 1 ? P3 : (f == 2 ? P0 : P2));
+                const V3 nrm = normalize(cross(sub(b, a), sub(cc, a)));
+                const V3 nn = (dot(nrm, a) != 0.0f) ? nrm : neg(nrm);                  // simplex.h:52
+                float u, v;
+                closest_triangle(a, b, cc, &u, &v);
+                const float dsq = magsq(add(add(a, mul(sub(b, a), u)), mul(sub(cc, a), v)));
+                if (f == 0) n0 = nn;
+                if (dsq < best) { best = dsq; bn = nn; any = true; }                  // strict '<': first minimum wins
+            }
+            if (!any) bn = n0;                                                        // every distance NaN: face 0 (the zero-pinned face_index)
+            const float dist = sqrtf(best);
+            conv = !(dist > NP_EPA_TOL);                                              // :424 -> :523-531
+            if (conv) {
+                const V3 pen = neg(normalize(bn));
+                flags[item] = NP_PAIR_HIT | NP_PAIR_SUCCESS;
+                contact[item] = make_float4(pen.x, pen.y, pen.z, dist);
+                n_conv++;
+            }
+        }
+        // the others go on to k_epa, filed by class: one atomic per class per warp
+        const unsigned peers = __match_any_sync(0xffffffffu, conv ? -1 : k);
+        if (!conv) {
+            const int leader = __ffs(peers) - 1;
+            int pos = 0;
+            if (lane == leader) pos = atomicAdd(next_count + k, __popc(peers));
+            pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1u));
+            next_list[(size_t)k * n_items + pos] = item;
+        }
+    }
+    if (ctr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_conv += __shfl_xor_sync(0xffffffffu, n_conv, o);
+        if ((threadIdx.x & 31) == 0 && n_conv) { atomicAdd(&ctr->epa_iters, (unsigned long long)n_conv); atomicAdd(&ctr->epa_tri_tests, 4ull * n_conv); }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -566,7 +748,7 @@ __global__ void __launch_bounds__(64) k_detect2d(int n, ShapeView sh, const int*
     flags[p] = fl; contact[p] = make_float4(pen.x, pen.y, pen.z, depth);
 }
 
-// poses (position[3] rotation[3]) or row-major 4x4 matrices -> SoA transforms [X_COUNT][n]  (GetTransform, physics.h:70-76)
+// poses (position[3] rotation[3]) or row-major 4x4 matrices -> transforms [n][X_COUNT]  (GetTransform, physics.h:70-76)
 __global__ void __launch_bounds__(256) k_pose_xf(int n, const float* __restrict__ pose, const float* __restrict__ xf16, float* __restrict__ out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -581,9 +763,7 @@ __global__ void __launch_bounds__(256) k_pose_xf(int n, const float* __restrict_
         const float* a = pose + 6 * (size_t)i;
         make_transform(mk(a[0], a[1], a[2]), mk(a[3], a[4], a[5]), R, &t);
     }
-#pragma unroll
-    for (int k = 0; k < 9; k++) out[(size_t)(X_R0 + k) * n + i] = R[k];
-    out[(size_t)X_TX * n + i] = t.x; out[(size_t)X_TY * n + i] = t.y; out[(size_t)X_TZ * n + i] = t.z;
+    store_xf(out, i, R, t);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -619,7 +799,7 @@ struct GridView {
 // K1b: world-space vertex cache (+ AABB for the grid).  8 lanes per body; world*p per vertex exactly as the support
 // mapping evaluates it (physics_util.cpp:17), so K3/K4 can take dot products of the cached vertices directly.
 // HBM: reads 48 B transform + the shape's local vertices (L2 resident), writes 16 B per vertex (+ 32 B AABB).
-template <bool AABB, bool WRITE = true>
+template <bool AABB, int WRITE = 1>      // WRITE: 0 nothing, 1 every body, 2 large bodies only (>= NP_COOP_MIN vertices, offsets in I_WVOFF_BIG)
 __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, GridView gv)
 {
     constexpr int G = 8;
@@ -633,11 +813,13 @@ __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, 
         load_xf(s.xf, cap, body, R, &t);
         int shp = s.ints[I_SHAPE * cap + body];
         const float4* v = sh.verts + sh.off[shp]; int n = sh.cnt[shp];
-        float4* out = s.wverts + s.ints[I_WVOFF * cap + body];
+        if (WRITE == 2 && !AABB && n < NP_COOP_MIN) n = 0;
+        const bool wr = WRITE == 1 || (WRITE == 2 && n >= NP_COOP_MIN);
+        float4* out = s.wverts + (wr ? s.ints[(WRITE == 2 ? I_WVOFF_BIG : I_WVOFF) * cap + body] : 0);
         for (int k = gl; k < n; k += G) {
             float4 q = v[k];
             V3 wp = xf_point(R, t, mk(q.x, q.y, q.z));
-            if (WRITE) out[k] = make_float4(wp.x, wp.y, wp.z, 0.0f);
+            if (wr) out[k] = make_float4(wp.x, wp.y, wp.z, 0.0f);
             if (AABB) {
                 lo[0] = fminf(lo[0], wp.x); lo[1] = fminf(lo[1], wp.y); lo[2] = fminf(lo[2], wp.z);
                 hi[0] = fmaxf(hi[0], wp.x); hi[1] = fmaxf(hi[1], wp.y); hi[2] = fmaxf(hi[2], wp.z);

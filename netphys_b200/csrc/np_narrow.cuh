@@ -152,6 +152,67 @@ NP_D V3 support_coop(bool want, const float4* __restrict__ v, int n, const float
     return res;
 }
 
+// Thread-per-pair kernels, second generation (k_gjk1).  A large shape's support is served by the whole warp as above, with two changes:
+//   * CBIG: bodies with at least NP_COOP_MIN vertices have their WORLD-space vertices cached once per step (k_world_verts, big bodies
+//     only), so serving a lane costs a pointer, a count and a direction broadcast plus 6 instructions per vertex instead of the
+//     transform's 21 flops -- the same world*p bits, computed once per body and step instead of once per support call;
+//   * shapes of up to 192 vertices (the icosphere has 162) run the vertex loop fully unrolled with all six loads in flight.
+template <bool CBIG>
+NP_D V3 support_coop1(bool want, const float4* __restrict__ v, int n, const float* R, V3 t, V3 d)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = (int)(threadIdx.x & 31u);
+    V3 res = mk(0.0f, 0.0f, 0.0f);
+    bool served = false;
+    const bool isbig = n >= NP_COOP_MIN;
+    unsigned big = __ballot_sync(full, want && isbig);
+    if (__popc(big) <= 20) {
+        while (big) {
+            const int src = __ffs(big) - 1; big &= big - 1;
+            const float4* sv = (const float4*)__shfl_sync(full, (unsigned long long)v, src);
+            const int sn = __shfl_sync(full, n, src);
+            float sR[9]; V3 st = mk(0.0f, 0.0f, 0.0f);
+            if (!CBIG) {
+#pragma unroll
+                for (int k = 0; k < 9; k++) sR[k] = __shfl_sync(full, R[k], src);
+                st = mk(__shfl_sync(full, t.x, src), __shfl_sync(full, t.y, src), __shfl_sync(full, t.z, src));
+            }
+            const V3 sd = mk(__shfl_sync(full, d.x, src), __shfl_sync(full, d.y, src), __shfl_sync(full, d.z, src));
+            float bd = -INFINITY; int bi = 0x7fffffff;
+            if (sn <= 192) {
+                float4 q[6];
+#pragma unroll
+                for (int u = 0; u < 6; u++) { const int k = lane + 32 * u; q[u] = (k < sn) ? sv[k] : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+                for (int u = 0; u < 6; u++) {
+                    const int k = lane + 32 * u;
+                    const V3 wp = CBIG ? mk(q[u].x, q[u].y, q[u].z) : xf_point(sR, st, mk(q[u].x, q[u].y, q[u].z));
+                    const float dp = dot(sd, wp);
+                    if (k < sn && dp > bd) { bd = dp; bi = k; }
+                }
+            } else {
+#pragma unroll 2
+                for (int k = lane; k < sn; k += 32) {
+                    const float4 q = sv[k];
+                    const V3 wp = CBIG ? mk(q.x, q.y, q.z) : xf_point(sR, st, mk(q.x, q.y, q.z));
+                    const float dp = dot(sd, wp);
+                    if (dp > bd) { bd = dp; bi = k; }
+                }
+            }
+            const int key = float_order(bd + 0.0f);
+            const int kmax = __reduce_max_sync(full, key);
+            const unsigned imin = __reduce_min_sync(full, (key == kmax) ? (unsigned)bi : 0xffffffffu);
+            if (lane == src) {
+                if (imin >= 0x7fffffffu) res = mk(0.0f, 0.0f, 0.0f);
+                else { const float4 q = sv[imin]; res = CBIG ? mk(q.x, q.y, q.z) : xf_point(sR, st, mk(q.x, q.y, q.z)); }
+                served = true;
+            }
+        }
+    }
+    if (want && !served) res = (CBIG && isbig) ? support<1, true>(v, n, R, t, d) : support<1, false>(v, n, R, t, d);
+    return res;
+}
+
 NP_D V3 sel4(V3 a, V3 b, V3 c, V3 d, int k) { return k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d)); }
 
 // ---------------------------------------------------------------------------------------------------
@@ -291,6 +352,131 @@ struct GjkMachine {
 };
 
 // ---------------------------------------------------------------------------------------------------
+// GJK, thread per pair, simplex in SHARED memory (k_gjk1).  The register-resident machine above needs 36 floats of
+// simplex plus the sel4 chains that compact it; with one pair per lane that is what pushed the kernel to 150 registers
+// and 3 resident blocks per SM.  Here the 4 x {p, A, B} slots live in a per-block shared array laid out
+// [36 rows][blockDim] (row-major, one column per thread: conflict free) and the solve's order-preserving compaction is a
+// permutation of slot numbers: `perm` maps logical vertex k to its physical slot, nothing moves.  Same arithmetic, same
+// order of the tests as GjkMachine (collision_detection.cpp:620-713).
+// ---------------------------------------------------------------------------------------------------
+#define NP_SX_ROWS 36
+struct GjkS {
+    enum { RUN = 0, MISS = 1, HIT = 2 };
+    float* sm;                 // this thread's column of the block's simplex array
+    int stride;                // blockDim.x
+    V3 d;
+    int nv, perm, kn, ksel;    // ksel = k0 | k1 << 2 | k2 << 4: logical vertices the last solve keeps (applied lazily, after the duplicate test)
+    int steps, status, seed_alive;
+
+    NP_D int slot(int k) const { return (perm >> (2 * k)) & 3; }
+    NP_D V3 ld(int row) const { return mk(sm[row * stride], sm[(row + 1) * stride], sm[(row + 2) * stride]); }
+    NP_D V3 ldP(int s) const { return ld(3 * s); }
+    NP_D V3 ldA(int s) const { return ld(12 + 3 * s); }
+    NP_D V3 ldB(int s) const { return ld(24 + 3 * s); }
+    NP_D void stv(int row, V3 v) { sm[row * stride] = v.x; sm[(row + 1) * stride] = v.y; sm[(row + 2) * stride] = v.z; }
+    NP_D void put(int s, V3 p, V3 a, V3 b) { stv(3 * s, p); stv(12 + 3 * s, a); stv(24 + 3 * s, b); }
+
+    NP_D void begin()
+    {
+        nv = 0; steps = 0; status = RUN; seed_alive = 1; perm = 0; kn = 0; ksel = 0 | (1 << 2) | (2 << 4);
+        d = mk(1.0f, 1.0f, 1.0f);                                                                 // :702-703
+    }
+    NP_D void produce(PairStats& st)
+    {
+        if (steps >= NP_GJK_MAX_STEPS) { status = MISS; return; }                                 // :710
+        steps++; st.gjk_steps++;
+        kn = nv; int k0 = 0, k1 = 1, k2 = 2;
+        if (nv == 2) {                                                                            // SolveLine :18-54
+            float u;
+            int r = closest_line(ldP(slot(0)), ldP(slot(1)), &u);
+            if (r == LINE_A) { kn = 1; }
+            else if (r == LINE_B) { kn = 1; k0 = 1; }
+        } else if (nv == 3) {                                                                     // SolveTriangle :56-118
+            float u, v;
+            int r = closest_triangle(ldP(slot(0)), ldP(slot(1)), ldP(slot(2)), &u, &v);
+            switch (r) {
+            case TRI_A: kn = 1; break;
+            case TRI_B: kn = 1; k0 = 1; break;
+            case TRI_C: kn = 1; k0 = 2; break;
+            case TRI_AB: kn = 2; break;
+            case TRI_AC: kn = 2; k1 = 2; break;
+            case TRI_BC: kn = 2; k0 = 1; k1 = 2; break;
+            default: break;
+            }
+        } else if (nv == 4) {                                                                     // SolveTetrahedron :121-259
+            float u, v, w;
+            int r = closest_tetra(ldP(slot(0)), ldP(slot(1)), ldP(slot(2)), ldP(slot(3)), &u, &v, &w);
+            switch (r) {
+            case TET_A: kn = 1; break;
+            case TET_B: kn = 1; k0 = 1; break;
+            case TET_C: kn = 1; k0 = 2; break;
+            case TET_D: kn = 1; k0 = 3; break;
+            case TET_AB: kn = 2; break;
+            case TET_AC: kn = 2; k1 = 2; break;
+            case TET_AD: kn = 2; k1 = 3; break;
+            case TET_BC: kn = 2; k0 = 1; k1 = 2; break;
+            case TET_BD: kn = 2; k0 = 1; k1 = 3; break;
+            case TET_CD: kn = 2; k0 = 2; k1 = 3; break;
+            case TET_ABC: kn = 3; break;
+            case TET_ABD: kn = 3; k2 = 3; break;
+            case TET_ACD: kn = 3; k1 = 2; k2 = 3; break;
+            case TET_BCD: kn = 3; k0 = 1; k1 = 2; k2 = 3; break;
+            default: break;                    // ABCD, or None under NDEBUG (:255): four points stay => overlap
+            }
+        }
+        if (kn == 4) { status = HIT; return; }                                                    // :648-652
+        ksel = k0 | (k1 << 2) | (k2 << 4);
+        const V3 q0 = ldP(slot(k0));
+        if (kn == 1) d = dir1(q0);
+        else {
+            const V3 q1 = ldP(slot(k1));
+            if (kn == 2) d = dir2(q0, q1);
+            else d = dir3(q0, q1, ldP(slot(k2)));
+        }
+        if (feq(magsq(d), 0.0f)) status = MISS;                                                   // :655-658
+    }
+    NP_D void consume(V3 sa, V3 sb)
+    {
+        const V3 sp = sub(sa, sb);
+        if (dot(d, sp) < 0) { status = MISS; return; }                                            // :667
+        bool dup = false;                                                                         // :674-680 against the PRE-solve points
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < nv) { const int s = slot(k); dup = dup || (veq(sa, ldA(s)) && veq(sb, ldB(s))); }
+        if (dup) { status = MISS; return; }
+        int np_ = perm;
+        if (kn != nv) {                                                                           // the solve's order-preserving compaction
+            const int k0 = ksel & 3, k1 = (ksel >> 2) & 3, k2 = (ksel >> 4) & 3;
+            np_ = slot(k0) | (slot(k1) << 2) | (slot(k2) << 4);
+            if (k0 != 0) seed_alive = 0;         // the seed (p = B - A) can only ever sit at index 0
+        }
+        int used = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) if (k < kn) used |= 1 << ((np_ >> (2 * k)) & 3);
+        const int fr = __ffs(~used & 15) - 1;
+        put(fr, sp, sa, sb);                                                                      // :683-691
+        perm = (np_ & ((1 << (2 * kn)) - 1)) | (fr << (2 * kn));
+        nv = kn + 1;
+    }
+    // a trip whose support pair was evaluated by the caller; call while status == RUN
+    NP_D void trip_with(int nverts, V3 sa, V3 sb, PairStats& st)
+    {
+        st.support_pairs++; st.support_verts += (unsigned)nverts;
+        if (nv == 0) { put(0, sub(sb, sa), sa, sb); perm = 0; nv = 1; kn = 1; }                   // :704  p = B - A
+        else consume(sa, sb);
+        if (status == RUN) produce(st);
+    }
+    // the final simplex in logical order, as k_epa reads it: A[4] then B[4], packed in 6 float4
+    NP_D void write_hit(float4* o) const
+    {
+        const V3 a0 = ldA(slot(0)), a1 = ldA(slot(1)), a2 = ldA(slot(2)), a3 = ldA(slot(3));
+        const V3 b0 = ldB(slot(0)), b1 = ldB(slot(1)), b2 = ldB(slot(2)), b3 = ldB(slot(3));
+        o[0] = make_float4(a0.x, a0.y, a0.z, a1.x); o[1] = make_float4(a1.y, a1.z, a2.x, a2.y); o[2] = make_float4(a2.z, a3.x, a3.y, a3.z);
+        o[3] = make_float4(b0.x, b0.y, b0.z, b1.x); o[4] = make_float4(b1.y, b1.z, b2.x, b2.y); o[5] = make_float4(b2.z, b3.x, b3.y, b3.z);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
 // polytope storage policies (one polytope per group)
 // ---------------------------------------------------------------------------------------------------
 #define NP_POLY_ACCESSORS                                                                                              \
@@ -387,11 +573,12 @@ struct EpaMachine {
             for (int k = 0; k < 4; k++) poly.setv(k, (k == 0 && seed_alive) ? sub(B4[0], A4[0]) : sub(A4[k], B4[k]), A4[k], B4[k]);
         }
         gsync<G>();
-        const int f0[4][3] = { { 0, 1, 2 }, { 0, 2, 3 }, { 3, 1, 0 }, { 1, 3, 2 } };
-        if (G >= 4) { int l = glane<G>(); if (l < 4) add_face_at(poly, l, f0[l][0], f0[l][1], f0[l][2]); }
+        // faces 012, 023, 310, 132 (simplex.h:29-36), two bits per index, face l in bits [6l, 6l+6): no indexed local array
+        const unsigned f0 = (0u | (1u << 2) | (2u << 4)) | ((0u | (2u << 2) | (3u << 4)) << 6) | ((3u | (1u << 2) | (0u << 4)) << 12) | ((1u | (3u << 2) | (2u << 4)) << 18);
+        if (G >= 4) { int l = glane<G>(); if (l < 4) { const unsigned f = f0 >> (6 * l); add_face_at(poly, l, f & 3, (f >> 2) & 3, (f >> 4) & 3); } }
         else if (glane<G>() == 0) {
 #pragma unroll
-            for (int l = 0; l < 4; l++) add_face_at(poly, l, f0[l][0], f0[l][1], f0[l][2]);
+            for (int l = 0; l < 4; l++) { const unsigned f = f0 >> (6 * l); add_face_at(poly, l, f & 3, (f >> 2) & 3, (f >> 4) & 3); }
         }
         gsync<G>();
     }

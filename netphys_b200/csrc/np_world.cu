@@ -60,13 +60,14 @@ struct np_world {
     int* d_zero = nullptr;            // [tickets and counts (32 ints), head[cap] of the incoming-collision lists]  -- one memset per step
     int *d_inc = nullptr /* next[] of the incoming-collision lists */, *d_sums = nullptr, *d_big_list = nullptr, *d_hit_list = nullptr;
     float4* d_simplex = nullptr;      // GJK result of every hit: A[4], B[4]
-    float4* d_wverts = nullptr; size_t wverts_cap = 0, wv_total = 0;   // per-step world-vertex cache (K1b), allocated on first use (ensure_cache)
+    float4* d_wverts = nullptr; size_t wverts_cap = 0, wv_total = 0, wv_total_big = 0;   // per-step world-vertex cache (K1b), allocated on first use (ensure_cache)
     float* d_ext = nullptr;           // adapter extension, allocated on first use: [4][cap] external force xyz + enabled flag
     // grid broad phase (allocated on first use)
     GridView grid = {}; int grid_cap = 0; int* d_grid_ints = nullptr; float* d_grid_f = nullptr;
     int max_verts = 0;                // largest shape
     int g_gjk_env = 0, g_epa_env = 0; // NP_G_GJK / NP_G_EPA overrides (tuning)
     int order_on = 1; bool order_dirty = true;   // NP_ORDER=0: search bodies in index order (tuning)
+    int gjk1_old = 0, cbig_on = 0, epa_first = 1;   // NP_GJK1_OLD=1: round-1 register-simplex kernel; NP_CBIG=1: large-body vertex cache for the cooperative supports (measured slower: 9 GB of DRAM reads per step); NP_EPA_FIRST=0 (tuning, A/B)
     bool coop = false; int coop_env = -1;   // large and small shapes mixed: warp-cooperative supports in the narrow kernels (NP_COOP=0/1 overrides)
     DevCounters* d_ctr = nullptr;
     SnapObj* d_snap = nullptr;
@@ -87,12 +88,13 @@ struct np_world {
 // ------------------------------------------------------------------------------------------------ helpers
 static StoreView view(np_world* w) { StoreView s; s.n = (int)w->bodies.size(); s.cap = w->cap; s.state = w->d_state; s.cst = w->d_cst; s.xf = w->d_xf; s.ints = w->d_ints; s.wverts = w->d_wverts; s.ext = w->d_ext; return s; }
 static ShapeView sview(np_world* w) { ShapeView s; s.verts = w->d_verts; s.off = w->d_soff; s.cnt = w->d_scnt; s.total_verts = w->total_verts; return s; }
-enum { Z_GJK_TICKET = 0, Z_EPA_TICKET, Z_MID_COUNT, Z_MID_TICKET, Z_BIG_COUNT, Z_BIG_TICKET, Z_HIT_COUNT = 8 /* NP_HIT_CLASSES counters */, Z_PAIR_CLASS = 12 /* 9 counts + 9 cursors */ };
+enum { Z_GJK_TICKET = 0, Z_EPA_TICKET, Z_MID_COUNT, Z_MID_TICKET, Z_BIG_COUNT, Z_BIG_TICKET, Z_HIT_COUNT = 8 /* NP_HIT_CLASSES counters */, Z_PAIR_CLASS = 12 /* 9 counts + 9 cursors */,
+       Z_HIT2_COUNT = 32 /* NP_HIT_CLASSES counters: hits that k_epa_first passes on to k_epa */, NP_ZERO_INTS = 64 };
 static int* hitj(np_world* w) { return w->x_hit_j ? w->x_hit_j : w->d_hit_j; }
 static int* cflags(np_world* w) { return w->x_cflags ? w->x_cflags : w->d_cflags; }
 static float4* contacts(np_world* w) { return w->x_contact ? w->x_contact : w->d_contact; }
 static bool sharded(np_world* w) { return w->shard_count >= 0; }
-static int* d_inc_cnt(np_world* w) { return w->d_zero + 32; }
+static int* d_inc_cnt(np_world* w) { return w->d_zero + NP_ZERO_INTS; }
 
 static void free_store(np_world* w)
 {
@@ -169,10 +171,10 @@ static int alloc_store(np_world* w, size_t c)
     CU(cudaMalloc((void**)&w->d_state, sizeof(float) * S_COUNT * c)); CU(cudaMalloc((void**)&w->d_cst, sizeof(float) * C_COUNT * c));
     CU(cudaMalloc((void**)&w->d_xf, sizeof(float) * X_COUNT * c)); CU(cudaMalloc((void**)&w->d_ints, sizeof(int) * I_COUNT * c));
     CU(cudaMalloc((void**)&w->d_hit_j, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_cflags, sizeof(int) * c)); CU(cudaMalloc((void**)&w->d_contact, sizeof(float4) * c));
-    CU(cudaMalloc((void**)&w->d_zero, sizeof(int) * (32 + c))); CU(cudaMalloc((void**)&w->d_inc, sizeof(int) * c));
+    CU(cudaMalloc((void**)&w->d_zero, sizeof(int) * (NP_ZERO_INTS + c))); CU(cudaMalloc((void**)&w->d_inc, sizeof(int) * c));
     CU(cudaMalloc((void**)&w->d_sums, sizeof(int) * (4 * c / NP_SCAN_BLOCK + 2))); CU(cudaMalloc((void**)&w->d_big_list, sizeof(int) * c));
     CU(cudaMalloc((void**)&w->d_snap, sizeof(SnapObj) * c));
-    CU(cudaMalloc((void**)&w->d_hit_list, sizeof(int) * NP_HIT_CLASSES * c)); CU(cudaMalloc((void**)&w->d_simplex, sizeof(float4) * 6 * c));
+    CU(cudaMalloc((void**)&w->d_hit_list, sizeof(int) * 2 * NP_HIT_CLASSES * c)); CU(cudaMalloc((void**)&w->d_simplex, sizeof(float4) * 6 * c));      // hit lists of k_gjk, then those k_epa_first passes on
     CU(cudaMemsetAsync(w->d_state, 0, sizeof(float) * S_COUNT * c, w->stream));
     CU(cudaMemsetAsync(w->d_hit_j, 0xff, sizeof(int) * c, w->stream)); CU(cudaMemsetAsync(w->d_cflags, 0, sizeof(int) * c, w->stream));
     CU(cudaMemsetAsync(w->d_contact, 0, sizeof(float4) * c, w->stream));
@@ -288,7 +290,13 @@ static int ensure_device(np_world* w)
         if (wv_total > 0x7fffffffu) return fail(NP_ERR_CAPACITY, "world-vertex cache exceeds 2^31 vertices");
         ints[I_WVOFF * cap + i] = (int)wv_total; wv_total += w->shapes[w->bodies[i].shape].xyz.size() / 3;
     }
-    w->wv_total = wv_total;               // the cache itself is allocated by ensure_cache, only for steps whose kernels read it
+    size_t wv_big = 0;
+    for (int i = 0; i < n; i++) {
+        const size_t nv = w->shapes[w->bodies[i].shape].xyz.size() / 3;
+        if (nv >= NP_COOP_MIN) { if (wv_big > 0x7fffffffu) return fail(NP_ERR_CAPACITY, "world-vertex cache exceeds 2^31 vertices"); ints[I_WVOFF_BIG * cap + i] = (int)wv_big; wv_big += nv; }
+        else ints[I_WVOFF_BIG * cap + i] = -1;
+    }
+    w->wv_total = wv_total; w->wv_total_big = wv_big;               // the cache itself is allocated by ensure_cache, only for steps whose kernels read it
     CU(cudaMemcpyAsync(w->d_cst, cst.data(), sizeof(float) * C_COUNT * cap, cudaMemcpyHostToDevice, w->stream));
     CU(cudaMemcpyAsync(w->d_ints, ints.data(), sizeof(int) * I_COUNT * cap, cudaMemcpyHostToDevice, w->stream));
     CU(cudaStreamSynchronize(w->stream));
@@ -307,6 +315,8 @@ static int ensure_arena(np_world* w)
     return NP_OK;
 }
 static bool shapes_in_smem(np_world* w) { return w->total_verts <= NP_SMEM_VERTS; }
+enum { CACHE_NONE = 0, CACHE_ALL = 1, CACHE_BIG = 2 };
+static int cache_mode(np_world* w, long long items);
 
 // ---- narrow-phase launch plumbing -------------------------------------------------------------------------------
 static size_t shapes_smem(np_world* w) { return shapes_in_smem(w) ? sizeof(float4) * (size_t)w->total_verts : 0; }
@@ -330,14 +340,22 @@ static int pick_group(np_world* w, long long items, int env, bool epa)
     if (items <= 300000) return epa ? 32 : (items <= 40000 ? 32 : 8);      // (GJK: a warp per body once there are few enough bodies for one wave)
     return epa ? (w->max_verts <= 16 ? 1 : 4) : 1;          // small shapes: thread-per-hit EPA wins (8.1e8 vs 7.6e8 box pairs/s)
 }
-struct NarrowBufs { int* zero; int* hit_j; int* flags; float4* contact; float4* simplex; int* hit_list; int* big_list; };
+struct NarrowBufs { int* zero; int* hit_j; int* flags; float4* contact; float4* simplex; int* hit_list; int* big_list; int* hit_list2; };
 
+static const size_t kSimplexSmem = sizeof(float) * NP_SX_ROWS * NP_NARROW_THREADS;      // k_gjk1: the block's simplices
 template <int G, bool WORLD>
 static int launch_gjk(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevCounters* ctr)
 {
     size_t smem = (WORLD && G >= 8) ? 0 : shapes_smem(w);
     auto kern = k_gjk<G, WORLD>;
-    if constexpr (G == 1 && WORLD) { if (w->coop) kern = k_gjk<G, WORLD, true>; }
+    if constexpr (G == 1) {
+        if (!w->gjk1_old) {
+            smem += kSimplexSmem;
+            kern = k_gjk1<WORLD, false, false>;
+            if (w->coop) kern = k_gjk1<WORLD, true, false>;
+            if constexpr (WORLD) { if (w->coop && cache_mode(w, in.n) == CACHE_BIG) kern = k_gjk1<true, true, true>; }
+        } else if constexpr (WORLD) { if (w->coop) kern = k_gjk<G, WORLD, true>; }
+    }
     int blocks = persistent_blocks(w, kern, smem, in.n, G);
     kern<<<blocks, NP_NARROW_THREADS, smem, w->stream>>>(in, sview(w), shapes_in_smem(w) ? 1 : 0, b.zero + Z_GJK_TICKET, b.hit_j, b.flags, b.contact, b.simplex,
                                                         b.hit_list, b.zero + Z_HIT_COUNT, ctr);
@@ -378,7 +396,14 @@ static int launch_epa(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevC
         } else cudaGetLastError();
     }
     int blocks = persistent_blocks(w, kern, smem, in.n, G);
-    kern<<<blocks, NP_NARROW_THREADS, smem, w->stream>>>(in, sview(w), stage, b.hit_list, b.zero + Z_HIT_COUNT, b.zero + Z_EPA_TICKET, b.hit_j, b.simplex,
+    const int* list = b.hit_list; const int* counts = b.zero + Z_HIT_COUNT;
+    if (G < 32 && w->epa_first) {            // throughput regime: the hits that converge before their first support never reach the group kernel
+        const int fb = (int)std::min<long long>((long long)w->sm_count * 8, ((long long)in.n + 255) / 256);
+        k_epa_first<WORLD><<<std::max(1, fb), 256, 0, w->stream>>>(in.n, b.hit_list, b.zero + Z_HIT_COUNT, b.simplex, b.flags, b.contact, b.hit_list2, b.zero + Z_HIT2_COUNT, ctr);
+        list = b.hit_list2; counts = b.zero + Z_HIT2_COUNT;
+        w->launches += 1;
+    }
+    kern<<<blocks, NP_NARROW_THREADS, smem, w->stream>>>(in, sview(w), stage, list, counts, b.zero + Z_EPA_TICKET, b.hit_j, b.simplex,
                                                         b.flags, b.contact, b.big_list, b.zero + Z_MID_COUNT, w->arena, ctr);
     w->launches += 1;
     return launch_epa_tiers<WORLD, TC>(w, in, b, ctr);
@@ -394,7 +419,16 @@ static void setup_kernels_t()
     cudaFuncSetAttribute(k_epa<32, NP_FMID, 1, NP_MID_THREADS, WORLD, WORLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_epa<32, NP_FMID, 1, NP_MID_THREADS, WORLD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
-static void setup_kernels() { setup_kernels_t<true>(); setup_kernels_t<false>(); }
+static void setup_kernels()
+{
+    setup_kernels_t<true>(); setup_kernels_t<false>();
+    const int bytes = 64 * 1024;               // staged shape table (<= 32 KB) + the block's simplices (18 KB)
+    cudaFuncSetAttribute(k_gjk1<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_gjk1<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_gjk1<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_gjk1<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_gjk1<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
 // supported group widths: GJK {1, 8, 32}, EPA {1, 4, 8, 32} (other requests round to the nearest supported one)
 template <bool WORLD>
 static int launch_narrow_t(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevCounters* ctr)
@@ -412,21 +446,28 @@ static int launch_narrow_t(np_world* w, const NarrowIn& in, const NarrowBufs& b,
     else r = launch_epa<32, WORLD, WORLD>(w, in, b, ctr);
     return r;
 }
-// does a world-mode search over `items` bodies read the world-vertex cache?  (same decision as launch_narrow_t)
-static bool wants_cache(np_world* w, long long items)
+// which world-vertex cache does a world-mode search over `items` bodies read?  (same decisions as launch_narrow_t / launch_gjk)
+//   ALL: wide groups read every body's vertices;  BIG: the thread-per-body kernel's cooperative supports read the large bodies' only
+static int cache_mode(np_world* w, long long items)
 {
-    return items > 0 && (pick_group(w, items, w->g_gjk_env, false) >= 8 || pick_group(w, items, w->g_epa_env, true) >= 8);
+    if (items <= 0) return CACHE_NONE;
+    const int gg = pick_group(w, items, w->g_gjk_env, false), ge = pick_group(w, items, w->g_epa_env, true);
+    if (gg >= 8 || ge >= 8) return CACHE_ALL;
+    if (gg <= 1 && w->coop && w->cbig_on && !w->gjk1_old) return CACHE_BIG;
+    return CACHE_NONE;
 }
 // the world-vertex cache is allocated the first time a step's kernels read it (never inside a stream capture); on failure nothing changes
 static int ensure_cache(np_world* w)
 {
     const int n = (int)w->bodies.size();
     const long long count = w->shard_count >= 0 ? w->shard_count : n;
-    if (!wants_cache(w, count) || w->wv_total <= w->wverts_cap) return NP_OK;
+    const int mode = cache_mode(w, count);
+    const size_t need = mode == CACHE_ALL ? w->wv_total : (mode == CACHE_BIG ? w->wv_total_big : 0);
+    if (need <= w->wverts_cap) return NP_OK;
     drop_graph(w);
     CU(cudaStreamSynchronize(w->stream));
     cudaFree(w->d_wverts); w->d_wverts = nullptr; w->wverts_cap = 0;
-    const size_t want = w->wv_total + w->wv_total / 4 + 1024;
+    const size_t want = need + need / 4 + 1024;
     CU(cudaMalloc((void**)&w->d_wverts, sizeof(float4) * want));
     w->wverts_cap = want;
     return NP_OK;
@@ -468,14 +509,15 @@ static int ensure_grid(np_world* w)
     return NP_OK;
 }
 // K2, enqueued between integrate and the narrow phase
-static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, bool cache, DevCounters* ctr)
+static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, int cache, DevCounters* ctr)
 {
     GridView& g = w->grid; g.h_option = w->grid_cell;
     const int n = s.n, b256 = (n + 255) / 256;
     k_grid_init<<<1, 32, 0, w->stream>>>(g);
     CU(cudaMemsetAsync(g.bucket_cnt, 0, sizeof(int) * 2 * (size_t)g.nbuckets, w->stream));
-    if (cache) k_world_verts<true, true><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), g);
-    else k_world_verts<true, false><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), g);
+    if (cache == CACHE_ALL) k_world_verts<true, 1><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), g);
+    else if (cache == CACHE_BIG) k_world_verts<true, 2><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), g);
+    else k_world_verts<true, 0><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), g);
     k_grid_params<<<1, 1, 0, w->stream>>>(n, g);
     k_grid_count<<<b256, 256, 0, w->stream>>>(s, g);
     enqueue_scan(w, g.nbuckets, g.bucket_cnt, g.bucket_off);
@@ -506,16 +548,17 @@ static int enqueue_search(np_world* w, float dt, bool timed)
     if (s.ext) k_integrate<true><<<b256, 256, 0, w->stream>>>(s, dt, 1); else k_integrate<false><<<b256, 256, 0, w->stream>>>(s, dt, 1);
     w->launches += 1;
     if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[1], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
-    const bool cache = wants_cache(w, count);
+    const int cache = cache_mode(w, count);
     if (w->broadphase == NP_BROADPHASE_GRID) { int r = enqueue_grid(w, s, first, count, cache, ctr); if (r) return r; }
-    else if (cache) { k_world_verts<false><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), w->grid); w->launches += 1; }
+    else if (cache == CACHE_ALL) { k_world_verts<false, 1><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), w->grid); w->launches += 1; }
+    else if (cache == CACHE_BIG) { k_world_verts<false, 2><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), w->grid); w->launches += 1; }
     if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[2], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
-    CU(cudaMemsetAsync(w->d_zero, 0, sizeof(int) * (32 + (size_t)w->cap), w->stream));        // counters, tickets and the incoming-list heads
+    CU(cudaMemsetAsync(w->d_zero, 0, sizeof(int) * (NP_ZERO_INTS + (size_t)w->cap), w->stream));        // counters, tickets and the incoming-list heads
     if (count > 0) {
         NarrowIn in; memset(&in, 0, sizeof in); in.world = 1; in.n = count; in.first = first; in.s = s;
         in.ordered = w->order_on;
         if (w->broadphase == NP_BROADPHASE_GRID) { in.cand = w->grid.cand; in.cand_off = w->grid.cand_off; in.cand_cnt = w->grid.cand_cnt; }
-        NarrowBufs nb = { w->d_zero, hitj(w), cflags(w), contacts(w), w->d_simplex, w->d_hit_list, w->d_big_list };
+        NarrowBufs nb = { w->d_zero, hitj(w), cflags(w), contacts(w), w->d_simplex, w->d_hit_list, w->d_big_list, w->d_hit_list + (size_t)NP_HIT_CLASSES * w->cap };
         int r = launch_narrow(w, in, nb, ctr); if (r) return r;
     }
     if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[3], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
@@ -575,6 +618,9 @@ np_world* np_world_create(int device)
     if (const char* e = getenv("NP_GRAPH")) w->graph_on = atoi(e) != 0;
     if (const char* e = getenv("NP_ORDER")) w->order_on = atoi(e) != 0;
     if (const char* e = getenv("NP_G_EPA")) w->g_epa_env = atoi(e);
+    if (const char* e = getenv("NP_GJK1_OLD")) w->gjk1_old = atoi(e) != 0;
+    if (const char* e = getenv("NP_CBIG")) w->cbig_on = atoi(e) != 0;
+    if (const char* e = getenv("NP_EPA_FIRST")) w->epa_first = atoi(e) != 0;
     if (cudaMalloc((void**)&w->d_ctr, sizeof(DevCounters)) != cudaSuccess || ensure_arena(w) != NP_OK) { fail(NP_ERR_CUDA, "cannot allocate device scratch"); np_world_destroy(w); return nullptr; }
     cudaMemsetAsync(w->d_ctr, 0, sizeof(DevCounters), w->stream);
     return w;
@@ -988,10 +1034,10 @@ static int run_pairs(np_world* w, int n, const int* d_sa, const float* d_pa, con
 {
     // scratch: counters | xfA | xfB (SoA) | simplex | hit_list | big_list
     const size_t N = (size_t)n;
-    const size_t o_zero = 0, o_xa = 128, o_xb = o_xa + 4 * X_COUNT * N, o_sx = (o_xb + 4 * X_COUNT * N + 15) / 16 * 16, o_hl = o_sx + 96 * N, o_bl = o_hl + 4 * NP_HIT_CLASSES * N, o_or = o_bl + 4 * N, total = o_or + 4 * N;
+    const size_t o_zero = 0, o_xa = 4 * NP_ZERO_INTS, o_xb = o_xa + 4 * X_COUNT * N, o_sx = (o_xb + 4 * X_COUNT * N + 15) / 16 * 16, o_hl = o_sx + 96 * N, o_h2 = o_hl + 4 * NP_HIT_CLASSES * N, o_bl = o_h2 + 4 * NP_HIT_CLASSES * N, o_or = o_bl + 4 * N, total = o_or + 4 * N;
     char* d = nullptr;
     CU(cudaMallocAsync((void**)&d, total, w->stream));
-    CU(cudaMemsetAsync(d + o_zero, 0, 128, w->stream));
+    CU(cudaMemsetAsync(d + o_zero, 0, 4 * NP_ZERO_INTS, w->stream));
     if (kernel_ms) CU(cudaEventRecord(w->ev[0], w->stream));
     const int b256 = (n + 255) / 256;
     k_pose_xf<<<b256, 256, 0, w->stream>>>(n, d_pa, d_xa, (float*)(d + o_xa));
@@ -1012,7 +1058,7 @@ static int run_pairs(np_world* w, int n, const int* d_sa, const float* d_pa, con
         in.order = (const int*)(d + o_or);
         w->launches += 2;
     }
-    NarrowBufs nb = { (int*)(d + o_zero), nullptr, d_hit, d_out, (float4*)(d + o_sx), (int*)(d + o_hl), (int*)(d + o_bl) };
+    NarrowBufs nb = { (int*)(d + o_zero), nullptr, d_hit, d_out, (float4*)(d + o_sx), (int*)(d + o_hl), (int*)(d + o_bl), (int*)(d + o_h2) };
     int r = launch_narrow(w, in, nb, w->counters_on ? w->d_ctr : nullptr);
     if (kernel_ms) CU(cudaEventRecord(w->ev[5], w->stream));
     CU(cudaGetLastError());
