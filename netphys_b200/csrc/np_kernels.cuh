@@ -218,6 +218,7 @@ struct NarrowIn {
     const float* xf_a; const float* xf_b;        // pair mode: transforms [n][X_COUNT]
     const int* order;                            // pair mode: item t is pair order[t] (pairs grouped by shape-size class, k_pair_order), or null
     const int* cand; const int* cand_off; const int* cand_cnt;   // world mode with a broad phase: per-body ascending candidate lists (null = all j > i)
+    const float4* seed;                                          // world mode: [2*body] support along (1,1,1), [2*body+1] along (-1,-1,-1) (k_seed_supports), or null
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -340,6 +341,24 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
     if (ctr) flush_stats<G>(ctr, st, n_tests, n_hits, 0u);
 }
 
+// K1c: the two seed supports of every body (see k_gjk1, SEED).  One thread per body, large shapes served by the warp; the same
+// support code, so the same bits as the per-pair evaluation it replaces.
+__global__ void __launch_bounds__(NP_NARROW_THREADS) k_seed_supports(StoreView s, ShapeView sh, int smem_shapes, float4* __restrict__ seed)
+{
+    extern __shared__ float4 s_dyn[];
+    const float4* verts = stage_shapes(sh, s_dyn, smem_shapes != 0);
+    const int nwarp = (s.n + 31) / 32;
+    for (int wb = blockIdx.x * (NP_NARROW_THREADS / 32) + (threadIdx.x >> 5); wb < nwarp; wb += gridDim.x * (NP_NARROW_THREADS / 32)) {   // warp-uniform
+        const int i = wb * 32 + (threadIdx.x & 31);
+        const bool valid = i < s.n;
+        float R[9] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f }; V3 t = mk(0.f, 0.f, 0.f); const float4* v = verts; int n = 0;
+        if (valid) { load_xf(s.xf, s.cap, i, R, &t); const int shp = s.ints[I_SHAPE * s.cap + i]; v = verts + sh.off[shp]; n = sh.cnt[shp]; }
+        const V3 a = support_coop1<false>(valid, v, n, R, t, mk(1.0f, 1.0f, 1.0f));
+        const V3 b = support_coop1<false>(valid, v, n, R, t, mk(-1.0f, -1.0f, -1.0f));
+        if (valid) { seed[2 * (size_t)i] = make_float4(a.x, a.y, a.z, 0.0f); seed[2 * (size_t)i + 1] = make_float4(b.x, b.y, b.z, 0.0f); }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K3, thread per item, second generation (the throughput regime: hundreds of thousands of bodies or pairs).  Same persistent
 // ticketed loop and the same results as k_gjk<1>, but
@@ -351,12 +370,16 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
 #ifndef NP_GJK1_MINB
 #define NP_GJK1_MINB 4
 #endif
-template <bool WORLD, bool COOP, bool CBIG>
+template <bool WORLD, bool COOP, bool CBIG, bool SEED = false>
 __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK1_MINB) k_gjk1(NarrowIn in, ShapeView sh, int smem_shapes, int* __restrict__ ticket, int* __restrict__ hit_j,
                                                            int* __restrict__ flags, float4* __restrict__ contact, float4* __restrict__ simplex,
                                                            int* __restrict__ hit_list, int* __restrict__ hit_count, DevCounters* ctr)
 {
     static_assert(!CBIG || (WORLD && COOP), "the large-body vertex cache serves the cooperative supports of a world step");
+    static_assert(!SEED || WORLD, "seed supports are tabulated per body of a world");
+    // SEED: DetectCollision's first support pair -- A along (1,1,1), B along (-1,-1,-1), collision_detection.cpp:701-703 -- depends on
+    // one body only, so a world step evaluates it once per body (k_seed_supports) instead of once per pair: a fresh pair's first
+    // trip takes both points from in.seed and asks for no support.
     extern __shared__ float4 s_dyn[];
     const float4* verts = stage_shapes(sh, s_dyn, smem_shapes != 0);
     GjkS m;
@@ -402,14 +425,23 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK1_MINB) k_gjk1(Narrow
             } else exhausted = true;
         }
         if (!__any_sync(0xffffffffu, have)) { if (__all_sync(0xffffffffu, exhausted)) break; else continue; }
-        V3 sa, sb;
-        if constexpr (COOP) {
-            sa = support_coop1<CBIG>(have, g.va, g.na, g.Ra, g.ta, m.d);
-            sb = support_coop1<CBIG>(have, g.vb, g.nb, g.Rb, g.tb, neg(m.d));
-        } else if (have) {
-            sa = support<1, false>(g.va, g.na, g.Ra, g.ta, m.d);
-            sb = support<1, false>(g.vb, g.nb, g.Rb, g.tb, neg(m.d));
+        V3 sa = mk(0.0f, 0.0f, 0.0f), sb = sa;
+        const bool fresh = SEED && have && m.nv == 0;
+        const bool want = have && !fresh;
+        // one copy of the support code for both sides (the kernel is instruction-cache bound: ncu shows no_instruction as a top stall)
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+            const float4* v = side ? g.vb : g.va; const int n = side ? g.nb : g.na;
+            float R[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) R[k] = side ? g.Rb[k] : g.Ra[k];
+            const V3 t = side ? g.tb : g.ta, dd = side ? neg(m.d) : m.d;
+            V3 r = mk(0.0f, 0.0f, 0.0f);
+            if constexpr (COOP) r = support_coop1<CBIG>(want, v, n, R, t, dd);
+            else if (want) r = support<1, false>(v, n, R, t, dd);
+            if (side) sb = r; else sa = r;
         }
+        if (fresh) { const float4 qa = in.seed[2 * (size_t)i], qb = in.seed[2 * (size_t)j + 1]; sa = mk(qa.x, qa.y, qa.z); sb = mk(qb.x, qb.y, qb.z); }
         if (have) {
             m.trip_with(g.na + g.nb, sa, sb, st);
             if (m.status != GjkS::RUN) {

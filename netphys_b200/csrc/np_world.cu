@@ -60,6 +60,7 @@ struct np_world {
     int* d_zero = nullptr;            // [tickets and counts (32 ints), head[cap] of the incoming-collision lists]  -- one memset per step
     int *d_inc = nullptr /* next[] of the incoming-collision lists */, *d_sums = nullptr, *d_big_list = nullptr, *d_hit_list = nullptr;
     float4* d_simplex = nullptr;      // GJK result of every hit: A[4], B[4]
+    float4* d_seed = nullptr;         // per body: the two seed supports of DetectCollision (k_seed_supports), thread-per-body search only
     float4* d_wverts = nullptr; size_t wverts_cap = 0, wv_total = 0, wv_total_big = 0;   // per-step world-vertex cache (K1b), allocated on first use (ensure_cache)
     float* d_ext = nullptr;           // adapter extension, allocated on first use: [4][cap] external force xyz + enabled flag
     // grid broad phase (allocated on first use)
@@ -67,7 +68,7 @@ struct np_world {
     int max_verts = 0;                // largest shape
     int g_gjk_env = 0, g_epa_env = 0; // NP_G_GJK / NP_G_EPA overrides (tuning)
     int order_on = 1; bool order_dirty = true;   // NP_ORDER=0: search bodies in index order (tuning)
-    int gjk1_old = 0, cbig_on = 0, epa_first = 1;   // NP_GJK1_OLD=1: round-1 register-simplex kernel; NP_CBIG=1: large-body vertex cache for the cooperative supports (measured slower: 9 GB of DRAM reads per step); NP_EPA_FIRST=0 (tuning, A/B)
+    int gjk1_old = 0, cbig_on = 0, epa_first = 1, seed_on = 0;   // NP_SEED=1: per-body table of DetectCollision's seed supports (measured slower: 4.01 vs 3.90 ms)   // NP_GJK1_OLD=1: round-1 register-simplex kernel; NP_CBIG=1: large-body vertex cache for the cooperative supports (measured slower: 9 GB of DRAM reads per step); NP_EPA_FIRST=0 (tuning, A/B)
     bool coop = false; int coop_env = -1;   // large and small shapes mixed: warp-cooperative supports in the narrow kernels (NP_COOP=0/1 overrides)
     DevCounters* d_ctr = nullptr;
     SnapObj* d_snap = nullptr;
@@ -100,7 +101,7 @@ static void free_store(np_world* w)
 {
     cudaFree(w->d_state); cudaFree(w->d_cst); cudaFree(w->d_xf); cudaFree(w->d_ints);
     cudaFree(w->d_hit_j); cudaFree(w->d_cflags); cudaFree(w->d_contact); cudaFree(w->d_zero);
-    cudaFree(w->d_inc); cudaFree(w->d_sums); cudaFree(w->d_big_list); cudaFree(w->d_snap); cudaFree(w->d_hit_list); cudaFree(w->d_simplex);
+    cudaFree(w->d_inc); cudaFree(w->d_sums); cudaFree(w->d_big_list); cudaFree(w->d_snap); cudaFree(w->d_hit_list); cudaFree(w->d_simplex); cudaFree(w->d_seed); w->d_seed = nullptr;
     w->d_state = w->d_cst = w->d_xf = nullptr; w->d_ints = nullptr; w->d_hit_j = w->d_cflags = nullptr; w->d_contact = nullptr;
     w->d_zero = w->d_inc = w->d_sums = w->d_big_list = w->d_hit_list = nullptr; w->d_snap = nullptr; w->d_simplex = nullptr;
     w->cap = 0;
@@ -175,6 +176,7 @@ static int alloc_store(np_world* w, size_t c)
     CU(cudaMalloc((void**)&w->d_sums, sizeof(int) * (4 * c / NP_SCAN_BLOCK + 2))); CU(cudaMalloc((void**)&w->d_big_list, sizeof(int) * c));
     CU(cudaMalloc((void**)&w->d_snap, sizeof(SnapObj) * c));
     CU(cudaMalloc((void**)&w->d_hit_list, sizeof(int) * 2 * NP_HIT_CLASSES * c)); CU(cudaMalloc((void**)&w->d_simplex, sizeof(float4) * 6 * c));      // hit lists of k_gjk, then those k_epa_first passes on
+    CU(cudaMalloc((void**)&w->d_seed, sizeof(float4) * 2 * c));
     CU(cudaMemsetAsync(w->d_state, 0, sizeof(float) * S_COUNT * c, w->stream));
     CU(cudaMemsetAsync(w->d_hit_j, 0xff, sizeof(int) * c, w->stream)); CU(cudaMemsetAsync(w->d_cflags, 0, sizeof(int) * c, w->stream));
     CU(cudaMemsetAsync(w->d_contact, 0, sizeof(float4) * c, w->stream));
@@ -353,7 +355,10 @@ static int launch_gjk(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevC
             smem += kSimplexSmem;
             kern = k_gjk1<WORLD, false, false>;
             if (w->coop) kern = k_gjk1<WORLD, true, false>;
-            if constexpr (WORLD) { if (w->coop && cache_mode(w, in.n) == CACHE_BIG) kern = k_gjk1<true, true, true>; }
+            if constexpr (WORLD) {
+                if (w->coop && cache_mode(w, in.n) == CACHE_BIG) kern = k_gjk1<true, true, true>;
+                else if (in.seed) kern = w->coop ? k_gjk1<true, true, false, true> : k_gjk1<true, false, false, true>;
+            }
         } else if constexpr (WORLD) { if (w->coop) kern = k_gjk<G, WORLD, true>; }
     }
     int blocks = persistent_blocks(w, kern, smem, in.n, G);
@@ -426,6 +431,9 @@ static void setup_kernels()
     cudaFuncSetAttribute(k_gjk1<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_gjk1<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_gjk1<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_gjk1<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_gjk1<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_seed_supports, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_gjk1<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_gjk1<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
@@ -558,6 +566,11 @@ static int enqueue_search(np_world* w, float dt, bool timed)
         NarrowIn in; memset(&in, 0, sizeof in); in.world = 1; in.n = count; in.first = first; in.s = s;
         in.ordered = w->order_on;
         if (w->broadphase == NP_BROADPHASE_GRID) { in.cand = w->grid.cand; in.cand_off = w->grid.cand_off; in.cand_cnt = w->grid.cand_cnt; }
+        if (w->seed_on && !w->gjk1_old && cache != CACHE_BIG && pick_group(w, count, w->g_gjk_env, false) <= 1) {      // thread-per-body search: tabulate the seed supports once per body
+            const int sb_ = std::min(w->sm_count * 8, (n + NP_NARROW_THREADS - 1) / NP_NARROW_THREADS);
+            k_seed_supports<<<std::max(1, sb_), NP_NARROW_THREADS, shapes_smem(w), w->stream>>>(s, sview(w), shapes_in_smem(w) ? 1 : 0, w->d_seed);
+            in.seed = w->d_seed; w->launches += 1;
+        }
         NarrowBufs nb = { w->d_zero, hitj(w), cflags(w), contacts(w), w->d_simplex, w->d_hit_list, w->d_big_list, w->d_hit_list + (size_t)NP_HIT_CLASSES * w->cap };
         int r = launch_narrow(w, in, nb, ctr); if (r) return r;
     }
@@ -621,6 +634,7 @@ np_world* np_world_create(int device)
     if (const char* e = getenv("NP_GJK1_OLD")) w->gjk1_old = atoi(e) != 0;
     if (const char* e = getenv("NP_CBIG")) w->cbig_on = atoi(e) != 0;
     if (const char* e = getenv("NP_EPA_FIRST")) w->epa_first = atoi(e) != 0;
+    if (const char* e = getenv("NP_SEED")) w->seed_on = atoi(e) != 0;
     if (cudaMalloc((void**)&w->d_ctr, sizeof(DevCounters)) != cudaSuccess || ensure_arena(w) != NP_OK) { fail(NP_ERR_CUDA, "cannot allocate device scratch"); np_world_destroy(w); return nullptr; }
     cudaMemsetAsync(w->d_ctr, 0, sizeof(DevCounters), w->stream);
     return w;
