@@ -236,6 +236,8 @@ int np_selftest_sincos_hash(np_world* w, uint32_t start, uint64_t count, uint64_
 /* measured non-FMA FP32 issue rate of this device (independent FADD/FMUL chains), in Tflop/s: the roofline
  * denominator of the narrow phase, whose arithmetic may not be contracted into FMAs */
 int np_selftest_fp32_peak(np_world* w, float* tflops);
+/* [0] the same scalar figure, [1] the chains on packed pairs (sm_100 FADD2 / FFMA2-as-multiply, never fused): the non-FMA FP32 roofline of the support loops */
+int np_selftest_fp32_peaks(np_world* w, float out[2]);
 /* util.h closest-point solvers on the device: kind 2/3/4 = line/triangle/tetrahedron; pts = kind points, origin query */
 int np_selftest_closest(np_world* w, int kind, const float* pts, int32_t* region, float uvw[3]);
 

@@ -62,29 +62,20 @@ NP_D void load_xf(const float* __restrict__ xf, int stride, int i, float* R, V3*
 // ---------------------------------------------------------------------------------------------------
 // EXT (worlds that used np_body_add_force / np_body_set_enabled; not reference semantics): a disabled body is not integrated; a
 // pending external force adds L += F*dt right after the gravity term and is consumed.
+// Physics::Update (physics.cpp:175-194) of body i on its state in registers; returns what changed (bit 0: L, bit 1: pos/rot)
 template <bool EXT>
-__global__ void __launch_bounds__(256) k_integrate(StoreView s, float dt, int write_xf)
+NP_D int integrate_regs(const StoreView& s, int i, float dt, V3& pos, V3& rot, V3& L, const V3& H)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s.n) return;
-    const int cap = s.cap;
-    float* st = s.state; const float* c = s.cst;
+    const int cap = s.cap; const float* c = s.cst;
     const bool enabled = !EXT || s.ext[3 * (size_t)cap + i] != 0.0f;
-    V3 pos = mk(st[S_PX * cap + i], st[S_PY * cap + i], st[S_PZ * cap + i]);
-    V3 rot = mk(st[S_RX * cap + i], st[S_RY * cap + i], st[S_RZ * cap + i]);
-    V3 L = mk(st[S_LX * cap + i], st[S_LY * cap + i], st[S_LZ * cap + i]);
-    V3 H = mk(st[S_HX * cap + i], st[S_HY * cap + i], st[S_HZ * cap + i]);
     V3 g = mk(c[C_GX * cap + i], c[C_GY * cap + i], c[C_GZ * cap + i]);
     float mass = c[C_MASS * cap + i];
-    if (enabled && !is_none(g)) {                                                                 // physics.cpp:178-181
-        L = add(L, mul(mul(g, mass), dt));
-        st[S_LX * cap + i] = L.x; st[S_LY * cap + i] = L.y; st[S_LZ * cap + i] = L.z;
-    }
+    int changed = 0;
+    if (enabled && !is_none(g)) { L = add(L, mul(mul(g, mass), dt)); changed |= 1; }                // physics.cpp:178-181
     if (EXT && enabled) {
         V3 f = mk(s.ext[i], s.ext[(size_t)cap + i], s.ext[2 * (size_t)cap + i]);
         if (f.x != 0.0f || f.y != 0.0f || f.z != 0.0f) {
-            L = add(L, mul(f, dt));
-            st[S_LX * cap + i] = L.x; st[S_LY * cap + i] = L.y; st[S_LZ * cap + i] = L.z;
+            L = add(L, mul(f, dt)); changed |= 1;
             s.ext[i] = 0.0f; s.ext[(size_t)cap + i] = 0.0f; s.ext[2 * (size_t)cap + i] = 0.0f;
         }
     }
@@ -96,6 +87,24 @@ __global__ void __launch_bounds__(256) k_integrate(StoreView s, float dt, int wr
         V3 w = m3mul(iinv, H);
         pos = add(pos, mul(v, dt));
         rot = add(rot, mul(w, dt));
+        changed |= 2;
+    }
+    return changed;
+}
+template <bool EXT>
+__global__ void __launch_bounds__(256) k_integrate(StoreView s, float dt, int write_xf)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    const int cap = s.cap;
+    float* st = s.state;
+    V3 pos = mk(st[S_PX * cap + i], st[S_PY * cap + i], st[S_PZ * cap + i]);
+    V3 rot = mk(st[S_RX * cap + i], st[S_RY * cap + i], st[S_RZ * cap + i]);
+    V3 L = mk(st[S_LX * cap + i], st[S_LY * cap + i], st[S_LZ * cap + i]);
+    V3 H = mk(st[S_HX * cap + i], st[S_HY * cap + i], st[S_HZ * cap + i]);
+    const int ch = integrate_regs<EXT>(s, i, dt, pos, rot, L, H);
+    if (ch & 1) { st[S_LX * cap + i] = L.x; st[S_LY * cap + i] = L.y; st[S_LZ * cap + i] = L.z; }
+    if (ch & 2) {
         st[S_PX * cap + i] = pos.x; st[S_PY * cap + i] = pos.y; st[S_PZ * cap + i] = pos.z;
         st[S_RX * cap + i] = rot.x; st[S_RY * cap + i] = rot.y; st[S_RZ * cap + i] = rot.z;
     }
@@ -485,7 +494,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK1_MINB) k_gjk1(Narrow
 // over from the simplex.
 // ---------------------------------------------------------------------------------------------------
 template <bool WORLD>
-__global__ void __launch_bounds__(256) k_epa_first(int n_items, const int* __restrict__ list, const int* __restrict__ count, const float4* __restrict__ simplex,
+__global__ void __launch_bounds__(256) k_epa_first(int n_items, const int* __restrict__ list, const int* __restrict__ count, const float4* __restrict__ simplex, int* __restrict__ hit_j,
                                                   int* __restrict__ flags, float4* __restrict__ contact, int* __restrict__ next_list, int* __restrict__ next_count, DevCounters* ctr)
 {
     int cum[NP_HIT_CLASSES]; int total = 0;
@@ -529,6 +538,7 @@ __global__ void __launch_bounds__(256) k_epa_first(int n_items, const int* __res
                 const V3 pen = neg(normalize(bn));
                 flags[item] = NP_PAIR_HIT | NP_PAIR_SUCCESS;
                 contact[item] = make_float4(pen.x, pen.y, pen.z, dist);
+                if (WORLD) hit_j[item] |= NP_HITJ_SUCCESS;
                 n_conv++;
             }
         }
@@ -562,7 +572,7 @@ struct BigArena { float* base; int slots; };
 template <int G, int FMAX, int TIER, int THREADS, bool WORLD, bool CACHED = (WORLD && G >= 8)>
 __global__ void __launch_bounds__(THREADS, (THREADS == NP_NARROW_THREADS) ? 4 : 1)
 k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, const int* __restrict__ count, int* __restrict__ ticket,
-      const int* __restrict__ hit_j, const float4* __restrict__ simplex, int* __restrict__ flags, float4* __restrict__ contact,
+      int* __restrict__ hit_j, const float4* __restrict__ simplex, int* __restrict__ flags, float4* __restrict__ contact,
       int* __restrict__ next_list, int* __restrict__ next_count, BigArena ar, DevCounters* ctr)
 {
     extern __shared__ float4 s_dyn[];
@@ -605,7 +615,7 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
                     item = list[(size_t)k * in.n + (t - base)];
                 } else item = list[t];
                 if (WORLD) {
-                    int i = item, j = hit_j[i];
+                    int i = item, j = hitj_body(hit_j[i]);
                     if (CACHED) {
                         g.va = s.wverts + s.ints[I_WVOFF * s.cap + i]; g.na = sh.cnt[s.ints[I_SHAPE * s.cap + i]];
                         g.vb = s.wverts + s.ints[I_WVOFF * s.cap + j]; g.nb = sh.cnt[s.ints[I_SHAPE * s.cap + j]];
@@ -647,7 +657,10 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
                 const bool requeue = (fl & NP_PAIR_OVERFLOW) && TIER < 2;
                 if (lead) {
                     if (requeue) next_list[atomicAdd(next_count, 1)] = item;                       // flags/simplex stay for the re-run
-                    else { flags[item] = fl & (NP_PAIR_HIT | NP_PAIR_SUCCESS | NP_PAIR_OVERFLOW); contact[item] = make_float4(pen.x, pen.y, pen.z, depth); }
+                    else {
+                        flags[item] = fl & (NP_PAIR_HIT | NP_PAIR_SUCCESS | NP_PAIR_OVERFLOW); contact[item] = make_float4(pen.x, pen.y, pen.z, depth);
+                        if (WORLD && (fl & NP_PAIR_SUCCESS)) hit_j[item] = hitj_body(hit_j[item]) | NP_HITJ_SUCCESS;
+                    }
                 }
                 if (requeue) { st = st0; if (TIER == 0) n_over++; }      // the next tier re-runs the pair: count its work there, once
                 have = false;
@@ -1040,7 +1053,7 @@ __global__ void __launch_bounds__(256) k_link(int n, int cap, const int* __restr
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int b = hit_j[i];
+    int b = hitj_body(hit_j[i]);
     if ((unsigned)b < (unsigned)n && ints[I_RESPONSE * cap + b] == 1) next[i] = atomicExch(&head[b], i + 1);      // (records may come from another process)
 }
 // exclusive scan of cnt[0..n) in three launches (per-block sums, scan of the sums, per-block scan + offset)
@@ -1141,18 +1154,24 @@ NP_D SnapObj snap_of(const StoreView& s, int i, V3 pos, uint32_t guid_base)
     o.enabled = (s.ext && s.ext[3 * (size_t)cap + i] == 0.0f) ? 0u : 1u;                          // dBodyIsEnabled, world_s.cpp:48
     return o;
 }
+// FUSE: the response of step k and Physics::Update of step k+1 in one pass over the state (np_world_step_n): the snapshot record is
+// that of step k (after the responses), then the body is integrated from the registers it already sits in and its new transform is
+// written -- one read and one write of the 48 B/body state per step instead of two, one launch fewer.  Same operations, same order.
+template <bool FUSE, bool EXT>
 __global__ void __launch_bounds__(256) k_resolve(StoreView s, const int* __restrict__ hit_j, const float4* __restrict__ contact,
-                                                const int* __restrict__ head, const int* __restrict__ next, SnapObj* __restrict__ snap, uint32_t guid_base)
+                                                const int* __restrict__ head, const int* __restrict__ next, SnapObj* __restrict__ snap, uint32_t guid_base, float dt_next)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= s.n) return;
     const int cap = s.cap;
     float* st = s.state; const float* c = s.cst;
     V3 pos = mk(st[S_PX * cap + k], st[S_PY * cap + k], st[S_PZ * cap + k]);
-    const int own = hit_j[k], first = head[k];
+    V3 L = mk(0.f, 0.f, 0.f), H = L;
+    if (FUSE) { L = mk(st[S_LX * cap + k], st[S_LY * cap + k], st[S_LZ * cap + k]); H = mk(st[S_HX * cap + k], st[S_HY * cap + k], st[S_HZ * cap + k]); }
+    const int own = hitj_body(hit_j[k]), first = head[k];
+    bool resolved = false;
     if (s.ints[I_RESPONSE * cap + k] == 1 && ((unsigned)own < (unsigned)s.n || first != 0)) {
-        V3 L = mk(st[S_LX * cap + k], st[S_LY * cap + k], st[S_LZ * cap + k]);
-        V3 H = mk(st[S_HX * cap + k], st[S_HY * cap + k], st[S_HZ * cap + k]);
+        if (!FUSE) { L = mk(st[S_LX * cap + k], st[S_LY * cap + k], st[S_LZ * cap + k]); H = mk(st[S_HX * cap + k], st[S_HY * cap + k], st[S_HZ * cap + k]); }
         float mass = c[C_MASS * cap + k], elast = c[C_ELAST * cap + k];
         float iinv[9];
 #pragma unroll
@@ -1171,11 +1190,24 @@ __global__ void __launch_bounds__(256) k_resolve(StoreView s, const int* __restr
             float4 cd = contact[k];
             impulse(pos, L, H, mass, elast, iinv, mk(cd.x, cd.y, cd.z), cd.w, b_normal);
         }
-        st[S_PX * cap + k] = pos.x; st[S_PY * cap + k] = pos.y; st[S_PZ * cap + k] = pos.z;
-        st[S_LX * cap + k] = L.x; st[S_LY * cap + k] = L.y; st[S_LZ * cap + k] = L.z;
+        resolved = true;
+        if (!FUSE) {
+            st[S_PX * cap + k] = pos.x; st[S_PY * cap + k] = pos.y; st[S_PZ * cap + k] = pos.z;
+            st[S_LX * cap + k] = L.x; st[S_LY * cap + k] = L.y; st[S_LZ * cap + k] = L.z;
+        }
         st[S_HX * cap + k] = H.x; st[S_HY * cap + k] = H.y; st[S_HZ * cap + k] = H.z;
     }
     if (snap) snap[k] = snap_of(s, k, pos, guid_base);
+    if (FUSE) {
+        V3 rot = mk(st[S_RX * cap + k], st[S_RY * cap + k], st[S_RZ * cap + k]);
+        const int ch = integrate_regs<EXT>(s, k, dt_next, pos, rot, L, H);
+        if (resolved || (ch & 1)) { st[S_LX * cap + k] = L.x; st[S_LY * cap + k] = L.y; st[S_LZ * cap + k] = L.z; }
+        if (resolved || (ch & 2)) { st[S_PX * cap + k] = pos.x; st[S_PY * cap + k] = pos.y; st[S_PZ * cap + k] = pos.z; }
+        if (ch & 2) { st[S_RX * cap + k] = rot.x; st[S_RY * cap + k] = rot.y; st[S_RZ * cap + k] = rot.z; }
+        float R[9]; V3 t;
+        make_transform(pos, rot, R, &t);
+        store_xf(s.xf, k, R, t);
+    }
 }
 
 // np_body_add_force / np_body_set_enabled on one body
@@ -1251,6 +1283,24 @@ __global__ void __launch_bounds__(256) k_fp32_peak(int iters, float* out)
     }
     float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 123.456f) out[0] = s;
+}
+// the same chains on packed pairs (FADD2 / FFMA2-as-multiply): 4 flop per loop body per chain
+__global__ void __launch_bounds__(256) k_fp32x2_peak(int iters, float* out)
+{
+    f32x2 a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = pk2(threadIdx.x * 1e-3f + k, threadIdx.x * 2e-3f + k);
+    const f32x2 m = pk2(0.999999f, 0.999998f), c = pk2(1e-6f, 2e-6f);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = (k & 1) ? add2(a[k], c) : mul2(a[k], m);
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = (k & 1) ? mul2(a[k], m) : add2(a[k], c);
+    }
+    f32x2 s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= a[k];
+    if (s == 123456ull) out[0] = 1.0f;
 }
 __global__ void k_selftest_closest(int kind, const float* pts, int* region, float* uvw)
 {

@@ -32,6 +32,10 @@ namespace np {
 #define NP_EPA_TOL 0.01f           // collision_detection.cpp:423
 
 enum PairFlags { NP_PAIR_HIT = 1, NP_PAIR_SUCCESS = 2, NP_PAIR_OVERFLOW = 4, NP_PAIR_SEED_ALIVE = 8 };
+// World mode: hit_j[i] = -1 (no collision) or the partner's index, with CollisionData::success in bit 30 -- the per-body collision
+// record is then hit_j + contact (20 bytes) and the flags array never has to leave the process that searched body i.
+#define NP_HITJ_SUCCESS 0x40000000
+__host__ __device__ __forceinline__ int hitj_body(int v) { return v < 0 ? v : (v & ~NP_HITJ_SUCCESS); }
 
 struct PairGeom {
     float Ra[9], Rb[9];
@@ -59,6 +63,44 @@ template <int G> NP_D void gsync() { if (G > 1) __syncwarp(gmask<G>()); }
 NP_D int float_order(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }      // monotone float -> int
 NP_D float order_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
+// ---------------------------------------------------------------------------------------------------
+// Packed binary32 pairs (sm_100 FADD2 / FFMA2).  mul.rn.f32x2 and add.rn.f32x2 round each half exactly like the scalar FMUL /
+// FADD (the product is taken as x*y + (-0): the correctly rounded product, signed zeros included), so two vertices go through the reference's transform-and-dot sequence (physics_util.cpp:17-21)
+// per instruction with the same bits as one.  Measured on B200: 51 Tflop/s of non-fused FADD/FMUL work against 35 scalar
+// (tools/mb/fp32x2_peak.cu) -- and half the issue slots, which is what the thread-per-pair kernels are short of.
+// ---------------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+NP_D f32x2 pk2(float lo, float hi) { f32x2 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d; }
+NP_D void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+// ptxas CONTRACTS mul.rn.f32x2 + add.rn.f32x2 into a fused FFMA2 whatever -fmad says (checked in SASS; so it does for an fma whose
+// addend is a literal -0), which would break parity.  The product is therefore an FFMA2 whose -0 addend comes from constant memory:
+// ptxas cannot fold it, and an fma cannot be contracted into the add that follows.
+__constant__ unsigned long long c_negz2 = 0x8000000080000000ull;
+NP_D f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c_negz2)); return d; }
+NP_D f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// transform + direction of one support call, every scalar duplicated into both halves
+struct SupPack {
+    f32x2 R[9], tx, ty, tz, dx, dy, dz;
+    NP_D void set(const float* r, V3 t, V3 d)
+    {
+#pragma unroll
+        for (int k = 0; k < 9; k++) R[k] = pk2(r[k], r[k]);
+        tx = pk2(t.x, t.x); ty = pk2(t.y, t.y); tz = pk2(t.z, t.z); dx = pk2(d.x, d.x); dy = pk2(d.y, d.y); dz = pk2(d.z, d.z);
+    }
+    // dot(d, world * p) of two shape-local vertices at once: xf_point then dot, the same operation order per half
+    NP_D void dots(float4 q0, float4 q1, float& dp0, float& dp1) const
+    {
+        const f32x2 X = pk2(q0.x, q1.x), Y = pk2(q0.y, q1.y), Z = pk2(q0.z, q1.z);
+        const f32x2 wx = add2(add2(add2(mul2(R[0], X), mul2(R[1], Y)), mul2(R[2], Z)), tx);
+        const f32x2 wy = add2(add2(add2(mul2(R[3], X), mul2(R[4], Y)), mul2(R[5], Z)), ty);
+        const f32x2 wz = add2(add2(add2(mul2(R[6], X), mul2(R[7], Y)), mul2(R[8], Z)), tz);
+        upk2(add2(add2(mul2(dx, wx), mul2(dy, wy)), mul2(dz, wz)), dp0, dp1);
+    }
+};
+
+#ifndef NP_PACKED
+#define NP_PACKED 0      // measured: unfused FFMA2 + FADD2 run at 2 cycles each -- 35.1 Tflop/s, the scalar rate -- and the pack/unpack moves make the 1M world 4 % slower
+#endif
 template <int G, bool CACHED>
 NP_D V3 support(const float4* __restrict__ v, int n, const float* R, V3 t, V3 d)
 {
@@ -66,6 +108,20 @@ NP_D V3 support(const float4* __restrict__ v, int n, const float* R, V3 t, V3 d)
     // xf_point evaluates here, so both variants see the same bits.
     float bd = -INFINITY;
     int bi = 0x7fffffff;
+    if (G == 1 && !CACHED && NP_PACKED) {
+        // throughput regime, two vertices per instruction (SupPack); visited in index order, so strict '>' keeps the first maximum
+        SupPack sp; sp.set(R, t, d);
+#pragma unroll 2
+        for (int k = 0; k < n; k += 2) {
+            const float4 q0 = v[k], q1 = v[(k + 1 < n) ? k + 1 : k];
+            float dp0, dp1; sp.dots(q0, q1, dp0, dp1);
+            if (dp0 > bd) { bd = dp0; bi = k; }
+            if (k + 1 < n && dp1 > bd) { bd = dp1; bi = k + 1; }
+        }
+        if (bi == 0x7fffffff) return mk(0.0f, 0.0f, 0.0f);      // no vertex, or every dot product NaN / -inf
+        float4 q = v[bi];
+        return xf_point(R, t, mk(q.x, q.y, q.z));
+    }
     if (G == 1) {
         // throughput regime: track (best dot, index) only and recompute the winner once -- same operands, same bits
 #pragma unroll 4
@@ -179,7 +235,19 @@ NP_D V3 support_coop1(bool want, const float4* __restrict__ v, int n, const floa
             }
             const V3 sd = mk(__shfl_sync(full, d.x, src), __shfl_sync(full, d.y, src), __shfl_sync(full, d.z, src));
             float bd = -INFINITY; int bi = 0x7fffffff;
-            if (sn <= 192) {
+            if (!CBIG && NP_PACKED && sn <= 192) {
+                SupPack sp; sp.set(sR, st, sd);
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    const int k0 = lane + 64 * u, k1 = k0 + 32;
+                    if (k0 < sn) {                                                   // (warp-uniform for u <= 1 whenever sn >= 96)
+                        const float4 q0 = sv[k0], q1 = sv[(k1 < sn) ? k1 : k0];
+                        float dp0, dp1; sp.dots(q0, q1, dp0, dp1);
+                        if (dp0 > bd) { bd = dp0; bi = k0; }
+                        if (k1 < sn && dp1 > bd) { bd = dp1; bi = k1; }
+                    }
+                }
+            } else if (sn <= 192) {
                 float4 q[6];
 #pragma unroll
                 for (int u = 0; u < 6; u++) { const int k = lane + 32 * u; q[u] = (k < sn) ? sv[k] : make_float4(0.f, 0.f, 0.f, 0.f); }

@@ -26,7 +26,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 struct HostShape { std::vector<float> xyz; };
 struct HostBody { np_static_physics_data sd; int shape; int island; int enabled = 1; };
-struct StepGraph { uint32_t dt_bits; void* snap; uint32_t guid; cudaGraphExec_t exec; unsigned long long launches; };   // one captured Physics_Update
+struct StepGraph { uint32_t dt_bits; void* snap; uint32_t guid; int kind; cudaGraphExec_t exec; unsigned long long launches; };   // one captured Physics_Update
 struct CommandFrame { unsigned id; double time_ms; std::vector<np_snapshot_object> objects; };      // world_s.cpp:12-17
 
 struct np_world {
@@ -68,6 +68,7 @@ struct np_world {
     int max_verts = 0;                // largest shape
     int g_gjk_env = 0, g_epa_env = 0; // NP_G_GJK / NP_G_EPA overrides (tuning)
     int order_on = 1; bool order_dirty = true;   // NP_ORDER=0: search bodies in index order (tuning)
+    int fuse_on = 1;      // NP_FUSE=0: np_world_step_n runs plain steps (A/B)
     int gjk1_old = 0, cbig_on = 0, epa_first = 1, seed_on = 0;   // NP_SEED=1: per-body table of DetectCollision's seed supports (measured slower: 4.01 vs 3.90 ms)   // NP_GJK1_OLD=1: round-1 register-simplex kernel; NP_CBIG=1: large-body vertex cache for the cooperative supports (measured slower: 9 GB of DRAM reads per step); NP_EPA_FIRST=0 (tuning, A/B)
     bool coop = false; int coop_env = -1;   // large and small shapes mixed: warp-cooperative supports in the narrow kernels (NP_COOP=0/1 overrides)
     DevCounters* d_ctr = nullptr;
@@ -404,7 +405,7 @@ static int launch_epa(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevC
     const int* list = b.hit_list; const int* counts = b.zero + Z_HIT_COUNT;
     if (G < 32 && w->epa_first) {            // throughput regime: the hits that converge before their first support never reach the group kernel
         const int fb = (int)std::min<long long>((long long)w->sm_count * 8, ((long long)in.n + 255) / 256);
-        k_epa_first<WORLD><<<std::max(1, fb), 256, 0, w->stream>>>(in.n, b.hit_list, b.zero + Z_HIT_COUNT, b.simplex, b.flags, b.contact, b.hit_list2, b.zero + Z_HIT2_COUNT, ctr);
+        k_epa_first<WORLD><<<std::max(1, fb), 256, 0, w->stream>>>(in.n, b.hit_list, b.zero + Z_HIT_COUNT, b.simplex, b.hit_j, b.flags, b.contact, b.hit_list2, b.zero + Z_HIT2_COUNT, ctr);
         list = b.hit_list2; counts = b.zero + Z_HIT2_COUNT;
         w->launches += 1;
     }
@@ -544,7 +545,7 @@ static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, i
 //   respond: OnCollision over every body's collisions -> snapshot                                  (physics.cpp:159-162)
 // A sharded world runs them as np_world_step_begin / np_world_step_end with the caller's all-gather of the collision
 // records in between; everything but the search itself is replicated and bit-identical on every process.
-static int enqueue_search(np_world* w, float dt, bool timed)
+static int enqueue_search(np_world* w, float dt, bool timed, bool integrate = true)
 {
     const int n = (int)w->bodies.size();
     if (n == 0) return NP_OK;
@@ -553,8 +554,10 @@ static int enqueue_search(np_world* w, float dt, bool timed)
     const int b256 = (n + 255) / 256;
     const int first = sharded(w) ? w->shard_first : 0, count = sharded(w) ? w->shard_count : n;
     if (timed && !w->capturing) CU(cudaEventRecord(w->ev[0], w->stream));
-    if (s.ext) k_integrate<true><<<b256, 256, 0, w->stream>>>(s, dt, 1); else k_integrate<false><<<b256, 256, 0, w->stream>>>(s, dt, 1);
-    w->launches += 1;
+    if (integrate) {                              // (a step that follows a fused response was integrated by it)
+        if (s.ext) k_integrate<true><<<b256, 256, 0, w->stream>>>(s, dt, 1); else k_integrate<false><<<b256, 256, 0, w->stream>>>(s, dt, 1);
+        w->launches += 1;
+    }
     if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[1], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     const int cache = cache_mode(w, count);
     if (w->broadphase == NP_BROADPHASE_GRID) { int r = enqueue_grid(w, s, first, count, cache, ctr); if (r) return r; }
@@ -578,7 +581,7 @@ static int enqueue_search(np_world* w, float dt, bool timed)
     CU(cudaGetLastError());
     return NP_OK;
 }
-static int enqueue_respond(np_world* w, bool timed)
+static int enqueue_respond(np_world* w, bool timed, const float* fuse_dt = nullptr)
 {
     const int n = (int)w->bodies.size();
     if (n == 0) return NP_OK;
@@ -586,19 +589,26 @@ static int enqueue_respond(np_world* w, bool timed)
     const int b256 = (n + 255) / 256;
     SnapObj* snap = w->snapshot_each_step ? (w->snap_target ? (SnapObj*)w->snap_target : w->d_snap) : nullptr;
     k_link<<<b256, 256, 0, w->stream>>>(n, w->cap, hitj(w), w->d_ints, d_inc_cnt(w), w->d_inc);
-    k_resolve<<<b256, 256, 0, w->stream>>>(s, hitj(w), contacts(w), d_inc_cnt(w), w->d_inc, snap, w->guid_base);      // + the snapshot record
+    // + the snapshot record; fuse_dt: also Physics::Update of the NEXT step (np_world_step_n)
+    if (fuse_dt) {
+        if (s.ext) k_resolve<true, true><<<b256, 256, 0, w->stream>>>(s, hitj(w), contacts(w), d_inc_cnt(w), w->d_inc, snap, w->guid_base, *fuse_dt);
+        else k_resolve<true, false><<<b256, 256, 0, w->stream>>>(s, hitj(w), contacts(w), d_inc_cnt(w), w->d_inc, snap, w->guid_base, *fuse_dt);
+    } else k_resolve<false, false><<<b256, 256, 0, w->stream>>>(s, hitj(w), contacts(w), d_inc_cnt(w), w->d_inc, snap, w->guid_base, 0.0f);
     if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[4], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     w->launches += 2;
     if (timed && !w->capturing) CU(cudaEventRecord(w->ev[5], w->stream));
     CU(cudaGetLastError());
     return NP_OK;
 }
-static int enqueue_step(np_world* w, float dt, bool timed)
+// kind of a step inside np_world_step_n: PLAIN = integrate .. resolve; OPEN = integrate .. resolve fused with the next integrate;
+// MID = (integrated by the previous step) .. fused; CLOSE = (integrated by the previous step) .. plain resolve
+enum { STEP_PLAIN = 0, STEP_OPEN = 1, STEP_MID = 2, STEP_CLOSE = 3 };
+static int enqueue_step(np_world* w, float dt, bool timed, int kind = STEP_PLAIN)
 {
     if (w->mid_step) return fail(NP_ERR_INVALID, "a step is open: np_world_step_begin must be closed by np_world_step_end");
     if (sharded(w)) return fail(NP_ERR_INVALID, "sharded world: step with np_world_step_begin / (all-gather) / np_world_step_end");
-    int r = enqueue_search(w, dt, timed); if (r) return r;
-    return enqueue_respond(w, timed);
+    int r = enqueue_search(w, dt, timed, kind == STEP_PLAIN || kind == STEP_OPEN); if (r) return r;
+    return enqueue_respond(w, timed, (kind == STEP_OPEN || kind == STEP_MID) ? &dt : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ library
@@ -635,6 +645,7 @@ np_world* np_world_create(int device)
     if (const char* e = getenv("NP_CBIG")) w->cbig_on = atoi(e) != 0;
     if (const char* e = getenv("NP_EPA_FIRST")) w->epa_first = atoi(e) != 0;
     if (const char* e = getenv("NP_SEED")) w->seed_on = atoi(e) != 0;
+    if (const char* e = getenv("NP_FUSE")) w->fuse_on = atoi(e) != 0;
     if (cudaMalloc((void**)&w->d_ctr, sizeof(DevCounters)) != cudaSuccess || ensure_arena(w) != NP_OK) { fail(NP_ERR_CUDA, "cannot allocate device scratch"); np_world_destroy(w); return nullptr; }
     cudaMemsetAsync(w->d_ctr, 0, sizeof(DevCounters), w->stream);
     return w;
@@ -876,18 +887,18 @@ int np_body_get_transform(np_world* w, int body, float out16[16])               
 // One captured Physics_Update per (dt, snapshot target): with thousands of bodies a step is a dozen kernels of a few microseconds and
 // the launch gaps of plain submission cost as much as the kernels (measured 0.31 -> 0.26 ms per step on the 10 k-body world).  The
 // phase events are recorded inside the graph, so np_world_last_step_ms keeps its breakdown.
-static int get_step_graph(np_world* w, float dt, StepGraph** out)
+static int get_step_graph(np_world* w, float dt, StepGraph** out, int kind = STEP_PLAIN)
 {
     uint32_t bits; memcpy(&bits, &dt, 4);
-    for (auto& g : w->graphs) if (g.dt_bits == bits && g.snap == w->snap_target && g.guid == w->guid_base) { *out = &g; return NP_OK; }
-    if (w->graphs.size() >= 4) { cudaGraphExecDestroy(w->graphs.front().exec); w->graphs.erase(w->graphs.begin()); }
+    for (auto& g : w->graphs) if (g.dt_bits == bits && g.snap == w->snap_target && g.guid == w->guid_base && g.kind == kind) { *out = &g; return NP_OK; }
+    if (w->graphs.size() >= 8) { cudaGraphExecDestroy(w->graphs.front().exec); w->graphs.erase(w->graphs.begin()); }
     cudaGraph_t g = nullptr;
     const unsigned long long l0 = w->launches;
     CU(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
     w->capturing = true;                                                  // (phase events become external event-record nodes)
-    int r = enqueue_step(w, dt, true);
+    int r = enqueue_step(w, dt, true, kind);
     w->capturing = false;
-    StepGraph sg = { bits, w->snap_target, w->guid_base, nullptr, w->launches - l0 };
+    StepGraph sg = { bits, w->snap_target, w->guid_base, kind, nullptr, w->launches - l0 };
     w->launches = l0;                                                     // counted per replay
     cudaError_t e = cudaStreamEndCapture(w->stream, &g);
     if (r) { if (g) cudaGraphDestroy(g); return r; }
@@ -899,11 +910,11 @@ static int get_step_graph(np_world* w, float dt, StepGraph** out)
     *out = &w->graphs.back();
     return NP_OK;
 }
-static int step_once(np_world* w, float dt)
+static int step_once(np_world* w, float dt, int kind = STEP_PLAIN)
 {
-    if (!w->graph_on || sharded(w) || w->mid_step) return enqueue_step(w, dt, true);
+    if (!w->graph_on || sharded(w) || w->mid_step) return enqueue_step(w, dt, true, kind);
     StepGraph* g = nullptr;
-    int r = get_step_graph(w, dt, &g); if (r) return r;
+    int r = get_step_graph(w, dt, &g, kind); if (r) return r;
     CU(cudaEventRecord(w->ev[0], w->stream));
     CU(cudaGraphLaunch(g->exec, w->stream));
     CU(cudaEventRecord(w->ev[5], w->stream));
@@ -966,7 +977,11 @@ int np_world_step_n(np_world* w, float dt, int steps)
     int r = ensure_device(w); if (r) return r;
     r = ensure_cache(w); if (r) return r;
     if (w->bodies.empty() || steps == 0) return NP_OK;
-    for (int i = 0; i < steps; i++) { r = step_once(w, dt); if (r) return r; }
+    // consecutive steps: the response of step k and the integration of step k+1 are one kernel (k_resolve<true>)
+    for (int i = 0; i < steps; i++) {
+        const int kind = (steps == 1 || !w->fuse_on || sharded(w)) ? STEP_PLAIN : (i == 0 ? STEP_OPEN : (i == steps - 1 ? STEP_CLOSE : STEP_MID));
+        r = step_once(w, dt, kind); if (r) return r;
+    }
     w->timed = true; w->steps += (unsigned long long)steps;                // (the phase events are those of the last step)
     return NP_OK;
 }
@@ -986,9 +1001,8 @@ int np_world_get_collisions(np_world* w, np_collision* out, int cap, int* count)
     int n = w->dev_n; if (!w->dev_state_valid || n == 0 || w->steps == 0) return NP_OK;
     CU(cudaSetDevice(w->device));
     { int rg = check_grid_error(w); if (rg) return rg; }
-    std::vector<int> hj(n), fl(n); std::vector<float4> cd(n);
+    std::vector<int> hj(n); std::vector<float4> cd(n);
     CU(cudaMemcpyAsync(hj.data(), hitj(w), sizeof(int) * n, cudaMemcpyDeviceToHost, w->stream));
-    CU(cudaMemcpyAsync(fl.data(), cflags(w), sizeof(int) * n, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaMemcpyAsync(cd.data(), contacts(w), sizeof(float4) * n, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
     int k = 0;
@@ -996,9 +1010,9 @@ int np_world_get_collisions(np_world* w, np_collision* out, int cap, int* count)
         if (hj[i] < 0) continue;
         if (out && k < cap) {
             np_collision& c = out[k]; memset(&c, 0, sizeof c);
-            c.a = i; c.b = hj[i];
+            c.a = i; c.b = hitj_body(hj[i]);
             c.data.penetration_direction[0] = cd[i].x; c.data.penetration_direction[1] = cd[i].y; c.data.penetration_direction[2] = cd[i].z;
-            c.data.depth = cd[i].w; c.data.success = (fl[i] & NP_PAIR_SUCCESS) ? 1 : 0;
+            c.data.depth = cd[i].w; c.data.success = (hj[i] & NP_HITJ_SUCCESS) ? 1 : 0;
         }
         k++;
     }
@@ -1291,6 +1305,26 @@ int np_selftest_fp32_peak(np_world* w, float* tflops)
     }
     CU(cudaFreeAsync(d, w->stream)); CU(cudaGetLastError());
     *tflops = best;
+    return NP_OK;
+}
+int np_selftest_fp32_peaks(np_world* w, float out[2])
+{
+    if (!w || !out) return fail(NP_ERR_INVALID, "bad arguments");
+    int r = np_selftest_fp32_peak(w, &out[0]); if (r) return r;
+    float* d = nullptr; CU(cudaMallocAsync((void**)&d, 4, w->stream));
+    const int iters = 20000, blocks = w->sm_count * 8;
+    k_fp32x2_peak<<<blocks, 256, 0, w->stream>>>(100, d);
+    float best = 0.0f;
+    for (int rep = 0; rep < 3; rep++) {
+        CU(cudaEventRecord(w->ev[0], w->stream));
+        k_fp32x2_peak<<<blocks, 256, 0, w->stream>>>(iters, d);
+        CU(cudaEventRecord(w->ev[5], w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+        float ms = 0.0f; CU(cudaEventElapsedTime(&ms, w->ev[0], w->ev[5]));
+        best = std::max(best, (float)((double)blocks * 256.0 * iters * 32.0 / (ms * 1e-3) / 1e12));
+    }
+    CU(cudaFreeAsync(d, w->stream)); CU(cudaGetLastError());
+    out[1] = best;
     return NP_OK;
 }
 #ifdef NP_TIMELINE

@@ -51,9 +51,10 @@ def padded_shard(n_bodies, rank, world_size):
 
 
 class CollisionExchange:
-    """The one exchange of a sharded world step (np_world_set_shard / step_begin / step_end): all-gather, in place, of the three
-    per-body collision arrays -- hit_j int32, flags int32, contact float32[4] (= physics.h:26-31 Collision records, 24 bytes per
-    body) -- each rank contributing the slot of bodies it searched.  Tensors are CUDA for nccl, CPU for gloo."""
+    """The one exchange of a sharded world step (np_world_set_shard / step_begin / step_end): all-gather, in place, of the per-body
+    collision records -- hit_j int32 (partner index, CollisionData::success in bit 30) and contact float32[4] (penetration direction,
+    depth): physics.h:26-31 Collision, 20 bytes per body -- each rank contributing the slot of bodies it searched.  `flags` is scratch
+    of the searching rank and does not travel.  Tensors are CUDA for nccl, CPU for gloo."""
 
     def __init__(self, n_bodies, device, world_size, rank):
         import torch
@@ -72,7 +73,7 @@ class CollisionExchange:
         if self.world_size == 1:
             return
         lo, hi = self.rank * self.slot, (self.rank + 1) * self.slot
-        for t in (self.hit_j, self.flags, self.contact):
+        for t in (self.hit_j, self.contact):
             piece = t[lo:hi]
             if not t.is_cuda:
                 piece = piece.clone()                   # gloo: no aliasing of input and output

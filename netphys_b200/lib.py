@@ -136,6 +136,7 @@ def load_library(variant="exact"):
     L.np_world_fill_packet.argtypes = [vp, C.c_int, vp, C.c_int]
     L.np_world_set_snapshot_target.argtypes = [vp, vp, C.c_uint32]
     L.np_selftest_fp32_peak.argtypes = [vp, f32p]
+    L.np_selftest_fp32_peaks.argtypes = [vp, f32p]
     L.np_selftest_sincos_hash.argtypes = [vp, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.np_selftest_closest.argtypes = [vp, C.c_int, f32p, i32p, f32p]
     _LIBS[path] = L
@@ -386,6 +387,10 @@ class World:
 
     def fp32_peak_tflops(self):
         out = np.zeros(1, np.float32); self._ck(self.L.np_selftest_fp32_peak(self.w, _f(out))); return float(out[0])
+
+    def fp32_peaks_tflops(self):
+        """(scalar, packed f32x2) non-FMA FP32 issue peaks measured on this device"""
+        out = np.zeros(2, np.float32); self._ck(self.L.np_selftest_fp32_peaks(self.w, _f(out))); return float(out[0]), float(out[1])
 
     # -- self tests ------------------------------------------------------------------------------
     def sincos_hash(self, start, count):

@@ -497,3 +497,70 @@ def test_world_step_every_kernel_configuration(npb, oracle, g_gjk, g_epa, coop, 
             else:
                 pt, hits, _ = ow.counters(); c = w.counters()
                 assert c["pair_tests"] == pt and c["hits"] == hits
+
+
+# ---- np_world_step_n: the response of step k fused with the integration of step k+1 ---------------------------------------
+@pytest.mark.parametrize("name,n", [("few_boxes", 30), ("test_physics", 30), ("lattice", 7)])
+def test_step_n_fused_equals_single_steps(npb, oracle, name, n):
+    """np_world_step_n(dt, n) runs k_resolve<FUSE> (OnCollision of step k + Physics::Update of step k+1, physics.cpp:27-46,175-194, in one
+    pass): states, collision list and snapshot are bit-identical to n calls of np_world_step, and to the oracle."""
+    sc = {"few_boxes": scenes.few_boxes_scene, "test_physics": scenes.test_physics_scene,
+          "lattice": lambda: scenes.lattice_scene(3000, spacing=1.0, seed=21, mix=(0.5, 0.3, 0.2))}[name]()
+    ow = oracle.world(scenes.resolve(sc, oracle))
+    with npb.World(0) as a, npb.World(0) as b:
+        for w in (a, b):
+            w.set_option(w.OPT_SNAPSHOT_EACH_STEP, 1); w.load_scene(sc)
+        for _ in range(n): a.step(sc["dt"])
+        b.step_n(sc["dt"], n)
+        for _ in range(n): last = ow.step(sc["dt"], True)
+        assert_biteq(a.states(), b.states(), "fused vs single steps"); assert_biteq(b.states(), ow.state(), "fused vs oracle")
+        ca, cb = a.collisions_as_arrays(), b.collisions_as_arrays()
+        assert np.array_equal(ca[0], cb[0]) and np.array_equal(ca[1], cb[1]) and np.array_equal(cb[0], last[0]) and np.array_equal(cb[1], last[1])
+        assert_biteq(ca[2], cb[2], "collision data"); assert_biteq(cb[2], last[2], "collision data vs oracle")
+        assert a.snapshot().tobytes() == b.snapshot().tobytes()
+        # a plain step after the fused run continues from the same state (the last step of step_n is not pre-integrated)
+        a.step(sc["dt"]); b.step(sc["dt"]); ow.step(sc["dt"])
+        assert_biteq(a.states(), b.states(), "step after step_n"); assert_biteq(b.states(), ow.state(), "step after step_n vs oracle")
+        # forces and a disabled body go through the fused kernel's EXT variant
+        for w in (a, b):
+            w.add_force(0, np.array([3.0, -2.0, 1.0], np.float32)); w.set_enabled(1, False)
+        ow.add_force(0, np.array([3.0, -2.0, 1.0], np.float32)); ow.set_enabled(1, False)
+        for _ in range(3): a.step(sc["dt"]); ow.step(sc["dt"])
+        b.step_n(sc["dt"], 3)
+        assert_biteq(a.states(), b.states(), "fused EXT vs single steps"); assert_biteq(b.states(), ow.state(), "fused EXT vs oracle")
+
+
+# ---- the device against the reference's OWN compiled sources (oracle/_ref), when the .so travelled to this box ----------------
+def test_device_equals_compiled_reference_directly(world, ref):
+    """No C port in between: DetectCollision over random pairs and Physics_Update over a mixed world, CUDA path vs oracle/_ref
+    (the reference's engine/*.cpp compiled by oracle/Makefile)."""
+    specs, sa, pa, sb, pb = scenes.random_pairs(30000, seed=77, extent=1.5, mix=(0.4, 0.3, 0.3))
+    shapes = scenes.resolve_specs(specs, ref_factory(ref))
+    ref.L.ref_world_clear(); ref.L.ref_shapes_clear()
+    rids = np.array([ref.mesh(s) for s in shapes], np.int32)
+    ids = np.array([world.create_mesh(s) for s in shapes], np.int32)
+    hit, out = world.detect_batch(ids[sa], pa, ids[sb], pb)
+    hr, orf = ref.detect_batch(rids[sa], pa, rids[sb], pb)
+    assert np.array_equal(hit, hr)
+    ok = (hit == 1) & (orf[:, 4] == 1)                      # converged hits: everything; other hits: depth is uninitialised in the reference
+    assert_biteq(out[ok], orf[ok], "CollisionData of the converged hits vs the compiled reference")
+    nk = (hit == 1) & (orf[:, 4] != 1)
+    assert_biteq(out[nk][:, [0, 1, 2, 4]], orf[nk][:, [0, 1, 2, 4]], "CollisionData of the non-converged hits vs the compiled reference")
+    sc = scenes.lattice_scene(400, spacing=1.1, seed=12, mix=(0.5, 0.3, 0.2))
+    scr = dict(sc); scr["shapes"] = scenes.resolve_specs(sc["shape_specs"], ref_factory(ref))
+    ref.load_scene(scr)
+    with type(world)(0) as w:
+        w.load_scene(sc)
+        for k in range(12):
+            w.step(sc["dt"]); a, b, d = w.collisions_as_arrays()
+            ar, br, dr = ref.step(sc["dt"], True)
+            assert np.array_equal(a, ar) and np.array_equal(b, br), "collision list vs the compiled reference, step %d" % k
+            assert_biteq(d[:, 6:11], dr[:, 6:11], "contact data vs the compiled reference, step %d" % k)
+            assert_biteq(w.states(), ref.state(), "state vs the compiled reference, step %d" % k)
+
+
+class ref_factory:
+    """scenes.resolve factory over the compiled reference's CreateSphere / CreateBox"""
+    def __init__(self, ref): self.ref = ref
+    def make_sphere(self, r): return self.ref.shape_verts(self.ref.sphere(r))
+    def make_box(self, w, d, h): return self.ref.shape_verts(self.ref.box(w, d, h))

@@ -1,6 +1,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) { unsigned long long d; asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__constant__ unsigned long long c_negz2 = 0x8000000080000000ull;
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) { unsigned long long d; asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c_negz2)); return d; }
 __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) { unsigned long long d; asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ unsigned long long pk(float x, float y) { unsigned long long d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(x), "f"(y)); return d; }
 __global__ void __launch_bounds__(256) k_x2(int iters, float* out)
