@@ -158,7 +158,7 @@ def run_sharded_world(npb, torch, dist, rank, local_rank, world_size):
     with W(local_rank) as w:
         w.set_option(W.OPT_PHASE_TIMING, 1)
         w.load_scene(sc)
-        sw = ShardedWorld(w, torch.device("cuda", local_rank), world_size, rank)
+        sw = ShardedWorld(w, torch.device("cuda", local_rank), world_size, rank)      # np_comm_init + np_world_shard_over_comm; step = np_world_step_sharded
         for _ in range(3): sw.step(sc["dt"])
         w.synchronize(); dist.barrier()
         ms = []
@@ -172,7 +172,7 @@ def run_sharded_world(npb, torch, dist, rank, local_rank, world_size):
     hs = torch.tensor(h, device="cuda"); lo = hs.clone(); hi = hs.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     return {"workload": "ONE world of %d bodies (the configs[2]/[4] generator, spacing 2.0) replicated on %d GPUs; exact first-hit search sharded by body index range, "
-                        "NCCL all-gather of the per-body collision records, responses applied on every rank" % (n, world_size),
+                        "one grouped ncclAllGather of the per-body collision records (hit_j + contact, 20 B/body) inside np_world_step_sharded, responses applied on every rank" % (n, world_size),
             "value": n / (float(ms[5]) * 1e-3), "unit": "body-steps/s", "ms_per_step": float(ms[5]), "scaling": "weak (%d searched bodies per GPU; integrate/response passes are replicated)" % per_gpu,
             "phase_ms": {"integrate": float(ms[0]), "world_verts": float(ms[1]), "search_owned": float(ms[2]), "allgather_and_respond": float(ms[3]), "snapshot": float(ms[4])},
             "collisions_per_step": int(len(a)), "state_bit_identical_on_all_ranks": bool(torch.equal(lo, hi)), "l2": "flushed before every timed step", "timing": "CUDA events on the world's stream, mean of 5 steps, max over ranks"}
@@ -192,43 +192,31 @@ def build_worlds_batch(npb, w, lo, hi):
 
 def run_worlds_batch(npb, torch, dist, rank, local_rank, world_size):
     """BASELINE configs[3]: 4096 independent 256-body worlds sharded over the ranks (contiguous blocks of worlds, islands of one store
-    per rank), no data-path collective; the per-step snapshot (36 B/body) is all-gathered for replication, one step behind."""
-    from netphys_b200.dist import SnapshotExchange, shard_range
+    per rank), no data-path collective; the per-step snapshot (36 B/body) is all-gathered for replication by np_world_step itself."""
+    from netphys_b200.dist import init_world_comm, shard_range
     lo, hi = shard_range(4096, rank, world_size)
     W = npb.World
-    dev = torch.device("cuda", local_rank)
     with W(local_rank) as w:
-        w.set_option(W.OPT_SNAPSHOT_EACH_STEP, 1)
         dt = build_worlds_batch(npb, w, lo, hi)
-        xchg = SnapshotExchange(36 * 256 * -(-4096 // world_size), dev, world_size, rank)
-        ext = torch.cuda.ExternalStream(w.L.np_world_stream(w.w), device=dev)
-        comm = torch.cuda.Stream(device=dev, priority=-1)
-        ev = lambda: torch.cuda.Event(enable_timing=True)
+        init_world_comm(w, rank, world_size)
+        w.set_snapshot_gather(256 * -(-4096 // world_size), lo * 256)
         def run(nsteps):
-            A, B, Cc = [], [], []
-            for k in range(nsteps):
-                if k >= 2: ext.wait_event(Cc[k - 2])
-                w.flush_l2()
-                buf = xchg.next_send_buffer(); w.set_snapshot_target(buf.data_ptr(), lo * 256)
-                a = ev(); a.record(ext); w.step(dt); b = ev(); b.record(ext)
-                with torch.cuda.stream(comm):
-                    comm.wait_event(b); xchg.exchange(buf); c = ev(); c.record(comm)
-                A.append(a); B.append(b); Cc.append(c)
-            torch.cuda.synchronize(); w.synchronize()
             tot = 0.0; ker = 0.0
             for k in range(nsteps):
-                s = A[k].elapsed_time(B[k]); ker += s
-                if k >= 1: s = max(s, A[k].elapsed_time(Cc[k - 1]))
+                w.flush_l2(); w.step(dt)
+                s = float(w.last_step_ms()[5]); ker += s
+                if k >= 1: s = max(s, float(w.last_gather_ms(1)[1]))
                 tot += s
-            tot += max(0.0, B[-1].elapsed_time(Cc[-1]))
+            tot += float(w.last_gather_ms(0)[1])
             return tot / nsteps, ker / nsteps
         run(3); dist.barrier()
-        r = np.array(run(6), np.float64)
+        r = np.array(run(8), np.float64)
+        w.comm_destroy()
     t = torch.tensor(r, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); r = t.cpu().numpy()
     return {"workload": "BASELINE configs[3]: 4096 independent 256-body worlds (C2 generator, seeds 1000..5095) sharded over %d GPUs, %d worlds per GPU as islands of one store; "
-                        "snapshot all-gather (36 B/body) one step behind on its own stream, exposed part charged" % (world_size, hi - lo),
+                        "snapshot all-gather (36 B/body) launched by np_world_step on the communicator's stream, one step behind, exposed part charged" % (world_size, hi - lo),
             "value": 4096 * 256 / (float(r[0]) * 1e-3), "unit": "body-steps/s", "ms_per_step": float(r[0]), "ms_step_kernels_only": float(r[1]),
-            "scaling": "strong (4096 worlds in total)", "timing": "CUDA events on the world's stream, mean of 6, max over ranks; L2 flushed"}
+            "scaling": "strong (4096 worlds in total)", "timing": "CUDA events inside the library (np_world_last_step_ms / np_world_last_gather_ms), mean of 8, max over ranks; L2 flushed"}
 
 
 def measured_traffic():
@@ -261,37 +249,26 @@ def run_ours(args, rank, local_rank, world_size):
     w.load_scene(scene)
     dt = scene["dt"]
     warm = max(args.warmup, 3)
-    xchg = ext = comm = None
+    xchg = None
     if world_size > 1:
-        from netphys_b200.dist import SnapshotExchange
-        dev = torch.device("cuda", local_rank)
-        xchg = SnapshotExchange(36 * BODIES, dev, world_size, rank)
-        ext = torch.cuda.ExternalStream(w.L.np_world_stream(w.w), device=dev)   # the world's own stream, seen by torch
-        comm = torch.cuda.Stream(device=dev, priority=-1)                        # high priority: the all-gather is not queued behind the persistent search grids
+        from netphys_b200.dist import init_world_comm
+        init_world_comm(w, rank, world_size)                          # the world's own NCCL communicator, behind the C ABI (np_comm_init)
+        w.set_snapshot_gather(BODIES, rank * BODIES)                  # every np_world_step now all-gathers its snapshot on a high-priority stream
+        xchg = True
 
     def overlapped(nsteps):
-        """N > 1: the all-gather of step k runs on its own stream while step k+1 computes (double-buffered snapshot), as a server would
-        run it; no host sync inside the loop.  A step is charged max(its kernels, the previous all-gather still in flight), both measured
-        from the step's first kernel with CUDA events; the last all-gather's exposed tail is added once."""
-        ev = lambda: torch.cuda.Event(enable_timing=True)
-        A, B, Cc = [], [], []
-        per = np.zeros((nsteps, 2))
+        """N > 1: np_world_step launches the all-gather of its snapshot on the communicator's own stream; it runs while the next step
+        computes (double-buffered gather buffer), as a server would run it.  Step k is charged max(its kernels, the time the all-gather
+        of step k-1 needed after step k-1's last kernel) -- step k may not finish before the previous snapshot is out -- all measured
+        with CUDA events inside the library; the last all-gather's tail is added once."""
+        per = np.zeros((nsteps, 2)); tot = 0.0
         for k in range(nsteps):
-            if k >= 2: ext.wait_event(Cc[k - 2])                      # the send buffer about to be rewritten has been gathered
-            w.flush_l2()
-            buf = xchg.next_send_buffer(); w.set_snapshot_target(buf.data_ptr(), rank * BODIES)
-            a = ev(); a.record(ext); w.step(dt); bb = ev(); bb.record(ext)
-            with torch.cuda.stream(comm):
-                comm.wait_event(bb); xchg.exchange(buf); c = ev(); c.record(comm)
-            A.append(a); B.append(bb); Cc.append(c)
-        torch.cuda.synchronize(); w.synchronize()
-        tot = 0.0
-        for k in range(nsteps):
-            s = A[k].elapsed_time(B[k]); per[k, 0] = s
+            w.flush_l2(); w.step(dt)
+            s = float(w.last_step_ms()[5]); per[k, 0] = s          # (waits for the world's stream only)
             if k >= 1:
-                lag = A[k].elapsed_time(Cc[k - 1]); per[k, 1] = max(0.0, lag - s); s = max(s, lag)
+                lag = float(w.last_gather_ms(1)[1]); per[k, 1] = max(0.0, lag - s); s = max(s, lag)
             tot += s
-        tail = max(0.0, B[-1].elapsed_time(Cc[-1])); per[-1, 1] += tail
+        tail = float(w.last_gather_ms(0)[1]); per[-1, 1] += tail
         return (tot + tail) / nsteps, per
 
     if xchg is None: timed_steps(w, dt, warm)
@@ -349,7 +326,7 @@ def run_ours(args, rank, local_rank, world_size):
     # ---- N > 1: ONE world with its pair search sharded over the ranks (BASELINE configs[4]); configs[3] sharded -----------------
     sharded = batch = None
     if dist is not None:
-        fp32_peak = w.fp32_peak_tflops() if rank == 0 else None
+        fp32_peak = max(w.fp32_peaks_tflops()) if rank == 0 else None
         w.close(); w = None                                          # free the headline world before the large legs
         try:
             sharded = run_sharded_world(npb, torch, dist, rank, local_rank, world_size)
@@ -360,7 +337,7 @@ def run_ours(args, rank, local_rank, world_size):
         except Exception as e:
             batch = {"error": repr(e)}
     else:
-        fp32_peak = w.fp32_peak_tflops()
+        fp32_peak = max(w.fp32_peaks_tflops())
     if rank != 0:
         if dist is not None: dist.destroy_process_group()
         return
@@ -381,7 +358,7 @@ def run_ours(args, rank, local_rank, world_size):
             "timing": "CUDA events on the world's stream around the narrow-phase kernels, %d steps with NP_OPT_PHASE_TIMING (step %.4f ms with the events, %.4f ms without)" % (phase_steps, phase_total_ms, kernels_ms),
             "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak if fp32_peak else None,
             "traffic": traffic, "traffic_source": traffic_src,
-            "peak_source": "measured in this run: non-FMA FADD/FMUL issue rate (np_selftest_fp32_peak); MEASURED_PEAKS.json has no FP32 figure and the parity build may not contract FMAs",
+            "peak_source": "measured in this run: non-FMA FP32 issue rate, the larger of scalar FADD/FMUL chains and packed FADD2/FFMA2-as-multiply chains (np_selftest_fp32_peaks; they come out equal); MEASURED_PEAKS.json has no FP32 figure and the parity build may not contract FMAs",
             "algorithmic_flop_per_step": flops_per_step, "flop_model": "27/support vertex + 120/GJK step + 110/EPA triangle test + 60/EPA iteration, reference arithmetic (SURVEY 8(d)), counted by the kernels"}
     roof_hbm = {"bound": "hbm", "kernel": "k_integrate", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,
                 "peak_source": hbm_src, "algorithmic_bytes_per_body": B_INTEGRATE, "ms": integ_ms}
@@ -471,7 +448,7 @@ def run_ours(args, rank, local_rank, world_size):
            "config": CONFIG,
            "method": {"l2": "flushed before every timed step (256 MiB memset on the launching stream); the world's arrays (~0.3 GB) exceed L2 anyway",
                       "timing": "CUDA events on the world's stream around each step, mean over steps, max over ranks" + ("; all-gather of step k overlapped with step k+1 on a high-priority stream, exposed part charged (see bench.py)" if world_size > 1 else ""),
-                      "collective": "nccl all_gather of the 36 B/body snapshot per step" if world_size > 1 else "none"},
+                      "collective": "ncclAllGather of the 36 B/body snapshot per step, issued by np_world_step itself over the world's communicator (np_comm_init; torch.distributed only distributes the unique id)" if world_size > 1 else "none"},
            "clocks": clk, "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
            "e2e": {"value": e2e, "unit": "body-steps/s", "h2d_bytes_per_step": 48 * BODIES, "d2h_bytes_per_step": 48 * BODIES,
                    "how": "np_world_step_host with page-locked host buffers (np_host_alloc): host state in, step, host state out, copies inside the call; wall clock over %d steps" % e2e_steps},

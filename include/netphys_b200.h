@@ -165,13 +165,35 @@ int np_world_step(np_world* w, float dt);
 int np_world_step_n(np_world* w, float dt, int steps);    /* `steps` consecutive Physics_Update(dt) calls, one submission */
 /* One world, pair search sharded over processes (one per GPU).  Every process holds the whole world; this one runs GetCollisions'
  * outer loop (physics.cpp:119) for bodies [first, first + count) only and writes their records into the caller's full-length device
- * arrays: d_hit_j int32[n] (partner b, or -1), d_flags int32[n] (& 2 = CollisionData::success), d_contact float[4][n]
- * (penetrationDirection.xyz, depth).  Per step:  np_world_step_begin (Physics::Update of every body + the owned part of
- * GetCollisions)  ->  caller all-gathers the three arrays (NCCL; the step's only exchange)  ->  np_world_step_end (OnCollision over
- * the complete list, snapshot).  State stays bit-identical on every process without being exchanged.  count < 0 = not sharded. */
+ * arrays: d_hit_j int32[n] (partner b with CollisionData::success in bit 30, or -1), d_contact float[4][n] (penetrationDirection.xyz,
+ * depth), and d_flags int32[n], scratch of the searching process that never travels.  Per step:  np_world_step_begin (Physics::Update
+ * of every body + the owned part of GetCollisions)  ->  all-gather of d_hit_j and d_contact (20 B/body, the step's only exchange; by the
+ * caller, or by np_world_step_sharded over the world's own NCCL communicator)  ->  np_world_step_end (OnCollision over the complete
+ * list, snapshot).  State stays bit-identical on every process without being exchanged.  count < 0 = not sharded. */
 int np_world_set_shard(np_world* w, int first, int count, void* d_hit_j, void* d_flags, void* d_contact);
 int np_world_step_begin(np_world* w, float dt);
 int np_world_step_end(np_world* w);
+/* ---- multi-GPU behind the C ABI: one process per GPU, NCCL (loaded with dlopen("libnccl.so.2") on first use, no link-time
+ * dependency).  The caller distributes the 128-byte id from rank 0 to every rank as it would an ncclUniqueId; what the server's C++
+ * loop (netphys_server/server.cpp:38-56) needs to run sharded steps and replicate snapshots without Python. */
+#define NP_COMM_ID_BYTES 128
+int np_comm_get_unique_id(void* id128);
+int np_comm_init(np_world* w, int nranks, int rank, const void* id128);
+int np_comm_destroy(np_world* w);
+/* Replication snapshot of independent worlds (one per rank): from now on every np_world_step packs this world's 36-byte records
+ * (guid = guid_base + body) into this rank's slot of a gather buffer [nranks][slot_bodies] and all-gathers it in place on a
+ * high-priority stream of its own, overlapped with the next step (double buffered).  np_world_gathered_snapshot waits for the most
+ * recent gather and returns the buffer every rank now holds.  slot_bodies >= this world's body count; 0 disables. */
+int np_world_set_snapshot_gather(np_world* w, int slot_bodies, uint32_t guid_base);
+int np_world_gathered_snapshot(np_world* w, void** d_ptr, size_t* bytes);
+/* device times (ms) of the all-gather launched by the most recent step (back = 0; waits for it) or by the step before (back = 1):
+ * [0] its duration on its own stream, [1] how long after its step's last kernel it finished (what a following step must cover) */
+int np_world_last_gather_ms(np_world* w, int back, float out[2]);
+/* ONE world sharded over the communicator's ranks: allocates the collision-record arrays (ceil(n / nranks) bodies per rank, padded)
+ * and sets this rank's shard; then np_world_step_sharded = step_begin -> ncclAllGather of hit_j and contact (one grouped call on the
+ * world's stream) -> step_end. */
+int np_world_shard_over_comm(np_world* w);
+int np_world_step_sharded(np_world* w, float dt);
 /* Physics::Update for every body only (physics.cpp:151-155), no collision phase */
 int np_world_integrate(np_world* w, float dt);
 /* collisions of the most recent step, in the reference's list order (ascending a) */

@@ -8,6 +8,8 @@
 #include "np_kernels.cuh"
 
 #include <algorithm>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -71,6 +73,12 @@ struct np_world {
     int fuse_on = 1;      // NP_FUSE=0: np_world_step_n runs plain steps (A/B)
     int gjk1_old = 0, cbig_on = 0, epa_first = 1, seed_on = 0;   // NP_SEED=1: per-body table of DetectCollision's seed supports (measured slower: 4.01 vs 3.90 ms)   // NP_GJK1_OLD=1: round-1 register-simplex kernel; NP_CBIG=1: large-body vertex cache for the cooperative supports (measured slower: 9 GB of DRAM reads per step); NP_EPA_FIRST=0 (tuning, A/B)
     bool coop = false; int coop_env = -1;   // large and small shapes mixed: warp-cooperative supports in the narrow kernels (NP_COOP=0/1 overrides)
+    // NCCL (np_comm_*): communicator, its high-priority stream, the double-buffered snapshot gather, the sharded step's record arrays
+    ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
+    cudaStream_t comm_stream = nullptr;
+    char* d_gather[2] = { nullptr, nullptr }; int gather_slot = 0, gather_flip = 0, gather_last = -1; uint32_t gather_guid = 0;
+    cudaEvent_t ev_step_done[2] = {}, ev_gather_begin[2] = {}, ev_gather_done[2] = {}; bool gather_pending[2] = { false, false };
+    int* d_shard_hit = nullptr; int* d_shard_flags = nullptr; float4* d_shard_contact = nullptr; int shard_slot = 0;
     DevCounters* d_ctr = nullptr;
     SnapObj* d_snap = nullptr;
     BigArena arena = {};
@@ -614,6 +622,8 @@ static int enqueue_step(np_world* w, float dt, bool timed, int kind = STEP_PLAIN
 // ------------------------------------------------------------------------------------------------ library
 extern "C" {
 
+static int gather_prepare(np_world* w);
+static int gather_launch(np_world* w);
 int np_abi_version(void) { return NETPHYS_B200_ABI_VERSION; }
 const char* np_last_error(void) { return g_err.c_str(); }
 int np_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
@@ -655,6 +665,7 @@ void np_world_destroy(np_world* w)
     if (!w) return;
     cudaSetDevice(w->device);
     if (w->stream) cudaStreamSynchronize(w->stream);
+    np_comm_destroy(w);
     drop_graph(w); free_store(w); cudaFree(w->d_ext);
     cudaFree(w->d_wverts); w->d_wverts = nullptr; w->wverts_cap = 0;
     cudaFree(w->d_aos); w->d_aos = nullptr; w->d_aos_bytes = 0;
@@ -927,9 +938,10 @@ int np_world_step(np_world* w, float dt)
     int r = ensure_device(w); if (r) return r;
     r = ensure_cache(w); if (r) return r;
     if (w->bodies.empty()) return NP_OK;
+    r = gather_prepare(w); if (r) return r;
     r = step_once(w, dt); if (r) return r;
     w->timed = true; w->steps++;
-    return NP_OK;
+    return gather_launch(w);
 }
 // Sharded pair search of ONE world across processes (BASELINE configs[4]).  Every process holds the whole world;
 // process r searches the first hit of bodies [first, first + count) only, and writes hit_j / flags / contact of those bodies into
@@ -1251,6 +1263,178 @@ int np_world_fill_packet(np_world* w, int packet_id, void* buffer, int cap)
     memcpy(p, &id, 4); memcpy(p + 4, &size, 4); memcpy(p + 8, &fid, 4); memcpy(p + 12, &f.time_ms, 8); memcpy(p + 20, &count, 4);
     if (count) memcpy(p + 24, f.objects.data(), 36 * (size_t)count);
     return (int)total;
+}
+
+// ------------------------------------------------------------------------------------------------ NCCL behind the C ABI
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+int load_nccl()
+{
+    if (g_nccl.lib) return NP_OK;
+    const char* names[] = { getenv("NP_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+    void* lib = nullptr;
+    for (const char* n : names) if (n && *n && (lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!lib) return fail(NP_ERR_INVALID, std::string("cannot load NCCL (libnccl.so.2; set NP_NCCL_LIB): ") + dlerror());
+    NcclApi a; a.lib = lib;
+    *(void**)&a.GetUniqueId = dlsym(lib, "ncclGetUniqueId"); *(void**)&a.CommInitRank = dlsym(lib, "ncclCommInitRank");
+    *(void**)&a.CommDestroy = dlsym(lib, "ncclCommDestroy"); *(void**)&a.AllGather = dlsym(lib, "ncclAllGather");
+    *(void**)&a.GroupStart = dlsym(lib, "ncclGroupStart"); *(void**)&a.GroupEnd = dlsym(lib, "ncclGroupEnd");
+    *(void**)&a.GetErrorString = dlsym(lib, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.GroupStart || !a.GroupEnd) return fail(NP_ERR_INVALID, "libnccl lacks a required symbol");
+    g_nccl = a;
+    return NP_OK;
+}
+}  // namespace
+#define NC(call)                                                                                                      \
+    do {                                                                                                              \
+        ncclResult_t e_ = (call);                                                                                     \
+        if (e_ != ncclSuccess) return fail(NP_ERR_CUDA, std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(e_) : "nccl error")); \
+    } while (0)
+
+int np_comm_get_unique_id(void* id128)
+{
+    if (!id128) return fail(NP_ERR_INVALID, "null id");
+    static_assert(sizeof(ncclUniqueId) == NP_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+    int r = load_nccl(); if (r) return r;
+    ncclUniqueId id; NC(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return NP_OK;
+}
+static void free_gather(np_world* w)
+{
+    for (int b = 0; b < 2; b++) { cudaFree(w->d_gather[b]); w->d_gather[b] = nullptr; w->gather_pending[b] = false; }
+    w->gather_slot = 0; w->gather_last = -1;
+}
+int np_comm_init(np_world* w, int nranks, int rank, const void* id128)
+{
+    if (!w || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(NP_ERR_INVALID, "bad arguments");
+    if (w->comm) return fail(NP_ERR_INVALID, "the world already has a communicator");
+    int r = load_nccl(); if (r) return r;
+    CU(cudaSetDevice(w->device));
+    ncclUniqueId id; memcpy(&id, id128, sizeof id);
+    NC(g_nccl.CommInitRank(&w->comm, nranks, id, rank));
+    w->nranks = nranks; w->rank = rank;
+    int lo = 0, hi = 0; CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));        // (hi = numerically lowest = highest priority)
+    CU(cudaStreamCreateWithPriority(&w->comm_stream, cudaStreamNonBlocking, hi));
+    for (int b = 0; b < 2; b++) { CU(cudaEventCreate(&w->ev_step_done[b])); CU(cudaEventCreate(&w->ev_gather_begin[b])); CU(cudaEventCreate(&w->ev_gather_done[b])); }
+    return NP_OK;
+}
+int np_comm_destroy(np_world* w)
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    if (!w->comm) return NP_OK;
+    CU(cudaSetDevice(w->device));
+    CU(cudaStreamSynchronize(w->stream)); CU(cudaStreamSynchronize(w->comm_stream));
+    drop_graph(w);
+    if (w->gather_slot) { w->snap_target = nullptr; w->snapshot_each_step = 0; }
+    free_gather(w);
+    if (w->d_shard_hit) { w->shard_first = 0; w->shard_count = -1; w->x_hit_j = w->x_cflags = nullptr; w->x_contact = nullptr; w->order_dirty = true; }
+    cudaFree(w->d_shard_hit); cudaFree(w->d_shard_flags); cudaFree(w->d_shard_contact); w->d_shard_hit = w->d_shard_flags = nullptr; w->d_shard_contact = nullptr; w->shard_slot = 0;
+    g_nccl.CommDestroy(w->comm); w->comm = nullptr; w->nranks = 1; w->rank = 0;
+    for (int b = 0; b < 2; b++) { cudaEventDestroy(w->ev_step_done[b]); cudaEventDestroy(w->ev_gather_begin[b]); cudaEventDestroy(w->ev_gather_done[b]); w->ev_step_done[b] = w->ev_gather_begin[b] = w->ev_gather_done[b] = nullptr; }
+    cudaStreamDestroy(w->comm_stream); w->comm_stream = nullptr;
+    return NP_OK;
+}
+int np_world_set_snapshot_gather(np_world* w, int slot_bodies, uint32_t guid_base)
+{
+    if (!w || slot_bodies < 0) return fail(NP_ERR_INVALID, "bad arguments");
+    if (!w->comm) return fail(NP_ERR_INVALID, "np_comm_init first");
+    CU(cudaSetDevice(w->device));
+    CU(cudaStreamSynchronize(w->stream)); CU(cudaStreamSynchronize(w->comm_stream));
+    drop_graph(w); free_gather(w);
+    w->snap_target = nullptr;
+    if (slot_bodies == 0) return NP_OK;
+    if (slot_bodies < (int)w->bodies.size()) return fail(NP_ERR_CAPACITY, "snapshot slot smaller than the world");
+    const size_t bytes = sizeof(SnapObj) * (size_t)slot_bodies * (size_t)w->nranks;
+    for (int b = 0; b < 2; b++) { CU(cudaMalloc((void**)&w->d_gather[b], bytes)); CU(cudaMemsetAsync(w->d_gather[b], 0, bytes, w->stream)); }
+    w->gather_slot = slot_bodies; w->gather_guid = guid_base; w->gather_flip = 0; w->snapshot_each_step = 1;
+    return NP_OK;
+}
+// before a step: aim the snapshot at this rank's slot of the next gather buffer, once that buffer's previous gather has drained
+static int gather_prepare(np_world* w)
+{
+    if (!w->gather_slot) return NP_OK;
+    const int b = w->gather_flip;
+    if (w->gather_pending[b]) CU(cudaStreamWaitEvent(w->stream, w->ev_gather_done[b], 0));
+    w->snap_target = w->d_gather[b] + sizeof(SnapObj) * (size_t)w->gather_slot * (size_t)w->rank;
+    w->guid_base = w->gather_guid;
+    return NP_OK;
+}
+// after a step's kernels: the all-gather, in place, on the communicator's own high-priority stream
+static int gather_launch(np_world* w)
+{
+    if (!w->gather_slot) return NP_OK;
+    const int b = w->gather_flip;
+    CU(cudaEventRecord(w->ev_step_done[b], w->stream));
+    CU(cudaStreamWaitEvent(w->comm_stream, w->ev_step_done[b], 0));
+    CU(cudaEventRecord(w->ev_gather_begin[b], w->comm_stream));
+    const size_t slot_bytes = sizeof(SnapObj) * (size_t)w->gather_slot;
+    NC(g_nccl.AllGather(w->d_gather[b] + slot_bytes * (size_t)w->rank, w->d_gather[b], slot_bytes, ncclChar, w->comm, w->comm_stream));
+    CU(cudaEventRecord(w->ev_gather_done[b], w->comm_stream));
+    w->gather_pending[b] = true; w->gather_last = b; w->gather_flip = b ^ 1;
+    return NP_OK;
+}
+int np_world_gathered_snapshot(np_world* w, void** d_ptr, size_t* bytes)
+{
+    if (!w || !d_ptr || !bytes) return fail(NP_ERR_INVALID, "bad arguments");
+    if (!w->gather_slot || w->gather_last < 0) return fail(NP_ERR_INVALID, "no snapshot gather has run");
+    CU(cudaSetDevice(w->device));
+    CU(cudaEventSynchronize(w->ev_gather_done[w->gather_last]));
+    *d_ptr = w->d_gather[w->gather_last]; *bytes = sizeof(SnapObj) * (size_t)w->gather_slot * (size_t)w->nranks;
+    return NP_OK;
+}
+int np_world_last_gather_ms(np_world* w, int back, float out[2])
+{
+    if (!w || !out || back < 0 || back > 1) return fail(NP_ERR_INVALID, "bad arguments");
+    out[0] = out[1] = 0.0f;
+    if (!w->gather_slot || w->gather_last < 0) return NP_OK;
+    const int b = back ? (w->gather_last ^ 1) : w->gather_last;
+    if (!w->gather_pending[b]) return NP_OK;
+    CU(cudaSetDevice(w->device));
+    CU(cudaEventSynchronize(w->ev_gather_done[b]));
+    CU(cudaEventElapsedTime(&out[0], w->ev_gather_begin[b], w->ev_gather_done[b]));
+    CU(cudaEventElapsedTime(&out[1], w->ev_step_done[b], w->ev_gather_done[b]));
+    return NP_OK;
+}
+int np_world_shard_over_comm(np_world* w)
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    if (!w->comm) return fail(NP_ERR_INVALID, "np_comm_init first");
+    int r = ensure_device(w); if (r) return r;
+    const int n = (int)w->bodies.size();
+    const int slot = std::max(1, (n + w->nranks - 1) / w->nranks);
+    const size_t total = (size_t)slot * (size_t)w->nranks;
+    CU(cudaStreamSynchronize(w->stream));
+    cudaFree(w->d_shard_hit); cudaFree(w->d_shard_flags); cudaFree(w->d_shard_contact); w->d_shard_hit = w->d_shard_flags = nullptr; w->d_shard_contact = nullptr;
+    CU(cudaMalloc((void**)&w->d_shard_hit, sizeof(int) * total)); CU(cudaMalloc((void**)&w->d_shard_flags, sizeof(int) * total)); CU(cudaMalloc((void**)&w->d_shard_contact, sizeof(float4) * total));
+    CU(cudaMemsetAsync(w->d_shard_hit, 0xff, sizeof(int) * total, w->stream)); CU(cudaMemsetAsync(w->d_shard_flags, 0, sizeof(int) * total, w->stream));
+    CU(cudaMemsetAsync(w->d_shard_contact, 0, sizeof(float4) * total, w->stream));
+    w->shard_slot = slot;
+    const int first = std::min(n, w->rank * slot), count = std::min(n, first + slot) - first;
+    return np_world_set_shard(w, first, count, w->d_shard_hit, w->d_shard_flags, w->d_shard_contact);
+}
+int np_world_step_sharded(np_world* w, float dt)
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    if (!w->comm || !w->d_shard_hit) return fail(NP_ERR_INVALID, "np_comm_init and np_world_shard_over_comm first");
+    int r = np_world_step_begin(w, dt); if (r) return r;
+    const size_t slot = (size_t)w->shard_slot, off = slot * (size_t)w->rank;
+    NC(g_nccl.GroupStart());
+    ncclResult_t e1 = g_nccl.AllGather(w->d_shard_hit + off, w->d_shard_hit, slot, ncclInt32, w->comm, w->stream);
+    ncclResult_t e2 = g_nccl.AllGather(w->d_shard_contact + off, w->d_shard_contact, slot * 4, ncclFloat32, w->comm, w->stream);
+    NC(g_nccl.GroupEnd());
+    if (e1 != ncclSuccess || e2 != ncclSuccess) { w->mid_step = false; return fail(NP_ERR_CUDA, "ncclAllGather of the collision records failed"); }
+    return np_world_step_end(w);
 }
 
 // ------------------------------------------------------------------------------------------------ device memory helpers

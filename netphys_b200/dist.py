@@ -80,19 +80,36 @@ class CollisionExchange:
             self.torch.distributed.all_gather_into_tensor(t, piece)
 
 
-class ShardedWorld:
-    """One world whose pair search is split over the ranks of a torch.distributed group (BASELINE configs[4]).  Every rank loads
-    the same scene; `step` = step_begin -> CollisionExchange -> step_end, all enqueued on the world's own CUDA stream."""
+def init_world_comm(world, rank, world_size):
+    """Give `world` its own NCCL communicator (np_comm_init, the C-ABI path a C++ server uses): rank 0 creates the 128-byte unique id,
+    torch.distributed only carries it to the other ranks."""
+    import torch.distributed as dist
+    box = [world.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    world.comm_init(world_size, rank, box[0])
 
-    def __init__(self, world, device, world_size, rank):
+
+class ShardedWorld:
+    """One world whose pair search is split over the ranks (BASELINE configs[4]).  Every rank loads the same scene.
+    lib_comm=True (default on GPUs): the library's own NCCL path -- np_world_shard_over_comm + np_world_step_sharded = step_begin ->
+    one grouped ncclAllGather of hit_j and contact on the world's stream -> step_end.  lib_comm=False: the same exchange through
+    torch.distributed (CollisionExchange), kept for the gloo tests and as a cross-check."""
+
+    def __init__(self, world, device, world_size, rank, lib_comm=True):
+        self.w = world; self.lib_comm = lib_comm
+        if lib_comm:
+            init_world_comm(world, rank, world_size)
+            world.shard_over_comm()
+            return
         import torch
         self.torch = torch
-        self.w = world
         self.x = CollisionExchange(world.n, device, world_size, rank)
         world.set_shard(self.x.first, self.x.count, *self.x.pointers())
         self.stream = torch.cuda.ExternalStream(world.L.np_world_stream(world.w), device=device)
 
     def step(self, dt):
+        if self.lib_comm:
+            self.w.step_sharded(dt); return
         self.w.step_begin(dt)
         with self.torch.cuda.stream(self.stream):       # the collective is ordered after the search and before the response
             self.x.exchange()

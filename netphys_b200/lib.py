@@ -135,6 +135,14 @@ def load_library(variant="exact"):
     L.np_world_frame_count.argtypes = [vp]
     L.np_world_fill_packet.argtypes = [vp, C.c_int, vp, C.c_int]
     L.np_world_set_snapshot_target.argtypes = [vp, vp, C.c_uint32]
+    L.np_comm_get_unique_id.argtypes = [vp]
+    L.np_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.np_comm_destroy.argtypes = [vp]
+    L.np_world_set_snapshot_gather.argtypes = [vp, C.c_int, C.c_uint32]
+    L.np_world_gathered_snapshot.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.np_world_last_gather_ms.argtypes = [vp, C.c_int, f32p]
+    L.np_world_shard_over_comm.argtypes = [vp]
+    L.np_world_step_sharded.argtypes = [vp, C.c_float]
     L.np_selftest_fp32_peak.argtypes = [vp, f32p]
     L.np_selftest_fp32_peaks.argtypes = [vp, f32p]
     L.np_selftest_sincos_hash.argtypes = [vp, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -384,6 +392,42 @@ class World:
         return buf[:nb].tobytes()
 
     def set_snapshot_target(self, d_ptr, guid_base=0): self._ck(self.L.np_world_set_snapshot_target(self.w, d_ptr, guid_base))
+
+    # -- NCCL behind the C ABI (np_comm_*) -----------------------------------------------------------
+    @staticmethod
+    def _prefer_bundled_nccl():
+        """inside a process that also runs torch, load the libnccl.so.2 torch ships (one NCCL per process)"""
+        if "NP_NCCL_LIB" not in os.environ:
+            try:
+                import nvidia.nccl as _n
+                for d in list(getattr(_n, "__path__", [])):
+                    p = os.path.join(d, "lib", "libnccl.so.2")
+                    if os.path.exists(p):
+                        os.environ["NP_NCCL_LIB"] = p; break
+            except Exception:
+                pass
+
+    def comm_unique_id(self):
+        self._prefer_bundled_nccl()
+        buf = (C.c_char * 128)(); self._ck(self.L.np_comm_get_unique_id(buf)); return bytes(buf)
+
+    def comm_init(self, nranks, rank, unique_id):
+        self._prefer_bundled_nccl()
+        assert len(unique_id) == 128
+        self._ck(self.L.np_comm_init(self.w, nranks, rank, C.c_char_p(unique_id)))
+
+    def comm_destroy(self): self._ck(self.L.np_comm_destroy(self.w))
+    def set_snapshot_gather(self, slot_bodies, guid_base=0): self._ck(self.L.np_world_set_snapshot_gather(self.w, slot_bodies, guid_base))
+
+    def gathered_snapshot(self):
+        p = C.c_void_p(); nb = C.c_size_t()
+        self._ck(self.L.np_world_gathered_snapshot(self.w, C.byref(p), C.byref(nb))); return p.value, nb.value
+
+    def last_gather_ms(self, back=0):
+        out = np.zeros(2, np.float32); self._ck(self.L.np_world_last_gather_ms(self.w, back, _f(out))); return out
+
+    def shard_over_comm(self): self._ck(self.L.np_world_shard_over_comm(self.w))
+    def step_sharded(self, dt): self._ck(self.L.np_world_step_sharded(self.w, float(np.float32(dt))))
 
     def fp32_peak_tflops(self):
         out = np.zeros(1, np.float32); self._ck(self.L.np_selftest_fp32_peak(self.w, _f(out))); return float(out[0])
