@@ -322,3 +322,32 @@ class Ref:
         st = f32(st)
         for i in range(self.n):
             self.L.ref_body_set_state(i, _f(st[i]))
+
+
+class RefPacket:
+    """The reference's own snapshot ring + wire serialiser (oracle/_ref/librefpacket.so = netphys_server/world_s.cpp compiled unchanged,
+    see oracle/ref/ref_packet.cpp).  Process-global frame list, like the reference's."""
+
+    def __init__(self):
+        L = self.L = C.CDLL(os.path.join(HERE, "_ref", "librefpacket.so"))
+        L.refpkt_set_objects.argtypes = [C.c_int, C.POINTER(C.c_uint32), f32p, f32p, i32p]
+        L.refpkt_update.argtypes = [C.c_double]
+        L.refpkt_fill.argtypes = [C.c_int, C.c_char_p, C.c_uint]
+        assert L.refpkt_object_size() == 36
+
+    def set_objects(self, uid, pos, quat, enabled):
+        uid = np.ascontiguousarray(uid, np.uint32); en = np.ascontiguousarray(enabled, np.int32)
+        self.L.refpkt_set_objects(len(uid), uid.ctypes.data_as(C.POINTER(C.c_uint32)), _f(f32(pos)), _f(f32(quat)), _i(en))
+
+    def update(self, now_ms): self.L.refpkt_update(float(now_ms))
+    def frame_count(self): return self.L.refpkt_frame_count()
+    def reset_frames(self): self.L.refpkt_reset_frames()
+
+    def fill(self, kind, cap=1 << 20):
+        buf = C.create_string_buffer(cap)
+        n = self.L.refpkt_fill(kind, buf, cap)
+        return buf.raw[:n]
+
+
+def refpacket_available():
+    return os.path.exists(os.path.join(HERE, "_ref", "librefpacket.so"))

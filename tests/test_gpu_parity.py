@@ -564,3 +564,24 @@ class ref_factory:
     def __init__(self, ref): self.ref = ref
     def make_sphere(self, r): return self.ref.shape_verts(self.ref.sphere(r))
     def make_box(self, w, d, h): return self.ref.shape_verts(self.ref.box(w, d, h))
+
+
+# ---- the wire packet against the REFERENCE's own serialiser bytes ---------------------------------------------
+def test_wire_packets_equal_the_reference_serialiser(world):
+    """np_world_record_frame + np_world_fill_packet vs tests/golden/packet_few_boxes.npz = the bytes netphys_server/world_s.cpp
+    (World_S_Update's 5-second frame ring, World_S_FillWorldUpdateMessage / FillNewConnectionMessage) and netphys_common/common.h
+    (Packet::Serialize, CommandFrameObject) produce for the same bodies -- compiled unchanged from the reference by oracle/Makefile,
+    generated by oracle/gen_golden_packet.py."""
+    g = gold("packet_few_boxes.npz"); sc = scenes.few_boxes_scene()
+    world.load_scene(sc)
+    world.set_snapshot_target(None, int(g["guid_base"]))
+    n = int(g["n"])
+    for k, t in enumerate(g["times_ms"]):
+        if k < 8: world.step(sc["dt"])
+        else: world.set_enabled(2, False)
+        assert_biteq(world.states(), g["state_%d" % k], "state of frame %d" % k)
+        assert world.record_frame(float(t)) == k + 1                                     # frame ids count from 1 (world_s.cpp:20)
+        assert world.frame_count() == int(g["frames_kept_%d" % k]), "5 s frame ring after frame %d" % k
+        assert world.fill_packet(2342144) == g["update_%d" % k].tobytes(), "ClientWorldStateUpdatePacket bytes, frame %d" % k
+        assert world.fill_packet(2342341) == g["newconn_%d" % k].tobytes(), "ClientNewConnection bytes, frame %d" % k
+        assert len(world.fill_packet(2342144, cap=24 + 36 * n - 1)) == int(g["too_small_%d" % k]) == 0

@@ -185,3 +185,33 @@ def test_live_ref_2d_mode(oracle, ref):
             assert_biteq(outo, outr, "2-D CollisionData of pair %d" % i)
         nhit += hr
     assert 0.05 < nhit / len(sa) < 0.95
+
+
+def test_golden_wire_packets_layout_and_regeneration():
+    """tests/golden/packet_few_boxes.npz (the reference server's own bytes, oracle/gen_golden_packet.py): the layout documented in
+    include/netphys_b200.h, and -- where oracle/_ref/librefpacket.so exists -- the same bytes again from the compiled reference."""
+    import struct
+    g = gold("packet_few_boxes.npz"); n = int(g["n"])
+    for k, t in enumerate(g["times_ms"]):
+        for name, pid in (("update", 2342144), ("newconn", 2342341)):
+            b = g["%s_%d" % (name, k)].tobytes()
+            assert len(b) == 8 + 16 + 36 * n
+            pkt, size, frame, tm, cnt = struct.unpack_from("<iiidi", b, 0)
+            assert (pkt, size, frame, tm, cnt) == (pid, 16 + 36 * n, k + 1, float(t), n)
+            rec = np.frombuffer(b, np.dtype([("guid", "<u4"), ("pos", "<f4", 3), ("rot", "<f4", 4), ("en", "u1"), ("pad", "u1", 3)]), offset=24)
+            assert list(rec["guid"]) == [int(g["guid_base"]) + i for i in range(n)] and not rec["pad"].any()
+            assert_biteq(rec["pos"], g["state_%d" % k][:, 0:3], "positions in the packet")
+            assert np.allclose(np.linalg.norm(rec["rot"], axis=1), 1.0, atol=1e-6) and list(rec["en"]) == [1, 1, 0 if k == 8 else 1, 1, 1][:n]
+    import os
+    from conftest import GOLD, ROOT
+    from oracle.bind import refpacket_available
+    if refpacket_available() and os.path.isdir("/root/reference/netphys_server"):
+        import subprocess, sys, tempfile, shutil
+        keep = os.path.join(GOLD, "packet_few_boxes.npz"); tmp = tempfile.mkdtemp()
+        try:
+            shutil.copy(keep, os.path.join(tmp, "before.npz"))
+            subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "gen_golden_packet.py")], check=True, capture_output=True)
+            a = np.load(os.path.join(tmp, "before.npz")); b = np.load(keep)
+            assert sorted(a.files) == sorted(b.files) and all(np.array_equal(a[f], b[f]) for f in a.files), "the committed fixture is what the compiled reference produces"
+        finally:
+            shutil.copy(os.path.join(tmp, "before.npz"), keep); shutil.rmtree(tmp)
