@@ -37,6 +37,14 @@ F_SUPPORT_VERT, F_GJK_STEP, F_EPA_TRI, F_EPA_ITER = 27, 120, 110, 60
 B_INTEGRATE = 48 + 56 + 36 + 48
 
 
+def log(msg):
+    if os.environ.get("NP_BENCH_VERBOSE"):
+        sys.stderr.write("[bench rank %s %.1fs] %s\n" % (os.environ.get("RANK", "0"), time.perf_counter() - T0, msg)); sys.stderr.flush()
+
+
+T0 = time.perf_counter()
+
+
 def make_scene(rank=0, n=None):
     return scenes.lattice_scene(n or BODIES, spacing=SPACING, jitter=JITTER, seed=SEED + rank, mix=MIX)
 
@@ -133,7 +141,7 @@ def run_reference(args, rank):
                       "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                       "dtype": "f32", "data": "synthetic", "config": CONFIG,
                       "cpu_baseline": {"value": v, "unit": "body-steps/s", "cores": 1, "kind": kind, "sample": sample},
-                      "e2e": {"value": v, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                      "e2e": {"value": v, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
 
 def timed_steps(w, dt, n, flush=True):
@@ -242,6 +250,7 @@ def run_ours(args, rank, local_rank, world_size):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     scene = make_scene(rank)
+    log('scene built')
     W = npb.World
     w = W(local_rank)
     w.set_option(W.OPT_COUNTERS, 1)
@@ -271,6 +280,7 @@ def run_ours(args, rank, local_rank, world_size):
         tail = float(w.last_gather_ms(0)[1]); per[-1, 1] += tail
         return (tot + tail) / nsteps, per
 
+    log('world loaded, comm ready')
     if xchg is None: timed_steps(w, dt, warm)
     else: overlapped(warm)
     if dist is not None:
@@ -288,6 +298,7 @@ def run_ours(args, rank, local_rank, world_size):
     if dist is not None:
         torch.cuda.synchronize(); dist.barrier()
     t_wall = time.perf_counter() - t_wall0
+    log('timed region done: %.3f ms/step' % step_ms)
     c1 = w.counters()
     clk = clocks.stop()
     per_rank_ms = [step_ms]
@@ -322,6 +333,7 @@ def run_ours(args, rank, local_rank, world_size):
         t = torch.tensor([t_e2e], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); t_e2e = float(t.item())
     e2e = world_size * BODIES * e2e_steps / t_e2e
     w.host_free(st_a); w.host_free(st_b)
+    log('e2e done')
 
     # ---- N > 1: ONE world with its pair search sharded over the ranks (BASELINE configs[4]); configs[3] sharded -----------------
     sharded = batch = None
@@ -338,6 +350,7 @@ def run_ours(args, rank, local_rank, world_size):
             batch = {"error": repr(e)}
     else:
         fp32_peak = max(w.fp32_peaks_tflops())
+    log('multi-GPU legs done')
     if rank != 0:
         if dist is not None: dist.destroy_process_group()
         return
@@ -466,7 +479,7 @@ def run_ours(args, rank, local_rank, world_size):
         out["pair_tests"] = pair
     if cpu is not None:
         out["cpu_baseline"] = cpu
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
     if w is not None: w.close()
     if dist is not None:
         dist.destroy_process_group()

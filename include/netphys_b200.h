@@ -143,6 +143,11 @@ int np_shape_support(np_world* w, int shape, const float dir[3], const float wor
 /* ---- bodies: class Physics, engine/physics.h:58-95 ------------------------------------------------ */
 int np_body_create(np_world* w, int shape, const np_static_physics_data* sd);            /* Physics::Physics, physics.cpp:11-18; returns body id */
 int np_body_create_batch(np_world* w, int n, const int32_t* shapes, const np_static_physics_data* sd); /* n ctor calls; returns first id */
+/* Physics::~Physics is a TODO in the reference ("remove from list", physics.cpp:20-23): the body leaves the world as if it had never
+ * been created (later bodies keep their relative order); every other body id stays valid, the destroyed id is never reused.
+ * np_world_get_states / set_states / snapshot then cover the live bodies in creation order; snapshot guids and np_collision a/b are ids. */
+int np_body_destroy(np_world* w, int body);
+int np_shape_destroy(np_world* w, int shape);                                            /* fails while a body still uses the shape */
 int np_body_reset(np_world* w, int body);                                                /* Physics::Reset, physics.cpp:166-172 */
 int np_body_get_state(np_world* w, int body, np_body_state* out);                         /* GetPosition/GetRotation (+ momenta) */
 int np_body_set_state(np_world* w, int body, const np_body_state* in);                    /* SetPosition/SetRotation, physics.h:82-85 */

@@ -20,7 +20,7 @@ namespace np {
 enum { S_PX = 0, S_PY, S_PZ, S_RX, S_RY, S_RZ, S_LX, S_LY, S_LZ, S_HX, S_HY, S_HZ, S_COUNT };          // dynamic state
 enum { C_GX = 0, C_GY, C_GZ, C_MASS, C_ELAST, C_IINV0, C_COUNT = C_IINV0 + 9 };                       // per-body constants
 enum { X_R0 = 0, X_TX = 9, X_TY, X_TZ, X_COUNT };                                                      // transform
-enum { I_RESPONSE = 0, I_SHAPE, I_ISLAND_END, I_WVOFF, I_ORDER, I_WVOFF_BIG, I_COUNT };     // I_WVOFF: first world vertex of the body in the per-step cache (I_WVOFF_BIG: in the cache of large bodies only, -1 for small ones); I_ORDER: search order (bodies grouped by shape)
+enum { I_RESPONSE = 0, I_SHAPE, I_ISLAND_END, I_WVOFF, I_ORDER, I_WVOFF_BIG, I_HANDLE, I_COUNT };     // I_WVOFF: first world vertex of the body in the per-step cache (I_WVOFF_BIG: in the cache of large bodies only, -1 for small ones); I_ORDER: search order (bodies grouped by shape); I_HANDLE: the caller's id of the body (differs from the slot once bodies were destroyed)
 
 struct StoreView {
     int n, cap;
@@ -1145,7 +1145,7 @@ NP_D SnapObj snap_of(const StoreView& s, int i, V3 pos, uint32_t guid_base)
     float sx, cx, sy, cy, sz, cz;
     np_sincosf(hx, &sx, &cx); np_sincosf(hy, &sy, &cy); np_sincosf(hz, &sz, &cz);
     SnapObj o;
-    o.guid = guid_base + (uint32_t)i;
+    o.guid = guid_base + (uint32_t)s.ints[I_HANDLE * cap + i];
     o.pos[0] = pos.x; o.pos[1] = pos.y; o.pos[2] = pos.z;
     o.rot[0] = cx * cy * cz + sx * sy * sz;
     o.rot[1] = sx * cy * cz - cx * sy * sz;

@@ -26,8 +26,8 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
         if (e_ != cudaSuccess) return fail(NP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
     } while (0)
 
-struct HostShape { std::vector<float> xyz; };
-struct HostBody { np_static_physics_data sd; int shape; int island; int enabled = 1; };
+struct HostShape { std::vector<float> xyz; bool dead = false; };
+struct HostBody { np_static_physics_data sd; int shape; int island; int enabled = 1; float pending_force[3] = { 0.f, 0.f, 0.f }; };
 struct StepGraph { uint32_t dt_bits; void* snap; uint32_t guid; int kind; cudaGraphExec_t exec; unsigned long long launches; };   // one captured Physics_Update
 struct CommandFrame { unsigned id; double time_ms; std::vector<np_snapshot_object> objects; };      // world_s.cpp:12-17
 
@@ -39,6 +39,9 @@ struct np_world {
     std::vector<HostShape> shapes;
     std::vector<HostBody> bodies;
     std::vector<np_body_state> host_state;   // authoritative until the first upload, refreshed on demand
+    // body ids handed to the caller are HANDLES (creation order, never reused); the device store is dense over the live bodies (slots).
+    // Identity until the first np_body_destroy.
+    std::vector<int> slot_of_handle, handle_of_slot; bool any_destroyed = false;
     int island = 0;
     std::vector<CommandFrame> frames; unsigned frame_counter = 1;      // world_s.cpp:19-21
     // options
@@ -48,7 +51,7 @@ struct np_world {
     int snapshot_each_step = 0; void* snap_target = nullptr; uint32_t guid_base = 0;
     void* d_flush = nullptr; unsigned long long launches = 0;
     // device store
-    bool dirty_bodies = true, dirty_shapes = true, dev_state_valid = false;
+    bool dirty_bodies = true, dirty_shapes = true, dev_state_valid = false, restore_ext = false;
     int cap = 0, dev_n = 0;
     float *d_state = nullptr, *d_cst = nullptr, *d_xf = nullptr;
     int* d_ints = nullptr;
@@ -290,6 +293,7 @@ static int ensure_device(np_world* w)
         cst[C_MASS * cap + i] = sd.mass; cst[C_ELAST * cap + i] = sd.elasticity;
         for (int k = 0; k < 9; k++) cst[(C_IINV0 + k) * cap + i] = sd.inverse_inertia_tensor[k];
         ints[I_RESPONSE * cap + i] = sd.collision_response; ints[I_SHAPE * cap + i] = w->bodies[i].shape; ints[I_ISLAND_END * cap + i] = island_end[i];
+        ints[I_HANDLE * cap + i] = w->handle_of_slot[i];
     }
     {   // large and small shapes side by side (and the large ones a minority): the thread-per-pair kernels serve large supports warp-wide
         long long big = 0;
@@ -314,6 +318,13 @@ static int ensure_device(np_world* w)
     int r = upload_states(w, w->host_state.data(), n); if (r) return r;
     if (n > 0) { k_transforms<<<(n + 255) / 256, 256, 0, w->stream>>>(view(w)); CU(cudaGetLastError()); }
     w->dev_n = n; w->dev_state_valid = true; w->dirty_bodies = false;
+    if (w->restore_ext && !w->d_ext) {                       // np_body_destroy dropped the extension arrays: pending forces and enabled flags come back from the host mirror
+        std::vector<float> f(3 * cap, 0.0f);
+        for (int i = 0; i < n; i++) for (int c = 0; c < 3; c++) f[(size_t)c * cap + i] = w->bodies[i].pending_force[c];
+        int re = ensure_ext(w, &f, (int)cap); if (re) return re;
+        for (auto& b : w->bodies) b.pending_force[0] = b.pending_force[1] = b.pending_force[2] = 0.0f;
+    }
+    w->restore_ext = false;
     { int ro = upload_order(w); if (ro) return ro; }
     if (w->broadphase == NP_BROADPHASE_GRID) { int rg = ensure_grid(w); if (rg) return rg; }
     return NP_OK;
@@ -767,7 +778,7 @@ int np_shape_create_sphere(np_world* w, float r)                                
     for (const V3& p : vl) mesh_add(mesh, p);
     return push_mesh(w, mesh);
 }
-int np_shape_vertex_count(const np_world* w, int shape) { if (!w || shape < 0 || shape >= (int)w->shapes.size()) return fail(NP_ERR_INVALID, "bad shape"); return (int)w->shapes[shape].xyz.size() / 3; }
+int np_shape_vertex_count(const np_world* w, int shape) { if (!w || shape < 0 || shape >= (int)w->shapes.size() || w->shapes[shape].dead) return fail(NP_ERR_INVALID, "bad shape"); return (int)w->shapes[shape].xyz.size() / 3; }
 int np_shape_get_vertices(const np_world* w, int shape, float* xyz, int cap_verts)
 {
     int n = np_shape_vertex_count(w, shape); if (n < 0) return n;
@@ -780,7 +791,7 @@ int np_shape_get_vertices(const np_world* w, int shape, float* xyz, int cap_vert
 int np_body_create_batch(np_world* w, int n, const int32_t* shapes, const np_static_physics_data* sd)
 {
     if (!w || n < 0 || (n > 0 && (!shapes || !sd))) return fail(NP_ERR_INVALID, "bad arguments");
-    for (int i = 0; i < n; i++) if (shapes[i] < 0 || shapes[i] >= (int)w->shapes.size()) return fail(NP_ERR_INVALID, "bad shape id");
+    for (int i = 0; i < n; i++) if (shapes[i] < 0 || shapes[i] >= (int)w->shapes.size() || w->shapes[shapes[i]].dead) return fail(NP_ERR_INVALID, "bad shape id");
     int first = (int)w->bodies.size();
     if ((long long)first + n > (1LL << 30)) return fail(NP_ERR_CAPACITY, "too many bodies");
     for (int i = 0; i < n; i++) {
@@ -789,13 +800,20 @@ int np_body_create_batch(np_world* w, int n, const int32_t* shapes, const np_sta
         np_body_state st; memset(&st, 0, sizeof st);                                     // physics.cpp:11-18: pos/rot from the static data, momenta vector3() == 0
         memcpy(st.position, sd[i].initial_position, 12); memcpy(st.rotation, sd[i].initial_rotation, 12);
         w->host_state.push_back(st);
+        w->handle_of_slot.push_back((int)w->slot_of_handle.size()); w->slot_of_handle.push_back((int)w->bodies.size() - 1);
     }
     if (n > 0) w->dirty_bodies = true;
-    return first;
+    return n > 0 ? w->handle_of_slot[first] : (int)w->slot_of_handle.size();
 }
 int np_body_create(np_world* w, int shape, const np_static_physics_data* sd) { int32_t s = shape; return np_body_create_batch(w, 1, &s, sd); }
 
-static int check_body(np_world* w, int body) { if (!w || body < 0 || body >= (int)w->bodies.size()) return fail(NP_ERR_INVALID, "bad body"); return NP_OK; }
+// validates a caller's body HANDLE and turns it into the slot of the dense store
+static int check_body(np_world* w, int& body)
+{
+    if (!w || body < 0 || body >= (int)w->slot_of_handle.size() || w->slot_of_handle[body] < 0) return fail(NP_ERR_INVALID, "bad body");
+    body = w->slot_of_handle[body];
+    return NP_OK;
+}
 int np_body_get_state(np_world* w, int body, np_body_state* out)
 {
     int r = check_body(w, body); if (r) return r;
@@ -806,10 +824,15 @@ int np_body_get_state(np_world* w, int body, np_body_state* out)
     CU(cudaStreamSynchronize(w->stream));
     return NP_OK;
 }
+static int set_state_slot(np_world* w, int body, const np_body_state* in);
 int np_body_set_state(np_world* w, int body, const np_body_state* in)
 {
     int r = check_body(w, body); if (r) return r;
     if (!in) return fail(NP_ERR_INVALID, "null in");
+    return set_state_slot(w, body, in);
+}
+static int set_state_slot(np_world* w, int body, const np_body_state* in)
+{
     w->host_state[body] = *in;
     if (w->dev_state_valid && body < w->dev_n) {
         CU(cudaSetDevice(w->device));
@@ -823,7 +846,7 @@ int np_body_reset(np_world* w, int body)                                        
     int r = check_body(w, body); if (r) return r;
     np_body_state st; memset(&st, 0, sizeof st);
     memcpy(st.position, w->bodies[body].sd.initial_position, 12); memcpy(st.rotation, w->bodies[body].sd.initial_rotation, 12);
-    return np_body_set_state(w, body, &st);
+    return set_state_slot(w, body, &st);
 }
 // ---- adapter extension for an ODE-shaped World facade (include/netphys/world.h).  Not reference semantics: the engine
 // has gravity only (physics.cpp:178-181).
@@ -848,6 +871,42 @@ int np_body_set_enabled(np_world* w, int body, int enabled)                     
     return NP_OK;
 }
 int np_body_is_enabled(np_world* w, int body) { int r = check_body(w, body); if (r) return r; return w->bodies[body].enabled; }   // dBodyIsEnabled, world_s.cpp:48
+// Physics::~Physics is a TODO in the reference ("remove from list", physics.cpp:20-23); here a destroyed body leaves the world as if it had
+// never been created: the bodies after it move up one slot (the reference's list order is creation order), handles stay valid.
+int np_body_destroy(np_world* w, int body)
+{
+    int r = check_body(w, body); if (r) return r;
+    if (w->mid_step) return fail(NP_ERR_INVALID, "np_body_destroy between step_begin and step_end");
+    CU(cudaSetDevice(w->device));
+    if (w->dev_state_valid && w->dev_n > 0) {                   // the device holds the current state: bring it (and pending forces) home first
+        r = download_states(w, w->host_state.data(), w->dev_n); if (r) return r;
+        if (w->d_ext) {
+            std::vector<float> ext(4 * (size_t)w->cap);
+            CU(cudaMemcpyAsync(ext.data(), w->d_ext, sizeof(float) * 4 * (size_t)w->cap, cudaMemcpyDeviceToHost, w->stream));
+            CU(cudaStreamSynchronize(w->stream));
+            for (int i = 0; i < w->dev_n; i++) for (int c = 0; c < 3; c++) w->bodies[i].pending_force[c] = ext[(size_t)c * w->cap + i];
+        }
+    }
+    const bool had_ext = w->d_ext != nullptr;
+    if (w->d_ext) { CU(cudaStreamSynchronize(w->stream)); cudaFree(w->d_ext); w->d_ext = nullptr; }
+    const int handle = w->handle_of_slot[body];
+    w->bodies.erase(w->bodies.begin() + body); w->host_state.erase(w->host_state.begin() + body); w->handle_of_slot.erase(w->handle_of_slot.begin() + body);
+    w->slot_of_handle[handle] = -1;
+    for (int i = body; i < (int)w->handle_of_slot.size(); i++) w->slot_of_handle[w->handle_of_slot[i]] = i;
+    w->any_destroyed = true; w->restore_ext = w->restore_ext || had_ext;
+    drop_graph(w);
+    w->dirty_bodies = true; w->dev_state_valid = false; w->dev_n = 0;
+    if (sharded(w)) w->order_dirty = true;
+    return NP_OK;
+}
+int np_shape_destroy(np_world* w, int shape)
+{
+    if (!w || shape < 0 || shape >= (int)w->shapes.size() || w->shapes[shape].dead) return fail(NP_ERR_INVALID, "bad shape");
+    for (const HostBody& b : w->bodies) if (b.shape == shape) return fail(NP_ERR_INVALID, "shape is still used by a body");
+    w->shapes[shape].xyz.clear(); w->shapes[shape].xyz.shrink_to_fit(); w->shapes[shape].dead = true;      // the id is not reused
+    w->dirty_shapes = true;
+    return NP_OK;
+}
 int np_world_clear_bodies(np_world* w)                                                    // World::Reset, netphys_common/world.cpp:129-141
 {
     if (!w) return fail(NP_ERR_INVALID, "null world");
@@ -855,6 +914,7 @@ int np_world_clear_bodies(np_world* w)                                          
     CU(cudaSetDevice(w->device)); CU(cudaStreamSynchronize(w->stream));
     drop_graph(w);
     w->bodies.clear(); w->host_state.clear(); w->island = 0;
+    w->slot_of_handle.clear(); w->handle_of_slot.clear(); w->any_destroyed = false;
     w->dirty_bodies = true; w->dev_state_valid = false; w->dev_n = 0;
     if (w->d_ext) { cudaFree(w->d_ext); w->d_ext = nullptr; }
     cudaFree(w->d_wverts); w->d_wverts = nullptr; w->wverts_cap = 0; w->wv_total = 0;
@@ -1022,7 +1082,7 @@ int np_world_get_collisions(np_world* w, np_collision* out, int cap, int* count)
         if (hj[i] < 0) continue;
         if (out && k < cap) {
             np_collision& c = out[k]; memset(&c, 0, sizeof c);
-            c.a = i; c.b = hitj_body(hj[i]);
+            c.a = w->handle_of_slot[i]; c.b = w->handle_of_slot[hitj_body(hj[i])];
             c.data.penetration_direction[0] = cd[i].x; c.data.penetration_direction[1] = cd[i].y; c.data.penetration_direction[2] = cd[i].z;
             c.data.depth = cd[i].w; c.data.success = (hj[i] & NP_HITJ_SUCCESS) ? 1 : 0;
         }
@@ -1110,7 +1170,7 @@ static int run_pairs(np_world* w, int n, const int* d_sa, const float* d_pa, con
 static int check_shapes(np_world* w, int n, const int32_t* a, const int32_t* b)
 {
     int ns = (int)w->shapes.size();
-    for (int i = 0; i < n; i++) if (a[i] < 0 || a[i] >= ns || b[i] < 0 || b[i] >= ns) return fail(NP_ERR_INVALID, "bad shape id in pair list");
+    for (int i = 0; i < n; i++) if (a[i] < 0 || a[i] >= ns || b[i] < 0 || b[i] >= ns || w->shapes[a[i]].dead || w->shapes[b[i]].dead) return fail(NP_ERR_INVALID, "bad shape id in pair list");
     return NP_OK;
 }
 static void expand_out(int n, const int* flags, const float4* cd, int32_t* hit, np_collision_data* out)

@@ -99,6 +99,7 @@ def load_library(variant="exact"):
     L.np_body_create.argtypes = [vp, C.c_int, C.POINTER(StaticPhysicsData)]
     L.np_body_create_batch.argtypes = [vp, C.c_int, i32p, vp]
     L.np_body_reset.argtypes = [vp, C.c_int]
+    L.np_body_destroy.argtypes = [vp, C.c_int]; L.np_shape_destroy.argtypes = [vp, C.c_int]
     L.np_body_get_state.argtypes = [vp, C.c_int, C.POINTER(BodyState)]
     L.np_body_set_state.argtypes = [vp, C.c_int, C.POINTER(BodyState)]
     L.np_body_get_transform.argtypes = [vp, C.c_int, f32p]
@@ -272,6 +273,8 @@ class World:
         self._ck(self.L.np_body_set_state(self.w, b, C.byref(s)))
 
     def reset_body(self, b): self._ck(self.L.np_body_reset(self.w, b))
+    def destroy_body(self, b): self._ck(self.L.np_body_destroy(self.w, b))
+    def destroy_shape(self, s): self._ck(self.L.np_shape_destroy(self.w, s))
 
     def transform(self, b):
         out = np.zeros(16, np.float32); self._ck(self.L.np_body_get_transform(self.w, b, _f(out))); return out

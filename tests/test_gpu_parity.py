@@ -585,3 +585,46 @@ def test_wire_packets_equal_the_reference_serialiser(world):
         assert world.fill_packet(2342144) == g["update_%d" % k].tobytes(), "ClientWorldStateUpdatePacket bytes, frame %d" % k
         assert world.fill_packet(2342341) == g["newconn_%d" % k].tobytes(), "ClientNewConnection bytes, frame %d" % k
         assert len(world.fill_packet(2342144, cap=24 + 36 * n - 1)) == int(g["too_small_%d" % k]) == 0
+
+
+# ---- np_body_destroy / np_shape_destroy (the reference's destructor is a TODO, physics.cpp:20-23) -----------------------------
+def test_body_and_shape_destroy(npb, oracle):
+    """A destroyed body leaves the world as if it had never been created: the remaining bodies step exactly like an oracle world built
+    without it (with its current states), ids of the others stay valid, collisions and snapshot guids report ids."""
+    sc = scenes.lattice_scene(600, spacing=1.1, seed=31, mix=(0.5, 0.3, 0.2))
+    gone = [0, 17, 18, 333, 599]
+    with npb.World(0) as w:
+        w.set_option(w.OPT_COUNTERS, 1)
+        ids = w.load_scene(sc)
+        ow = oracle.world(scenes.resolve(sc, oracle))
+        for _ in range(3): w.step(sc["dt"]); ow.step(sc["dt"])
+        w.add_force(5, np.array([1.0, 2.0, 3.0], np.float32)); ow.add_force(5, np.array([1.0, 2.0, 3.0], np.float32))      # pending force survives the rebuild
+        before = w.states()
+        for b in gone: w.destroy_body(b)
+        with pytest.raises(npb.NetphysError): w.body_state(17)
+        with pytest.raises(npb.NetphysError): w.destroy_body(17)
+        keep = np.array([i for i in range(600) if i not in gone])
+        assert w.n == 595
+        assert_biteq(w.states(), before[keep], "states of the survivors")
+        assert_biteq(w.body_state(19), before[19], "a surviving id still addresses its body")
+        # the oracle world without those bodies, continued from the same states
+        sc2 = dict(sc); sc2["body_shape"] = sc["body_shape"][keep]; sc2["sd"] = sc["sd"][keep]; sc2["response"] = sc["response"][keep]
+        ow2 = oracle.world(scenes.resolve(sc2, oracle)); ow2.set_state(before[keep])
+        ow2.add_force(int(np.searchsorted(keep, 5)), np.array([1.0, 2.0, 3.0], np.float32))
+        for k in range(4):
+            w.step(sc["dt"]); a, b, d = w.collisions_as_arrays()
+            ao, bo, do = ow2.step(sc["dt"], True)
+            assert np.array_equal(a, keep[ao]) and np.array_equal(b, keep[bo]), "collisions report ids, step %d" % k
+            assert_biteq(d, do, "collision data"); assert_biteq(w.states(), ow2.state(), "state after destroy, step %d" % k)
+        assert list(w.snapshot()["guid"]) == list(keep)
+        # shapes: in use -> refused; unused -> gone, its id is not reused
+        with pytest.raises(npb.NetphysError): w.destroy_shape(int(ids[0]))
+        extra = w.create_box(2.0, 2.0, 2.0)
+        w.destroy_shape(extra)
+        with pytest.raises(npb.NetphysError): w.shape_vertices(extra)
+        assert w.create_box(3.0, 3.0, 3.0) == extra + 1
+        w.step(sc["dt"]); ow2.step(sc["dt"])
+        assert_biteq(w.states(), ow2.state(), "state after a shape was destroyed")
+        # a body created after destroys gets a fresh id
+        nb = w.create_bodies(np.array([ids[0]], np.int32), npb.lib.sd_rows_to_struct(sc["sd"][:1], sc["response"][:1]))
+        assert nb == 600 and w.n == 596
