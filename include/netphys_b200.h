@@ -89,8 +89,11 @@ typedef struct np_world np_world;
 typedef enum np_broadphase {
     NP_BROADPHASE_EXACT = 0,  /* reference semantics: for each body i ascending, j = i+1.. until the first hit, then stop
                                  (GetCollisions, engine/physics.cpp:116-145).  Collision list identical to the reference. */
-    NP_BROADPHASE_GRID = 1    /* uniform-grid AABB culling first (the TODO at collision_detection.cpp:698 / todo.txt:7);
+    NP_BROADPHASE_GRID = 1,   /* uniform-grid AABB culling first (the TODO at collision_detection.cpp:698 / todo.txt:7);
                                  candidates are then searched in the same ascending-j, first-hit order */
+    NP_BROADPHASE_SWEPT = 2   /* the same grid over SWEPT boxes: each body's AABB united with its AABB of the previous step
+                                 ("broad-phase should do swept AABB from previous state to avoid tunnelling", todo.txt:8); a superset of
+                                 the GRID candidates, tested at the current poses.  The first step after bodies change has no previous box */
 } np_broadphase;
 
 typedef enum np_option {

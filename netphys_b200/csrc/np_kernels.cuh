@@ -839,6 +839,8 @@ struct GridView {
     int* spill_cursor;    // [1] next free entry of the spill region of cand (reset to cap * NP_CAND_SLOTS every step)
     int nbuckets, cand_cap, spill_base;
     float h_option;
+    float4* aabb_prev;    // [2*cap] NP_BROADPHASE_SWEPT: every body's own AABB of the previous step
+    int swept;            // 0: candidates from this step's AABBs; 1: swept mode, first step after a rebuild (no previous box yet); 2: union with the previous step's box
 };
 
 // K1b: world-space vertex cache (+ AABB for the grid).  8 lanes per body; world*p per vertex exactly as the support
@@ -883,6 +885,15 @@ __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, 
     // per-body record, and block-level reduction of (sum of extents, global min corner): 4 atomics per BLOCK
     float ext = 0.0f; int mn[3] = { 0x7fffffff, 0x7fffffff, 0x7fffffff };
     if (valid && gl == 0) {
+        if (gv.swept) {                                  // todo.txt:8 "swept AABB from previous state": the box the body swept through since the last step
+            const float4 clo = make_float4(lo[0], lo[1], lo[2], 0.0f), chi = make_float4(hi[0], hi[1], hi[2], 0.0f);
+            if (gv.swept == 2) {
+                const float4 plo = gv.aabb_prev[2 * body], phi = gv.aabb_prev[2 * body + 1];
+                lo[0] = fminf(lo[0], plo.x); lo[1] = fminf(lo[1], plo.y); lo[2] = fminf(lo[2], plo.z);
+                hi[0] = fmaxf(hi[0], phi.x); hi[1] = fmaxf(hi[1], phi.y); hi[2] = fmaxf(hi[2], phi.z);
+            }
+            gv.aabb_prev[2 * body] = clo; gv.aabb_prev[2 * body + 1] = chi;
+        }
         gv.aabb[2 * body] = make_float4(lo[0], lo[1], lo[2], 0.0f); gv.aabb[2 * body + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
         float e = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
         if (e == e && e < INFINITY) ext = e;

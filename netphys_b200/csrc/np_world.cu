@@ -70,6 +70,7 @@ struct np_world {
     float* d_ext = nullptr;           // adapter extension, allocated on first use: [4][cap] external force xyz + enabled flag
     // grid broad phase (allocated on first use)
     GridView grid = {}; int grid_cap = 0; int* d_grid_ints = nullptr; float* d_grid_f = nullptr;
+    bool swept_valid = false;         // NP_BROADPHASE_SWEPT: grid.aabb_prev holds the previous step's boxes of the current store
     int max_verts = 0;                // largest shape
     int g_gjk_env = 0, g_epa_env = 0; // NP_G_GJK / NP_G_EPA overrides (tuning)
     int order_on = 1; bool order_dirty = true;   // NP_ORDER=0: search bodies in index order (tuning)
@@ -326,7 +327,8 @@ static int ensure_device(np_world* w)
     }
     w->restore_ext = false;
     { int ro = upload_order(w); if (ro) return ro; }
-    if (w->broadphase == NP_BROADPHASE_GRID) { int rg = ensure_grid(w); if (rg) return rg; }
+    if (w->broadphase != NP_BROADPHASE_EXACT) { int rg = ensure_grid(w); if (rg) return rg; }
+    w->swept_valid = false;                                  // the store was rebuilt: no previous boxes
     return NP_OK;
 }
 static int ensure_arena(np_world* w)
@@ -524,12 +526,12 @@ static int ensure_grid(np_world* w)
     // ints: bucket_cnt[nb] bucket_cur[nb] (zeroed together) | bucket_off[nb] | items[c] | large[c] | cand_cnt[c] | cand_ub[c] | cand_off[c] | misc[32] | cand[cand_cap]
     const size_t n_ints = 3 * (size_t)nb + 5 * c + 32 + cand_cap;
     CU(cudaMalloc((void**)&w->d_grid_ints, sizeof(int) * n_ints));
-    CU(cudaMalloc((void**)&w->d_grid_f, sizeof(float) * (8 * c + 32)));
+    CU(cudaMalloc((void**)&w->d_grid_f, sizeof(float) * (16 * c + 32)));      // aabb[2c] float4 | aabb_prev[2c] float4 | params[32]
     GridView& g = w->grid;
     int* p = w->d_grid_ints;
     g.bucket_cnt = p; p += nb; g.bucket_cur = p; p += nb; g.bucket_off = p; p += nb; g.items = p; p += c; g.large = p; p += c;
     g.cand_cnt = p; p += c; g.cand_ub = p; p += c; g.cand_off = p; p += c; g.large_count = p; g.error = p + 1; g.spill_cursor = p + 2; p += 32; g.cand = p;
-    g.aabb = (float4*)w->d_grid_f; g.params = w->d_grid_f + 8 * c;
+    g.aabb = (float4*)w->d_grid_f; g.aabb_prev = (float4*)w->d_grid_f + 2 * c; g.params = w->d_grid_f + 16 * c;
     g.nbuckets = nb; g.cand_cap = (int)std::min<size_t>(cand_cap, 0x7fffffff); g.spill_base = (int)std::min<size_t>(c * NP_CAND_SLOTS, 0x7fffffff);
     if (g.spill_base >= g.cand_cap) return fail(NP_ERR_CAPACITY, "world too large for the grid broad phase's candidate store");
     CU(cudaMemsetAsync(g.large_count, 0, sizeof(int) * 32, w->stream));
@@ -540,6 +542,8 @@ static int ensure_grid(np_world* w)
 static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, int cache, DevCounters* ctr)
 {
     GridView& g = w->grid; g.h_option = w->grid_cell;
+    g.swept = w->broadphase == NP_BROADPHASE_SWEPT ? (w->swept_valid ? 2 : 1) : 0;
+    if (g.swept && !w->capturing) w->swept_valid = true;
     const int n = s.n, b256 = (n + 255) / 256;
     k_grid_init<<<1, 32, 0, w->stream>>>(g);
     CU(cudaMemsetAsync(g.bucket_cnt, 0, sizeof(int) * 2 * (size_t)g.nbuckets, w->stream));
@@ -579,7 +583,7 @@ static int enqueue_search(np_world* w, float dt, bool timed, bool integrate = tr
     }
     if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[1], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     const int cache = cache_mode(w, count);
-    if (w->broadphase == NP_BROADPHASE_GRID) { int r = enqueue_grid(w, s, first, count, cache, ctr); if (r) return r; }
+    if (w->broadphase != NP_BROADPHASE_EXACT) { int r = enqueue_grid(w, s, first, count, cache, ctr); if (r) return r; }
     else if (cache == CACHE_ALL) { k_world_verts<false, 1><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), w->grid); w->launches += 1; }
     else if (cache == CACHE_BIG) { k_world_verts<false, 2><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), w->grid); w->launches += 1; }
     if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[2], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
@@ -587,7 +591,7 @@ static int enqueue_search(np_world* w, float dt, bool timed, bool integrate = tr
     if (count > 0) {
         NarrowIn in; memset(&in, 0, sizeof in); in.world = 1; in.n = count; in.first = first; in.s = s;
         in.ordered = w->order_on;
-        if (w->broadphase == NP_BROADPHASE_GRID) { in.cand = w->grid.cand; in.cand_off = w->grid.cand_off; in.cand_cnt = w->grid.cand_cnt; }
+        if (w->broadphase != NP_BROADPHASE_EXACT) { in.cand = w->grid.cand; in.cand_off = w->grid.cand_off; in.cand_cnt = w->grid.cand_cnt; }
         if (w->seed_on && !w->gjk1_old && cache != CACHE_BIG && pick_group(w, count, w->g_gjk_env, false) <= 1) {      // thread-per-body search: tabulate the seed supports once per body
             const int sb_ = std::min(w->sm_count * 8, (n + NP_NARROW_THREADS - 1) / NP_NARROW_THREADS);
             k_seed_supports<<<std::max(1, sb_), NP_NARROW_THREADS, shapes_smem(w), w->stream>>>(s, sview(w), shapes_in_smem(w) ? 1 : 0, w->d_seed);
@@ -692,7 +696,7 @@ int np_world_set_option(np_world* w, int option, int64_t value)
     if (!w) return fail(NP_ERR_INVALID, "null world");
     switch (option) {
     case NP_OPT_BROADPHASE:
-        if (value != NP_BROADPHASE_EXACT && value != NP_BROADPHASE_GRID) return fail(NP_ERR_INVALID, "unknown broad-phase");
+        if (value != NP_BROADPHASE_EXACT && value != NP_BROADPHASE_GRID && value != NP_BROADPHASE_SWEPT) return fail(NP_ERR_INVALID, "unknown broad-phase");
         w->broadphase = (int)value; drop_graph(w); w->dirty_bodies = true; return NP_OK;
     case NP_OPT_GRID_CELL: { uint32_t u = (uint32_t)value; memcpy(&w->grid_cell, &u, 4); drop_graph(w); return NP_OK; }
     case NP_OPT_COUNTERS: w->counters_on = value ? 1 : 0; drop_graph(w); return NP_OK;
@@ -705,7 +709,7 @@ int np_world_begin_island(np_world* w) { if (!w) return fail(NP_ERR_INVALID, "nu
 int np_world_body_count(const np_world* w) { return w ? (int)w->bodies.size() : 0; }
 static int check_grid_error(np_world* w)
 {
-    if (w->broadphase != NP_BROADPHASE_GRID || !w->d_grid_ints) return NP_OK;
+    if (w->broadphase == NP_BROADPHASE_EXACT || !w->d_grid_ints) return NP_OK;
     int e = 0;
     CU(cudaMemcpyAsync(&e, w->grid.error, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
@@ -983,6 +987,9 @@ static int get_step_graph(np_world* w, float dt, StepGraph** out, int kind = STE
 }
 static int step_once(np_world* w, float dt, int kind = STEP_PLAIN)
 {
+    if (w->broadphase == NP_BROADPHASE_SWEPT && !w->swept_valid) {      // first swept step after a rebuild: plain launches (its AABB pass has no previous boxes), then the captured steps
+        return enqueue_step(w, dt, true, kind);              // (enqueue_grid marks the boxes valid)
+    }
     if (!w->graph_on || sharded(w) || w->mid_step) return enqueue_step(w, dt, true, kind);
     StepGraph* g = nullptr;
     int r = get_step_graph(w, dt, &g, kind); if (r) return r;

@@ -180,7 +180,7 @@ def sd_rows_to_struct(sd, response):
 class World:
     """np_world.  Mirrors the reference's implicit global world (engine/physics.cpp:9) as an explicit object."""
 
-    EXACT, GRID = 0, 1
+    EXACT, GRID, SWEPT = 0, 1, 2
     OPT_BROADPHASE, OPT_GRID_CELL, OPT_COUNTERS, OPT_SNAPSHOT_EACH_STEP, OPT_PHASE_TIMING = 1, 2, 3, 4, 5
 
     def __init__(self, device=-1, variant="exact"):

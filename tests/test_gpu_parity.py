@@ -628,3 +628,46 @@ def test_body_and_shape_destroy(npb, oracle):
         # a body created after destroys gets a fresh id
         nb = w.create_bodies(np.array([ids[0]], np.int32), npb.lib.sd_rows_to_struct(sc["sd"][:1], sc["response"][:1]))
         assert nb == 600 and w.n == 596
+
+
+# ---- swept-AABB broad phase (todo.txt:8) ------------------------------------------------------------------------
+def test_swept_broadphase_candidate_parity(npb, oracle):
+    """NP_BROADPHASE_SWEPT: candidates = pairs whose SWEPT boxes (this step's AABB united with the previous step's) overlap -- checked
+    against a brute force over the same boxes, a superset of the static-box candidates -- each tested at the current poses with the
+    oracle's result, first-hit order kept; fast bodies that tunnel past each other between two steps are still candidates."""
+    sc = scenes.lattice_scene(1200, spacing=1.0, seed=5, mix=(0.5, 0.2, 0.3))
+    sc["sd"][::3, 1] = -400.0                               # strong gravity on a third of the bodies: they move ~0.4+ per step after a few steps
+    shapes = scenes.resolve_specs(sc["shape_specs"], oracle)
+    with npb.World(0) as w, npb.World(0) as wg:
+        w.set_option(w.OPT_BROADPHASE, w.SWEPT); w.set_option(w.OPT_COUNTERS, 1); w.load_scene(sc)
+        wg.set_option(wg.OPT_BROADPHASE, wg.GRID); wg.set_option(wg.OPT_COUNTERS, 1); wg.load_scene(sc)
+        ow = oracle.world(scenes.resolve(sc, oracle))
+        prev_box = None; prev_c = 0; prev_g = 0; grew = False
+        for step in range(5):
+            w.step(sc["dt"]); w.synchronize(); wg.step(sc["dt"]); wg.synchronize()
+            st = w.states(); a, b, d = w.collisions_as_arrays()
+            ow.step(sc["dt"]); assert_biteq(st, ow.state(), "state")
+            lo, hi = _world_aabbs(oracle, shapes, sc["body_shape"], st)
+            slo, shi = (lo, hi) if prev_box is None else (np.minimum(lo, prev_box[0]), np.maximum(hi, prev_box[1]))
+            prev_box = (lo, hi)
+            N = len(st); exp = []; ncand = 0; nstatic = 0
+            pose = np.concatenate([st[:, 0:3], st[:, 3:6]], axis=1)
+            for i in range(N):
+                js = np.arange(i + 1, N)
+                ov = np.all((shi[i] >= slo[js]) & (shi[js] >= slo[i]), axis=1)
+                nstatic += int(np.all((hi[i] >= lo[js]) & (hi[js] >= lo[i]), axis=1).sum())
+                js = js[ov]; ncand += len(js)
+                if len(js) == 0: continue
+                ho, oo, _ = oracle.detect_batch(shapes, sc["body_shape"][np.full(len(js), i)], np.repeat(pose[i][None], len(js), 0), sc["body_shape"][js], pose[js])
+                h = np.flatnonzero(ho)
+                if len(h): exp.append((i, js[h[0]], oo[h[0]]))
+            c = w.counters()["candidates"]; cg = wg.counters()["candidates"]
+            assert c - prev_c == ncand, "swept candidate set differs from the brute force over swept boxes (step %d)" % step
+            assert cg - prev_g == nstatic and ncand >= nstatic
+            grew |= ncand > nstatic
+            prev_c, prev_g = c, cg
+            assert len(a) == len(exp) and np.array_equal(a, [e[0] for e in exp]) and np.array_equal(b, [e[1] for e in exp])
+            assert_biteq(d[:, 6:11], np.stack([e[2] for e in exp]), "CollisionData per swept candidate pair")
+        assert grew, "the workload no longer produces pairs that only the swept boxes catch"
+        w.step_n(sc["dt"], 3); ow.step(sc["dt"]); ow.step(sc["dt"]); ow.step(sc["dt"])        # captured + fused steps in swept mode
+        assert_biteq(w.states(), ow.state(), "state after step_n in swept mode")
