@@ -361,7 +361,9 @@ static int pick_group(np_world* w, long long items, int env, bool epa)
     if (env >= 1 && env <= 32) return env;
     // measured on B200 (tools/sweep2.sh, tools/sweep_world.sh): below a few hundred thousand items the step is bound by the
     // latency of its longest chains -> wide groups; above, by instruction throughput -> narrow groups
-    if (items <= 300000) return epa ? 32 : (items <= 40000 ? 32 : 8);      // (GJK: a warp per body once there are few enough bodies for one wave)
+    // (round 2, thread-per-body k_gjk1 + k_epa_first: 50/50 box/icosphere worlds, ms per step wide vs narrow groups -- 131 k bodies 1.36 vs 1.62,
+    // 262 k bodies 2.57 vs 2.05: the crossover moved from ~300 k to ~180 k items)
+    if (items <= 180000) return epa ? 32 : (items <= 40000 ? 32 : 8);      // (GJK: a warp per body once there are few enough bodies for one wave)
     return epa ? (w->max_verts <= 16 ? 1 : 4) : 1;          // small shapes: thread-per-hit EPA wins (8.1e8 vs 7.6e8 box pairs/s)
 }
 struct NarrowBufs { int* zero; int* hit_j; int* flags; float4* contact; float4* simplex; int* hit_list; int* big_list; int* hit_list2; };
