@@ -49,6 +49,14 @@ public:
     float dot(const vector3& b) const { return x * b.x + y * b.y + z * b.z; }
     float magnitude() const { return std::sqrt(x * x + y * y + z * z); }
 };
+namespace Coordinates {                           // vector.h:248-256
+inline vector3 GetUp() { return vector3(0.0f, 1.0f, 0.0f); }
+inline vector3 GetDown() { return vector3(0.0f, -1.0f, 0.0f); }
+inline vector3 GetLeft() { return vector3(0.0f, 0.0f, -1.0f); }
+inline vector3 GetRight() { return vector3(0.0f, 0.0f, 1.0f); }
+inline vector3 GetIn() { return vector3(1.0f, 0.0f, 0.0f); }
+inline vector3 GetOut() { return vector3(-1.0f, 0.0f, 0.0f); }
+}  // namespace Coordinates
 class matrix3 {
 public:
     float x1, x2, x3, y1, y2, y3, z1, z2, z3;
@@ -71,6 +79,11 @@ public:
     float x1, x2, x3, x4, y1, y2, y3, y4, z1, z2, z3, z4, w1, w2, w3, w4;   // rows, as engine/matrix.h:109-116
     matrix4() : x1(1), x2(0), x3(0), x4(0), y1(0), y2(1), y3(0), y4(0), z1(0), z2(0), z3(1), z4(0), w1(0), w2(0), w3(0), w4(1) {}
     explicit matrix4(const float in[16]) { std::memcpy(&x1, in, 64); }
+    // matrix.h:145-157: the point is promoted to (x, y, z, 1) and every row summed left to right; the w row is dropped by vector3(vector4)
+    vector3 operator*(const vector3& B) const
+    {
+        return vector3(x1 * B.x + x2 * B.y + x3 * B.z + x4 * 1.0f, y1 * B.x + y2 * B.y + y3 * B.z + y4 * 1.0f, z1 * B.x + z2 * B.y + z3 * B.z + z4 * 1.0f);
+    }
     void transpose()
     {
         matrix4 t = *this;
@@ -193,4 +206,79 @@ inline bool DetectCollision(const CollisionParams& p, bool is3D, CollisionData* 
         out->depth = c.depth; out->success = c.success != 0;
     }
     return hit != 0;
+}
+
+
+// ---- engine/simplex.h + the TEST_PROGRAM interface, engine/physics.h:115-127 -----------------------------------------------------
+// engine/test_3d.cpp:36-85 and test_2d.cpp:52-75 single-step GJK and EPA on a Simplex they keep between calls.  The container lives on
+// the host exactly as in the reference (two std::vectors the caller may resize, clear and index); every call ships it to the device,
+// where one thread runs the step, and back.  Always declared: the reference hides these behind #ifdef TEST_PROGRAM only to keep them
+// out of its game build.
+struct SimplexPoint {
+    vector3 p, A, B;
+};
+struct SimplexFace {
+    int point_index[3];
+    vector3 normal;
+};
+struct Simplex {
+    bool m_containsOrigin = false;
+    std::vector<SimplexPoint> verts;
+    std::vector<SimplexFace> faces;
+    int size() const { return (int)verts.size(); }
+    void AddFace(int va, int vb, int vc)                                   // simplex.h:37-53; the normal is computed by the library
+    {
+        static_assert(sizeof(SimplexPoint) == sizeof(np_simplex_point) && sizeof(SimplexFace) == sizeof(np_simplex_face), "simplex layouts");
+        SimplexFace f; f.point_index[0] = va; f.point_index[1] = vb; f.point_index[2] = vc;
+        np_simplex_face_normal(reinterpret_cast<const np_simplex_point*>(verts.data()), va, vb, vc, &f.normal.x);
+        faces.push_back(f);
+    }
+    void SetupForEPA() { AddFace(0, 1, 2); AddFace(0, 2, 3); AddFace(3, 1, 0); AddFace(1, 3, 2); }   // simplex.h:29-36
+    int insert(const SimplexPoint& point, int index = -1)                  // simplex.h:59-75
+    {
+        if (index < 0) { verts.push_back(point); return (int)verts.size() - 1; }
+        verts.insert(verts.begin() + index, point);
+        return index;
+    }
+};
+enum COLLISION_RESULT { COLLISION_RESULT_NONE, COLLISION_RESULT_OVERLAP, COLLISION_RESULT_NO_OVERLAP, COLLISION_RESULT_CONTINUE };
+inline COLLISION_RESULT DetectCollisionStep(const CollisionParams& p, bool is3D, Simplex& simplex)               // collision_detection.cpp:620-692
+{
+    np_simplex_point v[4]; int n = simplex.size(), contains = simplex.m_containsOrigin ? 1 : 0, result = COLLISION_RESULT_NONE;
+    if (n < 1 || n > 4) { netphys::last_status() = NP_ERR_INVALID; return COLLISION_RESULT_NONE; }
+    std::memcpy(v, simplex.verts.data(), sizeof(np_simplex_point) * (size_t)n);
+    if (netphys::check(np_gjk_step(netphys::default_world(), p.a->DeviceShape(), &p.aTransform.x1, p.b->DeviceShape(), &p.bTransform.x1, is3D ? 1 : 0,
+                                   v, &n, &contains, &result)) < 0) return COLLISION_RESULT_NONE;
+    simplex.verts.resize((size_t)n);
+    std::memcpy(simplex.verts.data(), v, sizeof(np_simplex_point) * (size_t)n);
+    simplex.m_containsOrigin = contains != 0;
+    return (COLLISION_RESULT)result;
+}
+inline bool FindIntersectionPoints(const CollisionParams& p, Simplex& simplex, int max_steps, bool is3D, CollisionData* out)   // :549-608
+{
+    // room for one new vertex per iteration; an expansion creates one face per horizon edge, at most three per face it removes
+    const int nv0 = simplex.size(), nf0 = (int)simplex.faces.size();
+    const int vcap = nv0 + (max_steps > 0 ? max_steps : 0);
+    int fcap = nf0 + 4;
+    for (int k = 0; k < max_steps && fcap < 8192; k++) fcap = 4 * fcap;
+    if (fcap > 8192) fcap = 8192;
+    int nv = nv0, nf = nf0, found = 0;
+    simplex.verts.resize((size_t)vcap); simplex.faces.resize((size_t)fcap);
+    np_collision_data c; std::memset(&c, 0, sizeof c);
+    int r = netphys::check(np_epa_steps(netphys::default_world(), p.a->DeviceShape(), &p.aTransform.x1, p.b->DeviceShape(), &p.bTransform.x1, max_steps, is3D ? 1 : 0,
+                                        reinterpret_cast<np_simplex_point*>(simplex.verts.data()), &nv, vcap,
+                                        reinterpret_cast<np_simplex_face*>(simplex.faces.data()), &nf, fcap, simplex.m_containsOrigin ? 1 : 0, &c, &found));
+    if (r < 0) { nv = nv0; nf = nf0; found = 0; }
+    simplex.verts.resize((size_t)nv); simplex.faces.resize((size_t)nf);
+    if (found && out) {
+        out->penetrationDirection = vector3(c.penetration_direction[0], c.penetration_direction[1], c.penetration_direction[2]);
+        out->depth = c.depth;
+    }
+    return found != 0;
+}
+inline vector3 GetSearchDirection(const Simplex& simplex)                                                          // :327-337
+{
+    vector3 d;
+    netphys::check(np_search_direction(netphys::default_world(), reinterpret_cast<const np_simplex_point*>(simplex.verts.data()), simplex.size(), &d.x));
+    return d;
 }

@@ -227,6 +227,30 @@ int np_detect_collision_batch_2d(np_world* w, int n, const int32_t* shape_a, con
 int np_detect_collision_batch_device(np_world* w, int n, const void* d_shape_a, const void* d_pose_a, const void* d_shape_b,
                                      const void* d_pose_b, void* d_hit, void* d_out, float* kernel_ms);
 
+/* ---- the algorithm one call at a time: the TEST_PROGRAM interface, engine/physics.h:115-127 ------------------------------------
+ * engine/test_3d.cpp:57-85 and test_2d.cpp:66,73 drive GJK and EPA step by step on a Simplex THEY hold between calls (engine/simplex.h).
+ * The simplex crosses the boundary as plain arrays; one device thread executes each call (an inspection interface, not a hot path). */
+typedef struct np_simplex_point { float p[3]; float A[3]; float B[3]; } np_simplex_point;          /* SimplexPoint, simplex.h:5-13 */
+typedef struct np_simplex_face { int32_t point_index[3]; float normal[3]; } np_simplex_face;       /* SimplexFace,  simplex.h:16-20 */
+enum np_collision_result {                                                                         /* COLLISION_RESULT, physics.h:116-123 */
+    NP_COLLISION_RESULT_NONE = 0, NP_COLLISION_RESULT_OVERLAP = 1, NP_COLLISION_RESULT_NO_OVERLAP = 2, NP_COLLISION_RESULT_CONTINUE = 3
+};
+/* DetectCollisionStep (collision_detection.cpp:620-692): solve the simplex, then either report OVERLAP (and set *contains_origin),
+ * NO_OVERLAP, or append one support point and CONTINUE.  verts has room for 4 points; *nverts in 1..4 (the reference asserts). */
+int np_gjk_step(np_world* w, int shape_a, const float a_transform[16], int shape_b, const float b_transform[16], int is3D,
+                np_simplex_point* verts, int* nverts, int* contains_origin, int* result);
+/* FindIntersectionPoints (collision_detection.cpp:549-608): up to max_steps EPA iterations on the caller's polytope (faces as built by
+ * Simplex::SetupForEPA/AddFace, stored normals kept), or the separated-shapes branches when !contains_origin.  *found = its return
+ * value; `out` (may be NULL) receives penetrationDirection and depth when found.  NP_ERR_CAPACITY when the polytope would outgrow
+ * verts_cap / faces_cap or 24 vertices (the reference's std::vector is unbounded; its own loop stops at 20 iterations, :716). */
+int np_epa_steps(np_world* w, int shape_a, const float a_transform[16], int shape_b, const float b_transform[16], int max_steps, int is3D,
+                 np_simplex_point* verts, int* nverts, int verts_cap, np_simplex_face* faces, int* nfaces, int faces_cap,
+                 int contains_origin, np_collision_data* out, int* found);
+/* GetSearchDirection (collision_detection.cpp:327-337) of a 1..3 point simplex */
+int np_search_direction(np_world* w, const np_simplex_point* verts, int nverts, float out[3]);
+/* the normal Simplex::AddFace stores for face (va, vb, vc) (simplex.h:37-53); host arithmetic, same binary32 operations as the device */
+void np_simplex_face_normal(const np_simplex_point* verts, int va, int vb, int vc, float out[3]);
+
 /* ---- replication snapshot (netphys_server/world_s.cpp:23-51 -> CommandFrameObject) ----------------- */
 int np_world_snapshot(np_world* w, np_snapshot_object* dst, int cap);      /* device -> host */
 /* device buffer holding the packed snapshot of the last step (for an NCCL all-gather by the host layer) */

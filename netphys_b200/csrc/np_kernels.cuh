@@ -715,6 +715,29 @@ NP_D void closest_edge2d(const Verts2D& s, float* distance, float* u, int* si, i
     }
     *distance = sqrtf(best); *u = bu;
 }
+// one FindIntersectionPointsStep in 2-D (collision_detection.cpp:412-547 with the :364-384 / :455-460 branches): closest edge, support along
+// its outward normal, convergence test, else the new point is inserted before the edge's end vertex (simplex.h:59-75).  true = converged.
+NP_D bool epa2d_step(const PairGeom& g, Verts2D& s, V3* pen, float* depth)
+{
+    float distance, u; int ea, eb;
+    closest_edge2d(s, &distance, &u, &ea, &eb);
+    V3 a = s.p[ea], b = s.p[eb];
+    V3 cp = add(a, mul(sub(b, a), u)), edge = sub(b, a);
+    V3 nrm = mk(edge.y, -edge.x, 0.0f);
+    V3 normal = dot(cp, nrm) > 0.0f ? nrm : neg(nrm);
+    bool close = true;
+    if (distance > NP_EPA_TOL) {
+        V3 sa = support<1, false>(g.va, g.na, g.Ra, g.ta, normal), sb = support<1, false>(g.vb, g.nb, g.Rb, g.tb, neg(normal));
+        close = false;
+        for (int i = 0; i < s.n; i++) if (veq(sa, s.A[i], NP_EPA_TOL) && veq(sb, s.B[i], NP_EPA_TOL)) { close = true; break; }
+        if (!close && s.n < NP_EPA_MAX_VERTS) {                                           // simplex.h:59-75 insert before eb
+            for (int i = s.n; i > eb; --i) { s.p[i] = s.p[i - 1]; s.A[i] = s.A[i - 1]; s.B[i] = s.B[i - 1]; }
+            s.p[eb] = sub(sa, sb); s.A[eb] = sa; s.B[eb] = sb; s.n++;
+        }
+    }
+    if (close) { *pen = neg(normalize(normal)); *depth = distance; }
+    return close;
+}
 __global__ void __launch_bounds__(64) k_detect2d(int n, ShapeView sh, const int* __restrict__ shape_a, const int* __restrict__ shape_b,
                                                 const float* __restrict__ xf_a, const float* __restrict__ xf_b, int* __restrict__ flags, float4* __restrict__ contact)
 {
@@ -766,31 +789,164 @@ __global__ void __launch_bounds__(64) k_detect2d(int n, ShapeView sh, const int*
     int fl = 0; V3 pen = mk(0.0f, 0.0f, 0.0f); float depth = 0.0f;
     if (result == OVERLAP) {
         fl |= NP_PAIR_HIT;
-        for (int it = 0; it < NP_EPA_MAX_STEPS; it++) {                                            // FindIntersectionPointsStep, 2-D branches
-            float distance, u; int ea, eb;
-            closest_edge2d(s, &distance, &u, &ea, &eb);
-            V3 a = s.p[ea], b = s.p[eb];
-            V3 cp = add(a, mul(sub(b, a), u)), edge = sub(b, a);
-            V3 nrm = mk(edge.y, -edge.x, 0.0f);
-            V3 normal = dot(cp, nrm) > 0.0f ? nrm : neg(nrm);
-            bool close = true;
-            if (distance > NP_EPA_TOL) {
-                V3 sa = support<1, false>(g.va, g.na, g.Ra, g.ta, normal), sb = support<1, false>(g.vb, g.nb, g.Rb, g.tb, neg(normal));
-                close = false;
-                for (int i = 0; i < s.n; i++) if (veq(sa, s.A[i], NP_EPA_TOL) && veq(sb, s.B[i], NP_EPA_TOL)) { close = true; break; }
-                if (!close) {                                                                     // simplex.h:59-75 insert before eb
-                    for (int i = s.n; i > eb; --i) { s.p[i] = s.p[i - 1]; s.A[i] = s.A[i - 1]; s.B[i] = s.B[i - 1]; }
-                    s.p[eb] = sub(sa, sb); s.A[eb] = sa; s.B[eb] = sb; s.n++;
-                }
-            }
-            if (close) { pen = neg(normalize(normal)); depth = distance; fl |= NP_PAIR_SUCCESS; break; }
-        }
+        for (int it = 0; it < NP_EPA_MAX_STEPS; it++)                                              // FindIntersectionPointsStep, 2-D branches
+            if (epa2d_step(g, s, &pen, &depth)) { fl |= NP_PAIR_SUCCESS; break; }
     } else if (s.n >= 2) {                                                                        // :590-605 separated: closest edge of the simplex
         float distance, u; int si, ei;
         closest_edge2d(s, &distance, &u, &si, &ei);
         pen = add(s.p[si], mul(sub(s.p[ei], s.p[si]), u)); depth = distance; fl |= NP_PAIR_SUCCESS;
     }
     flags[p] = fl; contact[p] = make_float4(pen.x, pen.y, pen.z, depth);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The reference's TEST_PROGRAM interface (engine/physics.h:115-127): DetectCollisionStep / FindIntersectionPoints / GetSearchDirection on
+// a simplex the CALLER holds between calls (engine/test_3d.cpp:57-85 and test_2d.cpp:66,73 single-step the algorithm with it).  One thread;
+// not a hot path.  The simplex travels as 9 floats per point (p, A, B: simplex.h:5-13) and, for EPA, 3 ints + 3 floats per face (:16-20).
+// ---------------------------------------------------------------------------------------------------
+NP_D void geom_from16(ShapeView sh, int sa, int sb, const float* xa, const float* xb, PairGeom& g)
+{
+#pragma unroll
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { g.Ra[3 * r + c] = xa[4 * r + c]; g.Rb[3 * r + c] = xb[4 * r + c]; }
+    g.ta = mk(xa[3], xa[7], xa[11]); g.tb = mk(xb[3], xb[7], xb[11]);
+    g.va = sh.verts + sh.off[sa]; g.na = sh.cnt[sa]; g.vb = sh.verts + sh.off[sb]; g.nb = sh.cnt[sb];
+}
+enum { STEP_RESULT_NONE = 0, STEP_RESULT_OVERLAP, STEP_RESULT_NO_OVERLAP, STEP_RESULT_CONTINUE };      // COLLISION_RESULT, physics.h:116-123
+NP_D V3 ld3(const float* p) { return mk(p[0], p[1], p[2]); }
+NP_D void st3(float* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+// io: [0] nverts (in/out), [1] m_containsOrigin (in/out), [2] result (out)
+__global__ void k_gjk_step(ShapeView sh, int sa, int sb, const float* xa, const float* xb, int is3D, float* verts, int* io)
+{
+    PairGeom g; geom_from16(sh, sa, sb, xa, xb, g);
+    int n = io[0];
+    V3 P[4], A[4], B[4], oA[4], oB[4];
+    for (int k = 0; k < n; k++) { P[k] = ld3(verts + 9 * k); A[k] = ld3(verts + 9 * k + 3); B[k] = ld3(verts + 9 * k + 6); oA[k] = A[k]; oB[k] = B[k]; }
+    const int nold = n;
+    int kn = n, ks[3] = { 0, 1, 2 };
+    if (n == 2) { float u; int r = closest_line(P[0], P[1], &u); if (r == LINE_A) kn = 1; else if (r == LINE_B) { kn = 1; ks[0] = 1; } }
+    else if (n == 3) {
+        float u, v; int r = closest_triangle(P[0], P[1], P[2], &u, &v);
+        switch (r) {
+        case TRI_A: kn = 1; break;
+        case TRI_B: kn = 1; ks[0] = 1; break;
+        case TRI_C: kn = 1; ks[0] = 2; break;
+        case TRI_AB: kn = 2; break;
+        case TRI_AC: kn = 2; ks[1] = 2; break;
+        case TRI_BC: kn = 2; ks[0] = 1; ks[1] = 2; break;
+        default: break;
+        }
+    } else if (n == 4) {
+        float u, v, w; int r = closest_tetra(P[0], P[1], P[2], P[3], &u, &v, &w);
+        switch (r) {
+        case TET_A: kn = 1; break;
+        case TET_B: kn = 1; ks[0] = 1; break;
+        case TET_C: kn = 1; ks[0] = 2; break;
+        case TET_D: kn = 1; ks[0] = 3; break;
+        case TET_AB: kn = 2; break;
+        case TET_AC: kn = 2; ks[1] = 2; break;
+        case TET_AD: kn = 2; ks[1] = 3; break;
+        case TET_BC: kn = 2; ks[0] = 1; ks[1] = 2; break;
+        case TET_BD: kn = 2; ks[0] = 1; ks[1] = 3; break;
+        case TET_CD: kn = 2; ks[0] = 2; ks[1] = 3; break;
+        case TET_ABC: kn = 3; break;
+        case TET_ABD: kn = 3; ks[2] = 3; break;
+        case TET_ACD: kn = 3; ks[1] = 2; ks[2] = 3; break;
+        case TET_BCD: kn = 3; ks[0] = 1; ks[1] = 2; ks[2] = 3; break;
+        default: break;
+        }
+    }
+    if (kn < n) {                                               // the solve's order-preserving compaction (:18-259)
+        V3 nP[3], nA[3], nB[3];
+        for (int k = 0; k < kn; k++) { nP[k] = P[ks[k]]; nA[k] = A[ks[k]]; nB[k] = B[ks[k]]; }
+        for (int k = 0; k < kn; k++) { P[k] = nP[k]; A[k] = nA[k]; B[k] = nB[k]; }
+        n = kn;
+    }
+    int result;
+    if (n == 4 || (!is3D && n == 3)) { io[1] = 1; result = STEP_RESULT_OVERLAP; }                   // :648-652
+    else {
+        V3 d = n == 1 ? dir1(P[0]) : (n == 2 ? dir2(P[0], P[1]) : dir3(P[0], P[1], P[2]));
+        if (feq(magsq(d), 0.0f)) result = STEP_RESULT_NO_OVERLAP;
+        else {
+            V3 a = support<1, false>(g.va, g.na, g.Ra, g.ta, d), b = support<1, false>(g.vb, g.nb, g.Rb, g.tb, neg(d));
+            V3 sp = sub(a, b);
+            result = STEP_RESULT_CONTINUE;
+            if (dot(d, sp) < 0) result = STEP_RESULT_NO_OVERLAP;
+            else {
+                for (int k = 0; k < nold; k++) if (veq(a, oA[k]) && veq(b, oB[k])) result = STEP_RESULT_NO_OVERLAP;
+                if (result == STEP_RESULT_CONTINUE) { P[n] = sp; A[n] = a; B[n] = b; n++; }
+            }
+        }
+    }
+    for (int k = 0; k < n; k++) { st3(verts + 9 * k, P[k]); st3(verts + 9 * k + 3, A[k]); st3(verts + 9 * k + 6, B[k]); }
+    io[0] = n; io[2] = result;
+}
+__global__ void k_search_direction(const float* verts, int n, float* out)
+{
+    V3 d = n == 1 ? dir1(ld3(verts)) : (n == 2 ? dir2(ld3(verts), ld3(verts + 9)) : dir3(ld3(verts), ld3(verts + 9), ld3(verts + 18)));
+    st3(out, d);
+}
+// FindIntersectionPoints (collision_detection.cpp:549-608) on the caller's simplex / polytope.
+// io: [0] nverts, [1] nfaces (both in/out), [2] m_containsOrigin (in), [3] return value (out), [4] error (out: 1 = vertex or face capacity)
+__global__ void k_epa_steps(ShapeView sh, int sa, int sb, const float* xa, const float* xb, int max_steps, int is3D, float* verts, int verts_cap,
+                            int* face_idx, float* face_n, int faces_cap, int* io, float* out4, BigArena ar)
+{
+    PairGeom g; geom_from16(sh, sa, sb, xa, xb, g);
+    const int nv = io[0], nf = io[1], contains = io[2];
+    io[3] = 0; io[4] = 0;
+    if (contains && is3D) {
+        PolyPtr poly = poly_from(ar.base, NP_FBIG, false);
+        EpaMachine<1, PolyPtr, false, false> m;
+        m.pnv = nv; m.pnf = nf; m.steps = 0; m.flags = NP_PAIR_HIT; m.pen = mk(0.f, 0.f, 0.f); m.depth = 0.f; m.dist = 0.f; m.done = false; m.d = mk(0.f, 0.f, 0.f);
+        for (int k = 0; k < nv; k++) poly.setv(k, ld3(verts + 9 * k), ld3(verts + 9 * k + 3), ld3(verts + 9 * k + 6));
+        for (int f = 0; f < nf; f++) {                          // the caller's faces with THEIR stored normals (Simplex::AddFace ran on the host)
+            const int va = face_idx[3 * f], vb = face_idx[3 * f + 1], vc = face_idx[3 * f + 2];
+            poly.setf(f, (uint32_t)va | ((uint32_t)vb << 8) | ((uint32_t)vc << 16), ld3(face_n + 3 * f));
+            float u, v; V3 a = poly.P(va), b = poly.P(vb), c = poly.P(vc);
+            closest_triangle(a, b, c, &u, &v);
+            poly.setD(f, magsq(add(add(a, mul(sub(b, a), u)), mul(sub(c, a), v))));
+        }
+        PairStats st = { 0, 0, 0, 0, 0 };
+        for (int it = 0; it < max_steps && !m.done; it++) {
+            if (m.pnv >= NP_EPA_MAX_VERTS || m.pnv >= verts_cap) { io[4] = 1; break; }
+            m.steps = 0; m.trip(g, poly, st);
+        }
+        if (m.flags & NP_PAIR_OVERFLOW) io[4] = 1;
+        if (m.pnf > faces_cap) io[4] = 1;
+        if (!io[4]) {
+            for (int k = 0; k < m.pnv; k++) { st3(verts + 9 * k, poly.P(k)); st3(verts + 9 * k + 3, poly.gA(k)); st3(verts + 9 * k + 6, poly.gB(k)); }
+            for (int f = 0; f < m.pnf; f++) { const uint32_t x = poly.F(f); face_idx[3 * f] = x & 0xff; face_idx[3 * f + 1] = (x >> 8) & 0xff; face_idx[3 * f + 2] = (x >> 16) & 0xff; st3(face_n + 3 * f, poly.N(f)); }
+            io[0] = m.pnv; io[1] = m.pnf;
+            if (m.flags & NP_PAIR_SUCCESS) { io[3] = 1; st3(out4, m.pen); out4[3] = m.depth; }
+        }
+    } else if (contains) {                                      // 2-D polygon EPA
+        Verts2D s; s.n = nv;
+        for (int k = 0; k < nv; k++) { s.p[k] = ld3(verts + 9 * k); s.A[k] = ld3(verts + 9 * k + 3); s.B[k] = ld3(verts + 9 * k + 6); }
+        V3 pen = mk(0.f, 0.f, 0.f); float depth = 0.f;
+        for (int it = 0; it < max_steps; it++) {
+            if (s.n >= NP_EPA_MAX_VERTS || s.n >= verts_cap) { io[4] = 1; break; }
+            if (epa2d_step(g, s, &pen, &depth)) { io[3] = 1; st3(out4, pen); out4[3] = depth; break; }
+        }
+        for (int k = 0; k < s.n; k++) { st3(verts + 9 * k, s.p[k]); st3(verts + 9 * k + 3, s.A[k]); st3(verts + 9 * k + 6, s.B[k]); }
+        io[0] = s.n;
+    } else if (is3D && nv >= 3) {                               // :567-589 separated shapes: closest face of the caller's polytope
+        if (nf > 0) {                                           // (with no faces the reference indexes an uninitialised face: defined here as `false`)
+            float best = 3.402823466e+38f, bu = 0.f, bv = 0.f; int bf = 0;
+            for (int f = 0; f < nf; f++) {
+                V3 a = ld3(verts + 9 * face_idx[3 * f]), b = ld3(verts + 9 * face_idx[3 * f + 1]), c = ld3(verts + 9 * face_idx[3 * f + 2]);
+                float u, v; closest_triangle(a, b, c, &u, &v);
+                float dsq = magsq(add(add(a, mul(sub(b, a), u)), mul(sub(c, a), v)));
+                if (dsq < best) { best = dsq; bf = f; bu = u; bv = v; }
+            }
+            V3 a = ld3(verts + 9 * face_idx[3 * bf]), b = ld3(verts + 9 * face_idx[3 * bf + 1]), c = ld3(verts + 9 * face_idx[3 * bf + 2]);
+            st3(out4, normalize(add(add(a, mul(sub(b, a), bu)), mul(sub(c, a), bv)))); out4[3] = sqrtf(best); io[3] = 1;
+        }
+    } else if (!is3D && nv >= 2) {                              // :590-605 separated shapes in 2-D: closest edge
+        Verts2D s; s.n = nv;
+        for (int k = 0; k < nv; k++) s.p[k] = ld3(verts + 9 * k);
+        float distance, u; int si, ei;
+        closest_edge2d(s, &distance, &u, &si, &ei);
+        st3(out4, add(s.p[si], mul(sub(s.p[ei], s.p[si]), u))); out4[3] = distance; io[3] = 1;
+    }
 }
 
 // poses (position[3] rotation[3]) or row-major 4x4 matrices -> transforms [n][X_COUNT]  (GetTransform, physics.h:70-76)

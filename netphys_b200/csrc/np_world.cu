@@ -1264,6 +1264,89 @@ int np_shape_support(np_world* w, int shape, const float dir[3], const float wor
     CU(cudaStreamSynchronize(w->stream));
     return NP_OK;
 }
+// ---- the reference's TEST_PROGRAM interface (engine/physics.h:115-127): the algorithm one call at a time on a simplex the caller owns
+static_assert(sizeof(np_simplex_point) == 36 && sizeof(np_simplex_face) == 24, "simplex.h:5-20 layouts");
+int np_gjk_step(np_world* w, int shape_a, const float a_transform[16], int shape_b, const float b_transform[16], int is3D,
+                np_simplex_point* verts, int* nverts, int* contains_origin, int* result)
+{
+    if (!w || !a_transform || !b_transform || !verts || !nverts || !contains_origin || !result) return fail(NP_ERR_INVALID, "bad arguments");
+    if (*nverts < 1 || *nverts > 4 || (!is3D && *nverts > 3)) return fail(NP_ERR_INVALID, "DetectCollisionStep takes a simplex of 1..4 points (1..3 in 2-D)");   // the reference asserts
+    int32_t sa = shape_a, sb = shape_b;
+    int r = check_shapes(w, 1, &sa, &sb); if (r) return r;
+    r = ensure_device(w); if (r) return r;
+    char* d = nullptr;
+    int io[3] = { *nverts, *contains_origin ? 1 : 0, 0 };
+    CU(cudaMallocAsync((void**)&d, 512, w->stream));                         // [0,64) xa  [64,128) xb  [128,272) 4 points  [288,300) io
+    CU(cudaMemcpyAsync(d, a_transform, 64, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + 64, b_transform, 64, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(d + 128, verts, 36 * (size_t)*nverts, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + 288, io, 12, cudaMemcpyHostToDevice, w->stream));
+    k_gjk_step<<<1, 1, 0, w->stream>>>(sview(w), sa, sb, (const float*)d, (const float*)(d + 64), is3D ? 1 : 0, (float*)(d + 128), (int*)(d + 288));
+    np_simplex_point out[4];
+    CU(cudaMemcpyAsync(out, d + 128, sizeof out, cudaMemcpyDeviceToHost, w->stream)); CU(cudaMemcpyAsync(io, d + 288, 12, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaFreeAsync(d, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    memcpy(verts, out, 36 * (size_t)io[0]);
+    *nverts = io[0]; *contains_origin = io[1]; *result = io[2];
+    return NP_OK;
+}
+int np_epa_steps(np_world* w, int shape_a, const float a_transform[16], int shape_b, const float b_transform[16], int max_steps, int is3D,
+                 np_simplex_point* verts, int* nverts, int verts_cap, np_simplex_face* faces, int* nfaces, int faces_cap,
+                 int contains_origin, np_collision_data* out, int* found)
+{
+    if (!w || !a_transform || !b_transform || !verts || !nverts || !nfaces || !found || *nverts < 0 || *nfaces < 0 || *nverts > verts_cap || *nfaces > faces_cap || (*nfaces > 0 && !faces))
+        return fail(NP_ERR_INVALID, "bad arguments");
+    if (*nverts > 255 || *nfaces > NP_FBIG) return fail(NP_ERR_CAPACITY, "polytope too large for the step interface");
+    for (int f = 0; f < *nfaces; f++) for (int k = 0; k < 3; k++)
+        if (faces[f].point_index[k] < 0 || faces[f].point_index[k] >= *nverts) return fail(NP_ERR_INVALID, "face refers to a vertex the simplex does not have");
+    int32_t sa = shape_a, sb = shape_b;
+    int r = check_shapes(w, 1, &sa, &sb); if (r) return r;
+    r = ensure_device(w); if (r) return r;
+    const size_t vcap = (size_t)std::max(verts_cap, 1), fcap = (size_t)std::max(faces_cap, 1);
+    const size_t o_v = 128, o_fi = o_v + 36 * vcap, o_fn = o_fi + 12 * fcap, o_io = o_fn + 12 * fcap, o_out = o_io + 32, total = o_out + 16;
+    std::vector<int32_t> fi(3 * fcap, 0); std::vector<float> fn(3 * fcap, 0.0f);
+    for (int f = 0; f < *nfaces; f++) for (int k = 0; k < 3; k++) { fi[3 * f + k] = faces[f].point_index[k]; fn[3 * f + k] = faces[f].normal[k]; }
+    int io[8] = { *nverts, *nfaces, contains_origin ? 1 : 0, 0, 0, 0, 0, 0 };
+    char* d = nullptr;
+    CU(cudaMallocAsync((void**)&d, total, w->stream));
+    CU(cudaMemcpyAsync(d, a_transform, 64, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + 64, b_transform, 64, cudaMemcpyHostToDevice, w->stream));
+    if (*nverts) CU(cudaMemcpyAsync(d + o_v, verts, 36 * (size_t)*nverts, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(d + o_fi, fi.data(), 12 * fcap, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + o_fn, fn.data(), 12 * fcap, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(d + o_io, io, 32, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemsetAsync(d + o_out, 0, 16, w->stream));
+    k_epa_steps<<<1, 1, 0, w->stream>>>(sview(w), sa, sb, (const float*)d, (const float*)(d + 64), max_steps, is3D ? 1 : 0, (float*)(d + o_v), verts_cap,
+                                        (int*)(d + o_fi), (float*)(d + o_fn), faces_cap, (int*)(d + o_io), (float*)(d + o_out), w->arena);
+    float o4[4];
+    CU(cudaMemcpyAsync(io, d + o_io, 32, cudaMemcpyDeviceToHost, w->stream)); CU(cudaMemcpyAsync(o4, d + o_out, 16, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    if (io[4]) { cudaFreeAsync(d, w->stream); return fail(NP_ERR_CAPACITY, "polytope outgrew verts_cap / faces_cap (or the 24-vertex step limit)"); }
+    if (io[0]) CU(cudaMemcpyAsync(verts, d + o_v, 36 * (size_t)io[0], cudaMemcpyDeviceToHost, w->stream));
+    if (io[1]) { CU(cudaMemcpyAsync(fi.data(), d + o_fi, 12 * (size_t)io[1], cudaMemcpyDeviceToHost, w->stream)); CU(cudaMemcpyAsync(fn.data(), d + o_fn, 12 * (size_t)io[1], cudaMemcpyDeviceToHost, w->stream)); }
+    CU(cudaFreeAsync(d, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    for (int f = 0; f < io[1]; f++) for (int k = 0; k < 3; k++) { faces[f].point_index[k] = fi[3 * f + k]; faces[f].normal[k] = fn[3 * f + k]; }
+    *nverts = io[0]; *nfaces = io[1]; *found = io[3];
+    if (out && io[3]) { memset(out, 0, sizeof *out); memcpy(out->penetration_direction, o4, 12); out->depth = o4[3]; }   // FindIntersectionPoints never writes `success` (:523-531)
+    return NP_OK;
+}
+int np_search_direction(np_world* w, const np_simplex_point* verts, int nverts, float out[3])
+{
+    if (!w || !verts || !out || nverts < 1 || nverts > 3) return fail(NP_ERR_INVALID, "GetSearchDirection takes 1..3 points");   // the reference returns an uninitialised vector otherwise
+    int r = ensure_device(w); if (r) return r;
+    float* d = nullptr;
+    CU(cudaMallocAsync((void**)&d, 128, w->stream));
+    CU(cudaMemcpyAsync(d, verts, 36 * (size_t)nverts, cudaMemcpyHostToDevice, w->stream));
+    k_search_direction<<<1, 1, 0, w->stream>>>(d, nverts, d + 28);
+    CU(cudaMemcpyAsync(out, d + 28, 12, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaFreeAsync(d, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return NP_OK;
+}
+void np_simplex_face_normal(const np_simplex_point* verts, int va, int vb, int vc, float out[3])
+{
+    // Simplex::AddFace (simplex.h:37-53) on the host: same binary32 operations as EpaMachine::add_face_at
+    V3 a = mk(verts[va].p[0], verts[va].p[1], verts[va].p[2]), b = mk(verts[vb].p[0], verts[vb].p[1], verts[vb].p[2]), c = mk(verts[vc].p[0], verts[vc].p[1], verts[vc].p[2]);
+    V3 n = normalize(cross(sub(b, a), sub(c, a)));
+    V3 nn = (dot(n, a) != 0.0f) ? n : neg(n);
+    out[0] = nn.x; out[1] = nn.y; out[2] = nn.z;
+}
 int np_body_apply_impulse_response(np_world* w, int body, const np_collision_data* data, const float normal[3])
 {
     // Physics::ApplyImpulseResponse (physics.cpp:27-46) as a stand-alone call on one body

@@ -203,3 +203,8 @@ double ref_time_detect(int n, const int* sa, const float* posea, const int* sb, 
 }
 
 }  // extern "C"
+
+// ---- the TEST_PROGRAM step interface (engine/physics.h:115-127), driven the way engine/test_3d.cpp:36-85 drives it ------------
+// The client code is tests/cpp/step_trace_body.h, compiled here against the reference's own headers and sources.
+#include "../../tests/cpp/step_trace_body.h"
+extern "C" int ref_step_trace(const char* in_path, const char* out_path, int max_calls) { return step_trace::run(in_path, out_path, max_calls); }
