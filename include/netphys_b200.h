@@ -101,8 +101,10 @@ typedef enum np_option {
     NP_OPT_GRID_CELL = 2,         /* float bits: grid cell edge; 0 = auto (largest AABB extent) */
     NP_OPT_COUNTERS = 3,          /* 1 = accumulate pair-test / hit / iteration counters (np_world_get_counters) */
     NP_OPT_SNAPSHOT_EACH_STEP = 4,/* 1 = np_world_step also packs the replication snapshot (world_s.cpp:23-51) */
-    NP_OPT_PHASE_TIMING = 5       /* 1 = time the phases of every step with CUDA events (np_world_last_step_ms [0..4]); the events cost a few
+    NP_OPT_PHASE_TIMING = 5,      /* 1 = time the phases of every step with CUDA events (np_world_last_step_ms [0..4]); the events cost a few
                                      microseconds each, so a step runs faster without them.  The total [5] is always measured. */
+    NP_OPT_SUPPORT_TABLES = 6     /* default 1: PhysUtil_GetPointFurthestInDirection (physics_util.cpp:5-35) evaluates only the vertices a per-shape
+                                     direction table proves can win (same result bits); 0 = scan every vertex as the reference does */
 } np_option;
 
 typedef struct np_counters {
@@ -287,6 +289,12 @@ int np_device_flush_l2(np_world* w);
 /* ---- self tests of device primitives (used by tests/; cheap) ---------------------------------------- */
 /* order-independent checksum of sinf/cosf over float bit patterns [start, start+count) computed on the device */
 int np_selftest_sincos_hash(np_world* w, uint32_t start, uint64_t count, uint64_t* hash_sin, uint64_t* hash_cos);
+/* n support queries (dirs[n][3], row-major 4x4 world transforms xf16[n][16]) on one shape, each answered by the reference's scan over every
+ * vertex and through the shape's direction table (NP_OPT_SUPPORT_TABLES); used[q] = 1 when the table answered.  The two must agree bit for bit. */
+int np_selftest_support_table(np_world* w, int shape, int n, const float* dirs, const float* xf16, float* out_scan, float* out_table, int32_t* used);
+/* host-side statistics of a shape's direction table: out = { cells per face edge, cells that fall back to the scan, mean candidates per cell,
+ * reach (largest |t|_1 the table is valid for) }.  Returns 1 when the shape has a table, 0 when it has none (fewer than 5 or more than 255 vertices). */
+int np_shape_support_table_info(np_world* w, int shape, float out[4]);
 /* measured non-FMA FP32 issue rate of this device (independent FADD/FMUL chains), in Tflop/s: the roofline
  * denominator of the narrow phase, whose arithmetic may not be contracted into FMAs */
 int np_selftest_fp32_peak(np_world* w, float* tflops);

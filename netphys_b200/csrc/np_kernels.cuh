@@ -36,6 +36,7 @@ struct ShapeView {
     const int* off;        // first vertex of shape s
     const int* cnt;        // vertex count of shape s
     int total_verts;
+    TabView tv;            // support-direction tables (np_narrow.cuh: support_tab); tv.tab == nullptr when the world runs without them
 };
 struct DevCounters {       // mirrors np_counters (all uint64)
     unsigned long long steps, pair_tests, hits, gjk_steps, support_pairs, epa_iters, epa_tri_tests, epa_overflow, candidates, support_verts;
@@ -228,6 +229,8 @@ struct NarrowIn {
     const int* order;                            // pair mode: item t is pair order[t] (pairs grouped by shape-size class, k_pair_order), or null
     const int* cand; const int* cand_off; const int* cand_cnt;   // world mode with a broad phase: per-body ascending candidate lists (null = all j > i)
     const float4* seed;                                          // world mode: [2*body] support along (1,1,1), [2*body+1] along (-1,-1,-1) (k_seed_supports), or null
+    int pf;                    // 1: k_gjk2 prefetches the lines of bodies far ahead in ticket order (NP_PREFETCH=0 switches it off)
+    int rot_known;             // 1: every transform is GetTransform's product of rotations (world bodies, poses): tab_arm skips its orthonormality test
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
     constexpr bool CACHED = WORLD && (G >= 8);      // wide groups read the per-step world-vertex cache (coalesced); narrow ones transform on the fly from shared memory
     const float4* verts = CACHED ? nullptr : stage_shapes(sh, s_dyn, smem_shapes != 0);
     GjkMachine<G, CACHED> m;
-    PairGeom g;
+    PairGeom g; g.cells = sh.tv.cells;
     PairStats st = { 0, 0, 0, 0, 0 };
     unsigned n_tests = 0, n_hits = 0;
     int i = -1, j = 0, jend = 0, cbase = 0, c = 0, cn = 0;
@@ -289,9 +292,9 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
                             g.vb = s.wverts + wv_off[j]; g.nb = sh.cnt[shape_of[j]];
                         } else {
                             load_xf(s.xf, s.cap, i, g.Ra, &g.ta);
-                            int sa = shape_of[i]; g.va = verts + sh.off[sa]; g.na = sh.cnt[sa];
+                            int sa = shape_of[i]; g.va = verts + sh.off[sa]; g.na = sh.cnt[sa]; g.taba = tab_arm(sh.tv, sa, g.Ra, g.ta, in.rot_known != 0);
                             load_xf(s.xf, s.cap, j, g.Rb, &g.tb);
-                            int sb = shape_of[j]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
+                            int sb = shape_of[j]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb]; g.tabb = tab_arm(sh.tv, sb, g.Rb, g.tb, in.rot_known != 0);
                         }
                         m.begin(); have = true;
                     } else if (lead) { hit_j[i] = -1; flags[i] = 0; }
@@ -299,6 +302,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
                     load_xf(in.xf_a, in.n, i, g.Ra, &g.ta); load_xf(in.xf_b, in.n, i, g.Rb, &g.tb);
                     int sa = in.shape_a[i], sb = in.shape_b[i];
                     g.va = verts + sh.off[sa]; g.na = sh.cnt[sa]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
+                    g.taba = tab_arm(sh.tv, sa, g.Ra, g.ta, in.rot_known != 0); g.tabb = tab_arm(sh.tv, sb, g.Rb, g.tb, in.rot_known != 0);
                     m.begin(); have = true;
                 }
             } else exhausted = true;
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
                     have = false;
                 } else if (WORLD && (in.cand ? (++c < cn ? ((j = in.cand[cbase + c]), true) : false) : (++j < jend))) {
                     if (CACHED) { g.vb = s.wverts + wv_off[j]; g.nb = sh.cnt[shape_of[j]]; }
-                    else { load_xf(s.xf, s.cap, j, g.Rb, &g.tb); int sb = shape_of[j]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb]; }
+                    else { load_xf(s.xf, s.cap, j, g.Rb, &g.tb); int sb = shape_of[j]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb]; g.tabb = tab_arm(sh.tv, sb, g.Rb, g.tb, in.rot_known != 0); }
                     m.begin();
                 } else {
                     if (lead) { if (WORLD) hit_j[i] = -1; flags[i] = 0; if (!WORLD) contact[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -394,7 +398,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK1_MINB) k_gjk1(Narrow
     GjkS m;
     m.sm = reinterpret_cast<float*>(s_dyn + (smem_shapes ? sh.total_verts : 0)) + threadIdx.x;
     m.stride = NP_NARROW_THREADS;
-    PairGeom g;
+    PairGeom g; g.cells = sh.tv.cells;
     PairStats st = { 0, 0, 0, 0, 0 };
     unsigned n_tests = 0, n_hits = 0;
     int i = -1, j = 0, jend = 0, cbase = 0, c = 0, cn = 0;
@@ -407,12 +411,12 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK1_MINB) k_gjk1(Narrow
     auto arm_a = [&](int body) {
         const int sa = shape_of[body]; g.na = sh.cnt[sa];
         if (CBIG && g.na >= NP_COOP_MIN) g.va = s.wverts + wv_big[body];
-        else { g.va = verts + sh.off[sa]; load_xf(s.xf, s.cap, body, g.Ra, &g.ta); }
+        else { g.va = verts + sh.off[sa]; load_xf(s.xf, s.cap, body, g.Ra, &g.ta); g.taba = tab_arm(sh.tv, sa, g.Ra, g.ta, in.rot_known != 0); }
     };
     auto arm_b = [&](int body) {
         const int sb = shape_of[body]; g.nb = sh.cnt[sb];
         if (CBIG && g.nb >= NP_COOP_MIN) g.vb = s.wverts + wv_big[body];
-        else { g.vb = verts + sh.off[sb]; load_xf(s.xf, s.cap, body, g.Rb, &g.tb); }
+        else { g.vb = verts + sh.off[sb]; load_xf(s.xf, s.cap, body, g.Rb, &g.tb); g.tabb = tab_arm(sh.tv, sb, g.Rb, g.tb, in.rot_known != 0); }
     };
     m.begin();
     for (;;) {
@@ -429,6 +433,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK1_MINB) k_gjk1(Narrow
                     load_xf(in.xf_a, in.n, i, g.Ra, &g.ta); load_xf(in.xf_b, in.n, i, g.Rb, &g.tb);
                     int sa = in.shape_a[i], sb = in.shape_b[i];
                     g.va = verts + sh.off[sa]; g.na = sh.cnt[sa]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
+                    g.taba = tab_arm(sh.tv, sa, g.Ra, g.ta, in.rot_known != 0); g.tabb = tab_arm(sh.tv, sb, g.Rb, g.tb, in.rot_known != 0);
                     m.begin(); have = true;
                 }
             } else exhausted = true;
@@ -446,8 +451,11 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK1_MINB) k_gjk1(Narrow
             for (int k = 0; k < 9; k++) R[k] = side ? g.Rb[k] : g.Ra[k];
             const V3 t = side ? g.tb : g.ta, dd = side ? neg(m.d) : m.d;
             V3 r = mk(0.0f, 0.0f, 0.0f);
-            if constexpr (COOP) r = support_coop1<CBIG>(want, v, n, R, t, dd);
-            else if (want) r = support<1, false>(v, n, R, t, dd);
+            const unsigned tb_ = side ? g.tabb : g.taba;
+            bool got = false;
+            if (want && tb_ != NP_TAB_NONE) got = support_tab(v, R, t, dd, tb_, g.cells, &r);
+            if constexpr (COOP) { const V3 r2 = support_coop1<CBIG>(want && !got, v, n, R, t, dd); if (!got) r = r2; }
+            else if (want && !got) r = support<1, false>(v, n, R, t, dd);
             if (side) sb = r; else sa = r;
         }
         if (fresh) { const float4 qa = in.seed[2 * (size_t)i], qb = in.seed[2 * (size_t)j + 1]; sa = mk(qa.x, qa.y, qa.z); sb = mk(qb.x, qb.y, qb.z); }
@@ -478,6 +486,198 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK1_MINB) k_gjk1(Narrow
                     if (!WORLD) contact[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     have = false;
                 }
+            }
+        }
+    }
+    if (ctr) flush_stats<1>(ctr, st, n_tests, n_hits, 0u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3, thread per item, third generation: the solves of a block regrouped by simplex size.
+//
+// With support-direction tables a trip's two supports cost a few dozen instructions, and what is left of k_gjk1 is the solve -- a
+// line, a triangle or a tetrahedron depending on how far each lane's pair has come -- executed by 5-7 of a warp's 32 lanes at a time
+// (ncu, profiles/r2_*: three solvers back to back in every warp on every trip).  Here a block runs its trips in lock step:
+//   1. every thread advances ITS pair to the solve: refill, the support pair, the termination tests, the new simplex point (the
+//      simplex lives in the block's shared array, one column per thread, as in k_gjk1);
+//   2. the pending solves are counted and ordered tetrahedra first, then triangles, then lines (ballots + one shared prefix);
+//   3. thread t takes the t-th solve of that order -- ANY thread's column (gjk_solve_col) -- so a warp runs one solver with all its
+//      lanes, and leaves (kept vertices, next direction, status) in shared memory;
+//   4. every thread takes its pair's result back and finishes the trip.
+// Three block barriers per trip; the other resident blocks of the SM fill the gaps.  Results are those of k_gjk1: the same operations
+// on the same operands, only on another lane.
+// ---------------------------------------------------------------------------------------------------
+#define NP_GJK2_EXTRA_WORDS (30 * NP_NARROW_THREADS + 32)      // per block, after the simplices: job word, result word, direction (3), order, counters, transforms (24)
+#ifndef NP_GJK2_MINB
+#define NP_GJK2_MINB 6     // 80 registers, no spills: 24 resident warps per SM (measured on the 1M world: 4 blocks 2.63 ms, 5 2.65, 6 2.57)
+#endif
+template <bool WORLD>
+__global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK2_MINB) k_gjk2(NarrowIn in, ShapeView sh, int smem_shapes, int* __restrict__ ticket, int* __restrict__ hit_j,
+                                                           int* __restrict__ flags, float4* __restrict__ contact, float4* __restrict__ simplex,
+                                                           int* __restrict__ hit_list, int* __restrict__ hit_count, DevCounters* ctr)
+{
+    constexpr int T = NP_NARROW_THREADS, NW = T / 32;
+    extern __shared__ float4 s_dyn[];
+    const float4* verts = stage_shapes(sh, s_dyn, smem_shapes != 0);
+    float* sx = reinterpret_cast<float*>(s_dyn + (smem_shapes ? sh.total_verts : 0));
+    int* jword = reinterpret_cast<int*>(sx + NP_SX_ROWS * T);      // [T] perm | nv << 8 of the thread's pending solve
+    int* jres = jword + T;                                         // [T] kn | ksel << 4 | status << 12
+    float* jdir = reinterpret_cast<float*>(jres + T);              // [3][T] next direction
+    int* jorder = reinterpret_cast<int*>(jdir + 3 * T);            // [T] owner thread of the t-th solve
+    int* jcnt = jorder + T;                                        // [4][NW]: tetrahedra, triangles, lines per warp; [3][w] = warp w still has work
+    float* sxf = reinterpret_cast<float*>(jcnt + 32) + threadIdx.x;   // [24][T] the two transforms of the thread's pair: read twice per trip, so not worth 24 registers
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    GjkS m;
+    m.sm = sx + tid;
+    m.stride = T;
+    PairGeom g; g.cells = sh.tv.cells;
+    PairStats st = { 0, 0, 0, 0, 0 };
+    unsigned n_tests = 0, n_hits = 0;
+    int i = -1, j = 0, jend = 0, cbase = 0, c = 0, cn = 0;
+    bool have = false, exhausted = false;
+    const StoreView& s = in.s;
+    const int* shape_of = s.ints + I_SHAPE * s.cap;
+    const int* island_end = s.ints + I_ISLAND_END * s.cap;
+    auto put_xf = [&](int side, const float* R, V3 tt) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) sxf[(12 * side + k) * T] = R[k];
+        sxf[(12 * side + 9) * T] = tt.x; sxf[(12 * side + 10) * T] = tt.y; sxf[(12 * side + 11) * T] = tt.z;
+    };
+    auto arm_a = [&](int body) {
+        const int sa = shape_of[body]; g.na = sh.cnt[sa];
+        float R[9]; V3 tt;
+        g.va = verts + sh.off[sa]; load_xf(s.xf, s.cap, body, R, &tt); g.taba = tab_arm(sh.tv, sa, R, tt, in.rot_known != 0); put_xf(0, R, tt);
+    };
+    auto arm_b = [&](int body) {
+        const int sb = shape_of[body]; g.nb = sh.cnt[sb];
+        float R[9]; V3 tt;
+        g.vb = verts + sh.off[sb]; load_xf(s.xf, s.cap, body, R, &tt); g.tabb = tab_arm(sh.tv, sb, R, tt, in.rot_known != 0); put_xf(1, R, tt);
+    };
+    m.begin();
+    // A refill is a chain of dependent loads (ticket -> body -> shape and transform -> partner's shape and transform) that the other 31
+    // lanes of the warp wait for; the bodies a ticket maps to are known in advance, so whoever draws ticket t asks the L2 for the lines
+    // ticket t + (everything in flight) will need.
+    const int ahead = (int)(gridDim.x * T) * 2;
+    int pf_body = -1;
+    for (;;) {
+        // ---- 1: own pair up to the solve
+        if (WORLD && pf_body >= 0) {
+            const char* px = reinterpret_cast<const char*>(s.xf) + 48 * (size_t)pf_body;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(px));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(px + 128));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(shape_of + pf_body));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(island_end + pf_body));
+            pf_body = -1;
+        }
+        int t = fetch_ticket<1>(ticket, !have && !exhausted);
+        if (!have && !exhausted) {
+            if (t < in.n) {
+                i = WORLD ? (in.ordered ? s.ints[I_ORDER * s.cap + in.first + t] : t + in.first) : (in.order ? in.order[t] : t);
+                if (WORLD && in.pf) { const int tp = min(t + ahead, in.n - 1); pf_body = in.ordered ? s.ints[I_ORDER * s.cap + in.first + tp] : tp + in.first; }
+                if (WORLD) {
+                    if (in.cand) { cbase = in.cand_off[i]; c = 0; cn = in.cand_cnt[i]; j = cn > 0 ? in.cand[cbase] : 0; jend = cn > 0 ? 0x7fffffff : 0; }
+                    else { j = i + 1; jend = island_end[i]; }
+                    if (j < jend) { arm_a(i); arm_b(j); m.begin(); have = true; }
+                    else { hit_j[i] = -1; flags[i] = 0; }
+                } else {
+                    float Ra[9], Rb[9]; V3 ta, tb;
+                    load_xf(in.xf_a, in.n, i, Ra, &ta); load_xf(in.xf_b, in.n, i, Rb, &tb);
+                    int sa = in.shape_a[i], sb = in.shape_b[i];
+                    g.va = verts + sh.off[sa]; g.na = sh.cnt[sa]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
+                    g.taba = tab_arm(sh.tv, sa, Ra, ta, in.rot_known != 0); g.tabb = tab_arm(sh.tv, sb, Rb, tb, in.rot_known != 0);
+                    put_xf(0, Ra, ta); put_xf(1, Rb, tb);
+                    m.begin(); have = true;
+                }
+            } else exhausted = true;
+        }
+        int cls = 0;                                   // 0: no solve pending; 1 line, 2 triangle, 3 tetrahedron
+        if (have) {
+            V3 sa = mk(0.0f, 0.0f, 0.0f), sb = sa;
+#pragma unroll 1
+            for (int side = 0; side < 2; side++) {
+                const float4* v = side ? g.vb : g.va; const int n = side ? g.nb : g.na;
+                float R[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) R[k] = sxf[(12 * side + k) * T];
+                const V3 tt = mk(sxf[(12 * side + 9) * T], sxf[(12 * side + 10) * T], sxf[(12 * side + 11) * T]), dd = side ? neg(m.d) : m.d;
+                const unsigned tb_ = side ? g.tabb : g.taba;
+                V3 r = mk(0.0f, 0.0f, 0.0f);
+                if (tb_ == NP_TAB_NONE || !support_tab(v, R, tt, dd, tb_, g.cells, &r)) r = support<1, false>(v, n, R, tt, dd);
+                if (side) sb = r; else sa = r;
+            }
+            st.support_pairs++; st.support_verts += (unsigned)(g.na + g.nb);
+            if (m.nv == 0) { m.put(0, sub(sb, sa), sa, sb); m.perm = 0; m.nv = 1; m.kn = 1; }         // :704  p = B - A
+            else m.consume(sa, sb);
+            if (m.status == GjkS::RUN) {                                                             // GjkS::produce, its solve deferred
+                if (m.steps >= NP_GJK_MAX_STEPS) m.status = GjkS::MISS;                              // :710
+                else {
+                    m.steps++; st.gjk_steps++;
+                    if (m.nv == 1) {                                                                 // a point: nothing to solve
+                        m.kn = 1; m.ksel = 0 | (1 << 2) | (2 << 4);
+                        m.d = dir1(m.ldP(m.slot(0)));
+                        if (feq(magsq(m.d), 0.0f)) m.status = GjkS::MISS;
+                    } else { cls = m.nv - 1; jword[tid] = m.perm | (m.nv << 8); }
+                }
+            }
+        }
+        // ---- 2: order the pending solves, largest simplex first
+        const unsigned b3 = __ballot_sync(0xffffffffu, cls == 3), b2 = __ballot_sync(0xffffffffu, cls == 2), b1 = __ballot_sync(0xffffffffu, cls == 1);
+        const unsigned alive = __ballot_sync(0xffffffffu, have || !exhausted);
+        if (lane == 0) { jcnt[0 * NW + warp] = __popc(b3); jcnt[1 * NW + warp] = __popc(b2); jcnt[2 * NW + warp] = __popc(b1); jcnt[3 * NW + warp] = alive != 0u; }
+        __syncthreads();
+        int tot3 = 0, tot2 = 0, tot1 = 0, before = 0, any_alive = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            const int c3 = jcnt[0 * NW + w], c2 = jcnt[1 * NW + w], c1 = jcnt[2 * NW + w];
+            tot3 += c3; tot2 += c2; tot1 += c1; any_alive |= jcnt[3 * NW + w];
+            if (w < warp) before += (cls == 3) ? c3 : ((cls == 2) ? c2 : c1);
+        }
+        if (!any_alive) break;                                                                       // (every thread of the block reads the same words)
+        if (cls) {
+            const unsigned mine = (cls == 3) ? b3 : ((cls == 2) ? b2 : b1);
+            const int base = (cls == 3) ? 0 : ((cls == 2) ? tot3 : tot3 + tot2);
+            jorder[base + before + __popc(mine & ((1u << lane) - 1u))] = tid;
+        }
+        __syncthreads();
+        // ---- 3: the t-th solve, whoever owns it
+        if (tid < tot3 + tot2 + tot1) {
+            const int owner = jorder[tid], word = jword[owner];
+            int kn = 0, ksel = 0 | (1 << 2) | (2 << 4), status = GjkS::RUN; V3 d = mk(0.0f, 0.0f, 0.0f);
+            gjk_solve_col(sx + owner, T, word & 0xff, word >> 8, kn, ksel, d, status);
+            jres[owner] = kn | (ksel << 4) | (status << 12);
+            jdir[owner] = d.x; jdir[T + owner] = d.y; jdir[2 * T + owner] = d.z;
+        }
+        __syncthreads();
+        // ---- 4: back to the own pair
+        if (cls) {
+            const int r = jres[tid];
+            m.kn = r & 15; m.ksel = (r >> 4) & 63; m.status = r >> 12;
+            if (m.status != GjkS::HIT) m.d = mk(jdir[tid], jdir[T + tid], jdir[2 * T + tid]);
+        }
+        if (have && m.status != GjkS::RUN) {
+            n_tests++;
+            if (m.status == GjkS::HIT) {
+                n_hits++;
+                if (WORLD) hit_j[i] = j;
+                flags[i] = NP_PAIR_HIT | (m.seed_alive ? NP_PAIR_SEED_ALIVE : 0);
+                m.write_hit(simplex + (size_t)i * 6);
+                const int hc = (g.na >= NP_COOP_MIN ? 2 : 0) + (g.nb >= NP_COOP_MIN ? 1 : 0);
+                {   // one atomic per class among the lanes that hit in this trip (opportunistic warp aggregation)
+                    const unsigned act = __activemask(), peers = __match_any_sync(act, hc);
+                    const int leader = __ffs(peers) - 1;
+                    int pos = 0;
+                    if (lane == leader) pos = atomicAdd(hit_count + hc, __popc(peers));
+                    pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1u));
+                    hit_list[(size_t)hc * in.n + pos] = i;
+                }
+                have = false;
+            } else if (WORLD && (in.cand ? (++c < cn ? ((j = in.cand[cbase + c]), true) : false) : (++j < jend))) {
+                arm_b(j); m.begin();
+            } else {
+                if (WORLD) hit_j[i] = -1;
+                flags[i] = 0;
+                if (!WORLD) contact[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                have = false;
             }
         }
     }
@@ -587,7 +787,7 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
     constexpr bool FAST = (TIER >= 1) || (G == 32);      // a full warp per pair: O(1)-per-edge horizon extraction
     if (TIER == 2) poly_ptr = poly_from(ar.base + (size_t)(blockIdx.x * GPB + gid) * poly_words_fast(NP_FBIG), NP_FBIG, true);
     else poly_ptr = poly_from((float*)(s_dyn + ((smem_shapes && !CACHED) ? sh.total_verts : 0)) + (size_t)gid * (FAST ? poly_words_fast(FMAX) : poly_words(FMAX)), FMAX, FAST);
-    PairGeom g;
+    PairGeom g; g.cells = sh.tv.cells;
     PairStats st = { 0, 0, 0, 0, 0 }, st0 = st;
     unsigned n_over = 0;
     // TIER 0 reads the GJK hits, NP_HIT_CLASSES lists of in.n entries (see k_gjk); the overflow tiers read one plain list
@@ -623,11 +823,13 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
                         load_xf(s.xf, s.cap, i, g.Ra, &g.ta); load_xf(s.xf, s.cap, j, g.Rb, &g.tb);
                         int sa = s.ints[I_SHAPE * s.cap + i], sb = s.ints[I_SHAPE * s.cap + j];
                         g.va = verts + sh.off[sa]; g.na = sh.cnt[sa]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
+                        g.taba = tab_arm(sh.tv, sa, g.Ra, g.ta, in.rot_known != 0); g.tabb = tab_arm(sh.tv, sb, g.Rb, g.tb, in.rot_known != 0);
                     }
                 } else {
                     load_xf(in.xf_a, in.n, item, g.Ra, &g.ta); load_xf(in.xf_b, in.n, item, g.Rb, &g.tb);
                     int sa = in.shape_a[item], sb = in.shape_b[item];
                     g.va = verts + sh.off[sa]; g.na = sh.cnt[sa]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
+                    g.taba = tab_arm(sh.tv, sa, g.Ra, g.ta, in.rot_known != 0); g.tabb = tab_arm(sh.tv, sb, g.Rb, g.tb, in.rot_known != 0);
                 }
                 const float4* o = simplex + (size_t)item * 6;
                 float4 q0 = o[0], q1 = o[1], q2 = o[2], q3 = o[3], q4 = o[4], q5 = o[5];
@@ -1482,8 +1684,31 @@ __global__ void k_selftest_support(ShapeView sh, int shape, const float* dir, co
 {
     float R[9]; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[3 * r + c] = xf16[4 * r + c];
     V3 t = mk(xf16[3], xf16[7], xf16[11]);
-    V3 r = support<1, false>(sh.verts + sh.off[shape], sh.cnt[shape], R, t, mk(dir[0], dir[1], dir[2]));
+    const V3 d = mk(dir[0], dir[1], dir[2]);
+    const unsigned e = tab_arm(sh.tv, shape, R, t, false);
+    V3 r;
+    if (e == NP_TAB_NONE || !support_tab(sh.verts + sh.off[shape], R, t, d, e, sh.tv.cells, &r))
+        r = support<1, false>(sh.verts + sh.off[shape], sh.cnt[shape], R, t, d);
     out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+// n support queries on one shape answered twice: by the reference's scan and through the direction table.  used[q] = 1 when the table
+// answered (0: the body or the direction was outside the table's guarantees and the scan ran)
+__global__ void __launch_bounds__(128) k_selftest_support_table(ShapeView sh, int shape, int n, const float* __restrict__ dirs, const float* __restrict__ xf16,
+                                                                float* __restrict__ out_scan, float* __restrict__ out_table, int* __restrict__ used)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const float* x = xf16 + 16 * (size_t)q;
+    float R[9]; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[3 * r + c] = x[4 * r + c];
+    const V3 t = mk(x[3], x[7], x[11]), d = mk(dirs[3 * q], dirs[3 * q + 1], dirs[3 * q + 2]);
+    const float4* v = sh.verts + sh.off[shape];
+    const V3 a = support<1, false>(v, sh.cnt[shape], R, t, d);
+    const unsigned e = tab_arm(sh.tv, shape, R, t, false);
+    V3 b = a; int u = 0;
+    if (e != NP_TAB_NONE && support_tab(v, R, t, d, e, sh.tv.cells, &b)) u = 1; else b = a;
+    out_scan[3 * q] = a.x; out_scan[3 * q + 1] = a.y; out_scan[3 * q + 2] = a.z;
+    out_table[3 * q] = b.x; out_table[3 * q + 1] = b.y; out_table[3 * q + 2] = b.z;
+    used[q] = u;
 }
 
 }  // namespace np

@@ -37,11 +37,14 @@ enum PairFlags { NP_PAIR_HIT = 1, NP_PAIR_SUCCESS = 2, NP_PAIR_OVERFLOW = 4, NP_
 #define NP_HITJ_SUCCESS 0x40000000
 __host__ __device__ __forceinline__ int hitj_body(int v) { return v < 0 ? v : (v & ~NP_HITJ_SUCCESS); }
 
+#define NP_TAB_NONE 0xffffffffu
 struct PairGeom {
     float Ra[9], Rb[9];
     V3 ta, tb;
     const float4* va; const float4* vb;   // shape-local vertices (x,y,z,-)
     int na, nb;
+    unsigned taba = NP_TAB_NONE, tabb = NP_TAB_NONE;   // support-direction table of each side (tab_arm), NP_TAB_NONE = scan every vertex
+    const uint2* cells = nullptr;
 };
 
 struct PairStats { unsigned gjk_steps, support_pairs, support_verts, epa_iters, epa_tri_tests; };
@@ -154,6 +157,88 @@ NP_D V3 support(const float4* __restrict__ v, int n, const float* R, V3 t, V3 d)
     if (imin >= 0x7fffffffu) return mk(0.0f, 0.0f, 0.0f);
     const float4 q = v[imin];
     return CACHED ? mk(q.x, q.y, q.z) : xf_point(R, t, mk(q.x, q.y, q.z));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Support-direction tables: the reference's vertex scan (physics_util.cpp:5-35) answered from a handful of candidates, same bits.
+//
+// The scan returns the FIRST vertex k whose binary32 value f_k = fl(d . fl(R p_k + t)) is the largest.  Write E_k for the same
+// expression in real arithmetic.  Every f_k is within delta = 7.001 u |d|_1 (rho r + |t|_inf) of E_k (u = 2^-24: four roundings per
+// transformed coordinate, three for the dot product; r = largest |p_k|, rho = largest row norm of R), so the winner -- and every vertex
+// that ties with it -- satisfies E_k >= max_j E_j - 2 delta.  E_k - E_j = (R^T d) . (p_k - p_j) does not involve t: which vertices can
+// win depends only on the DIRECTION of R^T d in shape space and on a margin mu >= 2 delta / |R^T d| (r/256).  np_suptab.h tabulates, per
+// shape, for every cell of a cube map of directions the set { k : u . p_k >= max_j u . p_j - mu for some u in the (dilated) cell },
+// at most 7 vertex indices in ascending order.  A support call transforms the direction (any rounding: it only picks the cell, and
+// the cells are dilated by more than that error), reads one 8-byte cell and evaluates ITS candidates with the reference's own
+// expression in index order under the same strict '>': the winner is the scan's winner, bit for bit, because the scan's winner is
+// among the candidates and the candidates are visited in the scan's order.
+//
+// The margin is only valid while 2 delta / |R^T d| <= mu: tab_arm (once per armed body) requires R^T R = I within 2^-10 and
+// |t|_inf + r within the reach stored with the shape, and a call whose direction is not finite or outside [1e-18, 1e18] -- or whose cell
+// holds more than 7 candidates -- falls back to the scan.  161 of an icosphere's 162 vertices are never touched.
+// ---------------------------------------------------------------------------------------------------
+struct TabView { const unsigned* tab; const float* tlim; const uint2* cells; };   // per shape: cell offset | log2(N) << 28; reach; all cells
+NP_D unsigned tab_arm(const TabView& tv, int shape, const float* R, V3 t, bool rot_known)
+{
+    if (!tv.tab) return NP_TAB_NONE;
+    const unsigned e = tv.tab[shape];
+    if (e == NP_TAB_NONE) return e;
+    const float tol = 0.0009765625f;
+    const float ax = fabsf(t.x), ay = fabsf(t.y), az = fabsf(t.z);
+    bool ok = (ax + ay + az) <= 3.0e38f && fmaxf(ax, fmaxf(ay, az)) <= tv.tlim[shape];             // (the sum catches a NaN, which fmaxf would drop)
+    // rot_known: R came out of make_transform (sines and cosines multiplied together): orthonormal to ~1e-6 unless an angle was not
+    // finite, and then every entry that angle touches is a NaN -- the sum below finds it
+    if (rot_known) return (ok && (R[0] + R[1] + R[2] + R[3] + R[4] + R[5] + R[6] + R[7] + R[8]) <= 9.0f) ? e : NP_TAB_NONE;
+    ok = ok && fabsf(R[0] * R[0] + R[3] * R[3] + R[6] * R[6] - 1.0f) <= tol && fabsf(R[1] * R[1] + R[4] * R[4] + R[7] * R[7] - 1.0f) <= tol
+            && fabsf(R[2] * R[2] + R[5] * R[5] + R[8] * R[8] - 1.0f) <= tol && fabsf(R[0] * R[1] + R[3] * R[4] + R[6] * R[7]) <= tol
+            && fabsf(R[0] * R[2] + R[3] * R[5] + R[6] * R[8]) <= tol && fabsf(R[1] * R[2] + R[4] * R[5] + R[7] * R[8]) <= tol;
+    return ok ? e : NP_TAB_NONE;
+}
+// true: *out is the support point (world space, the reference's bits).  false: the caller scans.
+NP_D bool support_tab(const float4* __restrict__ v, const float* R, V3 t, V3 d, unsigned e, const uint2* __restrict__ cells, V3* out)
+{
+    const float ux = __fmaf_rn(R[6], d.z, __fmaf_rn(R[3], d.y, R[0] * d.x));                       // R^T d
+    const float uy = __fmaf_rn(R[7], d.z, __fmaf_rn(R[4], d.y, R[1] * d.x));
+    const float uz = __fmaf_rn(R[8], d.z, __fmaf_rn(R[5], d.y, R[2] * d.x));
+    const float ax = fabsf(ux), ay = fabsf(uy), az = fabsf(uz);
+    const float sum = ax + ay + az;
+    if (!(sum >= 1e-18f && sum <= 1e18f)) return false;                                           // zero, denormal, huge, inf or NaN direction
+    float major, a, b; int f;
+    if (ax >= ay && ax >= az) { major = ux; a = uy; b = uz; f = 0; }
+    else if (ay >= az) { major = uy; a = uz; b = ux; f = 2; }
+    else { major = uz; a = ux; b = uy; f = 4; }
+    f += (major < 0.0f) ? 1 : 0;
+    const int lg = (int)(e >> 28), nm1 = (1 << lg) - 1;
+    const float half_n = (float)(1 << lg) * 0.5f;
+    const float sc = __fdividef(half_n, fabsf(major));
+    const int ia = min(max((int)__fmaf_rn(a, sc, half_n), 0), nm1), ib = min(max((int)__fmaf_rn(b, sc, half_n), 0), nm1);
+    const uint2 cell = __ldg(cells + (e & 0x0fffffffu) + ((((unsigned)f << lg) + (unsigned)ib) << lg) + (unsigned)ia);
+    const int cnt = (int)(cell.y >> 24);
+    if (cnt > 7) return false;
+    unsigned long long bits = (unsigned long long)cell.x | ((unsigned long long)cell.y << 32);
+    float bd = -INFINITY; V3 best = mk(0.0f, 0.0f, 0.0f); bool any = false;
+    for (int c = 0; c < cnt; c++) {
+        const float4 q = v[(int)(bits & 0xffu)]; bits >>= 8;
+        const V3 wp = xf_point(R, t, mk(q.x, q.y, q.z));
+        const float dp = dot(d, wp);
+        if (dp > bd) { bd = dp; best = wp; any = true; }
+    }
+    if (!any) return false;
+    *out = best;
+    return true;
+}
+// one side's support of a pair: from the table when the side is armed with one, else the scan
+template <int G, bool CACHED>
+NP_D V3 support_a(const PairGeom& g, V3 d)
+{
+    if (!CACHED && g.taba != NP_TAB_NONE && (G == 1 || g.na >= 12 * G)) { V3 r; if (support_tab(g.va, g.Ra, g.ta, d, g.taba, g.cells, &r)) return r; }   // (a group scans a small shape faster than it looks one up)
+    return support<G, CACHED>(g.va, g.na, g.Ra, g.ta, d);
+}
+template <int G, bool CACHED>
+NP_D V3 support_b(const PairGeom& g, V3 d)
+{
+    if (!CACHED && g.tabb != NP_TAB_NONE && (G == 1 || g.nb >= 12 * G)) { V3 r; if (support_tab(g.vb, g.Rb, g.tb, d, g.tabb, g.cells, &r)) return r; }
+    return support<G, CACHED>(g.vb, g.nb, g.Rb, g.tb, d);
 }
 
 // Thread-per-pair kernels: the lanes of a warp hold different pairs, and a per-lane vertex loop runs as long as the LARGEST shape in
@@ -401,8 +486,8 @@ struct GjkMachine {
 #ifdef NP_TIMELINE
         const long long c0 = clock64();
 #endif
-        V3 sa = support<G, CACHED>(g.va, g.na, g.Ra, g.ta, d);
-        V3 sb = support<G, CACHED>(g.vb, g.nb, g.Rb, g.tb, neg(d));
+        V3 sa = support_a<G, CACHED>(g, d);
+        V3 sb = support_b<G, CACHED>(g, neg(d));
 #ifdef NP_TIMELINE
         const long long c1 = clock64(); cyc[0] += c1 - c0;
 #endif
@@ -418,6 +503,64 @@ struct GjkMachine {
 #endif
     }
 };
+
+// The solve half of a GJK step (SolveLine / SolveTriangle / SolveTetrahedron, the containment test and GetSearchDirection,
+// collision_detection.cpp:18-259, 648-658) on a simplex held in ONE COLUMN of a block's shared simplex array -- any column, not only
+// the calling thread's own: k_gjk2 hands the block's pending solves out grouped by simplex size, so that a warp runs one solver.
+// in: perm (logical vertex k sits in slot (perm >> 2k) & 3), nv.  out: kn / ksel (the vertices the solve keeps), the next direction, status.
+NP_D void gjk_solve_col(const float* col, int stride, int perm, int nv, int& kn, int& ksel, V3& d, int& status)
+{
+    auto ldP = [&](int k) { const int s3 = 3 * ((perm >> (2 * k)) & 3); return mk(col[s3 * stride], col[(s3 + 1) * stride], col[(s3 + 2) * stride]); };
+    kn = nv; int k0 = 0, k1 = 1, k2 = 2;
+    if (nv == 2) {                                                                                // SolveLine :18-54
+        float u;
+        int r = closest_line(ldP(0), ldP(1), &u);
+        if (r == LINE_A) { kn = 1; }
+        else if (r == LINE_B) { kn = 1; k0 = 1; }
+    } else if (nv == 3) {                                                                         // SolveTriangle :56-118
+        float u, v;
+        int r = closest_triangle(ldP(0), ldP(1), ldP(2), &u, &v);
+        switch (r) {
+        case TRI_A: kn = 1; break;
+        case TRI_B: kn = 1; k0 = 1; break;
+        case TRI_C: kn = 1; k0 = 2; break;
+        case TRI_AB: kn = 2; break;
+        case TRI_AC: kn = 2; k1 = 2; break;
+        case TRI_BC: kn = 2; k0 = 1; k1 = 2; break;
+        default: break;
+        }
+    } else if (nv == 4) {                                                                         // SolveTetrahedron :121-259
+        float u, v, w;
+        int r = closest_tetra(ldP(0), ldP(1), ldP(2), ldP(3), &u, &v, &w);
+        switch (r) {
+        case TET_A: kn = 1; break;
+        case TET_B: kn = 1; k0 = 1; break;
+        case TET_C: kn = 1; k0 = 2; break;
+        case TET_D: kn = 1; k0 = 3; break;
+        case TET_AB: kn = 2; break;
+        case TET_AC: kn = 2; k1 = 2; break;
+        case TET_AD: kn = 2; k1 = 3; break;
+        case TET_BC: kn = 2; k0 = 1; k1 = 2; break;
+        case TET_BD: kn = 2; k0 = 1; k1 = 3; break;
+        case TET_CD: kn = 2; k0 = 2; k1 = 3; break;
+        case TET_ABC: kn = 3; break;
+        case TET_ABD: kn = 3; k2 = 3; break;
+        case TET_ACD: kn = 3; k1 = 2; k2 = 3; break;
+        case TET_BCD: kn = 3; k0 = 1; k1 = 2; k2 = 3; break;
+        default: break;                    // ABCD, or None under NDEBUG (:255): four points stay => overlap
+        }
+    }
+    if (kn == 4) { status = 2 /* HIT */; return; }                                                // :648-652
+    ksel = k0 | (k1 << 2) | (k2 << 4);
+    const V3 q0 = ldP(k0);
+    if (kn == 1) d = dir1(q0);
+    else {
+        const V3 q1 = ldP(k1);
+        if (kn == 2) d = dir2(q0, q1);
+        else d = dir3(q0, q1, ldP(k2));
+    }
+    if (feq(magsq(d), 0.0f)) status = 1 /* MISS */;                                               // :655-658
+}
 
 // ---------------------------------------------------------------------------------------------------
 // GJK, thread per pair, simplex in SHARED memory (k_gjk1).  The register-resident machine above needs 36 floats of
@@ -453,55 +596,7 @@ struct GjkS {
     {
         if (steps >= NP_GJK_MAX_STEPS) { status = MISS; return; }                                 // :710
         steps++; st.gjk_steps++;
-        kn = nv; int k0 = 0, k1 = 1, k2 = 2;
-        if (nv == 2) {                                                                            // SolveLine :18-54
-            float u;
-            int r = closest_line(ldP(slot(0)), ldP(slot(1)), &u);
-            if (r == LINE_A) { kn = 1; }
-            else if (r == LINE_B) { kn = 1; k0 = 1; }
-        } else if (nv == 3) {                                                                     // SolveTriangle :56-118
-            float u, v;
-            int r = closest_triangle(ldP(slot(0)), ldP(slot(1)), ldP(slot(2)), &u, &v);
-            switch (r) {
-            case TRI_A: kn = 1; break;
-            case TRI_B: kn = 1; k0 = 1; break;
-            case TRI_C: kn = 1; k0 = 2; break;
-            case TRI_AB: kn = 2; break;
-            case TRI_AC: kn = 2; k1 = 2; break;
-            case TRI_BC: kn = 2; k0 = 1; k1 = 2; break;
-            default: break;
-            }
-        } else if (nv == 4) {                                                                     // SolveTetrahedron :121-259
-            float u, v, w;
-            int r = closest_tetra(ldP(slot(0)), ldP(slot(1)), ldP(slot(2)), ldP(slot(3)), &u, &v, &w);
-            switch (r) {
-            case TET_A: kn = 1; break;
-            case TET_B: kn = 1; k0 = 1; break;
-            case TET_C: kn = 1; k0 = 2; break;
-            case TET_D: kn = 1; k0 = 3; break;
-            case TET_AB: kn = 2; break;
-            case TET_AC: kn = 2; k1 = 2; break;
-            case TET_AD: kn = 2; k1 = 3; break;
-            case TET_BC: kn = 2; k0 = 1; k1 = 2; break;
-            case TET_BD: kn = 2; k0 = 1; k1 = 3; break;
-            case TET_CD: kn = 2; k0 = 2; k1 = 3; break;
-            case TET_ABC: kn = 3; break;
-            case TET_ABD: kn = 3; k2 = 3; break;
-            case TET_ACD: kn = 3; k1 = 2; k2 = 3; break;
-            case TET_BCD: kn = 3; k0 = 1; k1 = 2; k2 = 3; break;
-            default: break;                    // ABCD, or None under NDEBUG (:255): four points stay => overlap
-            }
-        }
-        if (kn == 4) { status = HIT; return; }                                                    // :648-652
-        ksel = k0 | (k1 << 2) | (k2 << 4);
-        const V3 q0 = ldP(slot(k0));
-        if (kn == 1) d = dir1(q0);
-        else {
-            const V3 q1 = ldP(slot(k1));
-            if (kn == 2) d = dir2(q0, q1);
-            else d = dir3(q0, q1, ldP(slot(k2)));
-        }
-        if (feq(magsq(d), 0.0f)) status = MISS;                                                   // :655-658
+        gjk_solve_col(sm, stride, perm, nv, kn, ksel, d, status);
     }
     NP_D void consume(V3 sa, V3 sb)
     {
@@ -879,8 +974,8 @@ struct EpaMachine {
         long long c1 = clock64(); cyc[0] += c1 - c0;
 #endif
         if (done) return;
-        V3 sa = support<G, CACHED>(g.va, g.na, g.Ra, g.ta, d);
-        V3 sb = support<G, CACHED>(g.vb, g.nb, g.Rb, g.tb, neg(d));
+        V3 sa = support_a<G, CACHED>(g, d);
+        V3 sb = support_b<G, CACHED>(g, neg(d));
 #ifdef NP_TIMELINE
         long long c2 = clock64(); cyc[1] += c2 - c1;
 #endif

@@ -6,6 +6,7 @@
 // There is no CPU execution path: without a device np_world_create fails.
 #include "../../include/netphys_b200.h"
 #include "np_kernels.cuh"
+#include "np_suptab.h"
 
 #include <algorithm>
 #include <dlfcn.h>
@@ -13,6 +14,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -26,7 +30,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
         if (e_ != cudaSuccess) return fail(NP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
     } while (0)
 
-struct HostShape { std::vector<float> xyz; bool dead = false; };
+struct HostShape { std::vector<float> xyz; bool dead = false; int tab_state = 0 /* 0 not built, 1 built, -1 none */; SupTable tab; };
 struct HostBody { np_static_physics_data sd; int shape; int island; int enabled = 1; float pending_force[3] = { 0.f, 0.f, 0.f }; };
 struct StepGraph { uint32_t dt_bits; void* snap; uint32_t guid; int kind; cudaGraphExec_t exec; unsigned long long launches; };   // one captured Physics_Update
 struct CommandFrame { unsigned id; double time_ms; std::vector<np_snapshot_object> objects; };      // world_s.cpp:12-17
@@ -56,6 +60,7 @@ struct np_world {
     float *d_state = nullptr, *d_cst = nullptr, *d_xf = nullptr;
     int* d_ints = nullptr;
     float4* d_verts = nullptr; int *d_soff = nullptr, *d_scnt = nullptr; int total_verts = 0;
+    unsigned* d_tab = nullptr; float* d_tlim = nullptr; uint2* d_cells = nullptr; bool tables_on = true;   // support-direction tables (np_suptab.h)
     // per-step scratch
     int *d_hit_j = nullptr, *d_cflags = nullptr; float4* d_contact = nullptr;
     // sharded pair search (np_world_set_shard): this process searches bodies [shard_first, shard_first + shard_count); the per-body
@@ -75,8 +80,10 @@ struct np_world {
     int g_gjk_env = 0, g_epa_env = 0; // NP_G_GJK / NP_G_EPA overrides (tuning)
     int order_on = 1; bool order_dirty = true;   // NP_ORDER=0: search bodies in index order (tuning)
     int fuse_on = 1;      // NP_FUSE=0: np_world_step_n runs plain steps (A/B)
+    int tab_min_verts = 5;    // NP_TAB_MIN: shapes with fewer vertices are scanned (tuning)
+    int gjk2_on = 1;          // NP_GJK2=0: k_gjk1 (every lane solves its own simplex) instead of k_gjk2
     int gjk1_old = 0, cbig_on = 0, epa_first = 1, seed_on = 0;   // NP_SEED=1: per-body table of DetectCollision's seed supports (measured slower: 4.01 vs 3.90 ms)   // NP_GJK1_OLD=1: round-1 register-simplex kernel; NP_CBIG=1: large-body vertex cache for the cooperative supports (measured slower: 9 GB of DRAM reads per step); NP_EPA_FIRST=0 (tuning, A/B)
-    bool coop = false; int coop_env = -1;   // large and small shapes mixed: warp-cooperative supports in the narrow kernels (NP_COOP=0/1 overrides)
+    bool coop_scan = false, coop_tab = false; int coop_env = -1;   // large and small shapes mixed: warp-cooperative supports in the narrow kernels (NP_COOP=0/1 overrides)
     // NCCL (np_comm_*): communicator, its high-priority stream, the double-buffered snapshot gather, the sharded step's record arrays
     ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
     cudaStream_t comm_stream = nullptr;
@@ -101,7 +108,31 @@ struct np_world {
 
 // ------------------------------------------------------------------------------------------------ helpers
 static StoreView view(np_world* w) { StoreView s; s.n = (int)w->bodies.size(); s.cap = w->cap; s.state = w->d_state; s.cst = w->d_cst; s.xf = w->d_xf; s.ints = w->d_ints; s.wverts = w->d_wverts; s.ext = w->d_ext; return s; }
-static ShapeView sview(np_world* w) { ShapeView s; s.verts = w->d_verts; s.off = w->d_soff; s.cnt = w->d_scnt; s.total_verts = w->total_verts; return s; }
+// tables depend on the vertex list only: worlds of one process that create the same shapes (every test, every rank-local world) share them
+static bool cached_support_table(const std::vector<float>& xyz, SupTable& out)
+{
+    static std::mutex mu; static std::map<std::vector<uint32_t>, std::shared_ptr<SupTable>> cache;     // keyed by the coordinates' bits
+    std::lock_guard<std::mutex> lock(mu);
+    std::vector<uint32_t> key(xyz.size());
+    if (!xyz.empty()) memcpy(key.data(), xyz.data(), sizeof(float) * xyz.size());
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        auto t = std::make_shared<SupTable>();
+        if (!build_support_table(xyz, *t)) t.reset();
+        if (cache.size() >= 4096) cache.clear();
+        it = cache.emplace(std::move(key), t).first;
+    }
+    if (!it->second) return false;
+    out = *it->second;
+    return true;
+}
+static bool coop_on(const np_world* w) { return w->coop_env >= 0 ? w->coop_env != 0 : (w->tables_on ? w->coop_tab : w->coop_scan); }
+static ShapeView sview(np_world* w)
+{
+    ShapeView s; s.verts = w->d_verts; s.off = w->d_soff; s.cnt = w->d_scnt; s.total_verts = w->total_verts;
+    s.tv.tab = w->tables_on ? w->d_tab : nullptr; s.tv.tlim = w->d_tlim; s.tv.cells = w->d_cells;
+    return s;
+}
 enum { Z_GJK_TICKET = 0, Z_EPA_TICKET, Z_MID_COUNT, Z_MID_TICKET, Z_BIG_COUNT, Z_BIG_TICKET, Z_HIT_COUNT = 8 /* NP_HIT_CLASSES counters */, Z_PAIR_CLASS = 12 /* 9 counts + 9 cursors */,
        Z_HIT2_COUNT = 32 /* NP_HIT_CLASSES counters: hits that k_epa_first passes on to k_epa */, NP_ZERO_INTS = 64 };
 static int* hitj(np_world* w) { return w->x_hit_j ? w->x_hit_j : w->d_hit_j; }
@@ -252,6 +283,22 @@ static int ensure_device(np_world* w)
             CU(cudaMemcpyAsync(w->d_soff, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, w->stream));
             CU(cudaMemcpyAsync(w->d_scnt, cnt.data(), sizeof(int) * cnt.size(), cudaMemcpyHostToDevice, w->stream));
         }
+        // support-direction tables: built once per shape, concatenated
+        cudaFree(w->d_tab); cudaFree(w->d_tlim); cudaFree(w->d_cells); w->d_tab = nullptr; w->d_tlim = nullptr; w->d_cells = nullptr;
+        std::vector<unsigned> tab; std::vector<float> tlim; std::vector<uint64_t> cells;
+        for (auto& s : w->shapes) {
+            if (s.tab_state == 0) s.tab_state = (!s.dead && cached_support_table(s.xyz, s.tab)) ? 1 : -1;
+            if (s.tab_state == 1 && (int)(s.xyz.size() / 3) >= w->tab_min_verts && cells.size() + s.tab.cells.size() < (1u << 28)) {
+                tab.push_back((unsigned)cells.size() | ((unsigned)s.tab.log_n << 28)); tlim.push_back(s.tab.tlim);
+                cells.insert(cells.end(), s.tab.cells.begin(), s.tab.cells.end());
+            } else { tab.push_back(NP_TAB_NONE); tlim.push_back(0.0f); }
+        }
+        CU(cudaMalloc((void**)&w->d_tab, sizeof(unsigned) * ns)); CU(cudaMalloc((void**)&w->d_tlim, sizeof(float) * ns)); CU(cudaMalloc((void**)&w->d_cells, sizeof(uint64_t) * std::max<size_t>(cells.size(), 1)));
+        if (!tab.empty()) {
+            CU(cudaMemcpyAsync(w->d_tab, tab.data(), sizeof(unsigned) * tab.size(), cudaMemcpyHostToDevice, w->stream));
+            CU(cudaMemcpyAsync(w->d_tlim, tlim.data(), sizeof(float) * tlim.size(), cudaMemcpyHostToDevice, w->stream));
+        }
+        if (!cells.empty()) CU(cudaMemcpyAsync(w->d_cells, cells.data(), sizeof(uint64_t) * cells.size(), cudaMemcpyHostToDevice, w->stream));
         CU(cudaStreamSynchronize(w->stream));
         w->dirty_shapes = false;
     }
@@ -297,9 +344,14 @@ static int ensure_device(np_world* w)
         ints[I_HANDLE * cap + i] = w->handle_of_slot[i];
     }
     {   // large and small shapes side by side (and the large ones a minority): the thread-per-pair kernels serve large supports warp-wide
-        long long big = 0;
-        for (int i = 0; i < n; i++) big += (w->shapes[w->bodies[i].shape].xyz.size() / 3 >= NP_COOP_MIN) ? 1 : 0;
-        w->coop = w->coop_env >= 0 ? w->coop_env != 0 : (big > 0 && big * 100 <= (long long)n * 35);
+        // (a large shape with a support-direction table is answered per lane from its table: it does not count while tables are on)
+        long long big = 0, big_untabled = 0;
+        for (int i = 0; i < n; i++) {
+            const HostShape& hs = w->shapes[w->bodies[i].shape];
+            if (hs.xyz.size() / 3 >= NP_COOP_MIN) { big++; if (hs.tab_state != 1 || (int)(hs.xyz.size() / 3) < w->tab_min_verts) big_untabled++; }
+        }
+        w->coop_scan = big > 0 && big * 100 <= (long long)n * 35;
+        w->coop_tab = big_untabled > 0 && big_untabled * 100 <= (long long)n * 35;
     }
     size_t wv_total = 0;
     for (int i = 0; i < n; i++) {
@@ -378,12 +430,13 @@ static int launch_gjk(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevC
         if (!w->gjk1_old) {
             smem += kSimplexSmem;
             kern = k_gjk1<WORLD, false, false>;
-            if (w->coop) kern = k_gjk1<WORLD, true, false>;
+            if (coop_on(w)) kern = k_gjk1<WORLD, true, false>;
             if constexpr (WORLD) {
-                if (w->coop && cache_mode(w, in.n) == CACHE_BIG) kern = k_gjk1<true, true, true>;
-                else if (in.seed) kern = w->coop ? k_gjk1<true, true, false, true> : k_gjk1<true, false, false, true>;
+                if (coop_on(w) && cache_mode(w, in.n) == CACHE_BIG) kern = k_gjk1<true, true, true>;
+                else if (in.seed) kern = coop_on(w) ? k_gjk1<true, true, false, true> : k_gjk1<true, false, false, true>;
             }
-        } else if constexpr (WORLD) { if (w->coop) kern = k_gjk<G, WORLD, true>; }
+            if (w->gjk2_on && !coop_on(w) && !in.seed) { kern = k_gjk2<WORLD>; smem += sizeof(int) * NP_GJK2_EXTRA_WORDS; }      // solves regrouped by simplex size
+        } else if constexpr (WORLD) { if (coop_on(w)) kern = k_gjk<G, WORLD, true>; }
     }
     int blocks = persistent_blocks(w, kern, smem, in.n, G);
     kern<<<blocks, NP_NARROW_THREADS, smem, w->stream>>>(in, sview(w), shapes_in_smem(w) ? 1 : 0, b.zero + Z_GJK_TICKET, b.hit_j, b.flags, b.contact, b.simplex,
@@ -460,6 +513,8 @@ static void setup_kernels()
     cudaFuncSetAttribute(k_seed_supports, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_gjk1<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_gjk1<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_gjk2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + sizeof(int) * NP_GJK2_EXTRA_WORDS);
+    cudaFuncSetAttribute(k_gjk2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + sizeof(int) * NP_GJK2_EXTRA_WORDS);
 }
 // supported group widths: GJK {1, 8, 32}, EPA {1, 4, 8, 32} (other requests round to the nearest supported one)
 template <bool WORLD>
@@ -485,7 +540,7 @@ static int cache_mode(np_world* w, long long items)
     if (items <= 0) return CACHE_NONE;
     const int gg = pick_group(w, items, w->g_gjk_env, false), ge = pick_group(w, items, w->g_epa_env, true);
     if (gg >= 8 || ge >= 8) return CACHE_ALL;
-    if (gg <= 1 && w->coop && w->cbig_on && !w->gjk1_old) return CACHE_BIG;
+    if (gg <= 1 && coop_on(w) && w->cbig_on && !w->gjk1_old) return CACHE_BIG;
     return CACHE_NONE;
 }
 // the world-vertex cache is allocated the first time a step's kernels read it (never inside a stream capture); on failure nothing changes
@@ -591,7 +646,7 @@ static int enqueue_search(np_world* w, float dt, bool timed, bool integrate = tr
     if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[2], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     CU(cudaMemsetAsync(w->d_zero, 0, sizeof(int) * (NP_ZERO_INTS + (size_t)w->cap), w->stream));        // counters, tickets and the incoming-list heads
     if (count > 0) {
-        NarrowIn in; memset(&in, 0, sizeof in); in.world = 1; in.n = count; in.first = first; in.s = s;
+        NarrowIn in; memset(&in, 0, sizeof in); in.world = 1; in.n = count; in.first = first; in.s = s; in.rot_known = 1; in.pf = getenv("NP_PREFETCH") ? atoi(getenv("NP_PREFETCH")) : 1;
         in.ordered = w->order_on;
         if (w->broadphase != NP_BROADPHASE_EXACT) { in.cand = w->grid.cand; in.cand_off = w->grid.cand_off; in.cand_cnt = w->grid.cand_cnt; }
         if (w->seed_on && !w->gjk1_old && cache != CACHE_BIG && pick_group(w, count, w->g_gjk_env, false) <= 1) {      // thread-per-body search: tabulate the seed supports once per body
@@ -673,6 +728,9 @@ np_world* np_world_create(int device)
     if (const char* e = getenv("NP_EPA_FIRST")) w->epa_first = atoi(e) != 0;
     if (const char* e = getenv("NP_SEED")) w->seed_on = atoi(e) != 0;
     if (const char* e = getenv("NP_FUSE")) w->fuse_on = atoi(e) != 0;
+    if (const char* e = getenv("NP_TABLES")) w->tables_on = atoi(e) != 0;
+    if (const char* e = getenv("NP_GJK2")) w->gjk2_on = atoi(e) != 0;
+    if (const char* e = getenv("NP_TAB_MIN")) w->tab_min_verts = atoi(e);
     if (cudaMalloc((void**)&w->d_ctr, sizeof(DevCounters)) != cudaSuccess || ensure_arena(w) != NP_OK) { fail(NP_ERR_CUDA, "cannot allocate device scratch"); np_world_destroy(w); return nullptr; }
     cudaMemsetAsync(w->d_ctr, 0, sizeof(DevCounters), w->stream);
     return w;
@@ -686,7 +744,7 @@ void np_world_destroy(np_world* w)
     drop_graph(w); free_store(w); cudaFree(w->d_ext);
     cudaFree(w->d_wverts); w->d_wverts = nullptr; w->wverts_cap = 0;
     cudaFree(w->d_aos); w->d_aos = nullptr; w->d_aos_bytes = 0;
-    cudaFree(w->d_verts); cudaFree(w->d_soff); cudaFree(w->d_scnt); cudaFree(w->d_ctr); cudaFree(w->d_flush); cudaFree(w->d_grid_ints); cudaFree(w->d_grid_f);
+    cudaFree(w->d_verts); cudaFree(w->d_soff); cudaFree(w->d_scnt); cudaFree(w->d_tab); cudaFree(w->d_tlim); cudaFree(w->d_cells); cudaFree(w->d_ctr); cudaFree(w->d_flush); cudaFree(w->d_grid_ints); cudaFree(w->d_grid_f);
     cudaFree(w->arena.base);
     if (w->h_stage) cudaFreeHost(w->h_stage);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
@@ -704,6 +762,7 @@ int np_world_set_option(np_world* w, int option, int64_t value)
     case NP_OPT_COUNTERS: w->counters_on = value ? 1 : 0; drop_graph(w); return NP_OK;
     case NP_OPT_SNAPSHOT_EACH_STEP: w->snapshot_each_step = value ? 1 : 0; drop_graph(w); return NP_OK;
     case NP_OPT_PHASE_TIMING: w->phase_timing = value ? 1 : 0; drop_graph(w); return NP_OK;
+    case NP_OPT_SUPPORT_TABLES: w->tables_on = value != 0; drop_graph(w); return NP_OK;
     default: return fail(NP_ERR_INVALID, "unknown option");
     }
 }
@@ -1158,7 +1217,7 @@ static int run_pairs(np_world* w, int n, const int* d_sa, const float* d_pa, con
         CU(cudaGetLastError()); CU(cudaFreeAsync(d, w->stream));
         return NP_OK;
     }
-    NarrowIn in; memset(&in, 0, sizeof in); in.world = 0; in.n = n; in.s = view(w);
+    NarrowIn in; memset(&in, 0, sizeof in); in.world = 0; in.n = n; in.s = view(w); in.rot_known = (d_xa == nullptr && d_xb == nullptr) ? 1 : 0;
     in.shape_a = d_sa; in.shape_b = d_sb; in.xf_a = (const float*)(d + o_xa); in.xf_b = (const float*)(d + o_xb);
     if (w->order_on && pick_group(w, n, w->g_gjk_env, false) == 1 && w->shapes.size() > 1) {     // thread-per-pair regime, more than one shape
         int* cnts = (int*)(d + o_zero) + Z_PAIR_CLASS;
@@ -1346,6 +1405,33 @@ void np_simplex_face_normal(const np_simplex_point* verts, int va, int vb, int v
     V3 n = normalize(cross(sub(b, a), sub(c, a)));
     V3 nn = (dot(n, a) != 0.0f) ? n : neg(n);
     out[0] = nn.x; out[1] = nn.y; out[2] = nn.z;
+}
+int np_selftest_support_table(np_world* w, int shape, int n, const float* dirs, const float* xf16, float* out_scan, float* out_table, int32_t* used)
+{
+    if (!w || n < 0 || !dirs || !xf16 || !out_scan || !out_table || !used || shape < 0 || shape >= (int)w->shapes.size()) return fail(NP_ERR_INVALID, "bad arguments");
+    int r = ensure_device(w); if (r) return r;
+    if (n == 0) return NP_OK;
+    const size_t N = (size_t)n;
+    char* d = nullptr;
+    const size_t o_d = 0, o_x = o_d + 12 * N, o_a = o_x + 64 * N, o_b = o_a + 12 * N, o_u = o_b + 12 * N, total = o_u + 4 * N;
+    CU(cudaMallocAsync((void**)&d, total, w->stream));
+    CU(cudaMemcpyAsync(d + o_d, dirs, 12 * N, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + o_x, xf16, 64 * N, cudaMemcpyHostToDevice, w->stream));
+    k_selftest_support_table<<<(n + 127) / 128, 128, 0, w->stream>>>(sview(w), shape, n, (const float*)(d + o_d), (const float*)(d + o_x), (float*)(d + o_a), (float*)(d + o_b), (int*)(d + o_u));
+    CU(cudaMemcpyAsync(out_scan, d + o_a, 12 * N, cudaMemcpyDeviceToHost, w->stream)); CU(cudaMemcpyAsync(out_table, d + o_b, 12 * N, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaMemcpyAsync(used, d + o_u, 4 * N, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaFreeAsync(d, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return NP_OK;
+}
+// table statistics of a shape (host side): out = { N, cells that fall back to the scan, mean candidates per cell, |t|_1 reach }
+int np_shape_support_table_info(np_world* w, int shape, float out[4])
+{
+    if (!w || !out || shape < 0 || shape >= (int)w->shapes.size()) return fail(NP_ERR_INVALID, "bad arguments");
+    HostShape& s = w->shapes[(size_t)shape];
+    if (s.tab_state == 0) s.tab_state = (!s.dead && cached_support_table(s.xyz, s.tab)) ? 1 : -1;
+    if (s.tab_state != 1) { out[0] = out[1] = out[2] = out[3] = 0.0f; return 0; }
+    out[0] = (float)(1 << s.tab.log_n); out[1] = (float)s.tab.scan_cells; out[2] = (float)s.tab.mean_candidates; out[3] = s.tab.tlim;
+    return 1;
 }
 int np_body_apply_impulse_response(np_world* w, int body, const np_collision_data* data, const float normal[3])
 {

@@ -148,6 +148,8 @@ def load_library(variant="exact"):
     L.np_selftest_fp32_peaks.argtypes = [vp, f32p]
     L.np_selftest_sincos_hash.argtypes = [vp, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.np_selftest_closest.argtypes = [vp, C.c_int, f32p, i32p, f32p]
+    L.np_selftest_support_table.argtypes = [vp, C.c_int, C.c_int, f32p, f32p, f32p, f32p, i32p]
+    L.np_shape_support_table_info.argtypes = [vp, C.c_int, f32p]
     _LIBS[path] = L
     return L
 
@@ -181,7 +183,7 @@ class World:
     """np_world.  Mirrors the reference's implicit global world (engine/physics.cpp:9) as an explicit object."""
 
     EXACT, GRID, SWEPT = 0, 1, 2
-    OPT_BROADPHASE, OPT_GRID_CELL, OPT_COUNTERS, OPT_SNAPSHOT_EACH_STEP, OPT_PHASE_TIMING = 1, 2, 3, 4, 5
+    OPT_BROADPHASE, OPT_GRID_CELL, OPT_COUNTERS, OPT_SNAPSHOT_EACH_STEP, OPT_PHASE_TIMING, OPT_SUPPORT_TABLES = 1, 2, 3, 4, 5, 6
 
     def __init__(self, device=-1, variant="exact"):
         self.L = load_library(variant)
@@ -443,6 +445,18 @@ class World:
     def sincos_hash(self, start, count):
         hs = C.c_uint64(); hc = C.c_uint64()
         self._ck(self.L.np_selftest_sincos_hash(self.w, start, count, C.byref(hs), C.byref(hc))); return hs.value, hc.value
+
+    def support_table_check(self, shape, dirs, xf16):
+        """(scan results, table results, used) of n support queries: np_selftest_support_table."""
+        dirs = np.ascontiguousarray(dirs, np.float32); xf16 = np.ascontiguousarray(xf16, np.float32); n = len(dirs)
+        a = np.zeros((n, 3), np.float32); b = np.zeros((n, 3), np.float32); used = np.zeros(n, np.int32)
+        self._ck(self.L.np_selftest_support_table(self.w, shape, n, _f(dirs), _f(xf16), _f(a), _f(b), _i(used)))
+        return a, b, used
+
+    def support_table_info(self, shape):
+        out = np.zeros(4, np.float32)
+        has = self.L.np_shape_support_table_info(self.w, shape, _f(out))
+        return None if has <= 0 else {"n": int(out[0]), "scan_cells": int(out[1]), "mean_candidates": float(out[2]), "reach": float(out[3])}
 
     def closest(self, kind, pts):
         pts = np.ascontiguousarray(pts, np.float32).ravel(); reg = np.zeros(1, np.int32); uvw = np.zeros(3, np.float32)
