@@ -872,6 +872,229 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
     if (ctr) flush_stats<G>(ctr, st, 0u, 0u, n_over);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K4, second generation: EPA for the polytopes that stay small -- 12 vertices, 16 faces, at most 8 new faces per expansion: 93 % of
+// the hits that need EPA at all (oracle statistics over random and lattice pairs), the rest are passed on to k_epa -- with one
+// THREAD per pair for everything that is inherently serial and the block's threads for what is not.
+//
+// ncu on the 4-lane kernel (profiles/r2_*): 12 of 32 lanes active, 17 % of the instructions in a horizon extraction that one lane of
+// four performs on a list, four lanes repeating every support and every decision; on the thread-per-pair variant with the polytope in
+// local memory: 7 of 32 lanes, 38 % of the instructions in that same list walk at 3.4 active lanes, another 38 % in AddFace loops whose
+// trip counts differ from lane to lane.  Here
+//   * a block of 128 threads owns 64 polytopes in shared memory, one column each (A and B of every vertex -- P = A - B is recomputed,
+//     same operands, same bits -- and per face its stored normal, its cached squared distance and its three vertex numbers);
+//   * faces never move: a 64-bit register holds the face ORDER as sixteen 4-bit slot numbers, which is all that SetupForEPA / the
+//     erase-and-append of collision_detection.cpp:469-517 ever changes; "first minimum wins" and "edges in insertion order" follow it;
+//   * the horizon is two passes over the removed faces with a 12 x 16-bit adjacency mask in registers: an edge survives unless its
+//     reverse is an edge of a removed face.  That equals the reference's list semantics whenever no directed edge occurs twice among
+//     the removed faces; the mask detects the other case and the pair goes to k_epa, which replays the list;
+//   * Simplex::AddFace -- the arithmetic: a normalised cross product, the flip test, a closest-point-on-triangle -- is a JOB: the
+//     owners queue (slot, face, va, vb, vc) and after a block barrier every thread of the block takes jobs of its column, so the 128
+//     threads run the same straight-line code on 2 x 64 faces at a time.
+// Two barriers per round; a round is one FindIntersectionPointsStep for every live polytope of the block.
+// ---------------------------------------------------------------------------------------------------
+#ifdef NP_E2_DEBUG
+__device__ unsigned long long g_e2dbg[8];      // expansions, and why pairs were passed on (tools only)
+#endif
+#define NP_E2_SLOTS 64
+#define NP_E2_THREADS 128
+#define NP_E2_V 12
+#define NP_E2_F 16
+#define NP_E2_JOBS 8
+#define NP_E2_FACE0 (6 * NP_E2_V)
+#define NP_E2_ROWS (6 * NP_E2_V + 5 * NP_E2_F)
+#define NP_E2_SMEM_BYTES (4 * (NP_E2_ROWS * NP_E2_SLOTS + NP_E2_JOBS * NP_E2_SLOTS + NP_E2_SLOTS + 8))
+template <bool WORLD>
+__global__ void __launch_bounds__(NP_E2_THREADS, 5)
+k_epa2(NarrowIn in, ShapeView sh, const int* __restrict__ list, const int* __restrict__ count, int* __restrict__ ticket,
+       int* __restrict__ hit_j, const float4* __restrict__ simplex, int* __restrict__ flags, float4* __restrict__ contact,
+       int* __restrict__ next_list, int* __restrict__ next_count, DevCounters* ctr)
+{
+    constexpr int S = NP_E2_SLOTS;
+    extern __shared__ float4 s_dyn[];
+    float* sm = reinterpret_cast<float*>(s_dyn);
+    unsigned* jobs = reinterpret_cast<unsigned*>(sm + NP_E2_ROWS * S);      // [JOBS][S]: job e of slot s at jobs[e * S + s]
+    int* jn = reinterpret_cast<int*>(jobs + NP_E2_JOBS * S);                // [S] jobs queued by the slot this round
+    int* alive = jn + S;                                                    // [2] the owner warps still have work
+    const int tid = threadIdx.x, lane = tid & 31, slot = tid & (S - 1);
+    const bool owner = tid < S;
+    float* col = sm + slot;
+    auto ldA = [&](int i) { return mk(col[(6 * i) * S], col[(6 * i + 1) * S], col[(6 * i + 2) * S]); };
+    auto ldB = [&](int i) { return mk(col[(6 * i + 3) * S], col[(6 * i + 4) * S], col[(6 * i + 5) * S]); };
+    auto stAB = [&](int i, V3 a, V3 b) {
+        col[(6 * i) * S] = a.x; col[(6 * i + 1) * S] = a.y; col[(6 * i + 2) * S] = a.z;
+        col[(6 * i + 3) * S] = b.x; col[(6 * i + 4) * S] = b.y; col[(6 * i + 5) * S] = b.z;
+    };
+    auto ldN = [&](int f) { return mk(col[(NP_E2_FACE0 + 5 * f) * S], col[(NP_E2_FACE0 + 5 * f + 1) * S], col[(NP_E2_FACE0 + 5 * f + 2) * S]); };
+    auto ldD = [&](int f) { return col[(NP_E2_FACE0 + 5 * f + 3) * S]; };
+    auto ldI = [&](int f) { return __float_as_uint(col[(NP_E2_FACE0 + 5 * f + 4) * S]); };
+
+    PairGeom g; g.cells = sh.tv.cells;
+    PairStats st = { 0, 0, 0, 0, 0 }, st0 = st;
+    unsigned n_over = 0;
+    int cum[NP_HIT_CLASSES]; int total = 0;
+#pragma unroll
+    for (int k = 0; k < NP_HIT_CLASSES; k++) { total += count[k]; cum[k] = total; }
+    const StoreView& s = in.s;
+    const float4* verts = sh.verts;
+    int item = -1, pnv = 0, pnf = 0, steps = 0, seed = 0;
+    unsigned long long ord = 0;           // face order: nibble k = slot of the k-th face
+    unsigned freem = 0xffffu;             // free face slots
+    bool have = false, exhausted = !owner, fresh = false;
+
+    for (;;) {
+        int njobs = 0;
+        // ---- owners: refill, or one FindIntersectionPointsStep up to the new faces
+        const int t = fetch_ticket<1>(ticket, owner && !have && !exhausted);
+        if (owner && !have && !exhausted) {
+            if (t < total) {
+                int k = 0, base = 0;
+#pragma unroll
+                for (int q = 0; q < NP_HIT_CLASSES - 1; q++) if (t >= cum[q]) { k = q + 1; base = cum[q]; }
+                item = list[(size_t)k * in.n + (t - base)];
+                int sa, sb;
+                if (WORLD) {
+                    const int i = item, j = hitj_body(hit_j[i]);
+                    load_xf(s.xf, s.cap, i, g.Ra, &g.ta); load_xf(s.xf, s.cap, j, g.Rb, &g.tb);
+                    sa = s.ints[I_SHAPE * s.cap + i]; sb = s.ints[I_SHAPE * s.cap + j];
+                } else {
+                    load_xf(in.xf_a, in.n, item, g.Ra, &g.ta); load_xf(in.xf_b, in.n, item, g.Rb, &g.tb);
+                    sa = in.shape_a[item]; sb = in.shape_b[item];
+                }
+                g.va = verts + sh.off[sa]; g.na = sh.cnt[sa]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
+                g.taba = tab_arm(sh.tv, sa, g.Ra, g.ta, in.rot_known != 0); g.tabb = tab_arm(sh.tv, sb, g.Rb, g.tb, in.rot_known != 0);
+                const float4* o = simplex + (size_t)item * 6;
+                const float4 q0 = o[0], q1 = o[1], q2 = o[2], q3 = o[3], q4 = o[4], q5 = o[5];
+                stAB(0, mk(q0.x, q0.y, q0.z), mk(q3.x, q3.y, q3.z)); stAB(1, mk(q0.w, q1.x, q1.y), mk(q3.w, q4.x, q4.y));
+                stAB(2, mk(q1.z, q1.w, q2.x), mk(q4.z, q4.w, q5.x)); stAB(3, mk(q2.y, q2.z, q2.w), mk(q5.y, q5.z, q5.w));
+                seed = (flags[item] & NP_PAIR_SEED_ALIVE) ? 1 : 0;
+                pnv = 4; pnf = 4; steps = 0; ord = 0x3210ull; freem = 0xfff0u; st0 = st;
+                // SetupForEPA (simplex.h:29-36): faces 012, 023, 310, 132 in slots 0..3
+                const unsigned sd = (unsigned)slot | ((unsigned)seed << 22);
+                jobs[0 * S + slot] = sd | (0u << 6) | (0u << 10) | (1u << 14) | (2u << 18);
+                jobs[1 * S + slot] = sd | (1u << 6) | (0u << 10) | (2u << 14) | (3u << 18);
+                jobs[2 * S + slot] = sd | (2u << 6) | (3u << 10) | (1u << 14) | (0u << 18);
+                jobs[3 * S + slot] = sd | (3u << 6) | (1u << 10) | (3u << 14) | (2u << 18);
+                njobs = 4; have = true; fresh = true;
+            } else exhausted = true;
+        }
+        if (owner && have && !fresh) {
+            int fl = NP_PAIR_HIT; V3 pen = mk(0.0f, 0.0f, 0.0f); float depth = 0.0f;
+            bool done = false, requeue = false;
+            if (steps >= NP_EPA_MAX_STEPS || pnf == 0) done = true;                                 // not converged: success stays false
+            else {
+                steps++; st.epa_iters++; st.epa_tri_tests += (unsigned)pnf;
+                // closest face, in face order, strict '<' (GetClosestTriangleToOrigin :292-325 over the cached distances)
+                float best = 3.402823466e+38f; int bf = (int)(ord & 15u);                           // every distance NaN: the first face
+                for (int k = 0; k < pnf; k++) { const int f = (int)((ord >> (4 * k)) & 15u); const float dsq = ldD(f); if (dsq < best) { best = dsq; bf = f; } }
+                const float dist = sqrtf(best);
+                const V3 d = ldN(bf);                                                               // :408 the STORED normal
+                bool conv = !(dist > NP_EPA_TOL);                                                   // :424
+                V3 sa = mk(0.f, 0.f, 0.f), sb = sa;
+                if (!conv) {
+                    sa = support_a<1, false>(g, d); sb = support_b<1, false>(g, neg(d));
+                    st.support_pairs++; st.support_verts += (unsigned)(g.na + g.nb);
+                    for (int i = 0; i < pnv; i++) if (veq(sa, ldA(i), NP_EPA_TOL) && veq(sb, ldB(i), NP_EPA_TOL)) conv = true;   // :435-446
+                }
+                if (conv) { pen = neg(normalize(d)); depth = dist; fl |= NP_PAIR_SUCCESS; done = true; }                     // :523-531
+                else {
+                    // :469-510 faces whose stored normal faces the support POINT go; the others stay, in order
+                    const V3 sp = sub(sa, sb);
+                    unsigned long long kept = 0, gone = 0; int keep = 0, ngone = 0;
+                    for (int k = 0; k < pnf; k++) {
+                        const unsigned long long f = (ord >> (4 * k)) & 15ull;
+                        if (dot(ldN((int)f), sp) > 0) { gone |= f << (4 * ngone); ngone++; }
+                        else { kept |= f << (4 * keep); keep++; }
+                    }
+                    // horizon: directed edges of the removed faces as a 12 x 16-bit adjacency mask (row a = m[a >> 2] >> 16 (a & 3))
+                    unsigned long long m0 = 0, m1 = 0, m2 = 0; bool twice = false;
+                    for (int k = 0; k < ngone; k++) {
+                        const unsigned idx = ldI((int)((gone >> (4 * k)) & 15ull));
+#pragma unroll
+                        for (int e = 0; e < 3; e++) {
+                            const int a = (idx >> (4 * e)) & 15, b = (idx >> (4 * ((e + 1) % 3))) & 15;
+                            const unsigned long long bit = 1ull << (16 * (a & 3) + b);
+                            const int w = a >> 2;
+                            const unsigned long long cur = w == 0 ? m0 : (w == 1 ? m1 : m2);
+                            twice = twice || (cur & bit) != 0ull;
+                            if (w == 0) m0 |= bit; else if (w == 1) m1 |= bit; else m2 |= bit;
+                        }
+                    }
+                    unsigned nf = freem; int ne = 0;
+                    for (int k = 0; k < ngone; k++) nf |= 1u << (unsigned)((gone >> (4 * k)) & 15ull);     // their slots are free again
+                    unsigned long long nord = kept;
+                    const bool room = pnv < NP_E2_V;
+                    for (int k = 0; k < ngone && !twice; k++) {
+                        const unsigned idx = ldI((int)((gone >> (4 * k)) & 15ull));
+#pragma unroll
+                        for (int e = 0; e < 3; e++) {
+                            const int a = (idx >> (4 * e)) & 15, b = (idx >> (4 * ((e + 1) % 3))) & 15;
+                            const int w = b >> 2;
+                            const unsigned long long rev = (w == 0 ? m0 : (w == 1 ? m1 : m2)) >> (16 * (b & 3) + a);
+                            if (!(rev & 1ull)) {                                                   // its reverse is not an edge of a removed face: on the horizon
+                                if (ne < NP_E2_JOBS && keep + ne < NP_E2_F && room) {
+                                    const int f = __ffs(nf) - 1; nf &= nf - 1;
+                                    nord |= (unsigned long long)f << (4 * (keep + ne));
+                                    jobs[ne * S + slot] = (unsigned)slot | ((unsigned)f << 6) | ((unsigned)a << 10) | ((unsigned)b << 14) | ((unsigned)pnv << 18) | ((unsigned)seed << 22);
+                                }
+                                ne++;
+                            }
+                        }
+                    }
+#ifdef NP_E2_DEBUG
+                    atomicAdd(&g_e2dbg[0], 1ull); if (twice) atomicAdd(&g_e2dbg[1], 1ull); if (!room) atomicAdd(&g_e2dbg[2], 1ull);
+                    if (ne > NP_E2_JOBS) atomicAdd(&g_e2dbg[3], 1ull); if (keep + ne > NP_E2_F) atomicAdd(&g_e2dbg[4], 1ull);
+#endif
+                    if (twice || !room || ne > NP_E2_JOBS || keep + ne > NP_E2_F) { requeue = true; done = true; }
+                    else {
+                        stAB(pnv, sa, sb);                                                         // :512 (P = sa - sb is recomputed from these)
+                        ord = nord; freem = nf; pnf = keep + ne; pnv++; njobs = ne;
+                    }
+                }
+            }
+            if (done) {
+#ifdef NP_E2_DEBUG
+                atomicAdd(&g_e2dbg[requeue ? 6 : 5], 1ull);
+#endif
+                if (requeue) { next_list[atomicAdd(next_count, 1)] = item; st = st0; n_over++; }   // flags / simplex stay for the re-run in k_epa
+                else {
+                    flags[item] = fl; contact[item] = make_float4(pen.x, pen.y, pen.z, depth);
+                    if (WORLD && (fl & NP_PAIR_SUCCESS)) hit_j[item] = hitj_body(hit_j[item]) | NP_HITJ_SUCCESS;
+                }
+                have = false; njobs = 0;
+            }
+        }
+        fresh = false;
+        if (owner) jn[slot] = njobs;
+        const unsigned any = __ballot_sync(0xffffffffu, have || !exhausted);
+        if (owner && lane == 0) alive[tid >> 5] = any != 0u;
+        __syncthreads();
+        if (!(alive[0] | alive[1])) break;
+        // ---- every thread: Simplex::AddFace (simplex.h:37-53) for the queued faces of its column; warps 0-1 take the even jobs, 2-3 the odd ones
+        const int nj = jn[slot];
+#pragma unroll 1
+        for (int e = tid >> 6; e < NP_E2_JOBS; e += 2) {
+            if (!__any_sync(0xffffffffu, e < nj)) break;
+            if (e < nj) {
+                const unsigned jd = jobs[e * S + slot];
+                const int f = (jd >> 6) & 15, va = (jd >> 10) & 15, vb = (jd >> 14) & 15, vc = (jd >> 18) & 15, sd = (jd >> 22) & 1;
+                auto P = [&](int i) { return (i == 0 && sd) ? sub(ldB(0), ldA(0)) : sub(ldA(i), ldB(i)); };
+                const V3 a = P(va), b = P(vb), c = P(vc);
+                const V3 n = normalize(cross(sub(b, a), sub(c, a)));
+                const V3 nn = (dot(n, a) != 0.0f) ? n : neg(n);                                    // :52 float used as bool
+                float u, v;
+                closest_triangle(a, b, c, &u, &v);
+                const float dsq = magsq(add(add(a, mul(sub(b, a), u)), mul(sub(c, a), v)));
+                float* fr = col + (NP_E2_FACE0 + 5 * f) * S;
+                fr[0] = nn.x; fr[S] = nn.y; fr[2 * S] = nn.z; fr[3 * S] = dsq; fr[4 * S] = __uint_as_float((unsigned)va | ((unsigned)vb << 4) | ((unsigned)vc << 8));
+            }
+        }
+        __syncthreads();
+    }
+    (void)n_over;                                      // (epa_overflow counts polytopes that outgrow k_epa's shared-memory tier, not these)
+    if (ctr) flush_stats<1>(ctr, st, 0u, 0u, 0u);
+}
+
 // Pair lists arrive in the caller's order; for the thread-per-pair kernels the pairs are visited grouped by the vertex-count classes of
 // their two shapes (small <= 12 < medium < NP_COOP_MIN <= large: 9 classes), for the reason given at NarrowIn::ordered.  Counting sort:
 // k_pair_order<false> counts, k_pair_order<true> scatters (order inside a class is arbitrary; results do not depend on it).

@@ -80,6 +80,8 @@ struct np_world {
     int g_gjk_env = 0, g_epa_env = 0; // NP_G_GJK / NP_G_EPA overrides (tuning)
     int order_on = 1; bool order_dirty = true;   // NP_ORDER=0: search bodies in index order (tuning)
     int fuse_on = 1;      // NP_FUSE=0: np_world_step_n runs plain steps (A/B)
+    int epa2_tail32 = 1;      // NP_EPA2_TAIL=4: k_epa2's leftovers to the 4-lane kernel instead of a warp per pair
+    int epa2_on = 1;          // NP_EPA2=0: without k_epa2 (small polytopes, thread per pair + block-wide AddFace)
     int tab_min_verts = 5;    // NP_TAB_MIN: shapes with fewer vertices are scanned (tuning)
     int gjk2_on = 1;          // NP_GJK2=0: k_gjk1 (every lane solves its own simplex) instead of k_gjk2
     int gjk1_old = 0, cbig_on = 0, epa_first = 1, seed_on = 0;   // NP_SEED=1: per-body table of DetectCollision's seed supports (measured slower: 4.01 vs 3.90 ms)   // NP_GJK1_OLD=1: round-1 register-simplex kernel; NP_CBIG=1: large-body vertex cache for the cooperative supports (measured slower: 9 GB of DRAM reads per step); NP_EPA_FIRST=0 (tuning, A/B)
@@ -134,7 +136,8 @@ static ShapeView sview(np_world* w)
     return s;
 }
 enum { Z_GJK_TICKET = 0, Z_EPA_TICKET, Z_MID_COUNT, Z_MID_TICKET, Z_BIG_COUNT, Z_BIG_TICKET, Z_HIT_COUNT = 8 /* NP_HIT_CLASSES counters */, Z_PAIR_CLASS = 12 /* 9 counts + 9 cursors */,
-       Z_HIT2_COUNT = 32 /* NP_HIT_CLASSES counters: hits that k_epa_first passes on to k_epa */, NP_ZERO_INTS = 64 };
+       Z_HIT2_COUNT = 32 /* NP_HIT_CLASSES counters: hits that k_epa_first passes on to k_epa */,
+       Z_HIT3_COUNT = 36 /* NP_HIT_CLASSES counters (only [0] used): hits that k_epa2 passes on to k_epa */, Z_EPA2_TICKET = 40, NP_ZERO_INTS = 64 };
 static int* hitj(np_world* w) { return w->x_hit_j ? w->x_hit_j : w->d_hit_j; }
 static int* cflags(np_world* w) { return w->x_cflags ? w->x_cflags : w->d_cflags; }
 static float4* contacts(np_world* w) { return w->x_contact ? w->x_contact : w->d_contact; }
@@ -484,6 +487,26 @@ static int launch_epa(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevC
         k_epa_first<WORLD><<<std::max(1, fb), 256, 0, w->stream>>>(in.n, b.hit_list, b.zero + Z_HIT_COUNT, b.simplex, b.hit_j, b.flags, b.contact, b.hit_list2, b.zero + Z_HIT2_COUNT, ctr);
         list = b.hit_list2; counts = b.zero + Z_HIT2_COUNT;
         w->launches += 1;
+        if (w->epa2_on) {                    // ... and the polytopes that stay small are finished by k_epa2; what it passes on arrives as one plain list (class 0)
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epa2<WORLD>, NP_E2_THREADS, NP_E2_SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
+            const int eb = (int)std::max<long long>(1, std::min<long long>((long long)std::max(1, per_sm) * w->sm_count, ((long long)in.n + NP_E2_SLOTS - 1) / NP_E2_SLOTS));
+            k_epa2<WORLD><<<eb, NP_E2_THREADS, NP_E2_SMEM_BYTES, w->stream>>>(in, sview(w), list, counts, b.zero + Z_EPA2_TICKET, b.hit_j, b.simplex, b.flags, b.contact,
+                                                                               b.hit_list, b.zero + Z_HIT3_COUNT, ctr);
+            list = b.hit_list; counts = b.zero + Z_HIT3_COUNT;
+            w->launches += 1;
+            if (w->epa2_tail32) {
+                // what is left is under one percent of the hits (the horizons whose list semantics matter, the few polytopes that grow) and
+                // each runs long: a latency problem again, so a warp per pair -- the 256-face tier with the O(1) horizon, on the fly transforms
+                auto tail = k_epa<32, epa_fmax<32>(), 0, NP_NARROW_THREADS, WORLD, false>;
+                const size_t tsmem = epa_poly_smem<32>();
+                const int tb = persistent_blocks(w, tail, tsmem, in.n, 32);
+                tail<<<tb, NP_NARROW_THREADS, tsmem, w->stream>>>(in, sview(w), 0, list, counts, b.zero + Z_EPA_TICKET, b.hit_j, b.simplex,
+                                                                   b.flags, b.contact, b.big_list, b.zero + Z_MID_COUNT, w->arena, ctr);
+                w->launches += 1;
+                return launch_epa_tiers<WORLD, TC>(w, in, b, ctr);
+            }
+        }
     }
     kern<<<blocks, NP_NARROW_THREADS, smem, w->stream>>>(in, sview(w), stage, list, counts, b.zero + Z_EPA_TICKET, b.hit_j, b.simplex,
                                                         b.flags, b.contact, b.big_list, b.zero + Z_MID_COUNT, w->arena, ctr);
@@ -498,6 +521,7 @@ static void setup_kernels_t()
     cudaFuncSetAttribute(k_epa<4, epa_fmax<4>(), 0, NP_NARROW_THREADS, WORLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_epa<8, epa_fmax<8>(), 0, NP_NARROW_THREADS, WORLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_epa<32, epa_fmax<32>(), 0, NP_NARROW_THREADS, WORLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_epa<32, epa_fmax<32>(), 0, NP_NARROW_THREADS, WORLD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_epa<32, NP_FMID, 1, NP_MID_THREADS, WORLD, WORLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_epa<32, NP_FMID, 1, NP_MID_THREADS, WORLD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
@@ -513,6 +537,8 @@ static void setup_kernels()
     cudaFuncSetAttribute(k_seed_supports, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_gjk1<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(k_gjk1<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_epa2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NP_E2_SMEM_BYTES);
+    cudaFuncSetAttribute(k_epa2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NP_E2_SMEM_BYTES);
     cudaFuncSetAttribute(k_gjk2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + sizeof(int) * NP_GJK2_EXTRA_WORDS);
     cudaFuncSetAttribute(k_gjk2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + sizeof(int) * NP_GJK2_EXTRA_WORDS);
 }
@@ -730,6 +756,8 @@ np_world* np_world_create(int device)
     if (const char* e = getenv("NP_FUSE")) w->fuse_on = atoi(e) != 0;
     if (const char* e = getenv("NP_TABLES")) w->tables_on = atoi(e) != 0;
     if (const char* e = getenv("NP_GJK2")) w->gjk2_on = atoi(e) != 0;
+    if (const char* e = getenv("NP_EPA2")) w->epa2_on = atoi(e) != 0;
+    if (const char* e = getenv("NP_EPA2_TAIL")) w->epa2_tail32 = atoi(e) == 32;
     if (const char* e = getenv("NP_TAB_MIN")) w->tab_min_verts = atoi(e);
     if (cudaMalloc((void**)&w->d_ctr, sizeof(DevCounters)) != cudaSuccess || ensure_arena(w) != NP_OK) { fail(NP_ERR_CUDA, "cannot allocate device scratch"); np_world_destroy(w); return nullptr; }
     cudaMemsetAsync(w->d_ctr, 0, sizeof(DevCounters), w->stream);
@@ -1773,4 +1801,7 @@ int np_selftest_closest(np_world* w, int kind, const float* pts, int32_t* region
     return NP_OK;
 }
 
+#ifdef NP_E2_DEBUG
+int np_debug_e2(unsigned long long out[8]) { return cudaMemcpyFromSymbol(out, g_e2dbg, 64) == cudaSuccess ? 0 : -1; }
+#endif
 }  // extern "C"
