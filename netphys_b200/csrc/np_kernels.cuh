@@ -695,7 +695,8 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK2_MINB) k_gjk2(Narrow
 // ---------------------------------------------------------------------------------------------------
 template <bool WORLD>
 __global__ void __launch_bounds__(256) k_epa_first(int n_items, const int* __restrict__ list, const int* __restrict__ count, const float4* __restrict__ simplex, int* __restrict__ hit_j,
-                                                  int* __restrict__ flags, float4* __restrict__ contact, int* __restrict__ next_list, int* __restrict__ next_count, DevCounters* ctr)
+                                                  int* __restrict__ flags, float4* __restrict__ contact, int* __restrict__ next_list, int* __restrict__ next_count, DevCounters* ctr,
+                                                  float4* __restrict__ face0 = nullptr)      // face0: [4 * item] (stored normal, squared distance) of SetupForEPA's faces, for k_epa2
 {
     int cum[NP_HIT_CLASSES]; int total = 0;
 #pragma unroll
@@ -718,6 +719,7 @@ __global__ void __launch_bounds__(256) k_epa_first(int n_items, const int* __res
             const int fl = flags[item];
             const V3 P0 = (fl & NP_PAIR_SEED_ALIVE) ? sub(B0, A0) : sub(A0, B0), P1 = sub(A1, B1), P2 = sub(A2, B2), P3 = sub(A3, B3);
             float best = 3.402823466e+38f; V3 bn = mk(0.0f, 0.0f, 0.0f); bool any = false; V3 n0 = bn;
+            float4 frec[4];
 #pragma unroll
             for (int f = 0; f < 4; f++) {                                             // faces 012, 023, 310, 132
                 const V3 a = f == 0 ? P0 : (f == 1 ? P0 : (f == 2 ? P3 : P1));
@@ -729,6 +731,7 @@ __global__ void __launch_bounds__(256) k_epa_first(int n_items, const int* __res
                 closest_triangle(a, b, cc, &u, &v);
                 const float dsq = magsq(add(add(a, mul(sub(b, a), u)), mul(sub(cc, a), v)));
                 if (f == 0) n0 = nn;
+                frec[f] = make_float4(nn.x, nn.y, nn.z, dsq);
                 if (dsq < best) { best = dsq; bn = nn; any = true; }                  // strict '<': first minimum wins
             }
             if (!any) bn = n0;                                                        // every distance NaN: face 0 (the zero-pinned face_index)
@@ -740,6 +743,9 @@ __global__ void __launch_bounds__(256) k_epa_first(int n_items, const int* __res
                 contact[item] = make_float4(pen.x, pen.y, pen.z, dist);
                 if (WORLD) hit_j[item] |= NP_HITJ_SUCCESS;
                 n_conv++;
+            } else if (face0) {
+#pragma unroll
+                for (int f = 0; f < 4; f++) face0[4 * (size_t)item + f] = frec[f];
             }
         }
         // the others go on to k_epa, filed by class: one atomic per class per warp
@@ -908,7 +914,7 @@ template <bool WORLD>
 __global__ void __launch_bounds__(NP_E2_THREADS, 5)
 k_epa2(NarrowIn in, ShapeView sh, const int* __restrict__ list, const int* __restrict__ count, int* __restrict__ ticket,
        int* __restrict__ hit_j, const float4* __restrict__ simplex, int* __restrict__ flags, float4* __restrict__ contact,
-       int* __restrict__ next_list, int* __restrict__ next_count, DevCounters* ctr)
+       int* __restrict__ next_list, int* __restrict__ next_count, DevCounters* ctr, const float4* __restrict__ face0)
 {
     constexpr int S = NP_E2_SLOTS;
     extern __shared__ float4 s_dyn[];
@@ -976,6 +982,16 @@ k_epa2(NarrowIn in, ShapeView sh, const int* __restrict__ list, const int* __res
                 jobs[2 * S + slot] = sd | (2u << 6) | (3u << 10) | (1u << 14) | (0u << 18);
                 jobs[3 * S + slot] = sd | (3u << 6) | (1u << 10) | (3u << 14) | (2u << 18);
                 njobs = 4; have = true; fresh = true;
+                if (face0) {                 // k_epa_first evaluated these four faces already (same expressions): take them and start iterating at once
+#pragma unroll
+                    for (int f = 0; f < 4; f++) {
+                        const float4 r = face0[4 * (size_t)item + f];
+                        float* fr = col + (NP_E2_FACE0 + 5 * f) * S;
+                        const unsigned idx = f == 0 ? 0x210u : (f == 1 ? 0x320u : (f == 2 ? 0x013u : 0x231u));
+                        fr[0] = r.x; fr[S] = r.y; fr[2 * S] = r.z; fr[3 * S] = r.w; fr[4 * S] = __uint_as_float(idx);
+                    }
+                    njobs = 0; fresh = false;
+                }
             } else exhausted = true;
         }
         if (owner && have && !fresh) {

@@ -70,6 +70,7 @@ struct np_world {
     int* d_zero = nullptr;            // [tickets and counts (32 ints), head[cap] of the incoming-collision lists]  -- one memset per step
     int *d_inc = nullptr /* next[] of the incoming-collision lists */, *d_sums = nullptr, *d_big_list = nullptr, *d_hit_list = nullptr;
     float4* d_simplex = nullptr;      // GJK result of every hit: A[4], B[4]
+    float4* d_face0 = nullptr;        // SetupForEPA's four faces of the hits k_epa_first passes on (4 float4 per body)
     float4* d_seed = nullptr;         // per body: the two seed supports of DetectCollision (k_seed_supports), thread-per-body search only
     float4* d_wverts = nullptr; size_t wverts_cap = 0, wv_total = 0, wv_total_big = 0;   // per-step world-vertex cache (K1b), allocated on first use (ensure_cache)
     float* d_ext = nullptr;           // adapter extension, allocated on first use: [4][cap] external force xyz + enabled flag
@@ -148,7 +149,7 @@ static void free_store(np_world* w)
 {
     cudaFree(w->d_state); cudaFree(w->d_cst); cudaFree(w->d_xf); cudaFree(w->d_ints);
     cudaFree(w->d_hit_j); cudaFree(w->d_cflags); cudaFree(w->d_contact); cudaFree(w->d_zero);
-    cudaFree(w->d_inc); cudaFree(w->d_sums); cudaFree(w->d_big_list); cudaFree(w->d_snap); cudaFree(w->d_hit_list); cudaFree(w->d_simplex); cudaFree(w->d_seed); w->d_seed = nullptr;
+    cudaFree(w->d_inc); cudaFree(w->d_sums); cudaFree(w->d_big_list); cudaFree(w->d_snap); cudaFree(w->d_hit_list); cudaFree(w->d_simplex); cudaFree(w->d_face0); w->d_face0 = nullptr; cudaFree(w->d_seed); w->d_seed = nullptr;
     w->d_state = w->d_cst = w->d_xf = nullptr; w->d_ints = nullptr; w->d_hit_j = w->d_cflags = nullptr; w->d_contact = nullptr;
     w->d_zero = w->d_inc = w->d_sums = w->d_big_list = w->d_hit_list = nullptr; w->d_snap = nullptr; w->d_simplex = nullptr;
     w->cap = 0;
@@ -222,7 +223,7 @@ static int alloc_store(np_world* w, size_t c)
     CU(cudaMalloc((void**)&w->d_zero, sizeof(int) * (NP_ZERO_INTS + c))); CU(cudaMalloc((void**)&w->d_inc, sizeof(int) * c));
     CU(cudaMalloc((void**)&w->d_sums, sizeof(int) * (4 * c / NP_SCAN_BLOCK + 2))); CU(cudaMalloc((void**)&w->d_big_list, sizeof(int) * c));
     CU(cudaMalloc((void**)&w->d_snap, sizeof(SnapObj) * c));
-    CU(cudaMalloc((void**)&w->d_hit_list, sizeof(int) * 2 * NP_HIT_CLASSES * c)); CU(cudaMalloc((void**)&w->d_simplex, sizeof(float4) * 6 * c));      // hit lists of k_gjk, then those k_epa_first passes on
+    CU(cudaMalloc((void**)&w->d_hit_list, sizeof(int) * 2 * NP_HIT_CLASSES * c)); CU(cudaMalloc((void**)&w->d_simplex, sizeof(float4) * 6 * c)); CU(cudaMalloc((void**)&w->d_face0, sizeof(float4) * 4 * c));      // hit lists of k_gjk, then those k_epa_first passes on
     CU(cudaMalloc((void**)&w->d_seed, sizeof(float4) * 2 * c));
     CU(cudaMemsetAsync(w->d_state, 0, sizeof(float) * S_COUNT * c, w->stream));
     CU(cudaMemsetAsync(w->d_hit_j, 0xff, sizeof(int) * c, w->stream)); CU(cudaMemsetAsync(w->d_cflags, 0, sizeof(int) * c, w->stream));
@@ -418,10 +419,12 @@ static int pick_group(np_world* w, long long items, int env, bool epa)
     // latency of its longest chains -> wide groups; above, by instruction throughput -> narrow groups
     // (round 2, thread-per-body k_gjk1 + k_epa_first: 50/50 box/icosphere worlds, ms per step wide vs narrow groups -- 131 k bodies 1.36 vs 1.62,
     // 262 k bodies 2.57 vs 2.05: the crossover moved from ~300 k to ~180 k items)
-    if (items <= 180000) return epa ? 32 : (items <= 40000 ? 32 : 8);      // (GJK: a warp per body once there are few enough bodies for one wave)
+    // (with support-direction tables, k_gjk2 and k_epa2 the thread-per-item path took over everything above ~45 k items: 50/50 box/icosphere
+    // worlds, narrow phase in ms, wide groups vs thread per item -- 20 k 0.29 / 0.46, 40 k 0.50 / 0.54, 80 k 0.82 / 0.55, 131 k 1.29 / 0.63)
+    if (items <= 45000) return 32;                          // a warp per body / per hit: one wave, bound by its longest chains
     return epa ? (w->max_verts <= 16 ? 1 : 4) : 1;          // small shapes: thread-per-hit EPA wins (8.1e8 vs 7.6e8 box pairs/s)
 }
-struct NarrowBufs { int* zero; int* hit_j; int* flags; float4* contact; float4* simplex; int* hit_list; int* big_list; int* hit_list2; };
+struct NarrowBufs { int* zero; int* hit_j; int* flags; float4* contact; float4* simplex; int* hit_list; int* big_list; int* hit_list2; float4* face0; };
 
 static const size_t kSimplexSmem = sizeof(float) * NP_SX_ROWS * NP_NARROW_THREADS;      // k_gjk1: the block's simplices
 template <int G, bool WORLD>
@@ -484,7 +487,8 @@ static int launch_epa(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevC
     const int* list = b.hit_list; const int* counts = b.zero + Z_HIT_COUNT;
     if (G < 32 && w->epa_first) {            // throughput regime: the hits that converge before their first support never reach the group kernel
         const int fb = (int)std::min<long long>((long long)w->sm_count * 8, ((long long)in.n + 255) / 256);
-        k_epa_first<WORLD><<<std::max(1, fb), 256, 0, w->stream>>>(in.n, b.hit_list, b.zero + Z_HIT_COUNT, b.simplex, b.hit_j, b.flags, b.contact, b.hit_list2, b.zero + Z_HIT2_COUNT, ctr);
+        k_epa_first<WORLD><<<std::max(1, fb), 256, 0, w->stream>>>(in.n, b.hit_list, b.zero + Z_HIT_COUNT, b.simplex, b.hit_j, b.flags, b.contact, b.hit_list2, b.zero + Z_HIT2_COUNT, ctr,
+                                                                   w->epa2_on ? b.face0 : nullptr);
         list = b.hit_list2; counts = b.zero + Z_HIT2_COUNT;
         w->launches += 1;
         if (w->epa2_on) {                    // ... and the polytopes that stay small are finished by k_epa2; what it passes on arrives as one plain list (class 0)
@@ -492,7 +496,7 @@ static int launch_epa(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevC
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epa2<WORLD>, NP_E2_THREADS, NP_E2_SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
             const int eb = (int)std::max<long long>(1, std::min<long long>((long long)std::max(1, per_sm) * w->sm_count, ((long long)in.n + NP_E2_SLOTS - 1) / NP_E2_SLOTS));
             k_epa2<WORLD><<<eb, NP_E2_THREADS, NP_E2_SMEM_BYTES, w->stream>>>(in, sview(w), list, counts, b.zero + Z_EPA2_TICKET, b.hit_j, b.simplex, b.flags, b.contact,
-                                                                               b.hit_list, b.zero + Z_HIT3_COUNT, ctr);
+                                                                               b.hit_list, b.zero + Z_HIT3_COUNT, ctr, b.face0);
             list = b.hit_list; counts = b.zero + Z_HIT3_COUNT;
             w->launches += 1;
             if (w->epa2_tail32) {
@@ -680,7 +684,7 @@ static int enqueue_search(np_world* w, float dt, bool timed, bool integrate = tr
             k_seed_supports<<<std::max(1, sb_), NP_NARROW_THREADS, shapes_smem(w), w->stream>>>(s, sview(w), shapes_in_smem(w) ? 1 : 0, w->d_seed);
             in.seed = w->d_seed; w->launches += 1;
         }
-        NarrowBufs nb = { w->d_zero, hitj(w), cflags(w), contacts(w), w->d_simplex, w->d_hit_list, w->d_big_list, w->d_hit_list + (size_t)NP_HIT_CLASSES * w->cap };
+        NarrowBufs nb = { w->d_zero, hitj(w), cflags(w), contacts(w), w->d_simplex, w->d_hit_list, w->d_big_list, w->d_hit_list + (size_t)NP_HIT_CLASSES * w->cap, w->d_face0 };
         int r = launch_narrow(w, in, nb, ctr); if (r) return r;
     }
     if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[3], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
@@ -1230,7 +1234,7 @@ static int run_pairs(np_world* w, int n, const int* d_sa, const float* d_pa, con
 {
     // scratch: counters | xfA | xfB (SoA) | simplex | hit_list | big_list
     const size_t N = (size_t)n;
-    const size_t o_zero = 0, o_xa = 4 * NP_ZERO_INTS, o_xb = o_xa + 4 * X_COUNT * N, o_sx = (o_xb + 4 * X_COUNT * N + 15) / 16 * 16, o_hl = o_sx + 96 * N, o_h2 = o_hl + 4 * NP_HIT_CLASSES * N, o_bl = o_h2 + 4 * NP_HIT_CLASSES * N, o_or = o_bl + 4 * N, total = o_or + 4 * N;
+    const size_t o_zero = 0, o_xa = 4 * NP_ZERO_INTS, o_xb = o_xa + 4 * X_COUNT * N, o_sx = (o_xb + 4 * X_COUNT * N + 15) / 16 * 16, o_hl = o_sx + 96 * N, o_h2 = o_hl + 4 * NP_HIT_CLASSES * N, o_bl = o_h2 + 4 * NP_HIT_CLASSES * N, o_or = o_bl + 4 * N, o_f0 = (o_or + 4 * N + 15) / 16 * 16, total = o_f0 + 64 * N;
     char* d = nullptr;
     CU(cudaMallocAsync((void**)&d, total, w->stream));
     CU(cudaMemsetAsync(d + o_zero, 0, 4 * NP_ZERO_INTS, w->stream));
@@ -1254,7 +1258,7 @@ static int run_pairs(np_world* w, int n, const int* d_sa, const float* d_pa, con
         in.order = (const int*)(d + o_or);
         w->launches += 2;
     }
-    NarrowBufs nb = { (int*)(d + o_zero), nullptr, d_hit, d_out, (float4*)(d + o_sx), (int*)(d + o_hl), (int*)(d + o_bl), (int*)(d + o_h2) };
+    NarrowBufs nb = { (int*)(d + o_zero), nullptr, d_hit, d_out, (float4*)(d + o_sx), (int*)(d + o_hl), (int*)(d + o_bl), (int*)(d + o_h2), (float4*)(d + o_f0) };
     int r = launch_narrow(w, in, nb, w->counters_on ? w->d_ctr : nullptr);
     if (kernel_ms) CU(cudaEventRecord(w->ev[5], w->stream));
     CU(cudaGetLastError());
