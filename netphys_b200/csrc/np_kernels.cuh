@@ -500,11 +500,12 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK1_MINB) k_gjk1(Narrow
 // (ncu, profiles/r2_*: three solvers back to back in every warp on every trip).  Here a block runs its trips in lock step:
 //   1. every thread advances ITS pair to the solve: refill, the support pair, the termination tests, the new simplex point (the
 //      simplex lives in the block's shared array, one column per thread, as in k_gjk1);
-//   2. the pending solves are counted and ordered tetrahedra first, then triangles, then lines (ballots + one shared prefix);
-//   3. thread t takes the t-th solve of that order -- ANY thread's column (gjk_solve_col) -- so a warp runs one solver with all its
-//      lanes, and leaves (kept vertices, next direction, status) in shared memory;
+//   2. the pending solves are queued in one array, tetrahedra from the front, triangles and lines from the back;
+//   3. thread t takes the t-th entry -- ANY thread's column (gjk_solve_col) -- so a warp runs one solver with all its lanes (a line
+//      costs a third of a triangle: sharing a warp with triangles loses little), and leaves (kept vertices, next direction, status)
+//      in shared memory;
 //   4. every thread takes its pair's result back and finishes the trip.
-// Three block barriers per trip; the other resident blocks of the SM fill the gaps.  Results are those of k_gjk1: the same operations
+// Two block barriers per trip; the other resident blocks of the SM fill the gaps.  Results are those of k_gjk1: the same operations
 // on the same operands, only on another lane.
 // ---------------------------------------------------------------------------------------------------
 #define NP_GJK2_EXTRA_WORDS (30 * NP_NARROW_THREADS + 32)      // per block, after the simplices: job word, result word, direction (3), order, counters, transforms (24)
@@ -524,7 +525,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK2_MINB) k_gjk2(Narrow
     int* jres = jword + T;                                         // [T] kn | ksel << 4 | status << 12
     float* jdir = reinterpret_cast<float*>(jres + T);              // [3][T] next direction
     int* jorder = reinterpret_cast<int*>(jdir + 3 * T);            // [T] owner thread of the t-th solve
-    int* jcnt = jorder + T;                                        // [4][NW]: tetrahedra, triangles, lines per warp; [3][w] = warp w still has work
+    int* jcnt = jorder + T;                                        // [2][2]: solves queued from the front / from the back of jorder, for even and odd rounds
     float* sxf = reinterpret_cast<float*>(jcnt + 32) + threadIdx.x;   // [24][T] the two transforms of the thread's pair: read twice per trip, so not worth 24 registers
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     GjkS m;
@@ -559,6 +560,9 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK2_MINB) k_gjk2(Narrow
     // ticket t + (everything in flight) will need.
     const int ahead = (int)(gridDim.x * T) * 2;
     int pf_body = -1;
+    int round = 0;
+    if (tid < 4) jcnt[tid] = 0;
+    __syncthreads();
     for (;;) {
         // ---- 1: own pair up to the solve
         if (WORLD && pf_body >= 0) {
@@ -620,27 +624,24 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK2_MINB) k_gjk2(Narrow
                 }
             }
         }
-        // ---- 2: order the pending solves, largest simplex first
-        const unsigned b3 = __ballot_sync(0xffffffffu, cls == 3), b2 = __ballot_sync(0xffffffffu, cls == 2), b1 = __ballot_sync(0xffffffffu, cls == 1);
-        const unsigned alive = __ballot_sync(0xffffffffu, have || !exhausted);
-        if (lane == 0) { jcnt[0 * NW + warp] = __popc(b3); jcnt[1 * NW + warp] = __popc(b2); jcnt[2 * NW + warp] = __popc(b1); jcnt[3 * NW + warp] = alive != 0u; }
-        __syncthreads();
-        int tot3 = 0, tot2 = 0, tot1 = 0, before = 0, any_alive = 0;
-#pragma unroll
-        for (int w = 0; w < NW; w++) {
-            const int c3 = jcnt[0 * NW + w], c2 = jcnt[1 * NW + w], c1 = jcnt[2 * NW + w];
-            tot3 += c3; tot2 += c2; tot1 += c1; any_alive |= jcnt[3 * NW + w];
-            if (w < warp) before += (cls == 3) ? c3 : ((cls == 2) ? c2 : c1);
+        // ---- 2: order the pending solves: tetrahedra claim places from the front of jorder, triangles and lines from the back (two shared
+        // counters, one atomic per warp and end; the counters alternate between two pairs so that the idle pair can be cleared in peace)
+        {
+            const unsigned b3 = __ballot_sync(0xffffffffu, cls == 3), br = __ballot_sync(0xffffffffu, cls == 1 || cls == 2);
+            int* cnt = jcnt + 2 * (round & 1);
+            int base3 = 0, baser = 0;
+            if (lane == 0) { if (b3) base3 = atomicAdd(cnt, __popc(b3)); if (br) baser = atomicAdd(cnt + 1, __popc(br)); }
+            base3 = __shfl_sync(0xffffffffu, base3, 0); baser = __shfl_sync(0xffffffffu, baser, 0);
+            const unsigned lt = (1u << lane) - 1u;
+            if (cls == 3) jorder[base3 + __popc(b3 & lt)] = tid;
+            else if (cls) jorder[T - 1 - (baser + __popc(br & lt))] = tid;
         }
-        if (!any_alive) break;                                                                       // (every thread of the block reads the same words)
-        if (cls) {
-            const unsigned mine = (cls == 3) ? b3 : ((cls == 2) ? b2 : b1);
-            const int base = (cls == 3) ? 0 : ((cls == 2) ? tot3 : tot3 + tot2);
-            jorder[base + before + __popc(mine & ((1u << lane) - 1u))] = tid;
-        }
-        __syncthreads();
+        if (!__syncthreads_or(have || !exhausted)) break;
+        const int n3 = jcnt[2 * (round & 1)], nr = jcnt[2 * (round & 1) + 1];
+        if (tid == 0) { jcnt[2 * ((round + 1) & 1)] = 0; jcnt[2 * ((round + 1) & 1) + 1] = 0; }      // next round's pair (nobody touches it before the barrier below)
+        round++;
         // ---- 3: the t-th solve, whoever owns it
-        if (tid < tot3 + tot2 + tot1) {
+        if (tid < n3 || tid >= T - nr) {
             const int owner = jorder[tid], word = jword[owner];
             int kn = 0, ksel = 0 | (1 << 2) | (2 << 4), status = GjkS::RUN; V3 d = mk(0.0f, 0.0f, 0.0f);
             gjk_solve_col(sx + owner, T, word & 0xff, word >> 8, kn, ksel, d, status);
