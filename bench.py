@@ -367,7 +367,9 @@ def run_ours(args, rank, local_rank, world_size):
     ach_tf = flops_per_step / (narrow_ms * 1e-3) / 1e12
     ach_gbs = BODIES * B_INTEGRATE / (integ_ms * 1e-3) / 1e9
     traffic, traffic_src = measured_traffic()
-    roof = {"bound": "fp32", "kernel": "narrow phase = k_gjk* + k_epa* (%.0f%% of the phase-timed step)" % (100 * narrow_ms / phase_total_ms),
+    roof = {"bound": "fp32", "kernel": "narrow phase = k_gjk2 + k_epa_first + k_epa2 + the k_epa tiers (%.0f%% of the phase-timed step)" % (100 * narrow_ms / phase_total_ms),
+            "executed_note": "`achieved` counts the REFERENCE's arithmetic (27 flop per vertex its support scan visits): with support-direction tables the kernels "
+                             "evaluate only the few vertices that can win, so the executed FP32 work is far below this figure (ncu pipe_fma utilisation is in profiles/)",
             "timing": "CUDA events on the world's stream around the narrow-phase kernels, %d steps with NP_OPT_PHASE_TIMING (step %.4f ms with the events, %.4f ms without)" % (phase_steps, phase_total_ms, kernels_ms),
             "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak if fp32_peak else None,
             "traffic": traffic, "traffic_source": traffic_src,

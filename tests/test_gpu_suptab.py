@@ -104,3 +104,32 @@ def test_tables_do_not_change_a_world_step_or_pair_queries(npb, oracle):
             ids = np.array([w.create_mesh(s) for s in scenes.resolve_specs(specs, oracle)], np.int32)
             out.append(w.detect_batch(ids[sa], pa, ids[sb], pb))
     assert np.array_equal(out[0][0], out[1][0]); assert_biteq(out[0][1], out[1][1], "pair queries")
+
+
+@pytest.mark.parametrize("env", [{}, {"NP_GJK2": "0"}, {"NP_EPA2": "0"}, {"NP_EPA2_TAIL": "4"}, {"NP_TABLES": "0"}, {"NP_TAB_MIN": "17"}, {"NP_G_EPA": "1"}])
+def test_thread_per_item_kernel_variants_equal_the_oracle(npb, oracle, env, monkeypatch):
+    """The thread-per-item path forced onto a small workload (NP_G_GJK=1) with each of its kernels switched for the one it replaced, on shapes
+    that have tables and one that cannot (300 vertices: scanned by the whole warp): pair list and world step == the oracle, counters included."""
+    monkeypatch.setenv("NP_G_GJK", "1"); monkeypatch.setenv("NP_G_EPA", "4")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.RandomState(3)
+    specs = [("box", 1.0, 1.0, 1.0), ("sphere", 0.5), ("mesh", scenes.random_hull(rng, nverts=16)), ("mesh", scenes.random_hull(rng, nverts=300))]
+    _, sa, pa, sb, pb = scenes.random_pairs(60000, seed=77, extent=0.8, mix=(0.4, 0.3, 0.2, 0.1), shapes=specs)
+    shapes = scenes.resolve_specs(specs, oracle)
+    ho, oo, ctr = oracle.detect_batch(shapes, sa, pa, sb, pb, nthreads=8)
+    with npb.World(0) as w:
+        ids = np.array([w.create_mesh(s) for s in shapes], np.int32)
+        w.set_option(w.OPT_COUNTERS, 1)
+        hit, out = w.detect_batch(ids[sa], pa, ids[sb], pb)
+        c = w.counters()
+    assert np.array_equal(hit, ho); assert_biteq(out, oo, "pair list %s" % (env,))
+    assert c["pair_tests"] == len(sa) and c["hits"] == int(ho.sum()) and c["gjk_steps"] == ctr["gjk_steps"] and c["epa_iters"] == ctr["epa_iters"]
+    assert c["support_pairs"] == ctr["gjk_supports"] + ctr["epa_supports"] and c["epa_tri_tests"] == ctr["epa_tri_tests"]
+    sc = scenes.lattice_scene(1500, spacing=1.1, seed=8, mix=(0.5, 0.3, 0.2))
+    rs = scenes.resolve(sc, oracle)
+    with npb.World(0) as w:
+        w.load_scene(sc); ow = oracle.world(rs)
+        for _ in range(4):
+            w.step(sc["dt"]); ow.step(sc["dt"])
+        assert_biteq(w.states(), ow.state(), "world state %s" % (env,))
