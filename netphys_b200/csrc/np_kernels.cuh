@@ -904,7 +904,9 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
 __device__ unsigned long long g_e2dbg[8];      // expansions, and why pairs were passed on (tools only)
 #endif
 #define NP_E2_SLOTS 64
+#ifndef NP_E2_THREADS
 #define NP_E2_THREADS 128
+#endif
 #define NP_E2_V 12
 #define NP_E2_F 16
 #define NP_E2_JOBS 8
@@ -912,7 +914,7 @@ __device__ unsigned long long g_e2dbg[8];      // expansions, and why pairs were
 #define NP_E2_ROWS (6 * NP_E2_V + 5 * NP_E2_F)
 #define NP_E2_SMEM_BYTES (4 * (NP_E2_ROWS * NP_E2_SLOTS + NP_E2_JOBS * NP_E2_SLOTS + NP_E2_SLOTS + 8))
 template <bool WORLD>
-__global__ void __launch_bounds__(NP_E2_THREADS, 5)
+__global__ void __launch_bounds__(NP_E2_THREADS, NP_E2_THREADS == 128 ? 5 : 8)
 k_epa2(NarrowIn in, ShapeView sh, const int* __restrict__ list, const int* __restrict__ count, int* __restrict__ ticket,
        int* __restrict__ hit_j, const float4* __restrict__ simplex, int* __restrict__ flags, float4* __restrict__ contact,
        int* __restrict__ next_list, int* __restrict__ next_count, DevCounters* ctr, const float4* __restrict__ face0)
@@ -1090,7 +1092,7 @@ k_epa2(NarrowIn in, ShapeView sh, const int* __restrict__ list, const int* __res
         // ---- every thread: Simplex::AddFace (simplex.h:37-53) for the queued faces of its column; warps 0-1 take the even jobs, 2-3 the odd ones
         const int nj = jn[slot];
 #pragma unroll 1
-        for (int e = tid >> 6; e < NP_E2_JOBS; e += 2) {
+        for (int e = tid / S; e < NP_E2_JOBS; e += NP_E2_THREADS / S) {
             if (!__any_sync(0xffffffffu, e < nj)) break;
             if (e < nj) {
                 const unsigned jd = jobs[e * S + slot];
