@@ -43,6 +43,7 @@ def log(msg):
 
 
 T0 = time.perf_counter()
+_OUT = sys.stdout        # main() swaps in a private copy of the real stdout
 
 
 def make_scene(rank=0, n=None):
@@ -137,11 +138,11 @@ def run_reference(args, rank):
     t, kind, how = cpu_reference_steps(scene, args.steps, min(args.warmup, 1))
     v = BODIES * args.steps / t
     sample = "%d full steps of the %d-body world (%s)" % (args.steps, BODIES, how)
-    print(json.dumps({"impl": "reference", "metric": "body_steps_per_sec", "value": v, "unit": "body-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+    _OUT.write(json.dumps({"impl": "reference", "metric": "body_steps_per_sec", "value": v, "unit": "body-steps/s", "n_gpus": args.gpus, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                       "dtype": "f32", "data": "synthetic", "config": CONFIG,
                       "cpu_baseline": {"value": v, "unit": "body-steps/s", "cores": 1, "kind": kind, "sample": sample},
-                      "e2e": {"value": v, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+                      "e2e": {"value": v, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}) + "\n"); _OUT.flush()
 
 
 def timed_steps(w, dt, n, flush=True):
@@ -481,7 +482,7 @@ def run_ours(args, rank, local_rank, world_size):
         out["pair_tests"] = pair
     if cpu is not None:
         out["cpu_baseline"] = cpu
-    print(json.dumps(out), flush=True)
+    _OUT.write(json.dumps(out) + "\n"); _OUT.flush()
     if w is not None: w.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -495,6 +496,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on file descriptor 1), so the
+    # descriptor is handed to stderr for the duration of the run and the line goes to a private copy of the real stdout.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank)
     else:
