@@ -204,6 +204,22 @@ int np_world_last_gather_ms(np_world* w, int back, float out[2]);
  * world's stream) -> step_end. */
 int np_world_shard_over_comm(np_world* w);
 int np_world_step_sharded(np_world* w, float dt);
+/* PARTITIONED sharded step (exact search; SURVEY 8(e)-2's slabs, cut by body index because that is where the reference's partners are):
+ * with a halo of H > 0 bodies a rank runs Physics::Update, OnCollision and the snapshot for ITS OWN bodies only -- the per-step work and
+ * traffic of everything but the search divide by the rank count -- and exchanges with its two neighbours instead of all-gathering:
+ *   np_world_step_integrate   Physics::Update of the own bodies
+ *   (the next rank's first H transforms -> this rank's array, right after its own range: np_world_transforms_device, [n][12] floats)
+ *   np_world_step_search      GetCollisions of the own bodies; a search may look at most H bodies ahead
+ *   (the previous rank's last H collision records -> this rank's d_hit_j / d_contact, right before its own range)
+ *   np_world_step_end         OnCollision of the own bodies
+ * np_world_step_sharded does all five over the communicator (ncclSend / ncclRecv between neighbours).  A first-hit search that would
+ * have needed a partner more than H bodies ahead sets an error that np_world_synchronize / np_world_get_collisions report
+ * (NP_ERR_CAPACITY): results are the reference's or the step fails loudly.  State, transforms and records of bodies outside
+ * [first - H, first + count + H) are stale on this rank; np_world_get_collisions returns the own bodies' collisions. */
+int np_world_set_shard_halo(np_world* w, int halo_bodies);            /* 0 = off: replicated steps, all-gather of the records */
+int np_world_step_integrate(np_world* w, float dt);
+int np_world_step_search(np_world* w);
+int np_world_transforms_device(np_world* w, void** d_xf);
 /* Physics::Update for every body only (physics.cpp:151-155), no collision phase */
 int np_world_integrate(np_world* w, float dt);
 /* collisions of the most recent step, in the reference's list order (ascending a) */

@@ -93,10 +93,10 @@ NP_D int integrate_regs(const StoreView& s, int i, float dt, V3& pos, V3& rot, V
     return changed;
 }
 template <bool EXT>
-__global__ void __launch_bounds__(256) k_integrate(StoreView s, float dt, int write_xf)
+__global__ void __launch_bounds__(256) k_integrate(StoreView s, float dt, int write_xf, int lo, int hi)      // bodies [lo, hi)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s.n) return;
+    int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
     const int cap = s.cap;
     float* st = s.state;
     V3 pos = mk(st[S_PX * cap + i], st[S_PY * cap + i], st[S_PZ * cap + i]);
@@ -230,9 +230,18 @@ struct NarrowIn {
     const int* cand; const int* cand_off; const int* cand_cnt;   // world mode with a broad phase: per-body ascending candidate lists (null = all j > i)
     const float4* seed;                                          // world mode: [2*body] support along (1,1,1), [2*body+1] along (-1,-1,-1) (k_seed_supports), or null
     int pf;                    // 1: k_gjk2 prefetches the lines of bodies far ahead in ticket order (NP_PREFETCH=0 switches it off)
+    int halo;                  // world mode, partitioned sharded step: a body's search may look at most `halo` bodies ahead (their transforms came from the next rank; its own record reaches at most `halo` bodies); 0 = unlimited
+    int* halo_err;             // set to 1 when a first-hit search would have had to look further (np_world_synchronize reports it)
     int rot_known;             // 1: every transform is GetTransform's product of rotations (world bodies, poses): tab_arm skips its orthonormality test
 };
 
+// a first-hit search that ran out of partners: in a partitioned sharded step (np_world_set_shard_halo) that is only the reference's
+// answer when the island really ended -- if it was the halo that ended, flag it.  Always returns false.
+NP_D bool halo_exhausted(const NarrowIn& in, const int* __restrict__ island_end, int i, int jend)
+{
+    if (in.halo > 0 && jend == i + 1 + in.halo && island_end[i] > jend) atomicExch(in.halo_err, 1);
+    return false;
+}
 // ---------------------------------------------------------------------------------------------------
 // K3: GJK.
 //  world mode = GetCollisions (physics.cpp:116-145): item = body i; its group tests j = i+1, i+2, ... inside i's island
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
 #endif
                 if (WORLD) {
                     if (in.cand) { cbase = in.cand_off[i]; c = 0; jend = in.cand_cnt[i]; j = jend > 0 ? in.cand[cbase] : 0; if (jend > 0) jend = 0x7fffffff; cn = in.cand_cnt[i]; }
-                    else { j = i + 1; jend = island_end[i]; }
+                    else { j = i + 1; jend = island_end[i]; if (in.halo > 0) jend = min(jend, i + 1 + in.halo); }
                     if (j < jend) {
                         if (CACHED) {
                             g.va = s.wverts + wv_off[i]; g.na = sh.cnt[shape_of[i]];
@@ -339,7 +348,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
                         hit_list[(size_t)cls * in.n + atomicAdd(hit_count + cls, 1)] = i;
                     }
                     have = false;
-                } else if (WORLD && (in.cand ? (++c < cn ? ((j = in.cand[cbase + c]), true) : false) : (++j < jend))) {
+                } else if (WORLD && (in.cand ? (++c < cn ? ((j = in.cand[cbase + c]), true) : false) : (++j < jend || halo_exhausted(in, island_end, i, jend)))) {
                     if (CACHED) { g.vb = s.wverts + wv_off[j]; g.nb = sh.cnt[shape_of[j]]; }
                     else { load_xf(s.xf, s.cap, j, g.Rb, &g.tb); int sb = shape_of[j]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb]; g.tabb = tab_arm(sh.tv, sb, g.Rb, g.tb, in.rot_known != 0); }
                     m.begin();
@@ -426,7 +435,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK1_MINB) k_gjk1(Narrow
                 i = WORLD ? (in.ordered ? s.ints[I_ORDER * s.cap + in.first + t] : t + in.first) : (in.order ? in.order[t] : t);
                 if (WORLD) {
                     if (in.cand) { cbase = in.cand_off[i]; c = 0; cn = in.cand_cnt[i]; j = cn > 0 ? in.cand[cbase] : 0; jend = cn > 0 ? 0x7fffffff : 0; }
-                    else { j = i + 1; jend = island_end[i]; }
+                    else { j = i + 1; jend = island_end[i]; if (in.halo > 0) jend = min(jend, i + 1 + in.halo); }
                     if (j < jend) { arm_a(i); arm_b(j); m.begin(); have = true; }
                     else { hit_j[i] = -1; flags[i] = 0; }
                 } else {
@@ -478,7 +487,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK1_MINB) k_gjk1(Narrow
                         hit_list[(size_t)cls * in.n + pos] = i;
                     }
                     have = false;
-                } else if (WORLD && (in.cand ? (++c < cn ? ((j = in.cand[cbase + c]), true) : false) : (++j < jend))) {
+                } else if (WORLD && (in.cand ? (++c < cn ? ((j = in.cand[cbase + c]), true) : false) : (++j < jend || halo_exhausted(in, island_end, i, jend)))) {
                     arm_b(j); m.begin();
                 } else {
                     if (WORLD) hit_j[i] = -1;
@@ -580,7 +589,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK2_MINB) k_gjk2(Narrow
                 if (WORLD && in.pf) { const int tp = min(t + ahead, in.n - 1); pf_body = in.ordered ? s.ints[I_ORDER * s.cap + in.first + tp] : tp + in.first; }
                 if (WORLD) {
                     if (in.cand) { cbase = in.cand_off[i]; c = 0; cn = in.cand_cnt[i]; j = cn > 0 ? in.cand[cbase] : 0; jend = cn > 0 ? 0x7fffffff : 0; }
-                    else { j = i + 1; jend = island_end[i]; }
+                    else { j = i + 1; jend = island_end[i]; if (in.halo > 0) jend = min(jend, i + 1 + in.halo); }
                     if (j < jend) { arm_a(i); arm_b(j); m.begin(); have = true; }
                     else { hit_j[i] = -1; flags[i] = 0; }
                 } else {
@@ -672,7 +681,7 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK2_MINB) k_gjk2(Narrow
                     hit_list[(size_t)hc * in.n + pos] = i;
                 }
                 have = false;
-            } else if (WORLD && (in.cand ? (++c < cn ? ((j = in.cand[cbase + c]), true) : false) : (++j < jend))) {
+            } else if (WORLD && (in.cand ? (++c < cn ? ((j = in.cand[cbase + c]), true) : false) : (++j < jend || halo_exhausted(in, island_end, i, jend)))) {
                 arm_b(j); m.begin();
             } else {
                 if (WORLD) hit_j[i] = -1;
@@ -1660,10 +1669,10 @@ __global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, int firs
 // Two launches.  k_link threads every collision (i, k) onto an intrusive list per hit body k (head[k], next[i]; 0 = end, entries are
 // i + 1; head is zeroed with the step's counters); k_resolve walks k's list in ascending i -- the lists are short (one or two entries,
 // rarely more), so the next-smallest entry is found by re-walking -- then applies k's own collision, and packs the snapshot record.
-__global__ void __launch_bounds__(256) k_link(int n, int cap, const int* __restrict__ hit_j, const int* __restrict__ ints, int* __restrict__ head, int* __restrict__ next)
+__global__ void __launch_bounds__(256) k_link(int n, int cap, const int* __restrict__ hit_j, const int* __restrict__ ints, int* __restrict__ head, int* __restrict__ next, int lo, int hi)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    int i = lo + blockIdx.x * blockDim.x + threadIdx.x;           // collisions (i, b) of the bodies i in [lo, hi)
+    if (i >= hi) return;
     int b = hitj_body(hit_j[i]);
     if ((unsigned)b < (unsigned)n && ints[I_RESPONSE * cap + b] == 1) next[i] = atomicExch(&head[b], i + 1);      // (records may come from another process)
 }
@@ -1770,10 +1779,10 @@ NP_D SnapObj snap_of(const StoreView& s, int i, V3 pos, uint32_t guid_base)
 // written -- one read and one write of the 48 B/body state per step instead of two, one launch fewer.  Same operations, same order.
 template <bool FUSE, bool EXT>
 __global__ void __launch_bounds__(256) k_resolve(StoreView s, const int* __restrict__ hit_j, const float4* __restrict__ contact,
-                                                const int* __restrict__ head, const int* __restrict__ next, SnapObj* __restrict__ snap, uint32_t guid_base, float dt_next)
+                                                const int* __restrict__ head, const int* __restrict__ next, SnapObj* __restrict__ snap, uint32_t guid_base, float dt_next, int lo, int hi)
 {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= s.n) return;
+    int k = lo + blockIdx.x * blockDim.x + threadIdx.x;           // responses of the bodies k in [lo, hi)
+    if (k >= hi) return;
     const int cap = s.cap;
     float* st = s.state; const float* c = s.cst;
     V3 pos = mk(st[S_PX * cap + k], st[S_PY * cap + k], st[S_PZ * cap + k]);

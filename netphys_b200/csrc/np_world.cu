@@ -81,6 +81,10 @@ struct np_world {
     int g_gjk_env = 0, g_epa_env = 0; // NP_G_GJK / NP_G_EPA overrides (tuning)
     int order_on = 1; bool order_dirty = true;   // NP_ORDER=0: search bodies in index order (tuning)
     int fuse_on = 1;      // NP_FUSE=0: np_world_step_n runs plain steps (A/B)
+    int halo = 0;             // > 0: partitioned sharded step (np_world_set_shard_halo): this rank integrates / responds for its own bodies only and sees `halo` bodies past its range
+    int* d_halo_err = nullptr;
+    float step_dt = 0.0f;
+    int step_phase = 0;       // partitioned step in progress: 1 after np_world_step_integrate, 2 after np_world_step_search
     int epa2_tail32 = 1;      // NP_EPA2_TAIL=4: k_epa2's leftovers to the 4-lane kernel instead of a warp per pair
     int epa2_on = 1;          // NP_EPA2=0: without k_epa2 (small polytopes, thread per pair + block-wide AddFace)
     int tab_min_verts = 5;    // NP_TAB_MIN: shapes with fewer vertices are scanned (tuning)
@@ -655,20 +659,28 @@ static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, i
 //   respond: OnCollision over every body's collisions -> snapshot                                  (physics.cpp:159-162)
 // A sharded world runs them as np_world_step_begin / np_world_step_end with the caller's all-gather of the collision
 // records in between; everything but the search itself is replicated and bit-identical on every process.
-static int enqueue_search(np_world* w, float dt, bool timed, bool integrate = true)
+// part: 0 = Physics::Update of every body, then the search; 1 = Physics::Update only; 2 = the search only (partitioned sharded step)
+static int enqueue_search(np_world* w, float dt, bool timed, bool integrate = true, int part = 0)
 {
     const int n = (int)w->bodies.size();
     if (n == 0) return NP_OK;
     StoreView s = view(w);
     DevCounters* ctr = w->counters_on ? w->d_ctr : nullptr;
-    const int b256 = (n + 255) / 256;
     const int first = sharded(w) ? w->shard_first : 0, count = sharded(w) ? w->shard_count : n;
-    if (timed && !w->capturing) CU(cudaEventRecord(w->ev[0], w->stream));
-    if (integrate) {                              // (a step that follows a fused response was integrated by it)
-        if (s.ext) k_integrate<true><<<b256, 256, 0, w->stream>>>(s, dt, 1); else k_integrate<false><<<b256, 256, 0, w->stream>>>(s, dt, 1);
-        w->launches += 1;
+    const bool part_on = sharded(w) && w->halo > 0;
+    if (part != 2) {
+        if (timed && !w->capturing) CU(cudaEventRecord(w->ev[0], w->stream));
+        if (integrate) {                              // (a step that follows a fused response was integrated by it)
+            const int lo = part_on ? first : 0, hi = part_on ? first + count : n;      // a partitioned step integrates its own bodies; the halo's transforms arrive from their owner
+            if (hi > lo) {
+                const int ib = (hi - lo + 255) / 256;
+                if (s.ext) k_integrate<true><<<ib, 256, 0, w->stream>>>(s, dt, 1, lo, hi); else k_integrate<false><<<ib, 256, 0, w->stream>>>(s, dt, 1, lo, hi);
+                w->launches += 1;
+            }
+        }
+        if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[1], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+        if (part == 1) { CU(cudaGetLastError()); return NP_OK; }
     }
-    if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[1], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     const int cache = cache_mode(w, count);
     if (w->broadphase != NP_BROADPHASE_EXACT) { int r = enqueue_grid(w, s, first, count, cache, ctr); if (r) return r; }
     else if (cache == CACHE_ALL) { k_world_verts<false, 1><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), w->grid); w->launches += 1; }
@@ -678,6 +690,7 @@ static int enqueue_search(np_world* w, float dt, bool timed, bool integrate = tr
     if (count > 0) {
         NarrowIn in; memset(&in, 0, sizeof in); in.world = 1; in.n = count; in.first = first; in.s = s; in.rot_known = 1; in.pf = getenv("NP_PREFETCH") ? atoi(getenv("NP_PREFETCH")) : 1;
         in.ordered = w->order_on;
+        if (part_on) { in.halo = w->halo; in.halo_err = w->d_halo_err; }
         if (w->broadphase != NP_BROADPHASE_EXACT) { in.cand = w->grid.cand; in.cand_off = w->grid.cand_off; in.cand_cnt = w->grid.cand_cnt; }
         if (w->seed_on && !w->gjk1_old && cache != CACHE_BIG && pick_group(w, count, w->g_gjk_env, false) <= 1) {      // thread-per-body search: tabulate the seed supports once per body
             const int sb_ = std::min(w->sm_count * 8, (n + NP_NARROW_THREADS - 1) / NP_NARROW_THREADS);
@@ -696,14 +709,18 @@ static int enqueue_respond(np_world* w, bool timed, const float* fuse_dt = nullp
     const int n = (int)w->bodies.size();
     if (n == 0) return NP_OK;
     StoreView s = view(w);
-    const int b256 = (n + 255) / 256;
     SnapObj* snap = w->snapshot_each_step ? (w->snap_target ? (SnapObj*)w->snap_target : w->d_snap) : nullptr;
-    k_link<<<b256, 256, 0, w->stream>>>(n, w->cap, hitj(w), w->d_ints, d_inc_cnt(w), w->d_inc);
+    // partitioned sharded step: the responses of the own bodies, fed by the collisions of the own bodies and of the `halo` bodies before them
+    const bool part_on = sharded(w) && w->halo > 0;
+    const int lo = part_on ? w->shard_first : 0, hi = part_on ? w->shard_first + w->shard_count : n;
+    const int llo = part_on ? std::max(0, lo - w->halo) : 0;
+    const int b256 = (std::max(hi - lo, 1) + 255) / 256, lb256 = (std::max(hi - llo, 1) + 255) / 256;
+    k_link<<<lb256, 256, 0, w->stream>>>(n, w->cap, hitj(w), w->d_ints, d_inc_cnt(w), w->d_inc, llo, hi);
     // + the snapshot record; fuse_dt: also Physics::Update of the NEXT step (np_world_step_n)
     if (fuse_dt) {
-        if (s.ext) k_resolve<true, true><<<b256, 256, 0, w->stream>>>(s, hitj(w), contacts(w), d_inc_cnt(w), w->d_inc, snap, w->guid_base, *fuse_dt);
-        else k_resolve<true, false><<<b256, 256, 0, w->stream>>>(s, hitj(w), contacts(w), d_inc_cnt(w), w->d_inc, snap, w->guid_base, *fuse_dt);
-    } else k_resolve<false, false><<<b256, 256, 0, w->stream>>>(s, hitj(w), contacts(w), d_inc_cnt(w), w->d_inc, snap, w->guid_base, 0.0f);
+        if (s.ext) k_resolve<true, true><<<b256, 256, 0, w->stream>>>(s, hitj(w), contacts(w), d_inc_cnt(w), w->d_inc, snap, w->guid_base, *fuse_dt, lo, hi);
+        else k_resolve<true, false><<<b256, 256, 0, w->stream>>>(s, hitj(w), contacts(w), d_inc_cnt(w), w->d_inc, snap, w->guid_base, *fuse_dt, lo, hi);
+    } else k_resolve<false, false><<<b256, 256, 0, w->stream>>>(s, hitj(w), contacts(w), d_inc_cnt(w), w->d_inc, snap, w->guid_base, 0.0f, lo, hi);
     if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[4], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     w->launches += 2;
     if (timed && !w->capturing) CU(cudaEventRecord(w->ev[5], w->stream));
@@ -776,7 +793,7 @@ void np_world_destroy(np_world* w)
     drop_graph(w); free_store(w); cudaFree(w->d_ext);
     cudaFree(w->d_wverts); w->d_wverts = nullptr; w->wverts_cap = 0;
     cudaFree(w->d_aos); w->d_aos = nullptr; w->d_aos_bytes = 0;
-    cudaFree(w->d_verts); cudaFree(w->d_soff); cudaFree(w->d_scnt); cudaFree(w->d_tab); cudaFree(w->d_tlim); cudaFree(w->d_cells); cudaFree(w->d_ctr); cudaFree(w->d_flush); cudaFree(w->d_grid_ints); cudaFree(w->d_grid_f);
+    cudaFree(w->d_verts); cudaFree(w->d_soff); cudaFree(w->d_scnt); cudaFree(w->d_tab); cudaFree(w->d_tlim); cudaFree(w->d_cells); cudaFree(w->d_halo_err); cudaFree(w->d_ctr); cudaFree(w->d_flush); cudaFree(w->d_grid_ints); cudaFree(w->d_grid_f);
     cudaFree(w->arena.base);
     if (w->h_stage) cudaFreeHost(w->h_stage);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
@@ -802,6 +819,12 @@ int np_world_begin_island(np_world* w) { if (!w) return fail(NP_ERR_INVALID, "nu
 int np_world_body_count(const np_world* w) { return w ? (int)w->bodies.size() : 0; }
 static int check_grid_error(np_world* w)
 {
+    if (w->halo > 0 && w->d_halo_err) {
+        int e = 0;
+        CU(cudaMemcpyAsync(&e, w->d_halo_err, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+        if (e) { CU(cudaMemsetAsync(w->d_halo_err, 0, sizeof(int), w->stream)); return fail(NP_ERR_CAPACITY, "a first-hit search needed a partner beyond the shard halo: raise np_world_set_shard_halo (the step's result is incomplete)"); }
+    }
     if (w->broadphase == NP_BROADPHASE_EXACT || !w->d_grid_ints) return NP_OK;
     int e = 0;
     CU(cudaMemcpyAsync(&e, w->grid.error, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
@@ -1122,6 +1145,7 @@ int np_world_step_begin(np_world* w, float dt)
 {
     if (!w) return fail(NP_ERR_INVALID, "null world");
     if (w->mid_step) return fail(NP_ERR_INVALID, "np_world_step_begin called twice");
+    if (sharded(w) && w->halo > 0) return fail(NP_ERR_INVALID, "partitioned sharded world: np_world_step_integrate / (halo transforms) / np_world_step_search / (halo records) / np_world_step_end, or np_world_step_sharded");
     int r = ensure_device(w); if (r) return r;
     r = ensure_cache(w); if (r) return r;
     const int n = (int)w->bodies.size();
@@ -1143,6 +1167,55 @@ int np_world_step_end(np_world* w)
     w->timed = true; w->steps++;
     return NP_OK;
 }
+// ---- partitioned sharded step (exact search): every rank integrates and responds for its OWN bodies only -------------------------
+int np_world_set_shard_halo(np_world* w, int halo_bodies)
+{
+    if (!w || halo_bodies < 0) return fail(NP_ERR_INVALID, "bad arguments");
+    if (w->mid_step || w->step_phase) return fail(NP_ERR_INVALID, "np_world_set_shard_halo inside a step");
+    if (halo_bodies > 0 && w->broadphase != NP_BROADPHASE_EXACT) return fail(NP_ERR_INVALID, "partitioned steps support the exact (reference) pair search only");
+    CU(cudaSetDevice(w->device));
+    if (!w->d_halo_err) { CU(cudaMalloc((void**)&w->d_halo_err, sizeof(int))); CU(cudaMemset(w->d_halo_err, 0, sizeof(int))); }
+    drop_graph(w); w->halo = halo_bodies;
+    return NP_OK;
+}
+static void clip_shard(np_world* w)
+{
+    const int n = (int)w->bodies.size();
+    if (sharded(w) && (long long)w->shard_first + w->shard_count > n) {      // ranks past the end own an empty or clipped range
+        if (w->shard_first > n) w->shard_first = n;
+        w->shard_count = n - w->shard_first;
+    }
+}
+int np_world_step_integrate(np_world* w, float dt)
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    if (!(sharded(w) && w->halo > 0)) return fail(NP_ERR_INVALID, "np_world_step_integrate is the first phase of a PARTITIONED sharded step (np_world_set_shard + np_world_set_shard_halo)");
+    if (w->mid_step || w->step_phase) return fail(NP_ERR_INVALID, "a step is already open");
+    if (w->broadphase != NP_BROADPHASE_EXACT) return fail(NP_ERR_INVALID, "partitioned steps support the exact (reference) pair search only");
+    int r = ensure_device(w); if (r) return r;
+    r = ensure_cache(w); if (r) return r;
+    clip_shard(w);
+    r = enqueue_search(w, dt, true, true, 1); if (r) return r;
+    w->step_phase = 1; w->step_dt = dt;
+    return NP_OK;
+}
+int np_world_step_search(np_world* w)
+{
+    if (!w) return fail(NP_ERR_INVALID, "null world");
+    if (w->step_phase != 1) return fail(NP_ERR_INVALID, "np_world_step_search without np_world_step_integrate");
+    CU(cudaSetDevice(w->device));
+    w->step_phase = 0;
+    int r = enqueue_search(w, w->step_dt, true, false, 2); if (r) return r;
+    w->mid_step = true;                                  // np_world_step_end closes the step
+    return NP_OK;
+}
+int np_world_transforms_device(np_world* w, void** d_xf)
+{
+    if (!w || !d_xf) return fail(NP_ERR_INVALID, "bad arguments");
+    int r = ensure_device(w); if (r) return r;
+    *d_xf = w->d_xf;
+    return NP_OK;
+}
 int np_world_step_n(np_world* w, float dt, int steps)
 {
     if (!w || steps < 0) return fail(NP_ERR_INVALID, "bad arguments");
@@ -1162,7 +1235,7 @@ int np_world_integrate(np_world* w, float dt)
     if (!w) return fail(NP_ERR_INVALID, "null world");
     int r = ensure_device(w); if (r) return r;
     int n = (int)w->bodies.size(); if (n == 0) return NP_OK;
-    if (w->d_ext) k_integrate<true><<<(n + 255) / 256, 256, 0, w->stream>>>(view(w), dt, 1); else k_integrate<false><<<(n + 255) / 256, 256, 0, w->stream>>>(view(w), dt, 1);
+    if (w->d_ext) k_integrate<true><<<(n + 255) / 256, 256, 0, w->stream>>>(view(w), dt, 1, 0, n); else k_integrate<false><<<(n + 255) / 256, 256, 0, w->stream>>>(view(w), dt, 1, 0, n);
     CU(cudaGetLastError());
     return NP_OK;
 }
@@ -1178,7 +1251,9 @@ int np_world_get_collisions(np_world* w, np_collision* out, int cap, int* count)
     CU(cudaMemcpyAsync(cd.data(), contacts(w), sizeof(float4) * n, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
     int k = 0;
-    for (int i = 0; i < n; i++) {
+    const bool part_on = sharded(w) && w->halo > 0;       // partitioned step: this rank knows the collisions of its own bodies (and of the halo before them)
+    const int ilo = part_on ? std::min(n, w->shard_first) : 0, ihi = part_on ? std::min(n, w->shard_first + std::max(0, w->shard_count)) : n;
+    for (int i = ilo; i < ihi; i++) {
         if (hj[i] < 0) continue;
         if (out && k < cap) {
             np_collision& c = out[k]; memset(&c, 0, sizeof c);
@@ -1543,6 +1618,8 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -1560,6 +1637,7 @@ int load_nccl()
     *(void**)&a.CommDestroy = dlsym(lib, "ncclCommDestroy"); *(void**)&a.AllGather = dlsym(lib, "ncclAllGather");
     *(void**)&a.GroupStart = dlsym(lib, "ncclGroupStart"); *(void**)&a.GroupEnd = dlsym(lib, "ncclGroupEnd");
     *(void**)&a.GetErrorString = dlsym(lib, "ncclGetErrorString");
+    *(void**)&a.Send = dlsym(lib, "ncclSend"); *(void**)&a.Recv = dlsym(lib, "ncclRecv");
     if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.GroupStart || !a.GroupEnd) return fail(NP_ERR_INVALID, "libnccl lacks a required symbol");
     g_nccl = a;
     return NP_OK;
@@ -1697,6 +1775,44 @@ int np_world_step_sharded(np_world* w, float dt)
 {
     if (!w) return fail(NP_ERR_INVALID, "null world");
     if (!w->comm || !w->d_shard_hit) return fail(NP_ERR_INVALID, "np_comm_init and np_world_shard_over_comm first");
+    if (w->halo > 0) {
+        // Partitioned: integrate own -> the next rank's first `halo` transforms (ncclSend/Recv between neighbours) -> search own -> the
+        // previous rank's last `halo` collision records (their partners may be bodies of mine) -> respond own.  No all-gather.
+        if (!g_nccl.Send || !g_nccl.Recv) return fail(NP_ERR_INVALID, "libnccl lacks ncclSend / ncclRecv");
+        const int n = (int)w->bodies.size(), H = w->halo, slot = w->shard_slot;
+        if (H > slot) return fail(NP_ERR_INVALID, "shard halo larger than a rank's slot of bodies");
+        auto range = [&](int rk, int* f, int* c) { *f = (int)std::min<long long>(n, (long long)rk * slot); *c = (int)std::min<long long>(n, (long long)*f + slot) - *f; };
+        int first, count, nf = n, nc = 0, pf = 0, pc = 0;
+        range(w->rank, &first, &count);
+        if (w->rank + 1 < w->nranks) range(w->rank + 1, &nf, &nc);
+        if (w->rank > 0) range(w->rank - 1, &pf, &pc);
+        int r = np_world_step_integrate(w, dt); if (r) return r;
+        const int xs = (w->rank > 0 && pc > 0) ? std::min(H, count) : 0, xr = std::min(H, nc);       // transforms: mine to the previous rank, the next rank's to me
+        if (xs > 0 || xr > 0) {
+            NC(g_nccl.GroupStart());
+            ncclResult_t e1 = xs > 0 ? g_nccl.Send(w->d_xf + (size_t)X_COUNT * first, (size_t)X_COUNT * xs, ncclFloat32, w->rank - 1, w->comm, w->stream) : ncclSuccess;
+            ncclResult_t e2 = xr > 0 ? g_nccl.Recv(w->d_xf + (size_t)X_COUNT * nf, (size_t)X_COUNT * xr, ncclFloat32, w->rank + 1, w->comm, w->stream) : ncclSuccess;
+            NC(g_nccl.GroupEnd());
+            if (e1 != ncclSuccess || e2 != ncclSuccess) { w->step_phase = 0; return fail(NP_ERR_CUDA, "ncclSend/Recv of the halo transforms failed"); }
+        }
+        r = np_world_step_search(w); if (r) return r;
+        const int rs = (nc > 0) ? std::min(H, count) : 0, rr = (w->rank > 0 && count > 0) ? std::min(H, pc) : 0;       // records: my last ones to the next rank, the previous rank's last ones to me
+        if (rs > 0 || rr > 0) {
+            NC(g_nccl.GroupStart());
+            ncclResult_t e[4] = { ncclSuccess, ncclSuccess, ncclSuccess, ncclSuccess };
+            if (rs > 0) {
+                e[0] = g_nccl.Send(w->d_shard_hit + (first + count - rs), (size_t)rs, ncclInt32, w->rank + 1, w->comm, w->stream);
+                e[1] = g_nccl.Send(w->d_shard_contact + (first + count - rs), (size_t)rs * 4, ncclFloat32, w->rank + 1, w->comm, w->stream);
+            }
+            if (rr > 0) {
+                e[2] = g_nccl.Recv(w->d_shard_hit + (first - rr), (size_t)rr, ncclInt32, w->rank - 1, w->comm, w->stream);
+                e[3] = g_nccl.Recv(w->d_shard_contact + (first - rr), (size_t)rr * 4, ncclFloat32, w->rank - 1, w->comm, w->stream);
+            }
+            NC(g_nccl.GroupEnd());
+            for (ncclResult_t x : e) if (x != ncclSuccess) { w->mid_step = false; return fail(NP_ERR_CUDA, "ncclSend/Recv of the halo collision records failed"); }
+        }
+        return np_world_step_end(w);
+    }
     int r = np_world_step_begin(w, dt); if (r) return r;
     const size_t slot = (size_t)w->shard_slot, off = slot * (size_t)w->rank;
     NC(g_nccl.GroupStart());

@@ -144,6 +144,10 @@ def load_library(variant="exact"):
     L.np_world_last_gather_ms.argtypes = [vp, C.c_int, f32p]
     L.np_world_shard_over_comm.argtypes = [vp]
     L.np_world_step_sharded.argtypes = [vp, C.c_float]
+    L.np_world_set_shard_halo.argtypes = [vp, C.c_int]
+    L.np_world_step_integrate.argtypes = [vp, C.c_float]
+    L.np_world_step_search.argtypes = [vp]
+    L.np_world_transforms_device.argtypes = [vp, C.POINTER(vp)]
     L.np_selftest_fp32_peak.argtypes = [vp, f32p]
     L.np_selftest_fp32_peaks.argtypes = [vp, f32p]
     L.np_selftest_sincos_hash.argtypes = [vp, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -306,6 +310,12 @@ class World:
     def step_begin(self, dt): self._ck(self.L.np_world_step_begin(self.w, float(np.float32(dt))))
 
     def step_end(self): self._ck(self.L.np_world_step_end(self.w))
+    def set_shard_halo(self, halo): self._ck(self.L.np_world_set_shard_halo(self.w, int(halo)))
+    def step_integrate(self, dt): self._ck(self.L.np_world_step_integrate(self.w, float(np.float32(dt))))
+    def step_search(self): self._ck(self.L.np_world_step_search(self.w))
+
+    def transforms_device(self):
+        p = C.c_void_p(); self._ck(self.L.np_world_transforms_device(self.w, C.byref(p))); return p.value
     def integrate(self, dt): self._ck(self.L.np_world_integrate(self.w, float(np.float32(dt))))
     def synchronize(self): self._ck(self.L.np_world_synchronize(self.w))
 

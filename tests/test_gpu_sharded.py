@@ -123,3 +123,78 @@ def test_shard_changes_between_steps_and_bodies_added(npb, oracle):
             for x in (w, w2):
                 a, b, dd = x.collisions_as_arrays()
                 assert np.array_equal(a, ao) and np.array_equal(b, bo); assert_biteq(dd, do, "collision data"); assert_biteq(x.states(), ow.state(), "state step %d" % k)
+
+
+# ---- partitioned steps: every rank integrates / responds for its own bodies only, neighbours exchange halos ---------------------------
+def _partitioned_steps(npb, sc, n_ranks, halo, steps, check):
+    ranks = [_Rank(npb, sc, n_ranks, r, 0) for r in range(n_ranks)]
+    try:
+        for r in ranks: r.w.set_shard_halo(halo)
+        n = ranks[0].w.n
+        xf = [r.w.transforms_device() for r in ranks]
+        for k in range(steps):
+            for r in ranks: r.w.step_integrate(sc["dt"])
+            for q, r in enumerate(ranks[:-1]):                       # the next rank's first `halo` transforms (48 B each) -> right after the own range
+                nx = ranks[q + 1]; h = min(halo, nx.count)
+                if h > 0:
+                    buf = np.zeros((h, 12), np.float32); nx.w.dev_download(buf, xf[q + 1] + 48 * nx.first); r.w.dev_upload(xf[q] + 48 * nx.first, buf)
+            for r in ranks: r.w.step_search()
+            for q, r in enumerate(ranks[1:], 1):                     # the previous rank's last `halo` records -> right before the own range
+                pv = ranks[q - 1]; h = min(halo, pv.count)
+                if h > 0 and r.count > 0:
+                    for p_src, p_dst, width, dt_ in ((pv.d[0], r.d[0], 4, np.int32), (pv.d[2], r.d[2], 16, np.float32)):
+                        buf = np.zeros(h * width // 4, dt_); pv.w.dev_download(buf, p_src + width * (r.first - h)); r.w.dev_upload(p_dst + width * (r.first - h), buf)
+            for r in ranks: r.w.step_end()
+            check(k, ranks)
+        return [r.w.counters() for r in ranks]
+    finally:
+        for r in ranks: r.w.close()
+
+
+@pytest.mark.parametrize("n,n_ranks,halo", [(700, 2, 64), (1001, 3, 40), (2000, 4, 500), (49, 8, 7), (24, 3, 8)])
+def test_partitioned_world_equals_reference_on_the_owned_bodies(npb, oracle, n, n_ranks, halo):
+    """np_world_set_shard_halo: each rank steps its own index range (integrate, search, respond) and sees `halo` bodies past it; the host
+    plays the two neighbour exchanges.  Own bodies' state and collisions == the oracle's single world, every step; everything else on a
+    rank is allowed to be stale."""
+    sc = scenes.lattice_scene(n, spacing=1.1, seed=n, mix=(0.5, 0.3, 0.2))
+    ow = oracle.world(scenes.resolve(sc, oracle))
+
+    def check(k, ranks):
+        ao, bo, do = ow.step(sc["dt"], True); so = ow.state()
+        got_a = []; got_b = []; got_d = []
+        for r in ranks:
+            r.w.synchronize()
+            a, b, d = r.w.collisions_as_arrays()
+            assert len(a) == 0 or (a.min() >= r.first and a.max() < r.first + r.count)
+            got_a.append(a); got_b.append(b); got_d.append(d)
+            assert_biteq(r.w.states()[r.first:r.first + r.count], so[r.first:r.first + r.count], "own bodies' state, step %d rank range %d+%d" % (k, r.first, r.count))
+        assert np.array_equal(np.concatenate(got_a), ao) and np.array_equal(np.concatenate(got_b), bo), "collision list, step %d" % k
+        assert_biteq(np.concatenate(got_d), do, "collision data, step %d" % k)
+
+    ctrs = _partitioned_steps(npb, sc, n_ranks, halo, 8, check)
+    pt, hits, _ = ow.counters()
+    assert sum(c["pair_tests"] for c in ctrs) == pt and sum(c["hits"] for c in ctrs) == hits
+
+
+def test_partitioned_world_reports_a_halo_that_is_too_small(npb):
+    """a body whose first hit lies further ahead than the halo: the step must say so instead of returning a different collision list"""
+    sc = scenes.lattice_scene(600, spacing=1.1, seed=600, mix=(0.5, 0.3, 0.2))
+    with npb.World(0) as one:
+        one.load_scene(sc); one.step(sc["dt"]); a, b, _ = one.collisions_as_arrays()
+    reach = int((b - a).max())
+    assert reach > 1, "workload no longer has a first hit beyond the next body"
+    for halo, ok in ((reach, True), (reach - 1, False)):
+        w = npb.World(0)
+        try:
+            w.load_scene(sc)
+            d = [w.dev_alloc(4 * 600), w.dev_alloc(4 * 600), w.dev_alloc(16 * 600)]
+            w.set_shard(0, 600, *d); w.set_shard_halo(halo)
+            w.step_integrate(sc["dt"]); w.step_search(); w.step_end()
+            if ok:
+                w.synchronize(); a2, b2, _ = w.collisions_as_arrays()
+                assert np.array_equal(a2, a) and np.array_equal(b2, b)
+            else:
+                with pytest.raises(npb.NetphysError):
+                    w.synchronize()
+        finally:
+            w.close()
