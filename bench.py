@@ -177,6 +177,33 @@ def run_sharded_world(npb, torch, dist, rank, local_rank, world_size):
         st = w.states().view(np.uint32)
         h = np.array([int(np.bitwise_xor.reduce(st.ravel())), int(st.sum(dtype=np.uint64) & 0x7fffffff)], np.int64)
         a, b, _ = w.collisions_as_arrays()
+    # the same world and the same eight steps PARTITIONED: every rank integrates / responds for its own bodies only and exchanges halos with
+    # its neighbours (np_world_set_shard_halo); its own bodies must end up with the bits the replicated run gave them
+    halo = int(os.environ.get("NP_BENCH_SHARD_HALO", "4096"))
+    part = None
+    with W(local_rank) as w2:
+        w2.set_option(W.OPT_PHASE_TIMING, 1)
+        w2.load_scene(sc)
+        sw2 = ShardedWorld(w2, torch.device("cuda", local_rank), world_size, rank, halo=halo)
+        for _ in range(3): sw2.step(sc["dt"])
+        w2.synchronize(); dist.barrier()
+        ms2 = []
+        for _ in range(5):
+            w2.flush_l2(); sw2.step(sc["dt"]); ms2.append(w2.last_step_ms())
+        w2.synchronize()
+        ms2 = np.array(ms2, np.float64).mean(0)
+        slot = (n + world_size - 1) // world_size; lo_ = min(n, rank * slot); hi_ = min(n, lo_ + slot)
+        same = bool(np.array_equal(w2.states().view(np.uint32)[lo_:hi_], st[lo_:hi_]))
+        a2, _, _ = w2.collisions_as_arrays()
+        t2 = torch.tensor(list(ms2) + [0.0 if same else 1.0, float(len(a2))], device="cuda", dtype=torch.float64)
+        tmax = t2.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX); tsum = t2.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        tm = tmax.cpu().numpy()
+        part = {"workload": "the same world with PARTITIONED steps (np_world_set_shard_halo = %d bodies): each rank runs Physics::Update, the first-hit search and OnCollision for its own "
+                            "%d bodies, ncclSend/Recv of the halo transforms (48 B/body) and halo collision records (20 B/body) between neighbours, no all-gather" % (halo, slot),
+                "value": n / (float(tm[5]) * 1e-3), "unit": "body-steps/s", "ms_per_step": float(tm[5]),
+                "phase_ms": {"integrate_own": float(tm[0]), "halo_transforms": float(tm[1]), "search_owned": float(tm[2]), "halo_records_and_respond_own": float(tm[3]), "snapshot": float(tm[4])},
+                "own_bodies_bit_identical_to_the_replicated_run": bool(tm[6] == 0.0), "collisions_per_step_all_ranks": int(tsum.cpu().numpy()[7]),
+                "timing": "CUDA events on the world's stream, mean of 5 steps, max over ranks; L2 flushed"}
     t = torch.tensor(ms, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.cpu().numpy()
     hs = torch.tensor(h, device="cuda"); lo = hs.clone(); hi = hs.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
@@ -184,7 +211,8 @@ def run_sharded_world(npb, torch, dist, rank, local_rank, world_size):
                         "one grouped ncclAllGather of the per-body collision records (hit_j + contact, 20 B/body) inside np_world_step_sharded, responses applied on every rank" % (n, world_size),
             "value": n / (float(ms[5]) * 1e-3), "unit": "body-steps/s", "ms_per_step": float(ms[5]), "scaling": "weak (%d searched bodies per GPU; integrate/response passes are replicated)" % per_gpu,
             "phase_ms": {"integrate": float(ms[0]), "world_verts": float(ms[1]), "search_owned": float(ms[2]), "allgather_and_respond": float(ms[3]), "snapshot": float(ms[4])},
-            "collisions_per_step": int(len(a)), "state_bit_identical_on_all_ranks": bool(torch.equal(lo, hi)), "l2": "flushed before every timed step", "timing": "CUDA events on the world's stream, mean of 5 steps, max over ranks"}
+            "collisions_per_step": int(len(a)), "state_bit_identical_on_all_ranks": bool(torch.equal(lo, hi)), "l2": "flushed before every timed step", "timing": "CUDA events on the world's stream, mean of 5 steps, max over ranks",
+            "partitioned": part}
 
 
 def build_worlds_batch(npb, w, lo, hi):

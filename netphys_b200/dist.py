@@ -95,12 +95,15 @@ class ShardedWorld:
     one grouped ncclAllGather of hit_j and contact on the world's stream -> step_end.  lib_comm=False: the same exchange through
     torch.distributed (CollisionExchange), kept for the gloo tests and as a cross-check."""
 
-    def __init__(self, world, device, world_size, rank, lib_comm=True):
+    def __init__(self, world, device, world_size, rank, lib_comm=True, halo=0):
         self.w = world; self.lib_comm = lib_comm
         if lib_comm:
             init_world_comm(world, rank, world_size)
             world.shard_over_comm()
+            if halo > 0:
+                world.set_shard_halo(halo)      # partitioned steps: own bodies only, ncclSend/Recv of the halos between neighbours instead of the all-gather
             return
+        assert halo == 0, "partitioned steps go through the library's own NCCL path"
         import torch
         self.torch = torch
         self.x = CollisionExchange(world.n, device, world_size, rank)

@@ -5,7 +5,9 @@
 //
 // Every rank builds the same world; (1) ONE world sharded over the ranks with np_world_step_sharded (collision records all-gathered by
 // the library over NCCL) must stay bit-identical to an unsharded world stepped by rank 0 alone and on every rank; (2) independent
-// worlds with np_world_set_snapshot_gather: after a step every rank holds every rank's 36-byte records.  Exit code 0 = all checks passed.
+// worlds with np_world_set_snapshot_gather: after a step every rank holds every rank's 36-byte records; (3) the world of (1) once more
+// with PARTITIONED steps (np_world_set_shard_halo: own bodies only, ncclSend/Recv of the halos): every rank's own range == (1).
+// Exit code 0 = all checks passed.
 #include <dlfcn.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -14,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/netphys_b200.h"
@@ -29,6 +32,7 @@ static int run_rank(void* lib, int rank, int nranks, const unsigned char* id, in
     SYM(np_last_error) SYM(np_world_create) SYM(np_world_destroy) SYM(np_shape_create_box) SYM(np_shape_create_sphere) SYM(np_body_create_batch)
     SYM(np_comm_init) SYM(np_world_shard_over_comm) SYM(np_world_step_sharded) SYM(np_world_step) SYM(np_world_get_states) SYM(np_world_synchronize)
     SYM(np_world_set_snapshot_gather) SYM(np_world_gathered_snapshot) SYM(np_device_download) SYM(np_world_snapshot) SYM(np_comm_destroy)
+    SYM(np_world_set_shard_halo)
     np_world* w = p_np_world_create(rank);
     if (!w) { fprintf(stderr, "rank %d: np_world_create: %s\n", rank, p_np_last_error()); return 3; }
     auto build = [&](np_world* x, uint32_t seed) {
@@ -82,6 +86,20 @@ static int run_rank(void* lib, int rank, int nranks, const unsigned char* id, in
     for (int r = 0; r < nranks; r++) for (int i = 0; i < bodies; i += 97) if (all[(size_t)r * bodies + i].guid != (uint32_t)(r * bodies + i)) { ok = 0; }
     uint64_t hs = 1469598103934665603ull; for (size_t i = 0; i < nbytes; i++) hs = (hs ^ ((const unsigned char*)all.data())[i]) * 1099511628211ull;
     CK(p_np_comm_destroy(v)); p_np_world_destroy(v);
+    // (3) the sharded world of (1) again with PARTITIONED steps: own bodies only, halos between neighbours; the own range must match (1)
+    {
+        np_world* q = p_np_world_create(rank); if (!q) return 3;
+        CK(build(q, 12345u));
+        CK(p_np_comm_init(q, nranks, rank, id + 2 * NP_COMM_ID_BYTES));
+        CK(p_np_world_shard_over_comm(q));
+        const int slot = (bodies + nranks - 1) / nranks, first = std::min(bodies, rank * slot), count = std::min(bodies, first + slot) - first;
+        CK(p_np_world_set_shard_halo(q, std::min(256, slot)));
+        for (int k = 0; k < steps; k++) CK(p_np_world_step_sharded(q, dt));
+        CK(p_np_world_synchronize(q));                     // (reports a halo that was too small)
+        std::vector<np_body_state> sq(bodies); CK(p_np_world_get_states(q, sq.data(), bodies));
+        if (count > 0 && memcmp(sq.data() + first, st.data() + first, sizeof(np_body_state) * (size_t)count) != 0) { ok = 0; fprintf(stderr, "rank %d: partitioned steps changed the own bodies' state\n", rank); }
+        CK(p_np_comm_destroy(q)); p_np_world_destroy(q);
+    }
     uint64_t msg[3] = { (uint64_t)ok, h, hs };
     if (write(out_fd, msg, sizeof msg) != (ssize_t)sizeof msg) return 4;
     return ok ? 0 : 5;
@@ -97,8 +115,8 @@ int main(int argc, char** argv)
     auto dev_count = (decltype(&np_device_count))dlsym(lib, "np_device_count");
     auto last_error = (decltype(&np_last_error))dlsym(lib, "np_last_error");
     if (!get_id || !dev_count) return 2;
-    unsigned char id[2 * NP_COMM_ID_BYTES];
-    if (get_id(id) < 0 || get_id(id + NP_COMM_ID_BYTES) < 0) { fprintf(stderr, "np_comm_get_unique_id: %s\n", last_error()); return 2; }
+    unsigned char id[3 * NP_COMM_ID_BYTES];
+    if (get_id(id) < 0 || get_id(id + NP_COMM_ID_BYTES) < 0 || get_id(id + 2 * NP_COMM_ID_BYTES) < 0) { fprintf(stderr, "np_comm_get_unique_id: %s\n", last_error()); return 2; }
     std::vector<pid_t> kids; std::vector<int> fds;
     for (int r = 0; r < nranks; r++) {
         int pfd[2]; if (pipe(pfd)) return 2;
@@ -115,7 +133,7 @@ int main(int argc, char** argv)
         hstate.push_back(msg[1]); hsnap.push_back(msg[2]);
     }
     for (int r = 1; r < nranks; r++) if (hstate[r] != hstate[0] || hsnap[r] != hsnap[0]) { fprintf(stderr, "rank %d holds different state / gathered snapshot than rank 0\n", r); bad = 1; }
-    printf("%s: %d ranks, %d bodies, %d sharded steps: state hash %016llx on every rank == unsharded; gathered snapshot hash %016llx on every rank\n",
+    printf("%s: %d ranks, %d bodies, %d sharded steps: state hash %016llx on every rank == unsharded (and own ranges == after partitioned steps); gathered snapshot hash %016llx on every rank\n",
            bad ? "FAILED" : "ok", nranks, bodies, steps, (unsigned long long)hstate[0], (unsigned long long)hsnap[0]);
     return bad;
 }
