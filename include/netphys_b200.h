@@ -161,7 +161,7 @@ int np_body_apply_impulse_response(np_world* w, int body, const np_collision_dat
 int np_world_get_states(np_world* w, np_body_state* out, int cap);                        /* all bodies, creation order */
 int np_world_set_states(np_world* w, const np_body_state* in, int n);
 
-/* ---- adapter extension: what an ODE-shaped World facade (netphys_common/world.h:8-28; include/netphys/world.h) needs beyond the
+/* ---- adapter extension: what an ODE-shaped World facade (netphys_common/world.h:8-28; include/netphys/ode_shim/ode/ode.h) needs beyond the
  * engine's API.  NOT reference semantics -- engine/ has gravity only (physics.cpp:178-181) -- defined here and mirrored by the oracle:
  * a force acts during the next step only, as L += F*dt right after the gravity term of Physics::Update (calls accumulate, F = sum);
  * a disabled body is not integrated (it still collides) and reports isEnabled = 0 in the snapshot (world_s.cpp:48). */
