@@ -517,16 +517,19 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK1_MINB) k_gjk1(Narrow
 // Two block barriers per trip; the other resident blocks of the SM fill the gaps.  Results are those of k_gjk1: the same operations
 // on the same operands, only on another lane.
 // ---------------------------------------------------------------------------------------------------
-#define NP_GJK2_EXTRA_WORDS (30 * NP_NARROW_THREADS + 32)      // per block, after the simplices: job word, result word, direction (3), order, counters, transforms (24)
+#ifndef NP_GJK2_THREADS
+#define NP_GJK2_THREADS 128
+#endif
+#define NP_GJK2_EXTRA_WORDS (30 * NP_GJK2_THREADS + 32)      // per block, after the simplices: job word, result word, direction (3), order, counters, transforms (24)
 #ifndef NP_GJK2_MINB
 #define NP_GJK2_MINB 6     // 80 registers, no spills: 24 resident warps per SM (measured on the 1M world: 4 blocks 2.63 ms, 5 2.65, 6 2.57)
 #endif
 template <bool WORLD>
-__global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK2_MINB) k_gjk2(NarrowIn in, ShapeView sh, int smem_shapes, int* __restrict__ ticket, int* __restrict__ hit_j,
+__global__ void __launch_bounds__(NP_GJK2_THREADS, NP_GJK2_MINB) k_gjk2(NarrowIn in, ShapeView sh, int smem_shapes, int* __restrict__ ticket, int* __restrict__ hit_j,
                                                            int* __restrict__ flags, float4* __restrict__ contact, float4* __restrict__ simplex,
                                                            int* __restrict__ hit_list, int* __restrict__ hit_count, DevCounters* ctr)
 {
-    constexpr int T = NP_NARROW_THREADS, NW = T / 32;
+    constexpr int T = NP_GJK2_THREADS;
     extern __shared__ float4 s_dyn[];
     const float4* verts = stage_shapes(sh, s_dyn, smem_shapes != 0);
     float* sx = reinterpret_cast<float*>(s_dyn + (smem_shapes ? sh.total_verts : 0));

@@ -445,7 +445,16 @@ static int launch_gjk(np_world* w, const NarrowIn& in, const NarrowBufs& b, DevC
                 if (coop_on(w) && cache_mode(w, in.n) == CACHE_BIG) kern = k_gjk1<true, true, true>;
                 else if (in.seed) kern = coop_on(w) ? k_gjk1<true, true, false, true> : k_gjk1<true, false, false, true>;
             }
-            if (w->gjk2_on && !coop_on(w) && !in.seed) { kern = k_gjk2<WORLD>; smem += sizeof(int) * NP_GJK2_EXTRA_WORDS; }      // solves regrouped by simplex size
+            if (w->gjk2_on && !coop_on(w) && !in.seed) {      // solves regrouped by simplex size; its own block size
+                smem = shapes_smem(w) + sizeof(float) * NP_SX_ROWS * NP_GJK2_THREADS + sizeof(int) * NP_GJK2_EXTRA_WORDS;
+                int per_sm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gjk2<WORLD>, NP_GJK2_THREADS, smem) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
+                const int gb = (int)std::max<long long>(1, std::min<long long>((long long)std::max(1, per_sm) * w->sm_count, ((long long)in.n + NP_GJK2_THREADS - 1) / NP_GJK2_THREADS));
+                k_gjk2<WORLD><<<gb, NP_GJK2_THREADS, smem, w->stream>>>(in, sview(w), shapes_in_smem(w) ? 1 : 0, b.zero + Z_GJK_TICKET, b.hit_j, b.flags, b.contact, b.simplex,
+                                                                          b.hit_list, b.zero + Z_HIT_COUNT, ctr);
+                w->launches++;
+                return NP_OK;
+            }
         } else if constexpr (WORLD) { if (coop_on(w)) kern = k_gjk<G, WORLD, true>; }
     }
     int blocks = persistent_blocks(w, kern, smem, in.n, G);

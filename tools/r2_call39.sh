@@ -1,0 +1,7 @@
+#!/bin/bash
+for l in "" build/lib_g2t64.so build/lib_g2t256.so; do echo "== lib $l"
+  if [ -n "$l" ]; then export NETPHYS_B200_LIB=$PWD/$l; fi
+  python tools/prof_world.py 1000000 6 c3 2>&1 | tail -1 | cut -c1-150
+  python tools/prof_world.py 131072 20 c2 2>&1 | tail -1 | cut -c1-150
+  python tools/prof_pairs.py mix 2000000 3 2>&1 | tail -1 | cut -c1-100
+done
