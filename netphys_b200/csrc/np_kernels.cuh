@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(NP_GJK2_THREADS, NP_GJK2_MINB) k_gjk2(NarrowIn
     PairStats st = { 0, 0, 0, 0, 0 };
     unsigned n_tests = 0, n_hits = 0;
     int i = -1, j = 0, jend = 0, cbase = 0, c = 0, cn = 0;
-    bool have = false, exhausted = false;
+    bool have = false, exhausted = false, need_b = false;
     const StoreView& s = in.s;
     const int* shape_of = s.ints + I_SHAPE * s.cap;
     const int* island_end = s.ints + I_ISLAND_END * s.cap;
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(NP_GJK2_THREADS, NP_GJK2_MINB) k_gjk2(NarrowIn
                 if (WORLD) {
                     if (in.cand) { cbase = in.cand_off[i]; c = 0; cn = in.cand_cnt[i]; j = cn > 0 ? in.cand[cbase] : 0; jend = cn > 0 ? 0x7fffffff : 0; }
                     else { j = i + 1; jend = island_end[i]; if (in.halo > 0) jend = min(jend, i + 1 + in.halo); }
-                    if (j < jend) { arm_a(i); arm_b(j); m.begin(); have = true; }
+                    if (j < jend) { arm_a(i); need_b = true; have = true; }
                     else { hit_j[i] = -1; flags[i] = 0; }
                 } else {
                     float Ra[9], Rb[9]; V3 ta, tb;
@@ -606,6 +606,9 @@ __global__ void __launch_bounds__(NP_GJK2_THREADS, NP_GJK2_MINB) k_gjk2(NarrowIn
                 }
             } else exhausted = true;
         }
+        // one arming of the partner for the lanes that took a new body just now AND those whose pair missed at the end of the last trip:
+        // the same code, so it runs once with all of them instead of twice with a few lanes each
+        if (WORLD && need_b) { arm_b(j); m.begin(); need_b = false; }
         int cls = 0;                                   // 0: no solve pending; 1 line, 2 triangle, 3 tetrahedron
         if (have) {
             V3 sa = mk(0.0f, 0.0f, 0.0f), sb = sa;
@@ -685,7 +688,7 @@ __global__ void __launch_bounds__(NP_GJK2_THREADS, NP_GJK2_MINB) k_gjk2(NarrowIn
                 }
                 have = false;
             } else if (WORLD && (in.cand ? (++c < cn ? ((j = in.cand[cbase + c]), true) : false) : (++j < jend || halo_exhausted(in, island_end, i, jend)))) {
-                arm_b(j); m.begin();
+                need_b = true;
             } else {
                 if (WORLD) hit_j[i] = -1;
                 flags[i] = 0;
