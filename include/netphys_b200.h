@@ -208,7 +208,8 @@ int np_world_step_sharded(np_world* w, float dt);
  * with a halo of H > 0 bodies a rank runs Physics::Update, OnCollision and the snapshot for ITS OWN bodies only -- the per-step work and
  * traffic of everything but the search divide by the rank count -- and exchanges with its two neighbours instead of all-gathering:
  *   np_world_step_integrate   Physics::Update of the own bodies
- *   (the next rank's first H transforms -> this rank's array, right after its own range: np_world_transforms_device, [n][12] floats)
+ *   (the next rank's first H transform records -> this rank's array, right after its own range: np_world_transforms_device, [n][16] floats:
+ *    rotation 9, translation 3, then 4 ints of arming data the narrow phase reads next to them -- copy all 64 bytes)
  *   np_world_step_search      GetCollisions of the own bodies; a search may look at most H bodies ahead
  *   (the previous rank's last H collision records -> this rank's d_hit_j / d_contact, right before its own range)
  *   np_world_step_end         OnCollision of the own bodies

@@ -19,14 +19,15 @@ namespace np {
 // component indices of the SoA blocks
 enum { S_PX = 0, S_PY, S_PZ, S_RX, S_RY, S_RZ, S_LX, S_LY, S_LZ, S_HX, S_HY, S_HZ, S_COUNT };          // dynamic state
 enum { C_GX = 0, C_GY, C_GZ, C_MASS, C_ELAST, C_IINV0, C_COUNT = C_IINV0 + 9 };                       // per-body constants
-enum { X_R0 = 0, X_TX = 9, X_TY, X_TZ, X_COUNT };                                                      // transform
+enum { X_R0 = 0, X_TX = 9, X_TY, X_TZ, X_ARM = 12, X_COUNT = 16 };                                      // transform (12 floats) + arming record (4 ints): 64 bytes
 enum { I_RESPONSE = 0, I_SHAPE, I_ISLAND_END, I_WVOFF, I_ORDER, I_WVOFF_BIG, I_HANDLE, I_COUNT };     // I_WVOFF: first world vertex of the body in the per-step cache (I_WVOFF_BIG: in the cache of large bodies only, -1 for small ones); I_ORDER: search order (bodies grouped by shape); I_HANDLE: the caller's id of the body (differs from the slot once bodies were destroyed)
 
 struct StoreView {
     int n, cap;
     float* state;      // [S_COUNT][cap]
     const float* cst;  // [C_COUNT][cap]
-    float* xf;         // [cap][X_COUNT]: one body's transform is 48 contiguous bytes (3 float4) -- written coalesced by K1, gathered per pair by K3/K4
+    float* xf;         // [cap][X_COUNT]: one body's transform is 48 contiguous bytes (3 float4), followed by its arming record (ArmRec) -- written coalesced by K1, gathered per pair by K3/K4
+    const int* soff; const int* scnt; const unsigned* stab; const float* stlim;   // the shape table's per-shape arrays (ShapeView / TabView), for whoever writes a transform
     const int* ints;   // [I_COUNT][cap]
     float4* wverts;    // world-space vertices of every body, rewritten each step by k_world_verts
     float* ext;        // adapter extension, null unless used: [4][cap] = one-step external force xyz (np_body_add_force), enabled flag
@@ -45,17 +46,27 @@ struct DevCounters {       // mirrors np_counters (all uint64)
 // transform of body i: R[9] then t, 12 floats = 3 float4 (`stride` is kept in the signature for the callers; unused)
 NP_D void store_xf(float* __restrict__ xf, int i, const float* R, V3 t)
 {
-    float4* p = reinterpret_cast<float4*>(xf) + 3 * (size_t)i;
+    float4* p = reinterpret_cast<float4*>(xf) + (X_COUNT / 4) * (size_t)i;
     p[0] = make_float4(R[0], R[1], R[2], R[3]); p[1] = make_float4(R[4], R[5], R[6], R[7]); p[2] = make_float4(R[8], t.x, t.y, t.z);
 }
 NP_D void load_xf(const float* __restrict__ xf, int stride, int i, float* R, V3* t)
 {
     (void)stride;
-    const float4* p = reinterpret_cast<const float4*>(xf) + 3 * (size_t)i;
+    const float4* p = reinterpret_cast<const float4*>(xf) + (X_COUNT / 4) * (size_t)i;
     const float4 a = p[0], b = p[1], c = p[2];
     R[0] = a.x; R[1] = a.y; R[2] = a.z; R[3] = a.w; R[4] = b.x; R[5] = b.y; R[6] = b.z; R[7] = b.w; R[8] = c.x;
     *t = mk(c.y, c.z, c.w);
 }
+// The arming record of a body, the fourth float4 of its transform: (first vertex of its shape in the shape table, vertex count, its
+// support-direction table entry if the table may be used with this transform (tab_arm) else NP_TAB_NONE, shape id).  Written wherever the
+// transform is written, so that a narrow-phase kernel arms a body with ONE 16-byte load next to the transform instead of a chain of
+// dependent loads (shape -> offset, count, table, reach) and the usability test -- the refill paths run with a handful of lanes.
+NP_D void store_arm(const StoreView& s, float* __restrict__ xf, int i, int shape, const float* R, V3 t, bool rot_known)
+{
+    TabView tv; tv.tab = s.stab; tv.tlim = s.stlim; tv.cells = nullptr;
+    reinterpret_cast<int4*>(xf)[(X_COUNT / 4) * (size_t)i + 3] = make_int4(s.soff[shape], s.scnt[shape], (int)tab_arm(tv, shape, R, t, rot_known), shape);
+}
+NP_D int4 load_arm(const float* __restrict__ xf, int i) { return reinterpret_cast<const int4*>(xf)[(X_COUNT / 4) * (size_t)i + 3]; }
 
 // ---------------------------------------------------------------------------------------------------
 // K1: integrate + transform.  HBM-bound: per body 12 state floats + 14 constants read, 9 state floats +
@@ -113,6 +124,7 @@ __global__ void __launch_bounds__(256) k_integrate(StoreView s, float dt, int wr
         float R[9]; V3 t;
         make_transform(pos, rot, R, &t);
         store_xf(s.xf, i, R, t);
+        store_arm(s, s.xf, i, s.ints[I_SHAPE * cap + i], R, t, true);
     }
 }
 
@@ -150,6 +162,7 @@ __global__ void __launch_bounds__(256) k_transforms(StoreView s)
     float R[9]; V3 t;
     make_transform(pos, rot, R, &t);
     store_xf(s.xf, i, R, t);
+    store_arm(s, s.xf, i, s.ints[I_SHAPE * cap + i], R, t, true);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -557,14 +570,14 @@ __global__ void __launch_bounds__(NP_GJK2_THREADS, NP_GJK2_MINB) k_gjk2(NarrowIn
         sxf[(12 * side + 9) * T] = tt.x; sxf[(12 * side + 10) * T] = tt.y; sxf[(12 * side + 11) * T] = tt.z;
     };
     auto arm_a = [&](int body) {
-        const int sa = shape_of[body]; g.na = sh.cnt[sa];
+        const int4 ar = load_arm(s.xf, body);
         float R[9]; V3 tt;
-        g.va = verts + sh.off[sa]; load_xf(s.xf, s.cap, body, R, &tt); g.taba = tab_arm(sh.tv, sa, R, tt, in.rot_known != 0); put_xf(0, R, tt);
+        g.na = ar.y; g.va = verts + ar.x; g.taba = (unsigned)ar.z; load_xf(s.xf, s.cap, body, R, &tt); put_xf(0, R, tt);
     };
     auto arm_b = [&](int body) {
-        const int sb = shape_of[body]; g.nb = sh.cnt[sb];
+        const int4 ar = load_arm(s.xf, body);
         float R[9]; V3 tt;
-        g.vb = verts + sh.off[sb]; load_xf(s.xf, s.cap, body, R, &tt); g.tabb = tab_arm(sh.tv, sb, R, tt, in.rot_known != 0); put_xf(1, R, tt);
+        g.nb = ar.y; g.vb = verts + ar.x; g.tabb = (unsigned)ar.z; load_xf(s.xf, s.cap, body, R, &tt); put_xf(1, R, tt);
     };
     m.begin();
     // A refill is a chain of dependent loads (ticket -> body -> shape and transform -> partner's shape and transform) that the other 31
@@ -578,7 +591,7 @@ __global__ void __launch_bounds__(NP_GJK2_THREADS, NP_GJK2_MINB) k_gjk2(NarrowIn
     for (;;) {
         // ---- 1: own pair up to the solve
         if (WORLD && pf_body >= 0) {
-            const char* px = reinterpret_cast<const char*>(s.xf) + 48 * (size_t)pf_body;
+            const char* px = reinterpret_cast<const char*>(s.xf) + 4 * X_COUNT * (size_t)pf_body;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(px));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(px + 128));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(shape_of + pf_body));
@@ -598,9 +611,8 @@ __global__ void __launch_bounds__(NP_GJK2_THREADS, NP_GJK2_MINB) k_gjk2(NarrowIn
                 } else {
                     float Ra[9], Rb[9]; V3 ta, tb;
                     load_xf(in.xf_a, in.n, i, Ra, &ta); load_xf(in.xf_b, in.n, i, Rb, &tb);
-                    int sa = in.shape_a[i], sb = in.shape_b[i];
-                    g.va = verts + sh.off[sa]; g.na = sh.cnt[sa]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
-                    g.taba = tab_arm(sh.tv, sa, Ra, ta, in.rot_known != 0); g.tabb = tab_arm(sh.tv, sb, Rb, tb, in.rot_known != 0);
+                    const int4 aa = load_arm(in.xf_a, i), ab = load_arm(in.xf_b, i);
+                    g.va = verts + aa.x; g.na = aa.y; g.taba = (unsigned)aa.z; g.vb = verts + ab.x; g.nb = ab.y; g.tabb = (unsigned)ab.z;
                     put_xf(0, Ra, ta); put_xf(1, Rb, tb);
                     m.begin(); have = true;
                 }
@@ -976,17 +988,16 @@ k_epa2(NarrowIn in, ShapeView sh, const int* __restrict__ list, const int* __res
 #pragma unroll
                 for (int q = 0; q < NP_HIT_CLASSES - 1; q++) if (t >= cum[q]) { k = q + 1; base = cum[q]; }
                 item = list[(size_t)k * in.n + (t - base)];
-                int sa, sb;
+                int4 aa, ab;                                       // the two bodies' arming records sit next to their transforms
                 if (WORLD) {
                     const int i = item, j = hitj_body(hit_j[i]);
                     load_xf(s.xf, s.cap, i, g.Ra, &g.ta); load_xf(s.xf, s.cap, j, g.Rb, &g.tb);
-                    sa = s.ints[I_SHAPE * s.cap + i]; sb = s.ints[I_SHAPE * s.cap + j];
+                    aa = load_arm(s.xf, i); ab = load_arm(s.xf, j);
                 } else {
                     load_xf(in.xf_a, in.n, item, g.Ra, &g.ta); load_xf(in.xf_b, in.n, item, g.Rb, &g.tb);
-                    sa = in.shape_a[item]; sb = in.shape_b[item];
+                    aa = load_arm(in.xf_a, item); ab = load_arm(in.xf_b, item);
                 }
-                g.va = verts + sh.off[sa]; g.na = sh.cnt[sa]; g.vb = verts + sh.off[sb]; g.nb = sh.cnt[sb];
-                g.taba = tab_arm(sh.tv, sa, g.Ra, g.ta, in.rot_known != 0); g.tabb = tab_arm(sh.tv, sb, g.Rb, g.tb, in.rot_known != 0);
+                g.va = verts + aa.x; g.na = aa.y; g.taba = (unsigned)aa.z; g.vb = verts + ab.x; g.nb = ab.y; g.tabb = (unsigned)ab.z;
                 const float4* o = simplex + (size_t)item * 6;
                 const float4 q0 = o[0], q1 = o[1], q2 = o[2], q3 = o[3], q4 = o[4], q5 = o[5];
                 stAB(0, mk(q0.x, q0.y, q0.z), mk(q3.x, q3.y, q3.z)); stAB(1, mk(q0.w, q1.x, q1.y), mk(q3.w, q4.x, q4.y));
@@ -1409,7 +1420,7 @@ __global__ void k_epa_steps(ShapeView sh, int sa, int sb, const float* xa, const
 }
 
 // poses (position[3] rotation[3]) or row-major 4x4 matrices -> transforms [n][X_COUNT]  (GetTransform, physics.h:70-76)
-__global__ void __launch_bounds__(256) k_pose_xf(int n, const float* __restrict__ pose, const float* __restrict__ xf16, float* __restrict__ out)
+__global__ void __launch_bounds__(256) k_pose_xf(int n, const float* __restrict__ pose, const float* __restrict__ xf16, float* __restrict__ out, StoreView s, const int* __restrict__ shape)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1424,6 +1435,7 @@ __global__ void __launch_bounds__(256) k_pose_xf(int n, const float* __restrict_
         make_transform(mk(a[0], a[1], a[2]), mk(a[3], a[4], a[5]), R, &t);
     }
     store_xf(out, i, R, t);
+    store_arm(s, out, i, shape[i], R, t, xf16 == nullptr);          // (a caller's 4x4 matrix gets the full orthonormality test)
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1833,6 +1845,7 @@ __global__ void __launch_bounds__(256) k_resolve(StoreView s, const int* __restr
         float R[9]; V3 t;
         make_transform(pos, rot, R, &t);
         store_xf(s.xf, k, R, t);
+        store_arm(s, s.xf, k, s.ints[I_SHAPE * cap + k], R, t, true);
     }
 }
 

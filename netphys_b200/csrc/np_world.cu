@@ -114,7 +114,12 @@ struct np_world {
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
-static StoreView view(np_world* w) { StoreView s; s.n = (int)w->bodies.size(); s.cap = w->cap; s.state = w->d_state; s.cst = w->d_cst; s.xf = w->d_xf; s.ints = w->d_ints; s.wverts = w->d_wverts; s.ext = w->d_ext; return s; }
+static StoreView view(np_world* w)
+{
+    StoreView s; s.n = (int)w->bodies.size(); s.cap = w->cap; s.state = w->d_state; s.cst = w->d_cst; s.xf = w->d_xf; s.ints = w->d_ints; s.wverts = w->d_wverts; s.ext = w->d_ext;
+    s.soff = w->d_soff; s.scnt = w->d_scnt; s.stab = w->tables_on ? w->d_tab : nullptr; s.stlim = w->d_tlim;       // (for the arming records written next to the transforms)
+    return s;
+}
 // tables depend on the vertex list only: worlds of one process that create the same shapes (every test, every rank-local world) share them
 static bool cached_support_table(const std::vector<float>& xyz, SupTable& out)
 {
@@ -1324,8 +1329,8 @@ static int run_pairs(np_world* w, int n, const int* d_sa, const float* d_pa, con
     CU(cudaMemsetAsync(d + o_zero, 0, 4 * NP_ZERO_INTS, w->stream));
     if (kernel_ms) CU(cudaEventRecord(w->ev[0], w->stream));
     const int b256 = (n + 255) / 256;
-    k_pose_xf<<<b256, 256, 0, w->stream>>>(n, d_pa, d_xa, (float*)(d + o_xa));
-    k_pose_xf<<<b256, 256, 0, w->stream>>>(n, d_pb, d_xb, (float*)(d + o_xb));
+    k_pose_xf<<<b256, 256, 0, w->stream>>>(n, d_pa, d_xa, (float*)(d + o_xa), view(w), d_sa);
+    k_pose_xf<<<b256, 256, 0, w->stream>>>(n, d_pb, d_xb, (float*)(d + o_xb), view(w), d_sb);
     w->launches += 2;
     if (is2d) {
         k_detect2d<<<(n + 63) / 64, 64, 0, w->stream>>>(n, sview(w), d_sa, d_sb, (const float*)(d + o_xa), (const float*)(d + o_xb), d_hit, d_out);

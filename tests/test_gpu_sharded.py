@@ -134,10 +134,10 @@ def _partitioned_steps(npb, sc, n_ranks, halo, steps, check):
         xf = [r.w.transforms_device() for r in ranks]
         for k in range(steps):
             for r in ranks: r.w.step_integrate(sc["dt"])
-            for q, r in enumerate(ranks[:-1]):                       # the next rank's first `halo` transforms (48 B each) -> right after the own range
+            for q, r in enumerate(ranks[:-1]):                       # the next rank's first `halo` transform records (64 B each) -> right after the own range
                 nx = ranks[q + 1]; h = min(halo, nx.count)
                 if h > 0:
-                    buf = np.zeros((h, 12), np.float32); nx.w.dev_download(buf, xf[q + 1] + 48 * nx.first); r.w.dev_upload(xf[q] + 48 * nx.first, buf)
+                    buf = np.zeros((h, 16), np.float32); nx.w.dev_download(buf, xf[q + 1] + 64 * nx.first); r.w.dev_upload(xf[q] + 64 * nx.first, buf)
             for r in ranks: r.w.step_search()
             for q, r in enumerate(ranks[1:], 1):                     # the previous rank's last `halo` records -> right before the own range
                 pv = ranks[q - 1]; h = min(halo, pv.count)
