@@ -1477,10 +1477,14 @@ template <bool AABB, int WRITE = 1>      // WRITE: 0 nothing, 1 every body, 2 la
 __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, GridView gv)
 {
     constexpr int G = 8;
-    const int body = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int gl = threadIdx.x & (G - 1);
-    const bool valid = body < s.n;
     const int cap = s.cap;
+    // grid-stride over the bodies (the launch is capped): the extent statistics below cost four same-address atomics per BLOCK, and with a
+    // block per 32 bodies those atomics, not the boxes, were the kernel (154 us for a million bodies)
+    float ext_acc = 0.0f; int mn_acc[3] = { 0x7fffffff, 0x7fffffff, 0x7fffffff };
+    const int stride = (int)(gridDim.x * blockDim.x) / G;
+    for (int body = (int)(blockIdx.x * blockDim.x + threadIdx.x) / G; body - (int)((threadIdx.x & 31u) / G) < s.n; body += stride) {      // (warp-uniform trip count)
+    const bool valid = body < s.n;
     float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
     if (valid) {
         float R[9]; V3 t;
@@ -1490,7 +1494,28 @@ __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, 
         if (WRITE == 2 && !AABB && n < NP_COOP_MIN) n = 0;
         const bool wr = WRITE == 1 || (WRITE == 2 && n >= NP_COOP_MIN);
         float4* out = s.wverts + (wr ? s.ints[(WRITE == 2 ? I_WVOFF_BIG : I_WVOFF) * cap + body] : 0);
-        for (int k = gl; k < n; k += G) {
+        // Nothing to cache, only the box: its six faces are the support points along +-x, +-y, +-z, and those the direction table
+        // gives from a candidate or two each (d = e_x makes the scan's score the world x itself, so the candidates hold the
+        // extreme COORDINATE, the very float the loop below would find) -- six lanes, one lookup each, instead of every vertex.
+        bool boxed = false;
+        if (AABB && WRITE == 0) {
+            const unsigned tab = (unsigned)load_arm(s.xf, body).z;
+            bool ok = tab != NP_TAB_NONE;
+            float comp = 0.0f;
+            if (ok && gl < 6) {
+                const float sg = (gl & 1) ? -1.0f : 1.0f;
+                const V3 d = mk(gl < 2 ? sg : 0.0f, (gl >> 1) == 1 ? sg : 0.0f, gl >= 4 ? sg : 0.0f);
+                V3 wp;
+                ok = support_tab(v, R, t, d, tab, sh.tv.cells, &wp);
+                comp = gl < 2 ? wp.x : (gl < 4 ? wp.y : wp.z);
+            }
+            const unsigned all = (__ballot_sync(__activemask(), ok) >> ((threadIdx.x & 31u) & ~7u)) & 0xffu;
+            if (all == 0xffu) {
+                boxed = true;
+                if (gl < 6) { if (gl & 1) lo[gl >> 1] = comp; else hi[gl >> 1] = comp; }
+            }
+        }
+        for (int k = gl; k < n && !boxed; k += G) {
             float4 q = v[k];
             V3 wp = xf_point(R, t, mk(q.x, q.y, q.z));
             if (wr) out[k] = make_float4(wp.x, wp.y, wp.z, 0.0f);
@@ -1500,7 +1525,7 @@ __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, 
             }
         }
     }
-    if (!AABB) return;
+    if (!AABB) continue;
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
 #pragma unroll
@@ -1510,7 +1535,6 @@ __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, 
         }
     }
     // per-body record, and block-level reduction of (sum of extents, global min corner): 4 atomics per BLOCK
-    float ext = 0.0f; int mn[3] = { 0x7fffffff, 0x7fffffff, 0x7fffffff };
     if (valid && gl == 0) {
         if (gv.swept) {                                  // todo.txt:8 "swept AABB from previous state": the box the body swept through since the last step
             const float4 clo = make_float4(lo[0], lo[1], lo[2], 0.0f), chi = make_float4(hi[0], hi[1], hi[2], 0.0f);
@@ -1523,10 +1547,13 @@ __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, 
         }
         gv.aabb[2 * body] = make_float4(lo[0], lo[1], lo[2], 0.0f); gv.aabb[2 * body + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
         float e = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
-        if (e == e && e < INFINITY) ext = e;
+        if (e == e && e < INFINITY) ext_acc += e;
 #pragma unroll
-        for (int c = 0; c < 3; c++) if (lo[c] == lo[c]) mn[c] = float_order(lo[c]);
+        for (int c = 0; c < 3; c++) if (lo[c] == lo[c]) mn_acc[c] = min(mn_acc[c], float_order(lo[c]));
     }
+    }
+    if (!AABB) return;
+    float ext = ext_acc; int mn[3] = { mn_acc[0], mn_acc[1], mn_acc[2] };
     __shared__ float s_ext[8]; __shared__ int s_mn[8][3];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -1,0 +1,11 @@
+#!/bin/bash
+NP_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r3l_grid_launches.csv python tools/prof_grid.py 1000000 2.0 > gpurun_out/r3l_grid.log 2>&1
+tail -2 gpurun_out/r3l_grid.log | cut -c1-200
+python - <<'PY'
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/r3l_grid_launches.csv')) if len(r)>5]
+hdr=rows[0]; ik=hdr.index('Kernel Name'); iv=hdr.index('Metric Value')
+L=[(r[ik].split('(')[0].replace('void ','')[:40], float(r[iv])/1e3) for r in rows[1:]]
+idx=[i for i,(n,v) in enumerate(L) if n.startswith('k_integrate')]
+for n,v in L[idx[2]:idx[3]]: print("%-42s %8.1f us"%(n,v))
+PY
