@@ -83,6 +83,7 @@ struct np_world {
     int fuse_on = 1;      // NP_FUSE=0: np_world_step_n runs plain steps (A/B)
     int halo = 0;             // > 0: partitioned sharded step (np_world_set_shard_halo): this rank integrates / responds for its own bodies only and sees `halo` bodies past its range
     int* d_halo_err = nullptr;
+    char* d_one = nullptr;     // np_detect_collision's single-pair record
     float step_dt = 0.0f;
     int step_phase = 0;       // partitioned step in progress: 1 after np_world_step_integrate, 2 after np_world_step_search
     int epa2_tail32 = 1;      // NP_EPA2_TAIL=4: k_epa2's leftovers to the 4-lane kernel instead of a warp per pair
@@ -808,7 +809,7 @@ void np_world_destroy(np_world* w)
     drop_graph(w); free_store(w); cudaFree(w->d_ext);
     cudaFree(w->d_wverts); w->d_wverts = nullptr; w->wverts_cap = 0;
     cudaFree(w->d_aos); w->d_aos = nullptr; w->d_aos_bytes = 0;
-    cudaFree(w->d_verts); cudaFree(w->d_soff); cudaFree(w->d_scnt); cudaFree(w->d_tab); cudaFree(w->d_tlim); cudaFree(w->d_cells); cudaFree(w->d_halo_err); cudaFree(w->d_ctr); cudaFree(w->d_flush); cudaFree(w->d_grid_ints); cudaFree(w->d_grid_f);
+    cudaFree(w->d_verts); cudaFree(w->d_soff); cudaFree(w->d_scnt); cudaFree(w->d_tab); cudaFree(w->d_tlim); cudaFree(w->d_cells); cudaFree(w->d_halo_err); cudaFree(w->d_one); cudaFree(w->d_ctr); cudaFree(w->d_flush); cudaFree(w->d_grid_ints); cudaFree(w->d_grid_f);
     cudaFree(w->arena.base);
     if (w->h_stage) cudaFreeHost(w->h_stage);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
@@ -1410,16 +1411,18 @@ int np_detect_collision(np_world* w, int shape_a, const float a_transform[16], i
     int32_t sa = shape_a, sb = shape_b;
     int r = check_shapes(w, 1, &sa, &sb); if (r) return r;
     r = ensure_device(w); if (r) return r;
-    char* d = nullptr;
-    CU(cudaMallocAsync((void**)&d, 256, w->stream));
-    CU(cudaMemcpyAsync(d, a_transform, 64, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + 64, b_transform, 64, cudaMemcpyHostToDevice, w->stream));
-    CU(cudaMemcpyAsync(d + 128, &sa, 4, cudaMemcpyHostToDevice, w->stream)); CU(cudaMemcpyAsync(d + 132, &sb, 4, cudaMemcpyHostToDevice, w->stream));
-    r = run_pairs(w, 1, (int*)(d + 128), nullptr, (int*)(d + 132), nullptr, (float*)d, (float*)(d + 64), (int*)(d + 136), (float4*)(d + 144), nullptr, !is3D);
-    if (r) { cudaFreeAsync(d, w->stream); return r; }
-    int fl; float4 cd;
-    CU(cudaMemcpyAsync(&fl, d + 136, 4, cudaMemcpyDeviceToHost, w->stream)); CU(cudaMemcpyAsync(&cd, d + 144, 16, cudaMemcpyDeviceToHost, w->stream));
-    CU(cudaFreeAsync(d, w->stream));
+    // one pair: a persistent 256-byte device record and one copy each way ([0,64) A's matrix, [64,128) B's, [128,136) the shape ids | [144,160) contact, [160,164) flags)
+    if (!w->d_one) CU(cudaMalloc((void**)&w->d_one, 256));
+    char* d = w->d_one;
+    alignas(16) char h_in[136];
+    memcpy(h_in, a_transform, 64); memcpy(h_in + 64, b_transform, 64); memcpy(h_in + 128, &sa, 4); memcpy(h_in + 132, &sb, 4);
+    CU(cudaMemcpyAsync(d, h_in, sizeof h_in, cudaMemcpyHostToDevice, w->stream));       // (pageable source: staged by the driver before the call returns)
+    r = run_pairs(w, 1, (int*)(d + 128), nullptr, (int*)(d + 132), nullptr, (float*)d, (float*)(d + 64), (int*)(d + 160), (float4*)(d + 144), nullptr, !is3D);
+    if (r) return r;
+    alignas(16) char h_out[32];
+    CU(cudaMemcpyAsync(h_out, d + 144, 20, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
+    float4 cd; int fl; memcpy(&cd, h_out, 16); memcpy(&fl, h_out + 16, 4);
     int32_t h; expand_out(1, &fl, &cd, &h, out);
     if (hit) *hit = h;
     return NP_OK;
