@@ -40,11 +40,13 @@ def test_table_support_equals_scan(world, oracle, spec):
     assert info is not None and info["scan_cells"] <= 0.01 * 6 * info["n"] ** 2 and info["mean_candidates"] < 4.0, info
     dirs = hard_directions(verts, rng, 20000)
     n = len(dirs)
-    # poses: identity, random rotations near the origin, and far from it (up to 80 % of the table's reach)
+    # poses: identity, random rotations near the origin, and far from it (every coordinate up to 99 % of the table's reach)
     pos = rng.uniform(-3, 3, size=(n, 3)); rot = rng.uniform(-np.pi, np.pi, size=(n, 3))
     pos[: n // 8] = 0; rot[: n // 8] = 0
-    far = rng.rand(n) < 0.3
-    pos[far] = rng.uniform(-1, 1, size=(far.sum(), 3)) * info["reach"] * 0.8 / 3.0
+    far = rng.rand(n) < 0.5
+    pos[far] = rng.uniform(-1, 1, size=(far.sum(), 3)) * info["reach"] * 0.99
+    edge = far & (rng.rand(n) < 0.5)                                              # right at the limit: where the rounding the margin must cover is largest
+    pos[edge] = rng.choice([-1.0, 1.0], size=(edge.sum(), 3)) * rng.uniform(0.9, 0.99, size=(edge.sum(), 3)) * info["reach"]
     xf = np.stack([oracle.transform(pos[k].astype(np.float32), rot[k].astype(np.float32)) for k in range(n)]).reshape(n, 16)
     # in shape space the hard directions stay hard: rotate them with the body
     R = xf.reshape(n, 4, 4)[:, :3, :3].astype(np.float64)
