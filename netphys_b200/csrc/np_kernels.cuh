@@ -907,7 +907,7 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K4, second generation: EPA for the polytopes that stay small -- 12 vertices, 16 faces, at most 8 new faces per expansion: 93 % of
+// K4, second generation: EPA for the polytopes that stay small -- 14 vertices, 16 faces, at most 8 new faces per expansion: 95 % of
 // the hits that need EPA at all (oracle statistics over random and lattice pairs), the rest are passed on to k_epa -- with one
 // THREAD per pair for everything that is inherently serial and the block's threads for what is not.
 //
@@ -919,9 +919,10 @@ k_epa(NarrowIn in, ShapeView sh, int smem_shapes, const int* __restrict__ list, 
 //     same operands, same bits -- and per face its stored normal, its cached squared distance and its three vertex numbers);
 //   * faces never move: a 64-bit register holds the face ORDER as sixteen 4-bit slot numbers, which is all that SetupForEPA / the
 //     erase-and-append of collision_detection.cpp:469-517 ever changes; "first minimum wins" and "edges in insertion order" follow it;
-//   * the horizon is two passes over the removed faces with a 12 x 16-bit adjacency mask in registers: an edge survives unless its
+//   * the horizon is two passes over the removed faces with a 16 x 16-bit adjacency mask in registers: an edge survives unless its
 //     reverse is an edge of a removed face.  That equals the reference's list semantics whenever no directed edge occurs twice among
-//     the removed faces; the mask detects the other case and the pair goes to k_epa, which replays the list;
+//     the removed faces; the mask detects the other case (0.5 % of the expansions) and the pair goes to k_epa, which replays the list
+//     (replaying it here was measured: those polytopes run long and hold their slot's block back -- box pair lists 1.28 -> 1.08e9/s);
 //   * Simplex::AddFace -- the arithmetic: a normalised cross product, the flip test, a closest-point-on-triangle -- is a JOB: the
 //     owners queue (slot, face, va, vb, vc) and after a block barrier every thread of the block takes jobs of its column, so the 128
 //     threads run the same straight-line code on 2 x 64 faces at a time.
@@ -934,7 +935,7 @@ __device__ unsigned long long g_e2dbg[8];      // expansions, and why pairs were
 #ifndef NP_E2_THREADS
 #define NP_E2_THREADS 128
 #endif
-#define NP_E2_V 12
+#define NP_E2_V 14
 #define NP_E2_F 16
 #define NP_E2_JOBS 8
 #define NP_E2_FACE0 (6 * NP_E2_V)
@@ -1051,8 +1052,8 @@ k_epa2(NarrowIn in, ShapeView sh, const int* __restrict__ list, const int* __res
                         if (dot(ldN((int)f), sp) > 0) { gone |= f << (4 * ngone); ngone++; }
                         else { kept |= f << (4 * keep); keep++; }
                     }
-                    // horizon: directed edges of the removed faces as a 12 x 16-bit adjacency mask (row a = m[a >> 2] >> 16 (a & 3))
-                    unsigned long long m0 = 0, m1 = 0, m2 = 0; bool twice = false;
+                    // horizon: directed edges of the removed faces as a 16 x 16-bit adjacency mask (row a = m[a >> 2] >> 16 (a & 3))
+                    unsigned long long m0 = 0, m1 = 0, m2 = 0, m3 = 0; bool twice = false;
                     for (int k = 0; k < ngone; k++) {
                         const unsigned idx = ldI((int)((gone >> (4 * k)) & 15ull));
 #pragma unroll
@@ -1060,29 +1061,32 @@ k_epa2(NarrowIn in, ShapeView sh, const int* __restrict__ list, const int* __res
                             const int a = (idx >> (4 * e)) & 15, b = (idx >> (4 * ((e + 1) % 3))) & 15;
                             const unsigned long long bit = 1ull << (16 * (a & 3) + b);
                             const int w = a >> 2;
-                            const unsigned long long cur = w == 0 ? m0 : (w == 1 ? m1 : m2);
+                            const unsigned long long cur = w == 0 ? m0 : (w == 1 ? m1 : (w == 2 ? m2 : m3));
                             twice = twice || (cur & bit) != 0ull;
-                            if (w == 0) m0 |= bit; else if (w == 1) m1 |= bit; else m2 |= bit;
+                            if (w == 0) m0 |= bit; else if (w == 1) m1 |= bit; else if (w == 2) m2 |= bit; else m3 |= bit;
                         }
                     }
                     unsigned nf = freem; int ne = 0;
                     for (int k = 0; k < ngone; k++) nf |= 1u << (unsigned)((gone >> (4 * k)) & 15ull);     // their slots are free again
                     unsigned long long nord = kept;
                     const bool room = pnv < NP_E2_V;
-                    for (int k = 0; k < ngone && !twice; k++) {
-                        const unsigned idx = ldI((int)((gone >> (4 * k)) & 15ull));
+                    auto horizon_edge = [&](int a, int b) {                                        // one new face (a, b, new vertex), in the order the edges survive
+                        if (ne < NP_E2_JOBS && keep + ne < NP_E2_F && room) {
+                            const int f = __ffs(nf) - 1; nf &= nf - 1;
+                            nord |= (unsigned long long)f << (4 * (keep + ne));
+                            jobs[ne * S + slot] = (unsigned)slot | ((unsigned)f << 6) | ((unsigned)a << 10) | ((unsigned)b << 14) | ((unsigned)pnv << 18) | ((unsigned)seed << 22);
+                        }
+                        ne++;
+                    };
+                    if (!twice) {
+                        for (int k = 0; k < ngone; k++) {
+                            const unsigned idx = ldI((int)((gone >> (4 * k)) & 15ull));
 #pragma unroll
-                        for (int e = 0; e < 3; e++) {
-                            const int a = (idx >> (4 * e)) & 15, b = (idx >> (4 * ((e + 1) % 3))) & 15;
-                            const int w = b >> 2;
-                            const unsigned long long rev = (w == 0 ? m0 : (w == 1 ? m1 : m2)) >> (16 * (b & 3) + a);
-                            if (!(rev & 1ull)) {                                                   // its reverse is not an edge of a removed face: on the horizon
-                                if (ne < NP_E2_JOBS && keep + ne < NP_E2_F && room) {
-                                    const int f = __ffs(nf) - 1; nf &= nf - 1;
-                                    nord |= (unsigned long long)f << (4 * (keep + ne));
-                                    jobs[ne * S + slot] = (unsigned)slot | ((unsigned)f << 6) | ((unsigned)a << 10) | ((unsigned)b << 14) | ((unsigned)pnv << 18) | ((unsigned)seed << 22);
-                                }
-                                ne++;
+                            for (int e = 0; e < 3; e++) {
+                                const int a = (idx >> (4 * e)) & 15, b = (idx >> (4 * ((e + 1) % 3))) & 15;
+                                const int w = b >> 2;
+                                const unsigned long long rev = (w == 0 ? m0 : (w == 1 ? m1 : (w == 2 ? m2 : m3))) >> (16 * (b & 3) + a);
+                                if (!(rev & 1ull)) horizon_edge(a, b);                             // its reverse is not an edge of a removed face: on the horizon
                             }
                         }
                     }
