@@ -111,6 +111,39 @@ def cpu_reference_steps(scene, steps, warmup):
     return time.perf_counter() - t0, "port", "C restatement of Physics_Update (oracle/netphys_oracle.c), 1 thread"
 
 
+def _cpu_world_worker(args):
+    """one process = one copy of the reference engine (its body list is a process global): steps `count` 256-body worlds of configs[3] one after the other"""
+    first, count, steps = args
+    sys.path.insert(0, ROOT)
+    from oracle.bind import Oracle, Ref, ref_available
+    o = Oracle()
+    t = 0.0
+    for k in range(first, first + count):
+        sc = scenes.resolve(scenes.lattice_scene(256, spacing=2.5, seed=1000 + k), o)
+        if ref_available():
+            r = Ref(); r.load_scene(sc); r.step(sc["dt"]); t += r.time_steps(sc["dt"], steps)
+        else:
+            w = o.world(sc); w.step(sc["dt"]); t0 = time.perf_counter()
+            for _ in range(steps): w.step(sc["dt"])
+            t += time.perf_counter() - t0
+    return t
+
+
+def cpu_reference_worlds(worlds_per_proc=4, steps=20):
+    """SURVEY 8(d) CPU baseline (ii): configs[3] is embarrassingly parallel over worlds -- one PROCESS per world set, as many as the box has cores (8 at most)."""
+    import multiprocessing as mp
+    from oracle.bind import ref_available
+    nproc = min(8, os.cpu_count() or 1)
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(nproc) as pool:
+        busy = pool.map(_cpu_world_worker, [(p * worlds_per_proc, worlds_per_proc, steps) for p in range(nproc)])
+    wall = time.perf_counter() - t0
+    # the processes run side by side: throughput = all their body-steps over the longest one's stepping time (process start-up and scene building excluded)
+    return {"value": nproc * worlds_per_proc * 256 * steps / max(busy), "unit": "body-steps/s", "cores": nproc, "kind": "reference" if ref_available() else "port",
+            "sample": "%d processes x %d worlds x %d steps of the same generator (256 bodies per world, seeds 1000...), one copy of the engine per process; wall %.1f s incl. start-up" % (nproc, worlds_per_proc, steps, wall)}
+
+
 def cpu_reference_pairs(specs, sa, pa, sb, pb, n1, n8):
     """DetectCollision over a pair list on the host cores: the compiled reference with 1 and with 8 std::threads (SURVEY 8(d) CPU baseline iii)."""
     from oracle.bind import Oracle, Ref, ref_available
@@ -479,6 +512,10 @@ def run_ours(args, rank, local_rank, world_size):
                 tot = float(ms4[:, 5].mean())
                 extra["worlds_4096x256"] = {"workload": "BASELINE configs[3] on one GPU: 4096 independent 256-body worlds (C2 generator, seeds 1000..5095) as islands of one store",
                                             "value": 4096 * 256 / (tot * 1e-3), "unit": "body-steps/s", "ms_per_step": tot}
+            try:
+                extra["worlds_4096x256"]["cpu_baseline"] = cpu_reference_worlds()
+            except Exception as e:
+                extra["worlds_4096x256"]["cpu_baseline"] = {"error": repr(e)}
         except Exception as e:                                   # never lose the headline line to an auxiliary leg
             extra["error"] = repr(e)
     # ---- CPU baseline on this box's host cores (bounded sample) ---------------------------------------------------------
