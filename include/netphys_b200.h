@@ -47,7 +47,7 @@ typedef struct np_static_physics_data {
     float initial_rotation[3];          /* Euler XYZ radians, engine/matrix.h:283-288 */
     float mass;
     float elasticity;
-    float static_friction_coeff;        /* unused by the reference path (friction block is commented out, physics.cpp:49-72) */
+    float static_friction_coeff;        /* read only under NP_OPT_FRICTION (the reference's friction block is commented out, physics.cpp:49-72) */
     float dynamic_friction_coeff;
     int32_t collision_response;         /* np_collision_response */
     float moment_of_inertia;
@@ -103,8 +103,12 @@ typedef enum np_option {
     NP_OPT_SNAPSHOT_EACH_STEP = 4,/* 1 = np_world_step also packs the replication snapshot (world_s.cpp:23-51) */
     NP_OPT_PHASE_TIMING = 5,      /* 1 = time the phases of every step with CUDA events (np_world_last_step_ms [0..4]); the events cost a few
                                      microseconds each, so a step runs faster without them.  The total [5] is always measured. */
-    NP_OPT_SUPPORT_TABLES = 6     /* default 1: PhysUtil_GetPointFurthestInDirection (physics_util.cpp:5-35) evaluates only the vertices a per-shape
+    NP_OPT_SUPPORT_TABLES = 6,    /* default 1: PhysUtil_GetPointFurthestInDirection (physics_util.cpp:5-35) evaluates only the vertices a per-shape
                                      direction table proves can win (same result bits); 0 = scan every vertex as the reference does */
+    NP_OPT_FRICTION = 7           /* default 0 (the reference's behaviour).  1 = ApplyImpulseResponse also runs the friction block the reference
+                                     keeps commented out at physics.cpp:49-72, exactly as written there (static_friction_coeff of the body).  In
+                                     a world step the collision normals are zero (collision_detection.cpp:533-543 never writes them), so the
+                                     block only acts through np_body_apply_impulse_response with a caller's normal */
 } np_option;
 
 typedef struct np_counters {

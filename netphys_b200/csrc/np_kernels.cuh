@@ -18,7 +18,7 @@ namespace np {
 
 // component indices of the SoA blocks
 enum { S_PX = 0, S_PY, S_PZ, S_RX, S_RY, S_RZ, S_LX, S_LY, S_LZ, S_HX, S_HY, S_HZ, S_COUNT };          // dynamic state
-enum { C_GX = 0, C_GY, C_GZ, C_MASS, C_ELAST, C_IINV0, C_COUNT = C_IINV0 + 9 };                       // per-body constants
+enum { C_GX = 0, C_GY, C_GZ, C_MASS, C_ELAST, C_IINV0, C_SFRIC = C_IINV0 + 9, C_COUNT };                // per-body constants (C_SFRIC: m_staticFrictionCoeff, read only under NP_OPT_FRICTION)
 enum { X_R0 = 0, X_TX = 9, X_TY, X_TZ, X_ARM = 12, X_COUNT = 16 };                                      // transform (12 floats) + arming record (4 ints): 64 bytes
 enum { I_RESPONSE = 0, I_SHAPE, I_ISLAND_END, I_WVOFF, I_ORDER, I_WVOFF_BIG, I_HANDLE, I_COUNT };     // I_WVOFF: first world vertex of the body in the per-step cache (I_WVOFF_BIG: in the cache of large bodies only, -1 for small ones); I_ORDER: search order (bodies grouped by shape); I_HANDLE: the caller's id of the body (differs from the slot once bodies were destroyed)
 
@@ -31,6 +31,7 @@ struct StoreView {
     const int* ints;   // [I_COUNT][cap]
     float4* wverts;    // world-space vertices of every body, rewritten each step by k_world_verts
     float* ext;        // adapter extension, null unless used: [4][cap] = one-step external force xyz (np_body_add_force), enabled flag
+    int friction;      // NP_OPT_FRICTION: ApplyImpulseResponse runs the reference's commented-out friction block (physics.cpp:49-72)
 };
 struct ShapeView {
     const float4* verts;   // all shapes' local vertices, concatenated
@@ -1455,11 +1456,13 @@ __global__ void __launch_bounds__(256) k_pose_xf(int n, const float* __restrict_
 // ---------------------------------------------------------------------------------------------------
 struct GridView {
     float4* aabb;         // [2*cap]: lo.xyz + packed cell (as int bits, -1 = large) | hi.xyz
-    float* params;        // [0..2] origin, [3] h, [4] sum of extents, [5..7] global min (ordered ints), [8] H (ordered int), [9] large threshold
+    float* params;        // [0..2] origin, [3] h, [4] sum of extents, [5..7] global min (ordered ints), [8] H (ordered int), [9] large threshold,
+                          // [10..12] global max (ordered ints), [13..15] cells per axis (ints), [16] 1 = dense addressing (int): see k_grid_params
     int* bucket_cnt;      // [nbuckets]
     int* bucket_off;      // [nbuckets]
     int* bucket_cur;      // [nbuckets]
-    int* items;           // [cap] bodies grouped by bucket
+    int* items;           // [cap] (unused: the bucket-ordered boxes of saabb carry their body index)
+    float4* saabb;        // [2*cap] the boxes in bucket order: entry p = lo.xyz + packed cell | hi.xyz + body index (int bits) of items[p]
     int* large;           // [cap] large-body list
     int* large_count;     // [1]
     int* cand_cnt;        // [cap] actual candidates of body i
@@ -1470,6 +1473,8 @@ struct GridView {
     int* spill_cursor;    // [1] next free entry of the spill region of cand (reset to cap * NP_CAND_SLOTS every step)
     int nbuckets, cand_cap, spill_base;
     float h_option;
+    float h_scale;        // automatic cell edge = h_scale x the average box extent
+    int force_hash;       // tests: never use dense addressing
     float4* aabb_prev;    // [2*cap] NP_BROADPHASE_SWEPT: every body's own AABB of the previous step
     int swept;            // 0: candidates from this step's AABBs; 1: swept mode, first step after a rebuild (no previous box yet); 2: union with the previous step's box
 };
@@ -1485,7 +1490,7 @@ __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, 
     const int cap = s.cap;
     // grid-stride over the bodies (the launch is capped): the extent statistics below cost four same-address atomics per BLOCK, and with a
     // block per 32 bodies those atomics, not the boxes, were the kernel (154 us for a million bodies)
-    float ext_acc = 0.0f; int mn_acc[3] = { 0x7fffffff, 0x7fffffff, 0x7fffffff };
+    float ext_acc = 0.0f; int mn_acc[3] = { 0x7fffffff, 0x7fffffff, 0x7fffffff }, mx_acc[3] = { (int)0x80000000, (int)0x80000000, (int)0x80000000 };
     const int stride = (int)(gridDim.x * blockDim.x) / G;
     for (int body = (int)(blockIdx.x * blockDim.x + threadIdx.x) / G; body - (int)((threadIdx.x & 31u) / G) < s.n; body += stride) {      // (warp-uniform trip count)
     const bool valid = body < s.n;
@@ -1553,24 +1558,24 @@ __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, 
         float e = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
         if (e == e && e < INFINITY) ext_acc += e;
 #pragma unroll
-        for (int c = 0; c < 3; c++) if (lo[c] == lo[c]) mn_acc[c] = min(mn_acc[c], float_order(lo[c]));
+        for (int c = 0; c < 3; c++) { if (lo[c] == lo[c]) mn_acc[c] = min(mn_acc[c], float_order(lo[c])); if (hi[c] == hi[c]) mx_acc[c] = max(mx_acc[c], float_order(hi[c])); }
     }
     }
     if (!AABB) return;
-    float ext = ext_acc; int mn[3] = { mn_acc[0], mn_acc[1], mn_acc[2] };
-    __shared__ float s_ext[8]; __shared__ int s_mn[8][3];
+    float ext = ext_acc; int mn[3] = { mn_acc[0], mn_acc[1], mn_acc[2] }, mx[3] = { mx_acc[0], mx_acc[1], mx_acc[2] };
+    __shared__ float s_ext[8]; __shared__ int s_mn[8][3], s_mx[8][3];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         ext += __shfl_xor_sync(0xffffffffu, ext, o);
 #pragma unroll
-        for (int c = 0; c < 3; c++) mn[c] = min(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+        for (int c = 0; c < 3; c++) { mn[c] = min(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o)); mx[c] = max(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o)); }
     }
-    if ((threadIdx.x & 31) == 0) { s_ext[threadIdx.x >> 5] = ext; for (int c = 0; c < 3; c++) s_mn[threadIdx.x >> 5][c] = mn[c]; }
+    if ((threadIdx.x & 31) == 0) { s_ext[threadIdx.x >> 5] = ext; for (int c = 0; c < 3; c++) { s_mn[threadIdx.x >> 5][c] = mn[c]; s_mx[threadIdx.x >> 5][c] = mx[c]; } }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int wdx = 1; wdx < 8; wdx++) { ext += s_ext[wdx]; for (int c = 0; c < 3; c++) mn[c] = min(mn[c], s_mn[wdx][c]); }
+        for (int wdx = 1; wdx < 8; wdx++) { ext += s_ext[wdx]; for (int c = 0; c < 3; c++) { mn[c] = min(mn[c], s_mn[wdx][c]); mx[c] = max(mx[c], s_mx[wdx][c]); } }
         if (ext != 0.0f) atomicAdd(&gv.params[4], ext);
-        for (int c = 0; c < 3; c++) if (mn[c] != 0x7fffffff) atomicMin((int*)&gv.params[5 + c], mn[c]);
+        for (int c = 0; c < 3; c++) { if (mn[c] != 0x7fffffff) atomicMin((int*)&gv.params[5 + c], mn[c]); if (mx[c] != (int)0x80000000) atomicMax((int*)&gv.params[10 + c], mx[c]); }
     }
 }
 __global__ void k_grid_init(GridView gv)
@@ -1579,16 +1584,34 @@ __global__ void k_grid_init(GridView gv)
     else if (threadIdx.x < 8) ((int*)gv.params)[threadIdx.x] = 0x7fffffff;
     else if (threadIdx.x == 8) ((int*)gv.params)[8] = float_order(0.0f);
     if (threadIdx.x == 9) { *gv.large_count = 0; *gv.spill_cursor = gv.spill_base; }
+    if (threadIdx.x >= 10 && threadIdx.x < 13) ((int*)gv.params)[threadIdx.x] = (int)0x80000000;
+    if (threadIdx.x >= 13 && threadIdx.x < 17) ((int*)gv.params)[threadIdx.x] = 0;
 }
+NP_D int clamp_cell(float x) { int c = (int)floorf(x); return c < 0 ? 0 : (c > 1023 ? 1023 : c); }
+// Cell edge: the caller's (NP_OPT_GRID_CELL) or h_scale x the average box extent.  Addressing: when the cells that can hold a centre --
+// origin = the smallest box corner, up to the cell of the largest one; every centre lies between them and the cell expression is
+// monotone -- are at most nbuckets, bucket = cx + nx (cy + ny cz): the boxes come out of the counting sort ordered by (z, y, x), the
+// cells of one x-row of a body's neighbourhood are ONE contiguous run of saabb, and neighbours in that order walk the same rows (L1).
+// Otherwise (a world spread over more cells than that) cells are hashed into the buckets and every cell is looked up on its own.
 __global__ void k_grid_params(int n, GridView gv)
 {
-    float h = gv.h_option > 0.0f ? gv.h_option : gv.params[4] / (float)(n > 0 ? n : 1);
+    float h = gv.h_option > 0.0f ? gv.h_option : gv.h_scale * gv.params[4] / (float)(n > 0 ? n : 1);
     if (!(h > 1e-20f)) h = 1.0f;
     gv.params[3] = h; gv.params[9] = 4.0f * h;
     for (int c = 0; c < 3; c++) gv.params[c] = order_float(((int*)gv.params)[5 + c]);
+    long long total = 1;
+    for (int c = 0; c < 3; c++) {
+        const int d = clamp_cell((order_float(((int*)gv.params)[10 + c]) - gv.params[c]) / h) + 1;
+        ((int*)gv.params)[13 + c] = d; total *= d;
+    }
+    ((int*)gv.params)[16] = (total <= (long long)gv.nbuckets && !gv.force_hash) ? 1 : 0;
 }
 NP_D int cell_hash(int cx, int cy, int cz, int nbuckets) { return (int)(((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u) ^ ((unsigned)cz * 83492791u)) & (nbuckets - 1); }
-NP_D int clamp_cell(float x) { int c = (int)floorf(x); return c < 0 ? 0 : (c > 1023 ? 1023 : c); }
+NP_D int cell_bucket(const GridView& gv, int cx, int cy, int cz)
+{
+    const int* ip = (const int*)gv.params;
+    return ip[16] ? cx + ip[13] * (cy + ip[14] * cz) : cell_hash(cx, cy, cz, gv.nbuckets);
+}
 __global__ void __launch_bounds__(256) k_grid_count(StoreView s, GridView gv)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1602,7 +1625,7 @@ __global__ void __launch_bounds__(256) k_grid_count(StoreView s, GridView gv)
         else {
             int cx = clamp_cell((0.5f * (lo.x + hi.x) - gv.params[0]) / h), cy = clamp_cell((0.5f * (lo.y + hi.y) - gv.params[1]) / h), cz = clamp_cell((0.5f * (lo.z + hi.z) - gv.params[2]) / h);
             cell = cx | (cy << 10) | (cz << 20);
-            atomicAdd(&gv.bucket_cnt[cell_hash(cx, cy, cz, gv.nbuckets)], 1);
+            atomicAdd(&gv.bucket_cnt[cell_bucket(gv, cx, cy, cz)], 1);
             ext_small = ext;
         }
         gv.aabb[2 * i].w = __int_as_float(cell);
@@ -1619,10 +1642,13 @@ __global__ void __launch_bounds__(256) k_grid_fill(StoreView s, GridView gv)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.n) return;
-    int c = __float_as_int(gv.aabb[2 * i].w);
+    const float4 lo = gv.aabb[2 * i]; float4 hi = gv.aabb[2 * i + 1];
+    int c = __float_as_int(lo.w);
     if (c < 0) return;
-    int b = cell_hash(c & 1023, (c >> 10) & 1023, (c >> 20) & 1023, gv.nbuckets);
-    gv.items[gv.bucket_off[b] + atomicAdd(&gv.bucket_cur[b], 1)] = i;
+    int b = cell_bucket(gv, c & 1023, (c >> 10) & 1023, (c >> 20) & 1023);
+    const int p = gv.bucket_off[b] + atomicAdd(&gv.bucket_cur[b], 1);
+    hi.w = __int_as_float(i);
+    gv.saabb[2 * (size_t)p] = lo; gv.saabb[2 * (size_t)p + 1] = hi;
 }
 NP_D bool aabb_overlap(float4 lo, float4 hi, float4 jlo, float4 jhi)
 {
@@ -1657,17 +1683,33 @@ NP_D int cand_walk(const StoreView& s, const GridView& gv, int i, int jend, floa
     } else {
         int c0[3], c1[3];
         cell_range(gv, lo, hi, c0, c1);
+        const int* ip = (const int*)gv.params;
+        if (ip[16]) {                                    // dense addressing: one run of boxes per x-row
+            const int nx = ip[13], ny = ip[14], nz = ip[15];
+            c1[0] = min(c1[0], nx - 1); c1[1] = min(c1[1], ny - 1); c1[2] = min(c1[2], nz - 1);      // (no centre lies beyond)
+            if (c0[0] <= c1[0])
+                for (int z = c0[2]; z <= c1[2]; z++) for (int y = c0[1]; y <= c1[1]; y++) {
+                    const int row = nx * (y + ny * z);
+                    const int p0 = __ldg(gv.bucket_off + row + c0[0]), p1 = __ldg(gv.bucket_off + row + c1[0] + 1);      // bucket_off[nbuckets] = all of them
+                    for (int p = p0; p < p1; p++) {
+                        const float4 jhi = __ldg(gv.saabb + 2 * (size_t)p + 1);
+                        const int j = __float_as_int(jhi.w);
+                        if (j <= i || j >= jend) continue;
+                        if (aabb_overlap(lo, hi, __ldg(gv.saabb + 2 * (size_t)p), jhi)) { if (STORE && n < room) out[n] = j; n++; }
+                    }
+                }
+        } else
         for (int z = c0[2]; z <= c1[2]; z++) for (int y = c0[1]; y <= c1[1]; y++) for (int x = c0[0]; x <= c1[0]; x++) {
             const int b = cell_hash(x, y, z, gv.nbuckets);
-            const int cnt = gv.bucket_cnt[b];
+            const int o = __ldg(gv.bucket_off + b), cnt = __ldg(gv.bucket_off + b + 1) - o;
             if (cnt == 0) continue;
-            const int want = x | (y << 10) | (z << 20), o = gv.bucket_off[b];
+            const int want = x | (y << 10) | (z << 20);
             for (int q = 0; q < cnt; q++) {
-                int j = gv.items[o + q];
+                const float4 jlo = __ldg(gv.saabb + 2 * (size_t)(o + q)), jhi = __ldg(gv.saabb + 2 * (size_t)(o + q) + 1);
+                const int j = __float_as_int(jhi.w);
                 if (j <= i || j >= jend) continue;
-                float4 jlo = gv.aabb[2 * j];
                 if (__float_as_int(jlo.w) != want) continue;                       // another cell hashed into this bucket
-                if (aabb_overlap(lo, hi, jlo, gv.aabb[2 * j + 1])) { if (STORE && n < room) out[n] = j; n++; }
+                if (aabb_overlap(lo, hi, jlo, jhi)) { if (STORE && n < room) out[n] = j; n++; }
             }
         }
         const int nl = *gv.large_count;
@@ -1678,27 +1720,34 @@ NP_D int cand_walk(const StoreView& s, const GridView& gv, int i, int jend, floa
     }
     return n;
 }
+// One thread per body of the world, in BUCKET order (thread t takes the t-th box of saabb, the large bodies follow): with dense
+// addressing the threads of a warp sit in the same or neighbouring cells and walk the same rows.  Bodies outside the searched range
+// [first, first + count) of a sharded world are skipped.
 __global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, int first, int count, DevCounters* ctr)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     int n = 0;
-    if (i < count) {
-        i += first;
-        const int jend = s.ints[I_ISLAND_END * s.cap + i];
-        const float4 lo = gv.aabb[2 * i], hi = gv.aabb[2 * i + 1];
-        int* out = gv.cand + (size_t)i * NP_CAND_SLOTS;
-        int off = i * NP_CAND_SLOTS;
-        n = cand_walk<true>(s, gv, i, jend, lo, hi, out, NP_CAND_SLOTS);
-        if (n > NP_CAND_SLOTS) {
-            off = atomicAdd(gv.spill_cursor, n);
-            if ((long long)off + n > (long long)gv.cand_cap) { atomicExch(gv.error, 1); n = 0; }
-            else { out = gv.cand + off; cand_walk<true>(s, gv, i, jend, lo, hi, out, n); }
-        }
-        gv.cand_cnt[i] = n; gv.cand_off[i] = off;
-        for (int a = 1; a < n; a++) {                    // ascending j
-            int key = out[a], b = a - 1;
-            while (b >= 0 && out[b] > key) { out[b + 1] = out[b]; b--; }
-            out[b + 1] = key;
+    if (t < s.n) {
+        const int nl = *gv.large_count, ns = s.n - nl;
+        int i; float4 lo, hi;
+        if (t < ns) { lo = __ldg(gv.saabb + 2 * (size_t)t); hi = __ldg(gv.saabb + 2 * (size_t)t + 1); i = __float_as_int(hi.w); }
+        else { i = gv.large[t - ns]; lo = gv.aabb[2 * i]; hi = gv.aabb[2 * i + 1]; }
+        if (i >= first && i < first + count) {
+            const int jend = s.ints[I_ISLAND_END * s.cap + i];
+            int* out = gv.cand + (size_t)i * NP_CAND_SLOTS;
+            int off = i * NP_CAND_SLOTS;
+            n = cand_walk<true>(s, gv, i, jend, lo, hi, out, NP_CAND_SLOTS);
+            if (n > NP_CAND_SLOTS) {
+                off = atomicAdd(gv.spill_cursor, n);
+                if ((long long)off + n > (long long)gv.cand_cap) { atomicExch(gv.error, 1); n = 0; }
+                else { out = gv.cand + off; cand_walk<true>(s, gv, i, jend, lo, hi, out, n); }
+            }
+            gv.cand_cnt[i] = n; gv.cand_off[i] = off;
+            for (int a = 1; a < n; a++) {                    // ascending j
+                int key = out[a], b = a - 1;
+                while (b >= 0 && out[b] > key) { out[b + 1] = out[b]; b--; }
+                out[b + 1] = key;
+            }
         }
     }
     if (ctr) {
@@ -1791,8 +1840,11 @@ __global__ void __launch_bounds__(NP_SCAN_BLOCK) k_scan_apply(int n, const int* 
     __syncthreads();
     if (i < n) out[i] = sums[blockIdx.x] + warp_tot[wid] + x - v;
 }
-// Physics::ApplyImpulseResponse, physics.cpp:27-46
-NP_D void impulse(V3& pos, V3& L, V3& H, float mass, float elast, const float* iinv, V3 r, float cdepth, V3 n)
+// Physics::ApplyImpulseResponse, physics.cpp:27-46.  sfric: m_staticFrictionCoeff when the world runs with NP_OPT_FRICTION, else 0 --
+// the block the reference keeps commented out at physics.cpp:49-72, as written there: the velocity is re-derived from the NEW linear
+// momentum but the OLD angular velocity, `vt.normalize();` discards its result (vector.h:211-219 returns a copy), and clamp is the
+// macro max(a, min(x, b)) of lib.h:13-23 (its comparisons decide what a NaN does).
+NP_D void impulse(V3& pos, V3& L, V3& H, float mass, float elast, const float* iinv, V3 r, float cdepth, V3 n, float sfric = 0.0f)
 {
     V3 v = mul(L, 1.0f / mass);
     V3 w = m3mul(iinv, H);
@@ -1804,6 +1856,22 @@ NP_D void impulse(V3& pos, V3& L, V3& H, float mass, float elast, const float* i
     H = add(H, mul(cross(r, n), j));
     float adjust = cdepth * 1.01f;
     pos = add(pos, mul(n, adjust));
+    if (sfric != 0.0f) {                                                                          // :49  `if (m_static.m_staticFrictionCoeff)`: a NaN is true
+        v = mul(L, 1.0f / mass);                                                                  // :51
+        vp = add(v, cross(w, r));                                                                 // :52
+        const float rel = dot(vp, n);                                                             // :53
+        if (!feq(rel, 0.0f)) {                                                                    // :54
+            const V3 vt = sub(vp, mul(n, rel));                                                   // :56 (:57 normalizes a temporary)
+            const float it = dot(vp, vt);                                                         // :58
+            const float kt = (1.0f / mass) + dot(cross(m3mul(iinv, cross(r, vt)), r), vt);        // :59
+            const float fc = sfric * j;                                                           // :60
+            const float x = -it / kt, lo = -fc;                                                   // :61  clamp(x, lo, fc) = max(lo, min(x, fc))
+            const float mn = (x < fc) ? x : fc;
+            const float jt = (lo > mn) ? lo : mn;
+            L = add(L, mul(vt, jt));                                                              // :62
+            H = add(H, mul(cross(r, vt), jt));                                                    // :63
+        }
+    }
 }
 struct SnapObj { uint32_t guid; float pos[3]; float rot[4]; uint32_t enabled; };
 // CommandFrameObject of body i (netphys_server/world_s.cpp:37-48): position, quaternion (w,x,y,z) of the Euler rotation, isEnabled
@@ -1842,6 +1910,7 @@ __global__ void __launch_bounds__(256) k_resolve(StoreView s, const int* __restr
     if (s.ints[I_RESPONSE * cap + k] == 1 && ((unsigned)own < (unsigned)s.n || first != 0)) {
         if (!FUSE) { L = mk(st[S_LX * cap + k], st[S_LY * cap + k], st[S_LZ * cap + k]); H = mk(st[S_HX * cap + k], st[S_HY * cap + k], st[S_HZ * cap + k]); }
         float mass = c[C_MASS * cap + k], elast = c[C_ELAST * cap + k];
+        const float sfric = s.friction ? c[C_SFRIC * cap + k] : 0.0f;
         float iinv[9];
 #pragma unroll
         for (int q = 0; q < 9; q++) iinv[q] = c[(C_IINV0 + q) * cap + k];
@@ -1852,12 +1921,12 @@ __global__ void __launch_bounds__(256) k_resolve(StoreView s, const int* __restr
             for (int e = first; e != 0; e = next[e - 1]) { int i = e - 1; if (i > last && i < best) best = i; }
             if (best == 0x7fffffff) break;
             float4 cd = contact[best];
-            impulse(pos, L, H, mass, elast, iinv, mk(cd.x, cd.y, cd.z), cd.w, a_normal);
+            impulse(pos, L, H, mass, elast, iinv, mk(cd.x, cd.y, cd.z), cd.w, a_normal, sfric);
             last = best;
         }
         if ((unsigned)own < (unsigned)s.n) {                 // k is `a` of its own collision: normal = b_normal (physics.cpp:99)
             float4 cd = contact[k];
-            impulse(pos, L, H, mass, elast, iinv, mk(cd.x, cd.y, cd.z), cd.w, b_normal);
+            impulse(pos, L, H, mass, elast, iinv, mk(cd.x, cd.y, cd.z), cd.w, b_normal, sfric);
         }
         resolved = true;
         if (!FUSE) {
@@ -1895,7 +1964,7 @@ __global__ void k_impulse_one(StoreView s, int k, V3 r, float depth, V3 n)
     V3 H = mk(st[S_HX * cap + k], st[S_HY * cap + k], st[S_HZ * cap + k]);
     float iinv[9];
     for (int q = 0; q < 9; q++) iinv[q] = c[(C_IINV0 + q) * cap + k];
-    impulse(pos, L, H, c[C_MASS * cap + k], c[C_ELAST * cap + k], iinv, r, depth, n);
+    impulse(pos, L, H, c[C_MASS * cap + k], c[C_ELAST * cap + k], iinv, r, depth, n, s.friction ? c[C_SFRIC * cap + k] : 0.0f);
     st[S_PX * cap + k] = pos.x; st[S_PY * cap + k] = pos.y; st[S_PZ * cap + k] = pos.z;
     st[S_LX * cap + k] = L.x; st[S_LY * cap + k] = L.y; st[S_LZ * cap + k] = L.z;
     st[S_HX * cap + k] = H.x; st[S_HY * cap + k] = H.y; st[S_HZ * cap + k] = H.z;

@@ -111,13 +111,14 @@ struct np_world {
     unsigned long long steps = 0;
     // CUDA graph of one step (np_world_step_n)
     std::vector<StepGraph> graphs; int graph_on = 1; bool capturing = false;
+    int friction_on = 0;              // NP_OPT_FRICTION
     int phase_timing = 0;             // NP_OPT_PHASE_TIMING: per-phase events inside the step (they cost ~4 us each)      // np_world_step replays a captured step (NP_GRAPH=0: plain launches)
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
 static StoreView view(np_world* w)
 {
-    StoreView s; s.n = (int)w->bodies.size(); s.cap = w->cap; s.state = w->d_state; s.cst = w->d_cst; s.xf = w->d_xf; s.ints = w->d_ints; s.wverts = w->d_wverts; s.ext = w->d_ext;
+    StoreView s; s.n = (int)w->bodies.size(); s.cap = w->cap; s.state = w->d_state; s.cst = w->d_cst; s.xf = w->d_xf; s.ints = w->d_ints; s.wverts = w->d_wverts; s.ext = w->d_ext; s.friction = w->friction_on;
     s.soff = w->d_soff; s.scnt = w->d_scnt; s.stab = w->tables_on ? w->d_tab : nullptr; s.stlim = w->d_tlim;       // (for the arming records written next to the transforms)
     return s;
 }
@@ -352,7 +353,7 @@ static int ensure_device(np_world* w)
     for (int i = 0; i < n; i++) {
         const np_static_physics_data& sd = w->bodies[i].sd;
         cst[C_GX * cap + i] = sd.gravity[0]; cst[C_GY * cap + i] = sd.gravity[1]; cst[C_GZ * cap + i] = sd.gravity[2];
-        cst[C_MASS * cap + i] = sd.mass; cst[C_ELAST * cap + i] = sd.elasticity;
+        cst[C_MASS * cap + i] = sd.mass; cst[C_ELAST * cap + i] = sd.elasticity; cst[C_SFRIC * cap + i] = sd.static_friction_coeff;
         for (int k = 0; k < 9; k++) cst[(C_IINV0 + k) * cap + i] = sd.inverse_inertia_tensor[k];
         ints[I_RESPONSE * cap + i] = sd.collision_response; ints[I_SHAPE * cap + i] = w->bodies[i].shape; ints[I_ISLAND_END * cap + i] = island_end[i];
         ints[I_HANDLE * cap + i] = w->handle_of_slot[i];
@@ -622,6 +623,9 @@ static void enqueue_scan(np_world* w, int n, const int* in, int* out)
     w->launches += 3;
 }
 #define NP_CAND_PER_BODY 64
+#ifndef NP_GRID_H_SCALE
+#define NP_GRID_H_SCALE 1.5f      // automatic cell edge over the average box extent (measured on the 1M-body world)
+#endif
 static int ensure_grid(np_world* w)
 {
     if (w->grid_cap == w->cap && w->d_grid_ints) return NP_OK;
@@ -629,15 +633,15 @@ static int ensure_grid(np_world* w)
     const size_t c = (size_t)w->cap;
     int nb = 1024; while ((size_t)nb < 2 * c) nb <<= 1;
     const size_t cand_cap = std::min<size_t>((size_t)NP_CAND_PER_BODY * c, (size_t)1 << 30);
-    // ints: bucket_cnt[nb] bucket_cur[nb] (zeroed together) | bucket_off[nb] | items[c] | large[c] | cand_cnt[c] | cand_ub[c] | cand_off[c] | misc[32] | cand[cand_cap]
-    const size_t n_ints = 3 * (size_t)nb + 5 * c + 32 + cand_cap;
+    // ints: bucket_cnt[nb] bucket_cur[nb] (zeroed together) | bucket_off[nb + 1 (+31)] | items[c] | large[c] | cand_cnt[c] | cand_ub[c] | cand_off[c] | misc[32] | cand[cand_cap]
+    const size_t n_ints = 3 * (size_t)nb + 32 + 5 * c + 32 + cand_cap;
     CU(cudaMalloc((void**)&w->d_grid_ints, sizeof(int) * n_ints));
-    CU(cudaMalloc((void**)&w->d_grid_f, sizeof(float) * (16 * c + 32)));      // aabb[2c] float4 | aabb_prev[2c] float4 | params[32]
+    CU(cudaMalloc((void**)&w->d_grid_f, sizeof(float) * (24 * c + 32)));      // aabb[2c] float4 | aabb_prev[2c] float4 | saabb[2c] float4 | params[32]
     GridView& g = w->grid;
     int* p = w->d_grid_ints;
-    g.bucket_cnt = p; p += nb; g.bucket_cur = p; p += nb; g.bucket_off = p; p += nb; g.items = p; p += c; g.large = p; p += c;
+    g.bucket_cnt = p; p += nb; g.bucket_cur = p; p += nb; g.bucket_off = p; p += nb + 32; g.items = p; p += c; g.large = p; p += c;
     g.cand_cnt = p; p += c; g.cand_ub = p; p += c; g.cand_off = p; p += c; g.large_count = p; g.error = p + 1; g.spill_cursor = p + 2; p += 32; g.cand = p;
-    g.aabb = (float4*)w->d_grid_f; g.aabb_prev = (float4*)w->d_grid_f + 2 * c; g.params = w->d_grid_f + 16 * c;
+    g.aabb = (float4*)w->d_grid_f; g.aabb_prev = (float4*)w->d_grid_f + 2 * c; g.saabb = (float4*)w->d_grid_f + 4 * c; g.params = w->d_grid_f + 24 * c;
     g.nbuckets = nb; g.cand_cap = (int)std::min<size_t>(cand_cap, 0x7fffffff); g.spill_base = (int)std::min<size_t>(c * NP_CAND_SLOTS, 0x7fffffff);
     if (g.spill_base >= g.cand_cap) return fail(NP_ERR_CAPACITY, "world too large for the grid broad phase's candidate store");
     CU(cudaMemsetAsync(g.large_count, 0, sizeof(int) * 32, w->stream));
@@ -648,6 +652,7 @@ static int ensure_grid(np_world* w)
 static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, int cache, DevCounters* ctr)
 {
     GridView& g = w->grid; g.h_option = w->grid_cell;
+    { const char* e = getenv("NP_GRID_H_SCALE"); g.h_scale = e ? (float)atof(e) : NP_GRID_H_SCALE; const char* fh = getenv("NP_GRID_HASH"); g.force_hash = fh ? atoi(fh) : 0; }      // (tools and tests)
     g.swept = w->broadphase == NP_BROADPHASE_SWEPT ? (w->swept_valid ? 2 : 1) : 0;
     if (g.swept && !w->capturing) w->swept_valid = true;
     const int n = s.n, b256 = (n + 255) / 256;
@@ -659,10 +664,10 @@ static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, i
     else k_world_verts<true, 0><<<wvb, 256, 0, w->stream>>>(s, sview(w), g);
     k_grid_params<<<1, 1, 0, w->stream>>>(n, g);
     k_grid_count<<<b256, 256, 0, w->stream>>>(s, g);
-    enqueue_scan(w, g.nbuckets, g.bucket_cnt, g.bucket_off);
+    enqueue_scan(w, g.nbuckets + 1, g.bucket_cnt, g.bucket_off);      // one more than the buckets: bucket_cnt[nbuckets] is bucket_cur[0], still zero here, so bucket_off[nbuckets] = all of them
     k_grid_fill<<<b256, 256, 0, w->stream>>>(s, g);
     if (count > 0) {                 // candidates of the bodies this process searches (the whole world unless sharded)
-        k_cand<<<(count + 127) / 128, 128, 0, w->stream>>>(s, g, first, count, ctr);
+        k_cand<<<(n + 127) / 128, 128, 0, w->stream>>>(s, g, first, count, ctr);
         w->launches += 1;
     }
     w->launches += 5;
@@ -828,6 +833,7 @@ int np_world_set_option(np_world* w, int option, int64_t value)
     case NP_OPT_SNAPSHOT_EACH_STEP: w->snapshot_each_step = value ? 1 : 0; drop_graph(w); return NP_OK;
     case NP_OPT_PHASE_TIMING: w->phase_timing = value ? 1 : 0; drop_graph(w); return NP_OK;
     case NP_OPT_SUPPORT_TABLES: w->tables_on = value != 0; drop_graph(w); return NP_OK;
+    case NP_OPT_FRICTION: w->friction_on = value ? 1 : 0; drop_graph(w); return NP_OK;
     default: return fail(NP_ERR_INVALID, "unknown option");
     }
 }

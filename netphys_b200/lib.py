@@ -187,7 +187,7 @@ class World:
     """np_world.  Mirrors the reference's implicit global world (engine/physics.cpp:9) as an explicit object."""
 
     EXACT, GRID, SWEPT = 0, 1, 2
-    OPT_BROADPHASE, OPT_GRID_CELL, OPT_COUNTERS, OPT_SNAPSHOT_EACH_STEP, OPT_PHASE_TIMING, OPT_SUPPORT_TABLES = 1, 2, 3, 4, 5, 6
+    OPT_BROADPHASE, OPT_GRID_CELL, OPT_COUNTERS, OPT_SNAPSHOT_EACH_STEP, OPT_PHASE_TIMING, OPT_SUPPORT_TABLES, OPT_FRICTION = 1, 2, 3, 4, 5, 6, 7
 
     def __init__(self, device=-1, variant="exact"):
         self.L = load_library(variant)

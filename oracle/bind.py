@@ -68,6 +68,8 @@ class Oracle:
         L.npo_world_add_force.argtypes = [C.c_void_p, C.c_int, f32p]; L.npo_world_add_force.restype = None
         L.npo_world_set_enabled.argtypes = [C.c_void_p, C.c_int, C.c_int]; L.npo_world_set_enabled.restype = None
         L.npo_world_get_state.argtypes = [C.c_void_p, f32p]
+        L.npo_world_set_friction.argtypes = [C.c_void_p, C.c_int]; L.npo_world_set_friction.restype = None
+        L.npo_world_apply_impulse.argtypes = [C.c_void_p, C.c_int, f32p, C.c_float, f32p]; L.npo_world_apply_impulse.restype = None
         L.npo_world_set_state.argtypes = [C.c_void_p, f32p]
         L.npo_world_step.argtypes = [C.c_void_p, C.c_float, i32p, i32p, f32p, C.c_int]
         L.npo_world_counters.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(Counters)]
@@ -183,6 +185,12 @@ class OracleWorld:
     def set_state(self, st):
         self.o.L.npo_world_set_state(self.w, _f(f32(st)))
 
+    def set_friction(self, on):
+        self.o.L.npo_world_set_friction(self.w, int(bool(on)))
+
+    def apply_impulse_response(self, body, pen_dir, depth, normal):
+        self.o.L.npo_world_apply_impulse(self.w, int(body), _f(f32(pen_dir)), float(np.float32(depth)), _f(f32(normal)))
+
     def counters(self):
         pt = C.c_longlong(); h = C.c_longlong(); c = Counters()
         self.o.L.npo_world_counters(self.w, C.byref(pt), C.byref(h), C.byref(c))
@@ -206,9 +214,12 @@ def ref_available():
 class Ref:
     """The reference's own engine (process-global body list: one scene at a time)."""
 
-    def __init__(self):
+    def __init__(self, friction=False):
+        """friction=True: the variant compiled with the reference's friction block (physics.cpp:49-72) uncommented, see oracle/Makefile"""
         build()
-        L = self.L = C.CDLL(os.path.join(HERE, "_ref", "libnetphys_ref.so"))
+        L = self.L = C.CDLL(os.path.join(HERE, "_ref", "libnetphys_ref_friction.so" if friction else "libnetphys_ref.so"))
+        assert L.ref_has_friction() == int(bool(friction))
+        L.ref_body_apply_impulse.argtypes = [C.c_int, f32p, C.c_float, f32p]; L.ref_body_apply_impulse.restype = None
         L.ref_shape_sphere.argtypes = [C.c_float]
         L.ref_shape_box.argtypes = [C.c_float] * 3
         L.ref_shape_mesh.argtypes = [f32p, C.c_int]
@@ -311,6 +322,9 @@ class Ref:
         a = np.zeros(self.n + 1, np.int32); b = np.zeros(self.n + 1, np.int32); d = np.zeros((self.n + 1, 11), np.float32)
         nc = self.L.ref_update_traced(float(np.float32(dt)), _i(a), _i(b), _f(d), self.n + 1)
         return a[:nc].copy(), b[:nc].copy(), d[:nc].copy()
+
+    def apply_impulse_response(self, body, pen_dir, depth, normal):
+        self.L.ref_body_apply_impulse(int(body), _f(f32(pen_dir)), float(np.float32(depth)), _f(f32(normal)))
 
     def time_steps(self, dt, steps):
         return self.L.ref_time_update(float(np.float32(dt)), steps)

@@ -647,7 +647,7 @@ int npo_detect(const float* va, int na, const float xa[16], const float* vb, int
  * ============================================================================================ */
 typedef struct {
     v3 gravity, init_pos, init_rot;
-    float mass, elasticity;
+    float mass, elasticity, sfric;
     m3 inv_inertia;
     int response;
     int shape;
@@ -661,6 +661,7 @@ struct npo_world {
     shape* s; int ns, scap;
     long long pair_tests, hits;
     npo_counters sum;
+    int friction;        /* npo_world_set_friction: run the block the reference keeps commented out at physics.cpp:49-72 */
 };
 npo_world* npo_world_create(void) { return (npo_world*)calloc(1, sizeof(npo_world)); }
 void npo_world_destroy(npo_world* w)
@@ -683,7 +684,7 @@ int npo_world_add_body(npo_world* w, int shp, const float* sd, int response)    
     body* b = &w->b[w->nb];
     memset(b, 0, sizeof *b);
     b->gravity = v_ld(sd); b->init_pos = v_ld(sd + 3); b->init_rot = v_ld(sd + 6);
-    b->mass = sd[9]; b->elasticity = sd[10];
+    b->mass = sd[9]; b->elasticity = sd[10]; b->sfric = sd[11];
     memcpy(b->inv_inertia.m, sd + 23, 36);
     b->response = response; b->shape = shp;
     b->pos = b->init_pos; b->rot = b->init_rot;       /* momenta start at vector3() == 0 */
@@ -716,7 +717,7 @@ static void body_update(body* b, float dt)                                      
         b->rot = v_add(b->rot, v_mul(w, dt));
     }
 }
-static void body_impulse(body* b, const npo_contact* c, v3 n)                            /* physics.cpp:27-46 */
+static void body_impulse(body* b, const npo_contact* c, v3 n, int friction)              /* physics.cpp:27-46 */
 {
     v3 r = v_ld(c->pen_dir);
     v3 v = v_mul(b->L, 1.0f / b->mass);
@@ -729,6 +730,34 @@ static void body_impulse(body* b, const npo_contact* c, v3 n)                   
     b->H = v_add(b->H, v_mul(v_cross(r, n), j));
     float adjust = c->depth * 1.01f;
     b->pos = v_add(b->pos, v_mul(n, adjust));
+    /* physics.cpp:49-72, commented out in the reference; restated as written there.  Pinned against the reference compiled with that
+     * block uncommented (oracle/Makefile: _ref/libnetphys_ref_friction.so; tests/golden/friction.npz).  Notes: `w` is the angular
+     * velocity from BEFORE the impulse; `vt.normalize();` (:57) discards its result (vector.h:211-219 is const and returns a copy), so
+     * vt keeps its length; clamp(x,a,b) is the macro max(a, min(x, b)) of lib.h:13-23. */
+    if (friction && b->sfric) {
+        v = v_mul(b->L, 1.0f / b->mass);
+        vp = v_add(v, v_cross(w, r));
+        float rel = v_dot(vp, n);
+        if (!feq(rel, 0.0f, TOL_DEFAULT)) {
+            v3 vt = v_sub(vp, v_mul(n, rel));
+            float it = v_dot(vp, vt);
+            float kt = (1.0f / b->mass) + v_dot(v_cross(m3_mul(&b->inv_inertia, v_cross(r, vt)), r), vt);
+            float fc = b->sfric * j;
+            float x = -it / kt, lo = -fc;
+            float mn = (x < fc) ? x : fc;
+            float jt = (lo > mn) ? lo : mn;
+            b->L = v_add(b->L, v_mul(vt, jt));
+            b->H = v_add(b->H, v_mul(v_cross(r, vt), jt));
+        }
+    }
+}
+void npo_world_set_friction(npo_world* w, int on) { w->friction = on; }
+/* Physics::ApplyImpulseResponse on one body with a caller's contact and normal (the world step only ever passes the zero normals) */
+void npo_world_apply_impulse(npo_world* w, int i, const float* pen_dir, float depth, const float* n)
+{
+    npo_contact c; memset(&c, 0, sizeof c);
+    memcpy(c.pen_dir, pen_dir, 12); c.depth = depth;
+    if (i >= 0 && i < w->nb) body_impulse(&w->b[i], &c, v_ld(n), w->friction);
 }
 static void acc(npo_counters* s, const npo_counters* c)
 {
@@ -759,8 +788,8 @@ int npo_world_step(npo_world* w, float dt, int* oa, int* ob, float* odata, int c
     }
     for (int k = 0; k < nc; k++) {                                                       /* OnCollision :93-114 */
         body* a = &w->b[ca[k]]; body* b = &w->b[cb[k]];
-        if (a->response == 1) body_impulse(a, &cd[k], v_ld(cd[k].b_normal));
-        if (b->response == 1) body_impulse(b, &cd[k], v_ld(cd[k].a_normal));
+        if (a->response == 1) body_impulse(a, &cd[k], v_ld(cd[k].b_normal), w->friction);
+        if (b->response == 1) body_impulse(b, &cd[k], v_ld(cd[k].a_normal), w->friction);
         if (k < cap && oa) {
             oa[k] = ca[k]; ob[k] = cb[k];
             float* o = odata + 11 * k;

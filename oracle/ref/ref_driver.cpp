@@ -12,7 +12,11 @@
 // scenes and read the momenta.  collision_detection.cpp is a separate translation unit
 // (it needs the one-line guard described in oracle/Makefile).
 #define private public
+#ifdef REF_PHYSICS_CPP          // the friction variant: physics.cpp with the comment markers of lines 49-72 stripped on the fly (oracle/Makefile)
+#include REF_PHYSICS_CPP
+#else
 #include "physics.cpp"
+#endif
 #include "physics_util.cpp"
 #include "physics_shape.cpp"
 #undef private
@@ -82,6 +86,17 @@ void ref_body_set_state(int b, const float* in)
     p->m_position = load3(in); p->m_rotation = load3(in + 3);
     p->m_linearMomentum = load3(in + 6); p->m_angularMomentum = load3(in + 9);
 }
+// Physics::ApplyImpulseResponse (physics.cpp:27-46) with a caller's contact and normal
+void ref_body_apply_impulse(int b, const float* pen_dir, float depth, const float* n)
+{
+    CollisionData d; d.penetrationDirection = load3(pen_dir); d.depth = depth;
+    bodies()[b]->ApplyImpulseResponse(d, load3(n));
+}
+#ifdef REF_PHYSICS_CPP
+int ref_has_friction() { return 1; }
+#else
+int ref_has_friction() { return 0; }
+#endif
 void ref_world_get_state(float* out) { for (int i = 0; i < ref_world_count(); i++) ref_body_get_state(i, out + 12 * i); }
 void ref_body_reset(int b) { bodies()[b]->Reset(); }
 void ref_body_transform(int b, float* out16) { matrix4 m = bodies()[b]->GetTransform(); memcpy(out16, &m, 64); }

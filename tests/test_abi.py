@@ -85,8 +85,8 @@ def test_python_constants_match_the_header(npb):
     text = open(os.path.join(ROOT, "include", "netphys_b200.h")).read()
     enum = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(NP_[A-Z0-9_]+)\s*=\s*(-?\d+)", text)}
     W = npb.World
-    assert (W.OPT_BROADPHASE, W.OPT_GRID_CELL, W.OPT_COUNTERS, W.OPT_SNAPSHOT_EACH_STEP, W.OPT_PHASE_TIMING, W.OPT_SUPPORT_TABLES) == \
-        tuple(enum[k] for k in ("NP_OPT_BROADPHASE", "NP_OPT_GRID_CELL", "NP_OPT_COUNTERS", "NP_OPT_SNAPSHOT_EACH_STEP", "NP_OPT_PHASE_TIMING", "NP_OPT_SUPPORT_TABLES"))
+    assert (W.OPT_BROADPHASE, W.OPT_GRID_CELL, W.OPT_COUNTERS, W.OPT_SNAPSHOT_EACH_STEP, W.OPT_PHASE_TIMING, W.OPT_SUPPORT_TABLES, W.OPT_FRICTION) == \
+        tuple(enum[k] for k in ("NP_OPT_BROADPHASE", "NP_OPT_GRID_CELL", "NP_OPT_COUNTERS", "NP_OPT_SNAPSHOT_EACH_STEP", "NP_OPT_PHASE_TIMING", "NP_OPT_SUPPORT_TABLES", "NP_OPT_FRICTION"))
     assert (W.EXACT, W.GRID, W.SWEPT) == (enum["NP_BROADPHASE_EXACT"], enum["NP_BROADPHASE_GRID"], enum["NP_BROADPHASE_SWEPT"])
     assert enum["NP_OK"] == 0 and enum["NP_ERR_NO_DEVICE"] == -2
     defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(NP_PACKET_[A-Z_]+)\s+(\d+)", text)}

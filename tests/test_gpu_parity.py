@@ -223,6 +223,38 @@ def test_impulse_response_general_normal(world, oracle):
     assert_biteq(got[0:3], pos, "pos"); assert_biteq(got[6:9], L, "L"); assert_biteq(got[9:12], H, "H")
 
 
+def test_friction_block_vs_reference_golden(world, oracle):
+    """NP_OPT_FRICTION: the block the reference keeps commented out (physics.cpp:49-72) against what the reference computes with it
+    uncommented (tests/golden/friction.npz from oracle/_ref/libnetphys_ref_friction.so) -- 512 bodies with their own masses, tensors,
+    coefficients (0, NaN, negative), zero / axis / tangent / parallel normals, non-finite momenta -- and against the C port live.
+    Option off: the plain build's answers."""
+    g = gold("friction.npz"); nb = len(g["sd"])
+    sc = scenes._scene([("box", 1.0, 1.0, 1.0)], np.zeros(nb, np.int32), list(g["sd"]), np.ones(nb, np.int32), "friction_cases")
+    world.load_scene(sc)
+    for on, key in ((1, "out_friction"), (0, "out_plain")):
+        world.set_option(world.OPT_FRICTION, on); world.set_states(g["state"])
+        ow = oracle.world(scenes.resolve(sc, oracle)); ow.set_state(g["state"]); ow.set_friction(on)
+        for i in range(nb):
+            world.apply_impulse_response(i, g["r"][i], g["depth"][i], g["n"][i])
+            ow.apply_impulse_response(i, g["r"][i], g["depth"][i], g["n"][i])
+        got = world.states()
+        assert_biteq(got, g[key], key + " (reference)"); assert_biteq(got, ow.state(), key + " (oracle)")
+        ow.close()
+
+
+def test_friction_block_is_inert_in_world_steps(npb, oracle):
+    """the world step passes the never-written zero normals (physics.cpp:99,109): with NP_OPT_FRICTION on, 300 steps of the few-boxes
+    scene (static_friction_coeff 0.4 on every box) end where the reference's friction build ends -- which is where its plain build ends"""
+    g = gold("friction.npz"); sc = scenes.few_boxes_scene()
+    for fused in (False, True):
+        w = npb.World(0); w.set_option(w.OPT_FRICTION, 1); w.load_scene(sc)
+        if fused: w.step_n(sc["dt"], 300)
+        else:
+            for _ in range(300): w.step(sc["dt"])
+        assert_biteq(w.states(), g["few_boxes_300"], "few boxes, 300 steps, friction on, fused=%s" % fused)
+        w.close()
+
+
 # ---- BASELINE sizes: size-independent properties --------------------------------------------------------------
 def _check_first_hit_properties(world, oracle, sc, shapes, sample):
     """hit list ascending in a, a < b, one entry per a; on sampled bodies the oracle reproduces exactly the scan:
@@ -289,9 +321,13 @@ def _world_aabbs(oracle, shapes, body_shape, st):
     return lo, hi
 
 
-@pytest.mark.parametrize("n,spacing,with_ground,cell", [(1500, 0.9, True, 0.0), (3000, 1.1, False, 0.0), (800, 0.8, True, 1.5)])
-def test_grid_broadphase_candidate_parity(world, oracle, n, spacing, with_ground, cell):
-    """Candidate set == brute-force AABB overlap; per candidate pair the GJK/EPA result == the oracle's; first-hit order kept."""
+@pytest.mark.parametrize("n,spacing,with_ground,cell,hashed", [(1500, 0.9, True, 0.0, 0), (3000, 1.1, False, 0.0, 0), (800, 0.8, True, 1.5, 0), (1500, 0.9, True, 0.0, 1), (900, 1.0, False, 0.35, 1),
+                                                              (700, 1.0, True, 0.3, 0)])
+def test_grid_broadphase_candidate_parity(world, oracle, monkeypatch, n, spacing, with_ground, cell, hashed):
+    """Candidate set == brute-force AABB overlap; per candidate pair the GJK/EPA result == the oracle's; first-hit order kept.  Both
+    addressings of the grid: dense (cells ordered z, y, x: one run of boxes per x-row) and hashed (NP_GRID_HASH=1, what a world spread over
+    more cells than buckets falls back to); cells from a third of a body (everything is "large") to several bodies wide."""
+    if hashed: monkeypatch.setenv("NP_GRID_HASH", "1")
     sc = scenes.lattice_scene(n, spacing=spacing, seed=n, mix=(0.5, 0.2, 0.3))
     if with_ground:   # a body much wider than a cell exercises the large-body list
         sc["shape_specs"] = sc["shape_specs"] + [("box", 40.0, 40.0, 1.0)]

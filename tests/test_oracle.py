@@ -2,11 +2,12 @@
 (2) golden fixtures produced by the reference itself (oracle/gen_golden.py), (3) the compiled reference live,
 where it is available.  No GPU, no product code under test here except netphys_b200.scenes (numpy)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
 
-from conftest import assert_biteq, gold
+from conftest import ROOT, _bits, assert_biteq, gold
 from netphys_b200 import scenes
 
 Z = [0, 0, 0]
@@ -215,3 +216,50 @@ def test_golden_wire_packets_layout_and_regeneration():
             assert sorted(a.files) == sorted(b.files) and all(np.array_equal(a[f], b[f]) for f in a.files), "the committed fixture is what the compiled reference produces"
         finally:
             shutil.copy(os.path.join(tmp, "before.npz"), keep); shutil.rmtree(tmp)
+
+
+# ---- friction block (physics.cpp:49-72, commented out in the reference; NP_OPT_FRICTION) ------------------------------------------
+def friction_world_inputs():
+    g = gold("friction.npz")
+    sc = scenes._scene([("box", 1.0, 1.0, 1.0)], np.zeros(len(g["sd"]), np.int32), list(g["sd"]), np.ones(len(g["sd"]), np.int32), "friction_cases")
+    return g, sc
+
+
+def test_friction_block_oracle_vs_reference_golden(oracle):
+    """ApplyImpulseResponse with a caller's normal: the C port against what the reference computes with its friction block
+    uncommented (oracle/_ref/libnetphys_ref_friction.so, oracle/gen_golden_friction.py) and, with the option off, against the plain build."""
+    g, sc = friction_world_inputs()
+    sc = scenes.resolve(sc, oracle)
+    assert np.any(_bits(g["out_friction"]) != _bits(g["out_plain"]))
+    for on, key in ((True, "out_friction"), (False, "out_plain")):
+        w = oracle.world(sc); w.set_state(g["state"]); w.set_friction(on)
+        for i in range(len(g["sd"])):
+            w.apply_impulse_response(i, g["r"][i], g["depth"][i], g["n"][i])
+        assert_biteq(w.state(), g[key], key)
+        w.close()
+
+
+def test_friction_block_is_inert_in_a_world_step(oracle):
+    """Physics_Update passes the never-written zero normals (physics.cpp:99,109): 300 steps of the few-boxes scene are the same with the block on."""
+    g = gold("friction.npz")
+    sc = scenes.resolve(scenes.few_boxes_scene(), oracle)
+    w = oracle.world(sc); w.set_friction(True)
+    for _ in range(300):
+        w.step(sc["dt"])
+    assert_biteq(w.state(), g["few_boxes_300"], "few boxes, 300 steps, friction on")
+    w.close()
+
+
+def test_friction_golden_is_what_the_reference_computes():
+    """dev container only: regenerate the fixture's outputs from oracle/_ref live"""
+    from oracle.bind import ref_available
+    if not (ref_available() and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libnetphys_ref_friction.so"))):
+        pytest.skip("oracle/_ref not built")
+    from oracle.bind import Oracle
+    from oracle.gen_golden_friction import friction_cases, run_ref
+    g = gold("friction.npz")
+    sc, st, r, depth, n = friction_cases(int(g["seed"]))
+    sc = scenes.resolve(sc, Oracle())
+    assert_biteq(sc["sd"], g["sd"], "generator inputs")
+    assert_biteq(run_ref(True, sc, st, r, depth, n), g["out_friction"], "friction build")
+    assert_biteq(run_ref(False, sc, st, r, depth, n), g["out_plain"], "plain build")

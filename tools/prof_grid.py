@@ -6,7 +6,7 @@ from netphys_b200 import scenes
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 spacing = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 sc = scenes.lattice_scene(n, spacing=spacing, seed=43, mix=(0.7, 0.2, 0.1))
-for mode in (1, 0):
+for mode in ((1,) if len(sys.argv) > 3 and sys.argv[3] == "gridonly" else (1, 0)):
     with npb.World(0) as w:
         w.set_option(w.OPT_BROADPHASE, mode); w.set_option(w.OPT_PHASE_TIMING, 1); w.set_option(w.OPT_COUNTERS, 1)
         w.load_scene(sc)
