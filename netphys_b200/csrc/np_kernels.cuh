@@ -242,6 +242,8 @@ struct NarrowIn {
     const float* xf_a; const float* xf_b;        // pair mode: transforms [n][X_COUNT]
     const int* order;                            // pair mode: item t is pair order[t] (pairs grouped by shape-size class, k_pair_order), or null
     const int* cand; const int* cand_off; const int* cand_cnt;   // world mode with a broad phase: per-body ascending candidate lists (null = all j > i)
+    const int* active; const int* n_active;                      // world mode with a broad phase: the searched bodies that HAVE candidates and their number (k_cand; it answers the
+                                                                 // others itself: most bodies of a sparse world).  The items are these; any order gives the same results
     const float4* seed;                                          // world mode: [2*body] support along (1,1,1), [2*body+1] along (-1,-1,-1) (k_seed_supports), or null
     int pf;                    // 1: k_gjk2 prefetches the lines of bodies far ahead in ticket order (NP_PREFETCH=0 switches it off)
     int halo;                  // world mode, partitioned sharded step: a body's search may look at most `halo` bodies ahead (their transforms came from the next rank; its own record reaches at most `halo` bodies); 0 = unlimited
@@ -256,6 +258,13 @@ NP_D bool halo_exhausted(const NarrowIn& in, const int* __restrict__ island_end,
     if (in.halo > 0 && jend == i + 1 + in.halo && island_end[i] > jend) atomicExch(in.halo_err, 1);
     return false;
 }
+// world mode: the body item t stands for, and how many items there are (a broad phase leaves a list of the bodies that have candidates)
+NP_D int world_item(const NarrowIn& in, int t)
+{
+    if (in.active) return __ldg(in.active + t);
+    return in.ordered ? in.s.ints[I_ORDER * in.s.cap + in.first + t] : t + in.first;
+}
+NP_D int item_count(const NarrowIn& in) { return in.n_active ? __ldg(in.n_active) : in.n; }
 // ---------------------------------------------------------------------------------------------------
 // K3: GJK.
 //  world mode = GetCollisions (physics.cpp:116-145): item = body i; its group tests j = i+1, i+2, ... inside i's island
@@ -297,11 +306,12 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK_MINB) k_gjk(NarrowIn
     const int* island_end = s.ints + I_ISLAND_END * s.cap;
     const int* wv_off = s.ints + I_WVOFF * s.cap;
     m.begin();
+    const int n_items = WORLD ? item_count(in) : in.n;
     for (;;) {
         int t = fetch_ticket<G>(ticket, !have && !exhausted);
         if (!have && !exhausted) {
-            if (t < in.n) {
-                i = WORLD ? (in.ordered ? s.ints[I_ORDER * s.cap + in.first + t] : t + in.first) : (in.order ? in.order[t] : t);
+            if (t < n_items) {
+                i = WORLD ? world_item(in, t) : (in.order ? in.order[t] : t);
                 if (WORLD && lead) { NP_TL(i, 0); NP_TLV(i, 2, 0); NP_TLV(i, 3, 0); }
 #ifdef NP_TIMELINE
                 m.cyc[0] = m.cyc[1] = m.cyc[2] = 0;
@@ -442,11 +452,12 @@ __global__ void __launch_bounds__(NP_NARROW_THREADS, NP_GJK1_MINB) k_gjk1(Narrow
         else { g.vb = verts + sh.off[sb]; load_xf(s.xf, s.cap, body, g.Rb, &g.tb); g.tabb = tab_arm(sh.tv, sb, g.Rb, g.tb, in.rot_known != 0); }
     };
     m.begin();
+    const int n_items = WORLD ? item_count(in) : in.n;
     for (;;) {
         int t = fetch_ticket<1>(ticket, !have && !exhausted);
         if (!have && !exhausted) {
-            if (t < in.n) {
-                i = WORLD ? (in.ordered ? s.ints[I_ORDER * s.cap + in.first + t] : t + in.first) : (in.order ? in.order[t] : t);
+            if (t < n_items) {
+                i = WORLD ? world_item(in, t) : (in.order ? in.order[t] : t);
                 if (WORLD) {
                     if (in.cand) { cbase = in.cand_off[i]; c = 0; cn = in.cand_cnt[i]; j = cn > 0 ? in.cand[cbase] : 0; jend = cn > 0 ? 0x7fffffff : 0; }
                     else { j = i + 1; jend = island_end[i]; if (in.halo > 0) jend = min(jend, i + 1 + in.halo); }
@@ -589,6 +600,7 @@ __global__ void __launch_bounds__(NP_GJK2_THREADS, NP_GJK2_MINB) k_gjk2(NarrowIn
     int round = 0;
     if (tid < 4) jcnt[tid] = 0;
     __syncthreads();
+    const int n_items = WORLD ? item_count(in) : in.n;
     for (;;) {
         // ---- 1: own pair up to the solve
         if (WORLD && pf_body >= 0) {
@@ -601,9 +613,9 @@ __global__ void __launch_bounds__(NP_GJK2_THREADS, NP_GJK2_MINB) k_gjk2(NarrowIn
         }
         int t = fetch_ticket<1>(ticket, !have && !exhausted);
         if (!have && !exhausted) {
-            if (t < in.n) {
-                i = WORLD ? (in.ordered ? s.ints[I_ORDER * s.cap + in.first + t] : t + in.first) : (in.order ? in.order[t] : t);
-                if (WORLD && in.pf) { const int tp = min(t + ahead, in.n - 1); pf_body = in.ordered ? s.ints[I_ORDER * s.cap + in.first + tp] : tp + in.first; }
+            if (t < n_items) {
+                i = WORLD ? world_item(in, t) : (in.order ? in.order[t] : t);
+                if (WORLD && in.pf) pf_body = world_item(in, min(t + ahead, n_items - 1));
                 if (WORLD) {
                     if (in.cand) { cbase = in.cand_off[i]; c = 0; cn = in.cand_cnt[i]; j = cn > 0 ? in.cand[cbase] : 0; jend = cn > 0 ? 0x7fffffff : 0; }
                     else { j = i + 1; jend = island_end[i]; if (in.halo > 0) jend = min(jend, i + 1 + in.halo); }
@@ -1457,11 +1469,12 @@ __global__ void __launch_bounds__(256) k_pose_xf(int n, const float* __restrict_
 struct GridView {
     float4* aabb;         // [2*cap]: lo.xyz + packed cell (as int bits, -1 = large) | hi.xyz
     float* params;        // [0..2] origin, [3] h, [4] sum of extents, [5..7] global min (ordered ints), [8] H (ordered int), [9] large threshold,
-                          // [10..12] global max (ordered ints), [13..15] cells per axis (ints), [16] 1 = dense addressing (int): see k_grid_params
+                          // [10..12] global max (ordered ints), [13..15] cells per axis (ints), [16] 1 = dense addressing (int), [17] bucket entries in use (int): see k_grid_params
     int* bucket_cnt;      // [nbuckets]
     int* bucket_off;      // [nbuckets]
     int* bucket_cur;      // [nbuckets]
-    int* items;           // [cap] (unused: the bucket-ordered boxes of saabb carry their body index)
+    int* items;           // [cap] k_cand's output: the searched bodies that have at least one candidate (active_count of them, any order)
+    int* active_count;    // [1]
     float4* saabb;        // [2*cap] the boxes in bucket order: entry p = lo.xyz + packed cell | hi.xyz + body index (int bits) of items[p]
     int* large;           // [cap] large-body list
     int* large_count;     // [1]
@@ -1479,6 +1492,43 @@ struct GridView {
     int swept;            // 0: candidates from this step's AABBs; 1: swept mode, first step after a rebuild (no previous box yet); 2: union with the previous step's box
 };
 
+// a body's box goes on record (swept mode: united with the previous step's), and into the thread's share of the world statistics
+NP_D void box_record(const GridView& gv, int body, float* lo, float* hi, float& ext_acc, int* mn_acc, int* mx_acc)
+{
+    if (gv.swept) {                                  // todo.txt:8 "swept AABB from previous state": the box the body swept through since the last step
+        const float4 clo = make_float4(lo[0], lo[1], lo[2], 0.0f), chi = make_float4(hi[0], hi[1], hi[2], 0.0f);
+        if (gv.swept == 2) {
+            const float4 plo = gv.aabb_prev[2 * body], phi = gv.aabb_prev[2 * body + 1];
+            lo[0] = fminf(lo[0], plo.x); lo[1] = fminf(lo[1], plo.y); lo[2] = fminf(lo[2], plo.z);
+            hi[0] = fmaxf(hi[0], phi.x); hi[1] = fmaxf(hi[1], phi.y); hi[2] = fmaxf(hi[2], phi.z);
+        }
+        gv.aabb_prev[2 * body] = clo; gv.aabb_prev[2 * body + 1] = chi;
+    }
+    gv.aabb[2 * body] = make_float4(lo[0], lo[1], lo[2], 0.0f); gv.aabb[2 * body + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+    float e = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
+    if (e == e && e < INFINITY) ext_acc += e;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { if (lo[c] == lo[c]) mn_acc[c] = min(mn_acc[c], float_order(lo[c])); if (hi[c] == hi[c]) mx_acc[c] = max(mx_acc[c], float_order(hi[c])); }
+}
+// block-level reduction of (sum of extents, global min and max corner): 7 atomics per BLOCK (256 threads)
+NP_D void box_stats_flush(const GridView& gv, float ext_acc, const int* mn_acc, const int* mx_acc)
+{
+    float ext = ext_acc; int mn[3] = { mn_acc[0], mn_acc[1], mn_acc[2] }, mx[3] = { mx_acc[0], mx_acc[1], mx_acc[2] };
+    __shared__ float s_ext[8]; __shared__ int s_mn[8][3], s_mx[8][3];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ext += __shfl_xor_sync(0xffffffffu, ext, o);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { mn[c] = min(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o)); mx[c] = max(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o)); }
+    }
+    if ((threadIdx.x & 31) == 0) { s_ext[threadIdx.x >> 5] = ext; for (int c = 0; c < 3; c++) { s_mn[threadIdx.x >> 5][c] = mn[c]; s_mx[threadIdx.x >> 5][c] = mx[c]; } }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int wdx = 1; wdx < 8; wdx++) { ext += s_ext[wdx]; for (int c = 0; c < 3; c++) { mn[c] = min(mn[c], s_mn[wdx][c]); mx[c] = max(mx[c], s_mx[wdx][c]); } }
+        if (ext != 0.0f) atomicAdd(&gv.params[4], ext);
+        for (int c = 0; c < 3; c++) { if (mn[c] != 0x7fffffff) atomicMin((int*)&gv.params[5 + c], mn[c]); if (mx[c] != (int)0x80000000) atomicMax((int*)&gv.params[10 + c], mx[c]); }
+    }
+}
 // K1b: world-space vertex cache (+ AABB for the grid).  8 lanes per body; world*p per vertex exactly as the support
 // mapping evaluates it (physics_util.cpp:17), so K3/K4 can take dot products of the cached vertices directly.
 // HBM: reads 48 B transform + the shape's local vertices (L2 resident), writes 16 B per vertex (+ 32 B AABB).
@@ -1496,8 +1546,6 @@ __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, 
     const bool valid = body < s.n;
     float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
     if (valid) {
-        float R[9]; V3 t;
-        load_xf(s.xf, cap, body, R, &t);
         int shp = s.ints[I_SHAPE * cap + body];
         const float4* v = sh.verts + sh.off[shp]; int n = sh.cnt[shp];
         if (WRITE == 2 && !AABB && n < NP_COOP_MIN) n = 0;
@@ -1512,11 +1560,9 @@ __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, 
             bool ok = tab != NP_TAB_NONE;
             float comp = 0.0f;
             if (ok && gl < 6) {
-                const float sg = (gl & 1) ? -1.0f : 1.0f;
-                const V3 d = mk(gl < 2 ? sg : 0.0f, (gl >> 1) == 1 ? sg : 0.0f, gl >= 4 ? sg : 0.0f);
-                V3 wp;
-                ok = support_tab(v, R, t, d, tab, sh.tv.cells, &wp);
-                comp = gl < 2 ? wp.x : (gl < 4 ? wp.y : wp.z);
+                const int ax = gl >> 1;
+                const float* xr = s.xf + X_COUNT * (size_t)body;
+                ok = support_tab_axis(v, mk(xr[3 * ax], xr[3 * ax + 1], xr[3 * ax + 2]), xr[X_TX + ax], (gl & 1) ? -1.0f : 1.0f, tab, sh.tv.cells, &comp);
             }
             const unsigned all = (__ballot_sync(__activemask(), ok) >> ((threadIdx.x & 31u) & ~7u)) & 0xffu;
             if (all == 0xffu) {
@@ -1524,6 +1570,8 @@ __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, 
                 if (gl < 6) { if (gl & 1) lo[gl >> 1] = comp; else hi[gl >> 1] = comp; }
             }
         }
+        float R[9]; V3 t = mk(0.0f, 0.0f, 0.0f);
+        if (!boxed) load_xf(s.xf, cap, body, R, &t);
         for (int k = gl; k < n && !boxed; k += G) {
             float4 q = v[k];
             V3 wp = xf_point(R, t, mk(q.x, q.y, q.z));
@@ -1543,47 +1591,58 @@ __global__ void __launch_bounds__(256) k_world_verts(StoreView s, ShapeView sh, 
             hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o, G));
         }
     }
-    // per-body record, and block-level reduction of (sum of extents, global min corner): 4 atomics per BLOCK
-    if (valid && gl == 0) {
-        if (gv.swept) {                                  // todo.txt:8 "swept AABB from previous state": the box the body swept through since the last step
-            const float4 clo = make_float4(lo[0], lo[1], lo[2], 0.0f), chi = make_float4(hi[0], hi[1], hi[2], 0.0f);
-            if (gv.swept == 2) {
-                const float4 plo = gv.aabb_prev[2 * body], phi = gv.aabb_prev[2 * body + 1];
-                lo[0] = fminf(lo[0], plo.x); lo[1] = fminf(lo[1], plo.y); lo[2] = fminf(lo[2], plo.z);
-                hi[0] = fmaxf(hi[0], phi.x); hi[1] = fmaxf(hi[1], phi.y); hi[2] = fmaxf(hi[2], phi.z);
-            }
-            gv.aabb_prev[2 * body] = clo; gv.aabb_prev[2 * body + 1] = chi;
-        }
-        gv.aabb[2 * body] = make_float4(lo[0], lo[1], lo[2], 0.0f); gv.aabb[2 * body + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
-        float e = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
-        if (e == e && e < INFINITY) ext_acc += e;
-#pragma unroll
-        for (int c = 0; c < 3; c++) { if (lo[c] == lo[c]) mn_acc[c] = min(mn_acc[c], float_order(lo[c])); if (hi[c] == hi[c]) mx_acc[c] = max(mx_acc[c], float_order(hi[c])); }
-    }
+    if (valid && gl == 0) box_record(gv, body, lo, hi, ext_acc, mn_acc, mx_acc);
     }
     if (!AABB) return;
-    float ext = ext_acc; int mn[3] = { mn_acc[0], mn_acc[1], mn_acc[2] }, mx[3] = { mx_acc[0], mx_acc[1], mx_acc[2] };
-    __shared__ float s_ext[8]; __shared__ int s_mn[8][3], s_mx[8][3];
+    box_stats_flush(gv, ext_acc, mn_acc, mx_acc);
+}
+// K1b', the boxes alone (no world-vertex cache to write, every shape tabled): one THREAD per body.  A box face is the support point along
+// +-x, +-y, +-z, and the direction table answers each from a candidate or two (support_tab_axis), so a body costs six short lookups --
+// not a pass over its vertices, and no lanes to combine (8 lanes per body spent more instructions on the shuffles than on the boxes:
+// 131 us for a million bodies against 50 here).  A body whose lookup fails (no table with this transform, a crowded cell, a
+// non-finite coordinate) scans its vertices in the thread, with k_world_verts' expressions: the same floats either way.
+__global__ void __launch_bounds__(256) k_body_boxes(StoreView s, ShapeView sh, GridView gv)
+{
+    float ext_acc = 0.0f; int mn_acc[3] = { 0x7fffffff, 0x7fffffff, 0x7fffffff }, mx_acc[3] = { (int)0x80000000, (int)0x80000000, (int)0x80000000 };
+    for (int body = blockIdx.x * blockDim.x + threadIdx.x; body < s.n; body += gridDim.x * blockDim.x) {
+        float R[9]; V3 t;
+        load_xf(s.xf, s.cap, body, R, &t);
+        const int4 ar = load_arm(s.xf, body);
+        const float4* v = sh.verts + ar.x;
+        const unsigned tab = (unsigned)ar.z;
+        float lo[3] = { 0.0f, 0.0f, 0.0f }, hi[3] = { 0.0f, 0.0f, 0.0f };
+        bool ok = tab != NP_TAB_NONE;
+        const float tt[3] = { t.x, t.y, t.z };
+        if (ok) {
+            uint2 cell[6];                               // the six cells first: their loads are in flight together
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ext += __shfl_xor_sync(0xffffffffu, ext, o);
+            for (int q = 0; q < 6; q++) {
+                const uint2* c = tab_axis_cell(mk(R[3 * (q >> 1)], R[3 * (q >> 1) + 1], R[3 * (q >> 1) + 2]), (q & 1) ? -1.0f : 1.0f, tab, sh.tv.cells);
+                cell[q] = c ? __ldg(c) : make_uint2(0u, 0xff000000u);      // (a count the evaluation refuses)
+            }
 #pragma unroll
-        for (int c = 0; c < 3; c++) { mn[c] = min(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o)); mx[c] = max(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o)); }
+            for (int q = 0; q < 6; q++)
+                ok = tab_axis_eval(v, mk(R[3 * (q >> 1)], R[3 * (q >> 1) + 1], R[3 * (q >> 1) + 2]), tt[q >> 1], (q & 1) ? -1.0f : 1.0f, cell[q], (q & 1) ? &lo[q >> 1] : &hi[q >> 1]) && ok;
+        }
+        if (!ok) {
+            lo[0] = lo[1] = lo[2] = INFINITY; hi[0] = hi[1] = hi[2] = -INFINITY;
+            for (int k = 0; k < ar.y; k++) {
+                const float4 q = v[k];
+                const V3 wp = xf_point(R, t, mk(q.x, q.y, q.z));
+                lo[0] = fminf(lo[0], wp.x); lo[1] = fminf(lo[1], wp.y); lo[2] = fminf(lo[2], wp.z);
+                hi[0] = fmaxf(hi[0], wp.x); hi[1] = fmaxf(hi[1], wp.y); hi[2] = fmaxf(hi[2], wp.z);
+            }
+        }
+        box_record(gv, body, lo, hi, ext_acc, mn_acc, mx_acc);
     }
-    if ((threadIdx.x & 31) == 0) { s_ext[threadIdx.x >> 5] = ext; for (int c = 0; c < 3; c++) { s_mn[threadIdx.x >> 5][c] = mn[c]; s_mx[threadIdx.x >> 5][c] = mx[c]; } }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int wdx = 1; wdx < 8; wdx++) { ext += s_ext[wdx]; for (int c = 0; c < 3; c++) { mn[c] = min(mn[c], s_mn[wdx][c]); mx[c] = max(mx[c], s_mx[wdx][c]); } }
-        if (ext != 0.0f) atomicAdd(&gv.params[4], ext);
-        for (int c = 0; c < 3; c++) { if (mn[c] != 0x7fffffff) atomicMin((int*)&gv.params[5 + c], mn[c]); if (mx[c] != (int)0x80000000) atomicMax((int*)&gv.params[10 + c], mx[c]); }
-    }
+    box_stats_flush(gv, ext_acc, mn_acc, mx_acc);
 }
 __global__ void k_grid_init(GridView gv)
 {
     if (threadIdx.x < 5) gv.params[threadIdx.x] = 0.0f;
     else if (threadIdx.x < 8) ((int*)gv.params)[threadIdx.x] = 0x7fffffff;
     else if (threadIdx.x == 8) ((int*)gv.params)[8] = float_order(0.0f);
-    if (threadIdx.x == 9) { *gv.large_count = 0; *gv.spill_cursor = gv.spill_base; }
+    if (threadIdx.x == 9) { *gv.large_count = 0; *gv.spill_cursor = gv.spill_base; *gv.active_count = 0; }
     if (threadIdx.x >= 10 && threadIdx.x < 13) ((int*)gv.params)[threadIdx.x] = (int)0x80000000;
     if (threadIdx.x >= 13 && threadIdx.x < 17) ((int*)gv.params)[threadIdx.x] = 0;
 }
@@ -1604,7 +1663,9 @@ __global__ void k_grid_params(int n, GridView gv)
         const int d = clamp_cell((order_float(((int*)gv.params)[10 + c]) - gv.params[c]) / h) + 1;
         ((int*)gv.params)[13 + c] = d; total *= d;
     }
-    ((int*)gv.params)[16] = (total <= (long long)gv.nbuckets && !gv.force_hash) ? 1 : 0;
+    const int dense = (total <= (long long)gv.nbuckets && !gv.force_hash) ? 1 : 0;
+    ((int*)gv.params)[16] = dense;
+    ((int*)gv.params)[17] = dense ? (int)total + 1 : gv.nbuckets + 1;      // entries of bucket_cnt / bucket_off in use (and one for the total)
 }
 NP_D int cell_hash(int cx, int cy, int cz, int nbuckets) { return (int)(((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u) ^ ((unsigned)cz * 83492791u)) & (nbuckets - 1); }
 NP_D int cell_bucket(const GridView& gv, int cx, int cy, int cz)
@@ -1723,10 +1784,10 @@ NP_D int cand_walk(const StoreView& s, const GridView& gv, int i, int jend, floa
 // One thread per body of the world, in BUCKET order (thread t takes the t-th box of saabb, the large bodies follow): with dense
 // addressing the threads of a warp sit in the same or neighbouring cells and walk the same rows.  Bodies outside the searched range
 // [first, first + count) of a sharded world are skipped.
-__global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, int first, int count, DevCounters* ctr)
+__global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, int first, int count, DevCounters* ctr, int* __restrict__ hit_j, int* __restrict__ flags)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int n = 0;
+    int n = 0, listed = -1;
     if (t < s.n) {
         const int nl = *gv.large_count, ns = s.n - nl;
         int i; float4 lo, hi;
@@ -1743,11 +1804,23 @@ __global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, int firs
                 else { out = gv.cand + off; cand_walk<true>(s, gv, i, jend, lo, hi, out, n); }
             }
             gv.cand_cnt[i] = n; gv.cand_off[i] = off;
+            if (n > 0) listed = i;
+            else { hit_j[i] = -1; flags[i] = 0; }            // nobody to test: GetCollisions' inner loop never hits (the narrow phase only sees the listed bodies)
             for (int a = 1; a < n; a++) {                    // ascending j
                 int key = out[a], b = a - 1;
                 while (b >= 0 && out[b] > key) { out[b + 1] = out[b]; b--; }
                 out[b + 1] = key;
             }
+        }
+    }
+    {   // the bodies that have candidates, compacted (one atomic per warp)
+        const unsigned m = __ballot_sync(0xffffffffu, listed >= 0);
+        if (m) {
+            const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(gv.active_count, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (listed >= 0) gv.items[base + __popc(m & ((1u << lane) - 1u))] = listed;
         }
     }
     if (ctr) {
@@ -1774,13 +1847,22 @@ __global__ void __launch_bounds__(256) k_link(int n, int cap, const int* __restr
     int b = hitj_body(hit_j[i]);
     if ((unsigned)b < (unsigned)n && ints[I_RESPONSE * cap + b] == 1) next[i] = atomicExch(&head[b], i + 1);      // (records may come from another process)
 }
-// exclusive scan of cnt[0..n) in three launches (per-block sums, scan of the sums, per-block scan + offset)
+// exclusive scan of cnt[0..n) in three launches (per-block sums, scan of the sums, per-block scan + offset); four entries per thread.
+// limit (device, may be null): only the first *limit entries matter (the cells a dense grid uses): blocks beyond them do nothing.
 #define NP_SCAN_BLOCK 1024
-__global__ void __launch_bounds__(NP_SCAN_BLOCK) k_scan_block_sums(int n, const int* __restrict__ in, int* __restrict__ sums)
+#define NP_SCAN_ITEMS (4 * NP_SCAN_BLOCK)
+NP_D int4 scan_load4(const int* __restrict__ in, int e, int n)
+{
+    if (e + 3 < n) return *reinterpret_cast<const int4*>(in + e);
+    return make_int4(e < n ? in[e] : 0, e + 1 < n ? in[e + 1] : 0, e + 2 < n ? in[e + 2] : 0, 0);
+}
+__global__ void __launch_bounds__(NP_SCAN_BLOCK) k_scan_block_sums(int n, const int* __restrict__ in, int* __restrict__ sums, const int* __restrict__ limit)
 {
     __shared__ int warp_sum[32];
-    int i = blockIdx.x * NP_SCAN_BLOCK + threadIdx.x;
-    int v = i < n ? in[i] : 0;
+    if (limit) n = min(n, *limit);
+    if (blockIdx.x * NP_SCAN_ITEMS >= n) { if (threadIdx.x == 0) sums[blockIdx.x] = 0; return; }
+    const int4 q = scan_load4(in, (blockIdx.x * NP_SCAN_BLOCK + threadIdx.x) * 4, n);
+    int v = q.x + q.y + q.z + q.w;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
@@ -1821,11 +1903,15 @@ __global__ void __launch_bounds__(1024) k_scan_sums(int nb, int* __restrict__ su
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(NP_SCAN_BLOCK) k_scan_apply(int n, const int* __restrict__ in, const int* __restrict__ sums, int* __restrict__ out)
+__global__ void __launch_bounds__(NP_SCAN_BLOCK) k_scan_apply(int n, const int* __restrict__ in, const int* __restrict__ sums, int* __restrict__ out, const int* __restrict__ limit)
 {
     __shared__ int warp_tot[32];
-    int i = blockIdx.x * NP_SCAN_BLOCK + threadIdx.x;
-    int v = i < n ? in[i] : 0, x = v;
+    if (limit) n = min(n, *limit);
+    if (blockIdx.x * NP_SCAN_ITEMS >= n) return;
+    const int e = (blockIdx.x * NP_SCAN_BLOCK + threadIdx.x) * 4;
+    const int4 q = scan_load4(in, e, n);
+    const int v = q.x + q.y + q.z + q.w;
+    int x = v;
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -1838,7 +1924,10 @@ __global__ void __launch_bounds__(NP_SCAN_BLOCK) k_scan_apply(int n, const int* 
         warp_tot[lane] = z - w;
     }
     __syncthreads();
-    if (i < n) out[i] = sums[blockIdx.x] + warp_tot[wid] + x - v;
+    const int b0 = sums[blockIdx.x] + warp_tot[wid] + x - v;
+    const int4 r = make_int4(b0, b0 + q.x, b0 + q.x + q.y, b0 + q.x + q.y + q.z);
+    if (e + 3 < n) *reinterpret_cast<int4*>(out + e) = r;
+    else { if (e < n) out[e] = r.x; if (e + 1 < n) out[e + 1] = r.y; if (e + 2 < n) out[e + 2] = r.z; }
 }
 // Physics::ApplyImpulseResponse, physics.cpp:27-46.  sfric: m_staticFrictionCoeff when the world runs with NP_OPT_FRICTION, else 0 --
 // the block the reference keeps commented out at physics.cpp:49-72, as written there: the velocity is re-derived from the NEW linear

@@ -227,6 +227,47 @@ NP_D bool support_tab(const float4* __restrict__ v, const float* R, V3 t, V3 d, 
     *out = best;
     return true;
 }
+// The same lookup for a direction along a world axis, d = sg e_a (the faces of a body's box, k_world_verts): R^T d is sg x row a of R, and
+// the score d . (R p + t) is sg x the world coordinate a itself (the other two terms are products with zero), so only that coordinate
+// is evaluated -- with xf_point's expression -- and the extreme one among the cell's candidates is returned.  row = R[3a..3a+2], ta = t[a].
+// (in two halves, so that a caller with several directions has all its cell loads in flight before it evaluates any)
+NP_D const uint2* tab_axis_cell(V3 row, float sg, unsigned e, const uint2* __restrict__ cells)      // null: the caller scans
+{
+    const float ux = sg * row.x, uy = sg * row.y, uz = sg * row.z;
+    const float ax = fabsf(ux), ay = fabsf(uy), az = fabsf(uz);
+    const float sum = ax + ay + az;
+    if (!(sum >= 1e-18f && sum <= 1e18f)) return nullptr;
+    float major, a, b; int f;
+    if (ax >= ay && ax >= az) { major = ux; a = uy; b = uz; f = 0; }
+    else if (ay >= az) { major = uy; a = uz; b = ux; f = 2; }
+    else { major = uz; a = ux; b = uy; f = 4; }
+    f += (major < 0.0f) ? 1 : 0;
+    const int lg = (int)(e >> 28), nm1 = (1 << lg) - 1;
+    const float half_n = (float)(1 << lg) * 0.5f;
+    const float sc = __fdividef(half_n, fabsf(major));
+    const int ia = min(max((int)__fmaf_rn(a, sc, half_n), 0), nm1), ib = min(max((int)__fmaf_rn(b, sc, half_n), 0), nm1);
+    return cells + (e & 0x0fffffffu) + ((((unsigned)f << lg) + (unsigned)ib) << lg) + (unsigned)ia;
+}
+NP_D bool tab_axis_eval(const float4* __restrict__ v, V3 row, float ta, float sg, uint2 cell, float* out)
+{
+    const int cnt = (int)(cell.y >> 24);
+    if (cnt > 7) return false;
+    unsigned long long bits = (unsigned long long)cell.x | ((unsigned long long)cell.y << 32);
+    float bd = -INFINITY; bool any = false;
+    for (int c = 0; c < cnt; c++) {
+        const float4 q = v[(int)(bits & 0xffu)]; bits >>= 8;
+        const float dp = sg * (row.x * q.x + row.y * q.y + row.z * q.z + ta);
+        if (dp > bd) { bd = dp; any = true; }
+    }
+    if (!any) return false;
+    *out = sg * bd;
+    return true;
+}
+NP_D bool support_tab_axis(const float4* __restrict__ v, V3 row, float ta, float sg, unsigned e, const uint2* __restrict__ cells, float* out)
+{
+    const uint2* c = tab_axis_cell(row, sg, e, cells);
+    return c && tab_axis_eval(v, row, ta, sg, __ldg(c), out);
+}
 // one side's support of a pair: from the table when the side is armed with one, else the scan
 template <int G, bool CACHED>
 NP_D V3 support_a(const PairGeom& g, V3 d)

@@ -614,17 +614,17 @@ static int launch_narrow(np_world* w, const NarrowIn& in, const NarrowBufs& b, D
     return in.world ? launch_narrow_t<true>(w, in, b, ctr) : launch_narrow_t<false>(w, in, b, ctr);
 }
 
-static void enqueue_scan(np_world* w, int n, const int* in, int* out)
+static void enqueue_scan(np_world* w, int n, const int* in, int* out, const int* limit = nullptr)
 {
-    const int sb = (n + NP_SCAN_BLOCK - 1) / NP_SCAN_BLOCK;
-    k_scan_block_sums<<<sb, NP_SCAN_BLOCK, 0, w->stream>>>(n, in, w->d_sums);
+    const int sb = (n + NP_SCAN_ITEMS - 1) / NP_SCAN_ITEMS;
+    k_scan_block_sums<<<sb, NP_SCAN_BLOCK, 0, w->stream>>>(n, in, w->d_sums, limit);
     k_scan_sums<<<1, 1024, 0, w->stream>>>(sb, w->d_sums);
-    k_scan_apply<<<sb, NP_SCAN_BLOCK, 0, w->stream>>>(n, in, w->d_sums, out);
+    k_scan_apply<<<sb, NP_SCAN_BLOCK, 0, w->stream>>>(n, in, w->d_sums, out, limit);
     w->launches += 3;
 }
 #define NP_CAND_PER_BODY 64
 #ifndef NP_GRID_H_SCALE
-#define NP_GRID_H_SCALE 1.5f      // automatic cell edge over the average box extent (measured on the 1M-body world)
+#define NP_GRID_H_SCALE 1.25f     // automatic cell edge over the average box extent (measured on the 1M-body world)
 #endif
 static int ensure_grid(np_world* w)
 {
@@ -640,7 +640,7 @@ static int ensure_grid(np_world* w)
     GridView& g = w->grid;
     int* p = w->d_grid_ints;
     g.bucket_cnt = p; p += nb; g.bucket_cur = p; p += nb; g.bucket_off = p; p += nb + 32; g.items = p; p += c; g.large = p; p += c;
-    g.cand_cnt = p; p += c; g.cand_ub = p; p += c; g.cand_off = p; p += c; g.large_count = p; g.error = p + 1; g.spill_cursor = p + 2; p += 32; g.cand = p;
+    g.cand_cnt = p; p += c; g.cand_ub = p; p += c; g.cand_off = p; p += c; g.large_count = p; g.error = p + 1; g.spill_cursor = p + 2; g.active_count = p + 3; p += 32; g.cand = p;
     g.aabb = (float4*)w->d_grid_f; g.aabb_prev = (float4*)w->d_grid_f + 2 * c; g.saabb = (float4*)w->d_grid_f + 4 * c; g.params = w->d_grid_f + 24 * c;
     g.nbuckets = nb; g.cand_cap = (int)std::min<size_t>(cand_cap, 0x7fffffff); g.spill_base = (int)std::min<size_t>(c * NP_CAND_SLOTS, 0x7fffffff);
     if (g.spill_base >= g.cand_cap) return fail(NP_ERR_CAPACITY, "world too large for the grid broad phase's candidate store");
@@ -649,7 +649,7 @@ static int ensure_grid(np_world* w)
     return NP_OK;
 }
 // K2, enqueued between integrate and the narrow phase
-static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, int cache, DevCounters* ctr)
+static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, int cache, DevCounters* ctr, int* hit_j, int* flags)
 {
     GridView& g = w->grid; g.h_option = w->grid_cell;
     { const char* e = getenv("NP_GRID_H_SCALE"); g.h_scale = e ? (float)atof(e) : NP_GRID_H_SCALE; const char* fh = getenv("NP_GRID_HASH"); g.force_hash = fh ? atoi(fh) : 0; }      // (tools and tests)
@@ -661,13 +661,14 @@ static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, i
     const int wvb = (int)std::min<long long>(((long long)n * 8 + 255) / 256, (long long)w->sm_count * 16);      // grid-stride: few blocks, few same-address atomics
     if (cache == CACHE_ALL) k_world_verts<true, 1><<<wvb, 256, 0, w->stream>>>(s, sview(w), g);
     else if (cache == CACHE_BIG) k_world_verts<true, 2><<<wvb, 256, 0, w->stream>>>(s, sview(w), g);
+    else if (w->tables_on && w->d_tab) k_body_boxes<<<std::min((n + 255) / 256, w->sm_count * 8), 256, 0, w->stream>>>(s, sview(w), g);
     else k_world_verts<true, 0><<<wvb, 256, 0, w->stream>>>(s, sview(w), g);
     k_grid_params<<<1, 1, 0, w->stream>>>(n, g);
     k_grid_count<<<b256, 256, 0, w->stream>>>(s, g);
-    enqueue_scan(w, g.nbuckets + 1, g.bucket_cnt, g.bucket_off);      // one more than the buckets: bucket_cnt[nbuckets] is bucket_cur[0], still zero here, so bucket_off[nbuckets] = all of them
+    enqueue_scan(w, g.nbuckets + 1, g.bucket_cnt, g.bucket_off, (const int*)g.params + 17);      // one more than the buckets: bucket_cnt[nbuckets] is bucket_cur[0], still zero here, so bucket_off[nbuckets] = all of them
     k_grid_fill<<<b256, 256, 0, w->stream>>>(s, g);
     if (count > 0) {                 // candidates of the bodies this process searches (the whole world unless sharded)
-        k_cand<<<(n + 127) / 128, 128, 0, w->stream>>>(s, g, first, count, ctr);
+        k_cand<<<(n + 127) / 128, 128, 0, w->stream>>>(s, g, first, count, ctr, hit_j, flags);
         w->launches += 1;
     }
     w->launches += 5;
@@ -703,7 +704,7 @@ static int enqueue_search(np_world* w, float dt, bool timed, bool integrate = tr
         if (part == 1) { CU(cudaGetLastError()); return NP_OK; }
     }
     const int cache = cache_mode(w, count);
-    if (w->broadphase != NP_BROADPHASE_EXACT) { int r = enqueue_grid(w, s, first, count, cache, ctr); if (r) return r; }
+    if (w->broadphase != NP_BROADPHASE_EXACT) { int r = enqueue_grid(w, s, first, count, cache, ctr, hitj(w), cflags(w)); if (r) return r; }
     else if (cache == CACHE_ALL) { k_world_verts<false, 1><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), w->grid); w->launches += 1; }
     else if (cache == CACHE_BIG) { k_world_verts<false, 2><<<(n * 8 + 255) / 256, 256, 0, w->stream>>>(s, sview(w), w->grid); w->launches += 1; }
     if (timed && w->phase_timing) CU(cudaEventRecordWithFlags(w->ev[2], w->stream, w->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
@@ -712,7 +713,7 @@ static int enqueue_search(np_world* w, float dt, bool timed, bool integrate = tr
         NarrowIn in; memset(&in, 0, sizeof in); in.world = 1; in.n = count; in.first = first; in.s = s; in.rot_known = 1; in.pf = getenv("NP_PREFETCH") ? atoi(getenv("NP_PREFETCH")) : 1;
         in.ordered = w->order_on;
         if (part_on) { in.halo = w->halo; in.halo_err = w->d_halo_err; }
-        if (w->broadphase != NP_BROADPHASE_EXACT) { in.cand = w->grid.cand; in.cand_off = w->grid.cand_off; in.cand_cnt = w->grid.cand_cnt; }
+        if (w->broadphase != NP_BROADPHASE_EXACT) { in.cand = w->grid.cand; in.cand_off = w->grid.cand_off; in.cand_cnt = w->grid.cand_cnt; in.active = w->grid.items; in.n_active = w->grid.active_count; }
         if (w->seed_on && !w->gjk1_old && cache != CACHE_BIG && pick_group(w, count, w->g_gjk_env, false) <= 1) {      // thread-per-body search: tabulate the seed supports once per body
             const int sb_ = std::min(w->sm_count * 8, (n + NP_NARROW_THREADS - 1) / NP_NARROW_THREADS);
             k_seed_supports<<<std::max(1, sb_), NP_NARROW_THREADS, shapes_smem(w), w->stream>>>(s, sview(w), shapes_in_smem(w) ? 1 : 0, w->d_seed);
