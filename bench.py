@@ -326,6 +326,7 @@ def run_ours(args, rank, local_rank, world_size):
         init_world_comm(w, rank, world_size)                          # the world's own NCCL communicator, behind the C ABI (np_comm_init)
         w.set_snapshot_gather(BODIES, rank * BODIES)                  # every np_world_step now all-gathers its snapshot on a high-priority stream
         xchg = True
+    gather_mode = w.gather_mode()
 
     def overlapped(nsteps):
         """N > 1: np_world_step launches the all-gather of its snapshot on the communicator's own stream; it runs while the next step
@@ -529,7 +530,8 @@ def run_ours(args, rank, local_rank, world_size):
            "config": CONFIG,
            "method": {"l2": "flushed before every timed step (256 MiB memset on the launching stream); the world's arrays (~0.3 GB) exceed L2 anyway",
                       "timing": "CUDA events on the world's stream around each step, mean over steps, max over ranks" + ("; all-gather of step k overlapped with step k+1 on a high-priority stream, exposed part charged (see bench.py)" if world_size > 1 else ""),
-                      "collective": "ncclAllGather of the 36 B/body snapshot per step, issued by np_world_step itself over the world's communicator (np_comm_init; torch.distributed only distributes the unique id)" if world_size > 1 else "none"},
+                      "collective": {0: "none", 1: "ncclAllGather of the 36 B/body snapshot per step, issued by np_world_step itself over the world's communicator (np_comm_init; torch.distributed only distributes the unique id)",
+                                     2: "all-gather of the 36 B/body snapshot per step on the COPY ENGINES: np_world_step pushes this rank's slot into every peer's gather buffer (mapped through CUDA IPC) with device-to-device copies over NVLink, framed by two 4-byte ncclAllGather exchanges on the world's communicator (np_comm_init; torch.distributed only distributes the unique id) -- no SM is taken from the step it overlaps"}[gather_mode]},
            "clocks": clk, "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
            "e2e": {"value": e2e, "unit": "body-steps/s", "h2d_bytes_per_step": 48 * BODIES, "d2h_bytes_per_step": 48 * BODIES,
                    "how": "np_world_step_host with page-locked host buffers (np_host_alloc): host state in, step, host state out, copies inside the call; wall clock over %d steps" % e2e_steps},

@@ -197,8 +197,13 @@ int np_comm_destroy(np_world* w);
 /* Replication snapshot of independent worlds (one per rank): from now on every np_world_step packs this world's 36-byte records
  * (guid = guid_base + body) into this rank's slot of a gather buffer [nranks][slot_bodies] and all-gathers it in place on a
  * high-priority stream of its own, overlapped with the next step (double buffered).  np_world_gathered_snapshot waits for the most
- * recent gather and returns the buffer every rank now holds.  slot_bodies >= this world's body count; 0 disables. */
+ * recent gather and returns the buffer every rank now holds (valid until the next-but-one step is called).  slot_bodies >= this
+ * world's body count; 0 disables.  Collective.  With one process per GPU the gather runs on the COPY ENGINES: every rank maps its peers'
+ * buffers (CUDA IPC) and pushes its slot into each with device-to-device copies over NVLink, framed by two 4-byte NCCL exchanges, so it
+ * takes no SM from the step it overlaps; ranks that cannot map each other (or NP_GATHER_NCCL=1) use ncclAllGather.
+ * np_world_gather_mode: 0 = no gather, 1 = ncclAllGather, 2 = copy engines. */
 int np_world_set_snapshot_gather(np_world* w, int slot_bodies, uint32_t guid_base);
+int np_world_gather_mode(const np_world* w);
 int np_world_gathered_snapshot(np_world* w, void** d_ptr, size_t* bytes);
 /* device times (ms) of the all-gather launched by the most recent step (back = 0; waits for it) or by the step before (back = 1):
  * [0] its duration on its own stream, [1] how long after its step's last kernel it finished (what a following step must cover) */

@@ -97,6 +97,9 @@ struct np_world {
     cudaStream_t comm_stream = nullptr;
     char* d_gather[2] = { nullptr, nullptr }; int gather_slot = 0, gather_flip = 0, gather_last = -1; uint32_t gather_guid = 0;
     cudaEvent_t ev_step_done[2] = {}, ev_gather_begin[2] = {}, ev_gather_done[2] = {}; bool gather_pending[2] = { false, false };
+    // snapshot gather by copy engines: every peer's two gather buffers mapped here through CUDA IPC (peer_gather[b][rank], null for this rank), see gather_setup_dma
+    std::vector<char*> peer_gather[2]; bool gather_dma = false; int* d_bar = nullptr;
+    std::vector<cudaStream_t> peer_stream; std::vector<cudaEvent_t> ev_peer; cudaEvent_t ev_fan = nullptr;      // one stream per peer: the copies to different peers run on different copy engines
     int* d_shard_hit = nullptr; int* d_shard_flags = nullptr; float4* d_shard_contact = nullptr; int shard_slot = 0;
     DevCounters* d_ctr = nullptr;
     SnapObj* d_snap = nullptr;
@@ -765,6 +768,7 @@ extern "C" {
 
 static int gather_prepare(np_world* w);
 static int gather_launch(np_world* w);
+static int gather_setup_dma(np_world* w);
 int np_abi_version(void) { return NETPHYS_B200_ABI_VERSION; }
 const char* np_last_error(void) { return g_err.c_str(); }
 int np_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
@@ -1685,6 +1689,15 @@ int np_comm_get_unique_id(void* id128)
 }
 static void free_gather(np_world* w)
 {
+    for (int b = 0; b < 2; b++) { for (char* p : w->peer_gather[b]) if (p) cudaIpcCloseMemHandle(p); w->peer_gather[b].clear(); }
+    if (w->gather_dma && w->comm && w->d_bar) {      // nobody frees a buffer a peer still has mapped: every rank has closed its mappings once this (collective) exchange is through
+        if (g_nccl.AllGather(w->d_bar + w->rank, w->d_bar, sizeof(int), ncclChar, w->comm, w->comm_stream) == ncclSuccess) cudaStreamSynchronize(w->comm_stream);
+    }
+    w->gather_dma = false; cudaFree(w->d_bar); w->d_bar = nullptr; cudaGetLastError();
+    for (cudaStream_t st : w->peer_stream) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (cudaEvent_t e : w->ev_peer) if (e) cudaEventDestroy(e);
+    if (w->ev_fan) cudaEventDestroy(w->ev_fan);
+    w->peer_stream.clear(); w->ev_peer.clear(); w->ev_fan = nullptr;
     for (int b = 0; b < 2; b++) { cudaFree(w->d_gather[b]); w->d_gather[b] = nullptr; w->gather_pending[b] = false; }
     w->gather_slot = 0; w->gather_last = -1;
 }
@@ -1718,6 +1731,60 @@ int np_comm_destroy(np_world* w)
     cudaStreamDestroy(w->comm_stream); w->comm_stream = nullptr;
     return NP_OK;
 }
+// The snapshot all-gather WITHOUT SMs.  ncclAllGather runs as a kernel: on a GPU whose SMs are all held by the persistent narrow-phase
+// grids it takes blocks away from the step it is meant to hide behind (8 ranks: every step 0.15 ms longer than on a lone GPU).  The
+// payload is one contiguous slot per rank, so each rank can PUSH its slot into every peer's buffer with plain device-to-device copies
+// -- copy engines over NVLink / NVSwitch, no kernel -- once the peers' buffers are mapped here (CUDA IPC; one process per GPU).  Two
+// 4-byte NCCL all-gathers per step frame the copies: one before them (every rank has CALLED this step, so nobody still reads the
+// buffer about to be overwritten: the gathered snapshot of step k stays valid until step k + 2 is called, as with ncclAllGather) and
+// one after (every rank's copies have landed).  Set up collectively by np_world_set_snapshot_gather; if any rank cannot export or map
+// a buffer (ranks that share a process, a platform without peer access), or NP_GATHER_NCCL=1, every rank keeps ncclAllGather.
+static int gather_setup_dma(np_world* w)
+{
+    w->gather_dma = false;
+    if (w->nranks < 2) return NP_OK;
+    struct Rec { cudaIpcMemHandle_t h[2]; int ok; int pad[3]; };
+    static_assert(sizeof(Rec) == 2 * sizeof(cudaIpcMemHandle_t) + 16, "record layout");
+    const int n = w->nranks;
+    char* d_x = nullptr; CU(cudaMalloc((void**)&d_x, sizeof(Rec) * (size_t)n));
+    CU(cudaMalloc((void**)&w->d_bar, sizeof(int) * (size_t)(n + 1))); CU(cudaMemset(w->d_bar, 0, sizeof(int) * (size_t)(n + 1)));
+    std::vector<Rec> all(n);
+    auto exchange = [&](const Rec& mine) -> int {
+        CU(cudaMemcpy(d_x + sizeof(Rec) * (size_t)w->rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice));
+        NC(g_nccl.AllGather(d_x + sizeof(Rec) * (size_t)w->rank, d_x, sizeof(Rec), ncclChar, w->comm, w->comm_stream));
+        CU(cudaStreamSynchronize(w->comm_stream));
+        CU(cudaMemcpy(all.data(), d_x, sizeof(Rec) * (size_t)n, cudaMemcpyDeviceToHost));
+        return NP_OK;
+    };
+    Rec me; memset(&me, 0, sizeof me);
+    me.ok = !getenv("NP_GATHER_NCCL") || atoi(getenv("NP_GATHER_NCCL")) == 0;
+    for (int b = 0; b < 2 && me.ok; b++) if (cudaIpcGetMemHandle(&me.h[b], w->d_gather[b]) != cudaSuccess) { cudaGetLastError(); me.ok = 0; }
+    int r = exchange(me); if (r) { cudaFree(d_x); return r; }
+    bool every = true; for (int p = 0; p < n; p++) every = every && all[p].ok;
+    Rec second; memset(&second, 0, sizeof second); second.ok = every ? 1 : 0;
+    if (every) {
+        for (int b = 0; b < 2; b++) w->peer_gather[b].assign(n, nullptr);
+        for (int p = 0; p < n && second.ok; p++) {
+            if (p == w->rank) continue;
+            for (int b = 0; b < 2 && second.ok; b++) {
+                void* q = nullptr;
+                if (cudaIpcOpenMemHandle(&q, all[p].h[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); second.ok = 0; }
+                else w->peer_gather[b][p] = (char*)q;
+            }
+        }
+    }
+    r = exchange(second); cudaFree(d_x); if (r) return r;      // (every rank takes part in both exchanges, whatever happened to it)
+    bool use = every; for (int p = 0; p < n; p++) use = use && all[p].ok;
+    if (!use) { for (int b = 0; b < 2; b++) { for (char* q : w->peer_gather[b]) if (q) cudaIpcCloseMemHandle(q); w->peer_gather[b].clear(); } cudaGetLastError(); }
+    if (use) {
+        int lo = 0, hi = 0; CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        w->peer_stream.assign(n, nullptr); w->ev_peer.assign(n, nullptr);
+        for (int p = 0; p < n; p++) if (p != w->rank) { CU(cudaStreamCreateWithPriority(&w->peer_stream[p], cudaStreamNonBlocking, hi)); CU(cudaEventCreateWithFlags(&w->ev_peer[p], cudaEventDisableTiming)); }
+        CU(cudaEventCreateWithFlags(&w->ev_fan, cudaEventDisableTiming));
+    }
+    w->gather_dma = use;
+    return NP_OK;
+}
 int np_world_set_snapshot_gather(np_world* w, int slot_bodies, uint32_t guid_base)
 {
     if (!w || slot_bodies < 0) return fail(NP_ERR_INVALID, "bad arguments");
@@ -1731,7 +1798,7 @@ int np_world_set_snapshot_gather(np_world* w, int slot_bodies, uint32_t guid_bas
     const size_t bytes = sizeof(SnapObj) * (size_t)slot_bodies * (size_t)w->nranks;
     for (int b = 0; b < 2; b++) { CU(cudaMalloc((void**)&w->d_gather[b], bytes)); CU(cudaMemsetAsync(w->d_gather[b], 0, bytes, w->stream)); }
     w->gather_slot = slot_bodies; w->gather_guid = guid_base; w->gather_flip = 0; w->snapshot_each_step = 1;
-    return NP_OK;
+    return gather_setup_dma(w);
 }
 // before a step: aim the snapshot at this rank's slot of the next gather buffer, once that buffer's previous gather has drained
 static int gather_prepare(np_world* w)
@@ -1752,7 +1819,19 @@ static int gather_launch(np_world* w)
     CU(cudaStreamWaitEvent(w->comm_stream, w->ev_step_done[b], 0));
     CU(cudaEventRecord(w->ev_gather_begin[b], w->comm_stream));
     const size_t slot_bytes = sizeof(SnapObj) * (size_t)w->gather_slot;
-    NC(g_nccl.AllGather(w->d_gather[b] + slot_bytes * (size_t)w->rank, w->d_gather[b], slot_bytes, ncclChar, w->comm, w->comm_stream));
+    if (w->gather_dma) {
+        char* mine = w->d_gather[b] + slot_bytes * (size_t)w->rank;
+        NC(g_nccl.AllGather(w->d_bar + w->rank, w->d_bar, sizeof(int), ncclChar, w->comm, w->comm_stream));      // every rank is here: buffer b of every rank may be overwritten
+        CU(cudaEventRecord(w->ev_fan, w->comm_stream));
+        for (int k = 1; k < w->nranks; k++) {                                                                     // one stream per peer (a single stream moved 36 MB slots at ~250 GB/s, one copy engine's worth)
+            const int p = (w->rank + k) % w->nranks;
+            CU(cudaStreamWaitEvent(w->peer_stream[p], w->ev_fan, 0));
+            CU(cudaMemcpyAsync(w->peer_gather[b][p] + slot_bytes * (size_t)w->rank, mine, slot_bytes, cudaMemcpyDefault, w->peer_stream[p]));
+            CU(cudaEventRecord(w->ev_peer[p], w->peer_stream[p]));
+            CU(cudaStreamWaitEvent(w->comm_stream, w->ev_peer[p], 0));
+        }
+        NC(g_nccl.AllGather(w->d_bar + w->rank, w->d_bar, sizeof(int), ncclChar, w->comm, w->comm_stream));      // every rank's copies have landed
+    } else NC(g_nccl.AllGather(w->d_gather[b] + slot_bytes * (size_t)w->rank, w->d_gather[b], slot_bytes, ncclChar, w->comm, w->comm_stream));
     CU(cudaEventRecord(w->ev_gather_done[b], w->comm_stream));
     w->gather_pending[b] = true; w->gather_last = b; w->gather_flip = b ^ 1;
     return NP_OK;
@@ -1766,6 +1845,7 @@ int np_world_gathered_snapshot(np_world* w, void** d_ptr, size_t* bytes)
     *d_ptr = w->d_gather[w->gather_last]; *bytes = sizeof(SnapObj) * (size_t)w->gather_slot * (size_t)w->nranks;
     return NP_OK;
 }
+int np_world_gather_mode(const np_world* w) { return !w || !w->gather_slot ? 0 : (w->gather_dma ? 2 : 1); }
 int np_world_last_gather_ms(np_world* w, int back, float out[2])
 {
     if (!w || !out || back < 0 || back > 1) return fail(NP_ERR_INVALID, "bad arguments");

@@ -434,6 +434,8 @@ class World:
     def comm_destroy(self): self._ck(self.L.np_comm_destroy(self.w))
     def set_snapshot_gather(self, slot_bodies, guid_base=0): self._ck(self.L.np_world_set_snapshot_gather(self.w, slot_bodies, guid_base))
 
+    def gather_mode(self): return self.L.np_world_gather_mode(self.w)
+
     def gathered_snapshot(self):
         p = C.c_void_p(); nb = C.c_size_t()
         self._ck(self.L.np_world_gathered_snapshot(self.w, C.byref(p), C.byref(nb))); return p.value, nb.value

@@ -32,7 +32,7 @@ static int run_rank(void* lib, int rank, int nranks, const unsigned char* id, in
     SYM(np_last_error) SYM(np_world_create) SYM(np_world_destroy) SYM(np_shape_create_box) SYM(np_shape_create_sphere) SYM(np_body_create_batch)
     SYM(np_comm_init) SYM(np_world_shard_over_comm) SYM(np_world_step_sharded) SYM(np_world_step) SYM(np_world_get_states) SYM(np_world_synchronize)
     SYM(np_world_set_snapshot_gather) SYM(np_world_gathered_snapshot) SYM(np_device_download) SYM(np_world_snapshot) SYM(np_comm_destroy)
-    SYM(np_world_set_shard_halo)
+    SYM(np_world_set_shard_halo) SYM(np_world_gather_mode)
     np_world* w = p_np_world_create(rank);
     if (!w) { fprintf(stderr, "rank %d: np_world_create: %s\n", rank, p_np_last_error()); return 3; }
     auto build = [&](np_world* x, uint32_t seed) {
@@ -76,7 +76,8 @@ static int run_rank(void* lib, int rank, int nranks, const unsigned char* id, in
     CK(build(v, 777u + rank));
     CK(p_np_comm_init(v, nranks, rank, id + NP_COMM_ID_BYTES));
     CK(p_np_world_set_snapshot_gather(v, bodies, (uint32_t)(rank * bodies)));
-    for (int k = 0; k < 3; k++) CK(p_np_world_step(v, dt));
+    const int gmode = p_np_world_gather_mode(v);      // 2 = copy engines over CUDA IPC (one process per GPU: expected here), 1 = ncclAllGather
+    for (int k = 0; k < 5; k++) CK(p_np_world_step(v, dt));
     void* dptr = nullptr; size_t nbytes = 0; CK(p_np_world_gathered_snapshot(v, &dptr, &nbytes));
     std::vector<np_snapshot_object> all((size_t)bodies * nranks), mine(bodies);
     if (nbytes != all.size() * sizeof(np_snapshot_object)) ok = 0;
@@ -100,7 +101,7 @@ static int run_rank(void* lib, int rank, int nranks, const unsigned char* id, in
         if (count > 0 && memcmp(sq.data() + first, st.data() + first, sizeof(np_body_state) * (size_t)count) != 0) { ok = 0; fprintf(stderr, "rank %d: partitioned steps changed the own bodies' state\n", rank); }
         CK(p_np_comm_destroy(q)); p_np_world_destroy(q);
     }
-    uint64_t msg[3] = { (uint64_t)ok, h, hs };
+    uint64_t msg[4] = { (uint64_t)ok, h, hs, (uint64_t)gmode };
     if (write(out_fd, msg, sizeof msg) != (ssize_t)sizeof msg) return 4;
     return ok ? 0 : 5;
 }
@@ -124,16 +125,17 @@ int main(int argc, char** argv)
         if (pid == 0) { close(pfd[0]); int rc = run_rank(lib, r, nranks, id, bodies, steps, pfd[1]); _exit(rc); }
         close(pfd[1]); kids.push_back(pid); fds.push_back(pfd[0]);
     }
-    int bad = 0; std::vector<uint64_t> hstate, hsnap;
+    int bad = 0; std::vector<uint64_t> hstate, hsnap, gm;
     for (int r = 0; r < nranks; r++) {
-        uint64_t msg[3] = { 0, 0, 0 };
+        uint64_t msg[4] = { 0, 0, 0, 0 };
         if (read(fds[r], msg, sizeof msg) != (ssize_t)sizeof msg) bad = 1;
         int status = 0; waitpid(kids[r], &status, 0);
         if (!WIFEXITED(status) || WEXITSTATUS(status) != 0 || !msg[0]) { fprintf(stderr, "rank %d failed (status %d)\n", r, status); bad = 1; }
-        hstate.push_back(msg[1]); hsnap.push_back(msg[2]);
+        hstate.push_back(msg[1]); hsnap.push_back(msg[2]); gm.push_back(msg[3]);
     }
+    for (int r = 1; r < nranks; r++) if (gm[r] != gm[0]) { fprintf(stderr, "rank %d chose another gather mode than rank 0\n", r); bad = 1; }
     for (int r = 1; r < nranks; r++) if (hstate[r] != hstate[0] || hsnap[r] != hsnap[0]) { fprintf(stderr, "rank %d holds different state / gathered snapshot than rank 0\n", r); bad = 1; }
-    printf("%s: %d ranks, %d bodies, %d sharded steps: state hash %016llx on every rank == unsharded (and own ranges == after partitioned steps); gathered snapshot hash %016llx on every rank\n",
-           bad ? "FAILED" : "ok", nranks, bodies, steps, (unsigned long long)hstate[0], (unsigned long long)hsnap[0]);
+    printf("%s: %d ranks, %d bodies, %d sharded steps: state hash %016llx on every rank == unsharded (and own ranges == after partitioned steps); gathered snapshot hash %016llx on every rank, gather mode %d\n",
+           bad ? "FAILED" : "ok", nranks, bodies, steps, (unsigned long long)hstate[0], (unsigned long long)hsnap[0], (int)gm[0]);
     return bad;
 }
