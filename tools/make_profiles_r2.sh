@@ -8,4 +8,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node
 ncu --set full --clock-control none --cache-control none --graph-profiling node \
     -k regex:"k_gjk2|k_epa|k_integrate|k_resolve|k_link" -s 18 -c 9 -o gpurun_out/r2_full -f $CMD > gpurun_out/r2_ncu2.log 2>&1
 tail -2 gpurun_out/r2_ncu2.log
-# two GPUs are a separate call: tools/r2_call_n2.sh
+# two GPUs are a separate call: tools/gpu_calls/r2_call_n2.sh
