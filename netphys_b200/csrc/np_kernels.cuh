@@ -1736,12 +1736,8 @@ NP_D void cell_range(const GridView& gv, float4 lo, float4 hi, int* c0, int* c1)
 template <bool STORE>
 NP_D int cand_walk(const StoreView& s, const GridView& gv, int i, int jend, float4 lo, float4 hi, int* out, int room)
 {
-    const int ci = __float_as_int(lo.w);
     int n = 0;
-    if (ci < 0) {                                        // large body: every later body of the island
-        for (int j = i + 1; j < jend; j++)
-            if (aabb_overlap(lo, hi, gv.aabb[2 * j], gv.aabb[2 * j + 1])) { if (STORE && n < room) out[n] = j; n++; }
-    } else {
+    {                                                    // (a small body: the large ones are k_cand_large's)
         int c0[3], c1[3];
         cell_range(gv, lo, hi, c0, c1);
         const int* ip = (const int*)gv.params;
@@ -1790,9 +1786,8 @@ __global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, int firs
     int n = 0, listed = -1;
     if (t < s.n) {
         const int nl = *gv.large_count, ns = s.n - nl;
-        int i; float4 lo, hi;
-        if (t < ns) { lo = __ldg(gv.saabb + 2 * (size_t)t); hi = __ldg(gv.saabb + 2 * (size_t)t + 1); i = __float_as_int(hi.w); }
-        else { i = gv.large[t - ns]; lo = gv.aabb[2 * i]; hi = gv.aabb[2 * i + 1]; }
+        int i = -1; float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+        if (t < ns) { lo = __ldg(gv.saabb + 2 * (size_t)t); hi = __ldg(gv.saabb + 2 * (size_t)t + 1); i = __float_as_int(hi.w); }      // (the large bodies: k_cand_large)
         if (i >= first && i < first + count) {
             const int jend = s.ints[I_ISLAND_END * s.cap + i];
             int* out = gv.cand + (size_t)i * NP_CAND_SLOTS;
@@ -1828,6 +1823,60 @@ __global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, int firs
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if ((threadIdx.x & 31) == 0 && v) atomicAdd(&ctr->candidates, v);
+    }
+}
+
+// The candidates of a LARGE body (wider than four cells: a ground slab) are every later body of its island whose box overlaps its own --
+// tens of thousands of tests and a list of thousands, which a lone thread of k_cand took milliseconds over and then insertion-sorted.
+// Here a BLOCK takes the large body: pass 1 counts the overlaps (strided over j), one thread reserves the list (the body's own slots or
+// the spill region), pass 2 walks j in ascending chunks of a block and writes the hits in order (ballot + prefix ranks): the list comes out
+// sorted.  Blocks stride over the large-body list (its length is only known on the device).
+__global__ void __launch_bounds__(256) k_cand_large(StoreView s, GridView gv, int first, int count, DevCounters* ctr, int* __restrict__ hit_j, int* __restrict__ flags)
+{
+    __shared__ int s_warp[8], s_tot, s_off, s_ok;
+    const int nl = *gv.large_count, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int q = blockIdx.x; q < nl; q += gridDim.x) {
+        const int i = gv.large[q];
+        if (i < first || i >= first + count) continue;                       // (block-uniform)
+        const int jend = s.ints[I_ISLAND_END * s.cap + i];
+        const float4 lo = gv.aabb[2 * i], hi = gv.aabb[2 * i + 1];
+        int n = 0;
+        for (int j = i + 1 + (int)threadIdx.x; j < jend; j += 256) n += aabb_overlap(lo, hi, gv.aabb[2 * j], gv.aabb[2 * j + 1]) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        __syncthreads();                                                     // (the shared words of the previous body are no longer read)
+        if (lane == 0) s_warp[wid] = n;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0; for (int k = 0; k < 8; k++) tot += s_warp[k];
+            int off = i * NP_CAND_SLOTS, ok = 1;
+            if (tot > NP_CAND_SLOTS) {
+                off = atomicAdd(gv.spill_cursor, tot);
+                if ((long long)off + tot > (long long)gv.cand_cap) { atomicExch(gv.error, 1); ok = 0; }
+            }
+            if (!ok) tot = 0;
+            s_tot = tot; s_off = off; s_ok = ok;
+            gv.cand_cnt[i] = tot; gv.cand_off[i] = off;
+            if (tot > 0) gv.items[atomicAdd(gv.active_count, 1)] = i; else { hit_j[i] = -1; flags[i] = 0; }
+            if (ctr && tot) atomicAdd(&ctr->candidates, (unsigned long long)tot);
+        }
+        __syncthreads();
+        if (s_tot == 0) continue;
+        int* out = gv.cand + s_off;
+        int base = 0;
+        for (int j0 = i + 1; j0 < jend; j0 += 256) {                           // ascending chunks; within a chunk the threads are in ascending j
+            const int j = j0 + (int)threadIdx.x;
+            const bool hit = j < jend && aabb_overlap(lo, hi, gv.aabb[2 * j], gv.aabb[2 * j + 1]);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            __syncthreads();
+            if (lane == 0) s_warp[wid] = __popc(m);
+            __syncthreads();
+            int before = 0, chunk = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const int c = s_warp[k]; if (k < wid) before += c; chunk += c; }
+            if (hit) out[base + before + __popc(m & ((1u << lane) - 1u))] = j;
+            base += chunk;
+        }
     }
 }
 

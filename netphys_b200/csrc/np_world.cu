@@ -672,7 +672,8 @@ static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, i
     k_grid_fill<<<b256, 256, 0, w->stream>>>(s, g);
     if (count > 0) {                 // candidates of the bodies this process searches (the whole world unless sharded)
         k_cand<<<(n + 127) / 128, 128, 0, w->stream>>>(s, g, first, count, ctr, hit_j, flags);
-        w->launches += 1;
+        k_cand_large<<<32, 256, 0, w->stream>>>(s, g, first, count, ctr, hit_j, flags);      // (returns at once in a world without large bodies)
+        w->launches += 2;
     }
     w->launches += 5;
     CU(cudaGetLastError());

@@ -322,14 +322,19 @@ def _world_aabbs(oracle, shapes, body_shape, st):
 
 
 @pytest.mark.parametrize("n,spacing,with_ground,cell,hashed", [(1500, 0.9, True, 0.0, 0), (3000, 1.1, False, 0.0, 0), (800, 0.8, True, 1.5, 0), (1500, 0.9, True, 0.0, 1), (900, 1.0, False, 0.35, 1),
-                                                              (700, 1.0, True, 0.3, 0)])
+                                                              (700, 1.0, True, 0.3, 0), (1500, 0.9, "first", 0.0, 0), (600, 0.9, "first", 0.4, 1)])
 def test_grid_broadphase_candidate_parity(world, oracle, monkeypatch, n, spacing, with_ground, cell, hashed):
     """Candidate set == brute-force AABB overlap; per candidate pair the GJK/EPA result == the oracle's; first-hit order kept.  Both
     addressings of the grid: dense (cells ordered z, y, x: one run of boxes per x-row) and hashed (NP_GRID_HASH=1, what a world spread over
     more cells than buckets falls back to); cells from a third of a body (everything is "large") to several bodies wide."""
     if hashed: monkeypatch.setenv("NP_GRID_HASH", "1")
     sc = scenes.lattice_scene(n, spacing=spacing, seed=n, mix=(0.5, 0.2, 0.3))
-    if with_ground:   # a body much wider than a cell exercises the large-body list
+    if with_ground == "first":   # the slab is body 0 and reaches into the lowest layers: ITS candidate list is hundreds long (spill region, k_cand_large's ordered fill)
+        sc["shape_specs"] = sc["shape_specs"] + [("box", 40.0, 40.0, 1.0)]
+        sc["sd"] = np.concatenate([scenes.static_data((0, 0, 0), (5.0, 0.3, 5.0), (0, 0, 0), 0.0, 0.0)[None], sc["sd"]]).astype(np.float32)
+        sc["body_shape"] = np.concatenate([[len(sc["shape_specs"]) - 1], sc["body_shape"]]).astype(np.int32)
+        sc["response"] = np.concatenate([[0], sc["response"]]).astype(np.int32)
+    elif with_ground:   # a body much wider than a cell exercises the large-body list
         sc["shape_specs"] = sc["shape_specs"] + [("box", 40.0, 40.0, 1.0)]
         sc["sd"] = np.concatenate([sc["sd"], scenes.static_data((0, 0, 0), (5.0, -2.0, 5.0), (0, 0, 0), 0.0, 0.0)[None]]).astype(np.float32)
         sc["body_shape"] = np.concatenate([sc["body_shape"], [len(sc["shape_specs"]) - 1]]).astype(np.int32)
