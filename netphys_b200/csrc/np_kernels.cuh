@@ -1833,7 +1833,7 @@ __global__ void __launch_bounds__(128) k_cand(StoreView s, GridView gv, int firs
 // sorted.  Blocks stride over the large-body list (its length is only known on the device).
 __global__ void __launch_bounds__(256) k_cand_large(StoreView s, GridView gv, int first, int count, DevCounters* ctr, int* __restrict__ hit_j, int* __restrict__ flags)
 {
-    __shared__ int s_warp[8], s_tot, s_off, s_ok;
+    __shared__ int s_warp[8], s_quarter[4][8], s_tot, s_off, s_ok;
     const int nl = *gv.large_count, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int q = blockIdx.x; q < nl; q += gridDim.x) {
         const int i = gv.large[q];
@@ -1841,7 +1841,13 @@ __global__ void __launch_bounds__(256) k_cand_large(StoreView s, GridView gv, in
         const int jend = s.ints[I_ISLAND_END * s.cap + i];
         const float4 lo = gv.aabb[2 * i], hi = gv.aabb[2 * i + 1];
         int n = 0;
-        for (int j = i + 1 + (int)threadIdx.x; j < jend; j += 256) n += aabb_overlap(lo, hi, gv.aabb[2 * j], gv.aabb[2 * j + 1]) ? 1 : 0;
+        for (int j0 = i + 1 + (int)threadIdx.x; j0 < jend; j0 += 4 * 256) {      // four boxes in flight per thread: the block is alone with the latency of its loads
+            float4 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int j = min(j0 + 256 * u, jend - 1); a[u] = gv.aabb[2 * j]; b[u] = gv.aabb[2 * j + 1]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) n += (j0 + 256 * u < jend && aabb_overlap(lo, hi, a[u], b[u])) ? 1 : 0;
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
         __syncthreads();                                                     // (the shared words of the previous body are no longer read)
@@ -1864,18 +1870,23 @@ __global__ void __launch_bounds__(256) k_cand_large(StoreView s, GridView gv, in
         if (s_tot == 0) continue;
         int* out = gv.cand + s_off;
         int base = 0;
-        for (int j0 = i + 1; j0 < jend; j0 += 256) {                           // ascending chunks; within a chunk the threads are in ascending j
-            const int j = j0 + (int)threadIdx.x;
-            const bool hit = j < jend && aabb_overlap(lo, hi, gv.aabb[2 * j], gv.aabb[2 * j + 1]);
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            __syncthreads();
-            if (lane == 0) s_warp[wid] = __popc(m);
-            __syncthreads();
-            int before = 0, chunk = 0;
+        for (int j0 = i + 1; j0 < jend; j0 += 4 * 256) {                       // ascending chunks of 4 x 256; within a quarter the threads are in ascending j
+            float4 a[4], b[4]; bool hit[4]; unsigned m[4];
 #pragma unroll
-            for (int k = 0; k < 8; k++) { const int c = s_warp[k]; if (k < wid) before += c; chunk += c; }
-            if (hit) out[base + before + __popc(m & ((1u << lane) - 1u))] = j;
-            base += chunk;
+            for (int u = 0; u < 4; u++) { const int j = min(j0 + 256 * u + (int)threadIdx.x, jend - 1); a[u] = gv.aabb[2 * j]; b[u] = gv.aabb[2 * j + 1]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) { hit[u] = j0 + 256 * u + (int)threadIdx.x < jend && aabb_overlap(lo, hi, a[u], b[u]); m[u] = __ballot_sync(0xffffffffu, hit[u]); }
+            __syncthreads();
+            if (lane == 0) { for (int u = 0; u < 4; u++) s_quarter[u][wid] = __popc(m[u]); }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                int before = 0, quarter = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) { const int c = s_quarter[u][k]; if (k < wid) before += c; quarter += c; }
+                if (hit[u]) out[base + before + __popc(m[u] & ((1u << lane) - 1u))] = j0 + 256 * u + (int)threadIdx.x;
+                base += quarter;
+            }
         }
     }
 }
