@@ -1472,7 +1472,7 @@ struct GridView {
                           // [10..12] global max (ordered ints), [13..15] cells per axis (ints), [16] 1 = dense addressing (int), [17] bucket entries in use (int): see k_grid_params
     int* bucket_cnt;      // [nbuckets]
     int* bucket_off;      // [nbuckets]
-    int* bucket_cur;      // [nbuckets]
+    int* bucket_cur;      // [nbuckets] (only its first word is used: bucket_cnt[nbuckets] = 0 for the scan's last entry)
     int* items;           // [cap] k_cand's output: the searched bodies that have at least one candidate (active_count of them, any order)
     int* active_count;    // [1]
     float4* saabb;        // [2*cap] the boxes in bucket order: entry p = lo.xyz + packed cell | hi.xyz + body index (int bits) of items[p]
@@ -1686,7 +1686,8 @@ __global__ void __launch_bounds__(256) k_grid_count(StoreView s, GridView gv)
         else {
             int cx = clamp_cell((0.5f * (lo.x + hi.x) - gv.params[0]) / h), cy = clamp_cell((0.5f * (lo.y + hi.y) - gv.params[1]) / h), cz = clamp_cell((0.5f * (lo.z + hi.z) - gv.params[2]) / h);
             cell = cx | (cy << 10) | (cz << 20);
-            atomicAdd(&gv.bucket_cnt[cell_bucket(gv, cx, cy, cz)], 1);
+            const int rank = atomicAdd(&gv.bucket_cnt[cell_bucket(gv, cx, cy, cz)], 1);      // the body's place inside its bucket: k_grid_fill needs no atomic of its own
+            gv.aabb[2 * i + 1].w = __int_as_float(rank);
             ext_small = ext;
         }
         gv.aabb[2 * i].w = __int_as_float(cell);
@@ -1707,7 +1708,7 @@ __global__ void __launch_bounds__(256) k_grid_fill(StoreView s, GridView gv)
     int c = __float_as_int(lo.w);
     if (c < 0) return;
     int b = cell_bucket(gv, c & 1023, (c >> 10) & 1023, (c >> 20) & 1023);
-    const int p = gv.bucket_off[b] + atomicAdd(&gv.bucket_cur[b], 1);
+    const int p = gv.bucket_off[b] + __float_as_int(hi.w);
     hi.w = __int_as_float(i);
     gv.saabb[2 * (size_t)p] = lo; gv.saabb[2 * (size_t)p + 1] = hi;
 }

@@ -660,7 +660,7 @@ static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, i
     if (g.swept && !w->capturing) w->swept_valid = true;
     const int n = s.n, b256 = (n + 255) / 256;
     k_grid_init<<<1, 32, 0, w->stream>>>(g);
-    CU(cudaMemsetAsync(g.bucket_cnt, 0, sizeof(int) * 2 * (size_t)g.nbuckets, w->stream));
+    CU(cudaMemsetAsync(g.bucket_cnt, 0, sizeof(int) * ((size_t)g.nbuckets + 32), w->stream));
     const int wvb = (int)std::min<long long>(((long long)n * 8 + 255) / 256, (long long)w->sm_count * 16);      // grid-stride: few blocks, few same-address atomics
     if (cache == CACHE_ALL) k_world_verts<true, 1><<<wvb, 256, 0, w->stream>>>(s, sview(w), g);
     else if (cache == CACHE_BIG) k_world_verts<true, 2><<<wvb, 256, 0, w->stream>>>(s, sview(w), g);
