@@ -1470,16 +1470,14 @@ struct GridView {
     float4* aabb;         // [2*cap]: lo.xyz + packed cell (as int bits, -1 = large) | hi.xyz
     float* params;        // [0..2] origin, [3] h, [4] sum of extents, [5..7] global min (ordered ints), [8] H (ordered int), [9] large threshold,
                           // [10..12] global max (ordered ints), [13..15] cells per axis (ints), [16] 1 = dense addressing (int), [17] bucket entries in use (int): see k_grid_params
-    int* bucket_cnt;      // [nbuckets]
+    int* bucket_cnt;      // [nbuckets + 32] (the entries past the buckets stay zero: the scan's last entry, bucket_off[nbuckets] = all of them)
     int* bucket_off;      // [nbuckets]
-    int* bucket_cur;      // [nbuckets] (only its first word is used: bucket_cnt[nbuckets] = 0 for the scan's last entry)
     int* items;           // [cap] k_cand's output: the searched bodies that have at least one candidate (active_count of them, any order)
     int* active_count;    // [1]
     float4* saabb;        // [2*cap] the boxes in bucket order: entry p = lo.xyz + packed cell | hi.xyz + body index (int bits) of items[p]
     int* large;           // [cap] large-body list
     int* large_count;     // [1]
     int* cand_cnt;        // [cap] actual candidates of body i
-    int* cand_ub;         // [cap] (unused)
     int* cand_off;        // [cap] start of body i's region in cand
     int* cand;            // [cand_cap]
     int* error;           // [1] set when cand_cap is exceeded

@@ -636,14 +636,14 @@ static int ensure_grid(np_world* w)
     const size_t c = (size_t)w->cap;
     int nb = 1024; while ((size_t)nb < 2 * c) nb <<= 1;
     const size_t cand_cap = std::min<size_t>((size_t)NP_CAND_PER_BODY * c, (size_t)1 << 30);
-    // ints: bucket_cnt[nb] bucket_cur[nb] (zeroed together) | bucket_off[nb + 1 (+31)] | items[c] | large[c] | cand_cnt[c] | cand_ub[c] | cand_off[c] | misc[32] | cand[cand_cap]
-    const size_t n_ints = 3 * (size_t)nb + 32 + 5 * c + 32 + cand_cap;
+    // ints: bucket_cnt[nb + 32] (zeroed every step) | bucket_off[nb + 1 (+31)] | items[c] | large[c] | cand_cnt[c] | cand_off[c] | misc[32] | cand[cand_cap]
+    const size_t n_ints = 2 * ((size_t)nb + 32) + 4 * c + 32 + cand_cap;
     CU(cudaMalloc((void**)&w->d_grid_ints, sizeof(int) * n_ints));
     CU(cudaMalloc((void**)&w->d_grid_f, sizeof(float) * (24 * c + 32)));      // aabb[2c] float4 | aabb_prev[2c] float4 | saabb[2c] float4 | params[32]
     GridView& g = w->grid;
     int* p = w->d_grid_ints;
-    g.bucket_cnt = p; p += nb; g.bucket_cur = p; p += nb; g.bucket_off = p; p += nb + 32; g.items = p; p += c; g.large = p; p += c;
-    g.cand_cnt = p; p += c; g.cand_ub = p; p += c; g.cand_off = p; p += c; g.large_count = p; g.error = p + 1; g.spill_cursor = p + 2; g.active_count = p + 3; p += 32; g.cand = p;
+    g.bucket_cnt = p; p += nb + 32; g.bucket_off = p; p += nb + 32; g.items = p; p += c; g.large = p; p += c;
+    g.cand_cnt = p; p += c; g.cand_off = p; p += c; g.large_count = p; g.error = p + 1; g.spill_cursor = p + 2; g.active_count = p + 3; p += 32; g.cand = p;
     g.aabb = (float4*)w->d_grid_f; g.aabb_prev = (float4*)w->d_grid_f + 2 * c; g.saabb = (float4*)w->d_grid_f + 4 * c; g.params = w->d_grid_f + 24 * c;
     g.nbuckets = nb; g.cand_cap = (int)std::min<size_t>(cand_cap, 0x7fffffff); g.spill_base = (int)std::min<size_t>(c * NP_CAND_SLOTS, 0x7fffffff);
     if (g.spill_base >= g.cand_cap) return fail(NP_ERR_CAPACITY, "world too large for the grid broad phase's candidate store");
@@ -668,7 +668,7 @@ static int enqueue_grid(np_world* w, const StoreView& s, int first, int count, i
     else k_world_verts<true, 0><<<wvb, 256, 0, w->stream>>>(s, sview(w), g);
     k_grid_params<<<1, 1, 0, w->stream>>>(n, g);
     k_grid_count<<<b256, 256, 0, w->stream>>>(s, g);
-    enqueue_scan(w, g.nbuckets + 1, g.bucket_cnt, g.bucket_off, (const int*)g.params + 17);      // one more than the buckets: bucket_cnt[nbuckets] is bucket_cur[0], still zero here, so bucket_off[nbuckets] = all of them
+    enqueue_scan(w, g.nbuckets + 1, g.bucket_cnt, g.bucket_off, (const int*)g.params + 17);      // one more than the buckets: bucket_cnt[nbuckets] is zero, so bucket_off[nbuckets] = all of them
     k_grid_fill<<<b256, 256, 0, w->stream>>>(s, g);
     if (count > 0) {                 // candidates of the bodies this process searches (the whole world unless sharded)
         k_cand<<<(n + 127) / 128, 128, 0, w->stream>>>(s, g, first, count, ctr, hit_j, flags);
