@@ -56,15 +56,17 @@ def narrow_flops(c0, c1):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  The timed region is tens of milliseconds
+    and nvidia-smi needs longer than that to start (several ranks start one each): it is started BEFORE the warm-up, mark() notes where
+    the timed region begins, and the samples from there to 0.15 s after its end are the ones reported."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
-        self.rows = []; self.p = None; self.gpu = gpu_index
+        self.rows = []; self.p = None; self.gpu = gpu_index; self.t0 = None
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
@@ -74,7 +76,10 @@ class ClockSampler:
         for line in self.p.stdout:
             f = [x.strip() for x in line.split(",")]
             if len(f) >= 9:
-                self.rows.append(f)
+                self.rows.append((time.perf_counter(), f))
+
+    def mark(self):
+        self.t0 = time.perf_counter()
 
     def stop(self):
         if not self.p:
@@ -84,14 +89,19 @@ class ClockSampler:
             self.p.wait(timeout=2)
         except Exception:
             self.p.kill()
-        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        allrows = list(self.rows)
+        rows = [f for (t, f) in allrows if self.t0 is None or t >= self.t0]
+        window = "from the start of the timed region to 0.15 s after its end"
+        if not rows and allrows:
+            rows = [f for (t, f) in allrows[-3:]]; window = "the last samples before the timed region (warm-up steps of the same world; none arrived inside it)"
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_reference_steps(scene, steps, warmup):
@@ -344,12 +354,13 @@ def run_ours(args, rank, local_rank, world_size):
         return (tot + tail) / nsteps, per
 
     log('world loaded, comm ready')
+    clocks = ClockSampler(local_rank); clocks.start()              # (nvidia-smi is up and sampling by the time the warm-up is through)
     if xchg is None: timed_steps(w, dt, warm)
     else: overlapped(warm)
     if dist is not None:
         dist.barrier(); torch.cuda.synchronize()
     w.synchronize()
-    clocks = ClockSampler(local_rank); clocks.start()
+    clocks.mark()
     c0 = w.counters()
     t_wall0 = time.perf_counter()
     if xchg is None:
