@@ -42,3 +42,24 @@ def test_product_arm_refuses_to_run_without_a_gpu(npb):
         pytest.skip("a GPU is visible here")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_clock_sampler_reports_the_samples_of_the_timed_region():
+    """The sampler runs from before the warm-up; what it reports are the rows that arrived after mark() (or, if none did, the last
+    rows before it, and it says so).  Throttle reasons come from the reported rows only."""
+    import time
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+    row = lambda mhz, cap: ["0", str(mhz), "1965", "400", "x", "Not Active", "Not Active", "Not Active", cap]
+    now = time.perf_counter()
+    c = bench.ClockSampler(0)
+    c.p = types.SimpleNamespace(terminate=lambda: None, wait=lambda timeout=None: None, kill=lambda: None)
+    c.rows = [(now - 1.0, row(1800, "Active")), (now - 0.5, row(1900, "Not Active"))]
+    c.t0 = now - 0.2
+    out = c.stop()
+    assert out["samples"] == 2 and out["sm_mhz"] == 1850.0 and "before the timed region" in out["window"] and out["reasons"] == ["sw_power_cap"]
+    c.rows.append((now + 0.01, row(1965, "Not Active")))
+    out = c.stop()
+    assert out["samples"] == 1 and out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == [] and "timed region to" in out["window"]
+    assert bench.ClockSampler(0).stop()["reasons"] == ["nvidia-smi unavailable"]
