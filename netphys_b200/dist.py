@@ -1,6 +1,8 @@
 """Multi-GPU host logic: independent worlds are sharded over ranks (no data-path collective); the only exchange is
 the all-gather of the per-step replication snapshot (36-byte CommandFrameObject records, netphys_common/common.h:120-127)
-that the networking layer sends to clients.  torch.distributed is the plumbing (nccl on GPUs, gloo in the CPU tests)."""
+that the networking layer sends to clients.  torch.distributed is the plumbing (nccl on GPUs, gloo in the CPU tests); on GPUs the
+exchange itself is the library's (init_world_comm + World.set_snapshot_gather: every np_world_step pushes its slot into the peers'
+buffers with the copy engines -- peers mapped through CUDA IPC, ncclAllGather as the fall-back -- see DESIGN.md section 6)."""
 import numpy as np
 
 
